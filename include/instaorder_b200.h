@@ -1,0 +1,168 @@
+/*
+ * instaorder_b200 -- C ABI of the B200-native pairwise-order hot path (libinstaorder_b200.so).
+ *
+ * The reference (POSTECH-CVLab/InstaOrder) is pure Python and has no FFI of its own; its boundary for this path is
+ * the Python API in inference.py / models/*.py.  This header is the interface a reference maintainer would bind
+ * with ctypes to replace the per-pair cv2 / torch-eager work with hand-written sm_100a kernels (INTEGRATION.md
+ * shows the stub).  Every entry point cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  `_dev` pointers are device memory owned by the caller
+ *     (e.g. torch tensors), `_host` pointers are host memory.  The library owns only what lives inside io_net_t.
+ *   - every device call takes the cudaStream_t to launch on (as void*) and never synchronises.
+ *   - return value: 0 = ok, negative = error (IO_ERR_*); io_last_error() returns the message (thread-local).
+ *   - one io_net_t per device; a handle is not thread-safe.
+ *   - there is no CPU fallback: a device entry point on a box without a GPU returns IO_ERR_CUDA.
+ */
+#ifndef INSTAORDER_B200_H_
+#define INSTAORDER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IO_ABI_VERSION 1
+
+#if defined(IO_BUILD)
+#define IO_API __attribute__((visibility("default")))
+#else
+#define IO_API
+#endif
+
+#define IO_OK 0
+#define IO_ERR_ARG (-1)       /* bad argument (shape, null pointer, unsupported size) */
+#define IO_ERR_CUDA (-2)      /* CUDA runtime / driver error */
+#define IO_ERR_DEGENERATE (-3) /* a pair whose crop side int(size) == 0: cv2.resize asserts in the reference */
+#define IO_ERR_STATE (-4)     /* handle used before weights were loaded, etc. */
+
+/* head kinds: how logits are turned into order decisions */
+#define IO_HEAD_OCC 1       /* 2 logits, sigmoid          -- inference.py:196-214 net_forward_occ        */
+#define IO_HEAD_DEPTH 2     /* 3 logits, softmax          -- inference.py:172-193 net_forward_depth      */
+#define IO_HEAD_ORDERNET 3  /* 3 or 4 logits, softmax     -- inference.py:44-76   net_forward_OrderNet   */
+
+IO_API int io_abi_version(void);
+IO_API const char* io_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* G -- pair construction                                                                                        */
+/* ------------------------------------------------------------------------------------------------------------ */
+
+/* Row-major (i, j), i < j, into out_pairs_host[2 * N(N-1)/2]; returns the count.
+ * Replaces the loops at inference.py:355-356, 443-444, 521-522. */
+IO_API int io_pair_enumerate(int n, int32_t* out_pairs_host);
+
+/* Tester.expand_bbox, tools/test.py:155-163: xywh (float64) -> square int boxes; out_host[4 n]. */
+IO_API int io_expand_bbox(const double* boxes_host, int n, double enlarge_box, int32_t* out_host);
+
+/* Crop window of every pair: combine_bbox (utils/data_utils.py:61-72) + inference.py:362-365.
+ * boxes_host[4 N] xywh float64 (integer boxes are passed as their float64 image), pairs_host[2 P],
+ * out_host[4 P] = (x, y, S, S) with python int() truncation.  Returns IO_ERR_DEGENERATE if some S <= 0
+ * (out is still filled so the caller can see which). */
+IO_API int io_pair_crop_boxes(const double* boxes_host, const int32_t* pairs_host, int p, int32_t* out_host);
+
+/* bordering(), inference.py:691-696, for P candidate pairs of one image:
+ * flags_dev[k] = any((dilate(mask[i], 3x3 cross) == 1) & mask[j]).  masks_dev is [N, H, W] u8. */
+IO_API int io_pair_bordering(const uint8_t* masks_dev, int n, int h, int w, const int32_t* pairs_dev, int p,
+                      uint8_t* flags_dev, void* stream);
+
+/* One record per pair for the fused gather.  Offsets are in bytes from the base pointers passed to the call. */
+typedef struct io_pair_desc {
+  int64_t image_off;  /* start of the pair's H x W x 3 u8 image                         */
+  int64_t mask_a_off; /* start of instance i's H x W u8 modal mask                       */
+  int64_t mask_b_off; /* start of instance j's H x W u8 modal mask                       */
+  int32_t h, w;       /* image size                                                      */
+  int32_t x, y, s;    /* crop window (io_pair_crop_boxes); ignored in resize mode        */
+  int32_t rgb_slot;   /* resize mode: index of the image's pre-resized rgb plane         */
+} io_pair_desc;
+
+/* Geometry of the gather output ("pair tensor"): [P, D + 6, row_pitch, 8] bf16, NHWC with 3 zero pixels of border
+ * on every side (conv1's padding, materialised) and channels (maskA, maskB, R, G, B, 0, 0, 0).  The interior
+ * [3:3+D, 3:3+D, 0:5] equals bf16(torch.cat([modal_i, modal_j, transform_rgb(rgb)], 1)) of inference.py:141-145;
+ * the (B, A) direction is the same tensor with channels 0/1 exchanged and is never materialised. */
+IO_API int64_t io_pair_tensor_row_pitch(int d);          /* pixels per padded row (multiple of 8, >= d + 6)          */
+IO_API int64_t io_pair_tensor_bytes(int p, int d);       /* bytes of a [p] pair tensor                                */
+
+/* Fused `patch` mode pair construction (inference.py:360-375 + utils/data_utils.py:28-34,104-124 + :141-145):
+ * crop_padding + cv2.INTER_CUBIC (OpenCV generic 8-bit path, bit-exact) of the rgb crop + cv2.INTER_NEAREST of both
+ * modal masks + /255, (x - mean) / std + bf16, written once into the pair tensor.
+ * images_dev / masks_dev: base pointers of the packed u8 images / masks; descs_dev[P]; mean/std: 3 floats (host). */
+IO_API int io_pair_gather_patch(const uint8_t* images_dev, const uint8_t* masks_dev, const io_pair_desc* descs_dev, int p,
+                         int d, const float* mean_host, const float* std_host, void* out_dev, void* stream);
+
+/* `resize` mode (inference.py:395-399, utils/data_utils.py:37-53, midas/transforms.py:48-235):
+ * step 1, once per image: image/255 -> cubic (float taps, no u8 rounding) to d x d -> normalise -> fp32 plane
+ * rgb_planes_dev[slot][d][d][3]; step 2, per pair: nearest-resized masks + the image's plane -> pair tensor. */
+IO_API int io_image_resize_rgb(const uint8_t* image_dev, int h, int w, int d, const float* mean_host, const float* std_host,
+                        float* rgb_plane_dev, void* stream);
+IO_API int io_pair_gather_resize(const float* rgb_planes_dev, const uint8_t* masks_dev, const io_pair_desc* descs_dev,
+                          int p, int d, void* out_dev, void* stream);
+
+/* (u8 / 255 - mean) / std in fp32 exactly as torchvision computes it; out_host[3 * 256].  Host only. */
+IO_API int io_normalize_lut(const float* mean_host, const float* std_host, float* out_host);
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* N -- network: 5-channel ResNet-50 classifier, models/backbone/resnet_cls.py:75-222                            */
+/* ------------------------------------------------------------------------------------------------------------ */
+
+typedef struct io_net io_net_t;
+
+/* n_heads = 1 (`fc`, num_classes int) or 2 (`fc_occ`, `fc_depth`; num_classes list) -- resnet_cls.py:153-160.
+ * input_size: 256 or 384 (any multiple of 32); max_pairs: largest P of a forward call (workspace is sized once). */
+IO_API int io_net_create(const int32_t* num_classes, int n_heads, int input_size, int max_pairs, io_net_t** out);
+IO_API int io_net_destroy(io_net_t* net);
+
+/* Loads a reference checkpoint's state_dict (models/single_stage_model.py:54-61, utils/common_utils.py:128-149):
+ * names[k] are the reference keys *without* the `module.` prefix ("conv1.weight", "layer1.0.bn1.running_var",
+ * "fc_occ.bias", ...), ptrs_host[k] the fp32 tensors in the reference's own layout (conv: [Cout, Cin, kh, kw]).
+ * Eval-mode BatchNorm is folded into the bf16 GEMM weights (scale) and an fp32 bias; missing keys are an error
+ * (num_batches_tracked is ignored). */
+IO_API int io_net_load_state(io_net_t* net, const char* const* names, const float* const* ptrs_host,
+                      const int64_t* numels, int n);
+
+/* Eval-mode forward of both directions of P pairs from a pair tensor (io_pair_gather_*):
+ * logits_dev[P][2][K] fp32 with K = sum(num_classes); [p][0] = f(A, B), [p][1] = f(B, A) (inference.py:144-145). */
+IO_API int io_net_forward_pairs(io_net_t* net, const void* pair_tensor_dev, int p, float* logits_dev, void* stream);
+
+/* number of kernel launches the last io_net_forward_pairs issued (bench.py's gpu_launches) */
+IO_API int io_net_last_launches(const io_net_t* net);
+
+/* H1-H5: probabilities, direction average, decision and scatter into the per-image order matrices.
+ * logits_dev[P][2][K]; head_kind/head_off/head_k select the columns of one head.
+ * pair_ij_dev[2 P]; mat_off_dev[P] = element offset of the pair's image matrix inside mat_dev (int64, row stride
+ * mat_n_dev[P]).  Matrices must be zero-initialised: like the reference, only decided entries are written
+ * (occ: ones; depth: both (i,j) and (j,i)) -- inference.py:416-434, 507-510, 612-623.
+ * margin_dev[P] (optional): decision margin, min |p - 0.5| (occ) or top1 - top2 (softmax heads). */
+IO_API int io_order_decide(const float* logits_dev, int p, int k_total, int head_kind, int head_off, int head_k,
+                    const int32_t* pair_ij_dev, const int64_t* mat_off_dev, const int32_t* mat_n_dev,
+                    int64_t* mat_dev, float* margin_dev, void* stream);
+
+/* Single convolution + folded BN (+ residual) (+ ReLU) on NHWC bf16, the building block of io_net_forward_pairs,
+ * exported for the per-layer parity tests.  w_dev: [Cout][kh*kw*Cin] bf16 (tap-major, channel-minor);
+ * kernel 1 or 3, stride 1 or 2, padding = kernel / 2; Cin, Cout multiples of 64. */
+IO_API int io_conv_bn_act(const void* x_dev, int b, int h, int w, int cin, const void* w_dev, const float* bias_dev,
+                   const void* residual_dev, int cout, int kernel, int stride, int relu, void* y_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* M -- metrics, batched over images                                                                             */
+/* ------------------------------------------------------------------------------------------------------------ */
+
+/* eval_order_recall_precision_f1, inference.py:794-802 (sklearn binary scores over entries with gt != -1, x100,
+ * zero_division = zd).  order_dev / gt_dev: packed int64 matrices, image b at mat_off_host-style offsets
+ * off_dev[b] with side n_dev[b].  out_dev[b][3] = (recall, precision, f1) float64, bit-identical to sklearn.
+ * An image with no entry gt != -1 yields NaN (the reference raises). */
+IO_API int io_metrics_prf(const int64_t* order_dev, const int64_t* gt_dev, const int64_t* off_dev, const int32_t* n_dev,
+                   int batch, int zd, double* out_dev, void* stream);
+
+/* eval_depth_order_whdr, inference.py:757-791: 9 WHDR variants over the strict upper triangle; out_dev[b][9] in
+ * the order ovlX_eq, ovlX_neq, ovlX_all, ovlO_eq, ..., ovlOX_all; -1 where the selection mask is empty.
+ * Sums follow numpy's pairwise summation order so results are bit-identical to the reference. */
+IO_API int io_metrics_whdr(const int64_t* order_dev, const int64_t* gt_order_dev, const int64_t* gt_overlap_dev,
+                    const int64_t* gt_count_dev, const int64_t* off_dev, const int32_t* n_dev, int batch,
+                    double* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSTAORDER_B200_H_ */

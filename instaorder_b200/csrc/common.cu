@@ -1,0 +1,85 @@
+// Error reporting, device query and TMA descriptor encoding for libinstaorder_b200.
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+
+namespace io {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return IO_ERR_CUDA;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, bool swizzle128) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return IO_ERR_CUDA;
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims,
+                  gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (rank %d dims %llu %llu %llu %llu %llu box %u %u %u %u %u base %p)",
+              static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+              rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0, base);
+    return IO_ERR_CUDA;
+  }
+  return IO_OK;
+}
+
+}  // namespace io
+
+extern "C" int io_abi_version(void) { return IO_ABI_VERSION; }
+extern "C" const char* io_last_error(void) { return io::g_err; }

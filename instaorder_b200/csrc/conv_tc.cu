@@ -1,0 +1,403 @@
+// Implicit-GEMM convolution for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (fp32 accumulators in
+// TMEM, double buffered) -> tcgen05.ld epilogue with folded-BN bias, residual add and ReLU fused, bf16 NHWC out.
+//
+// Replaces nn.Conv2d + nn.BatchNorm2d(eval) + ReLU (+ `out += identity`) of the reference's Bottleneck
+// (models/backbone/resnet_cls.py:96-116) and the stem conv1/bn1/relu (:204-206).
+//
+// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) and TMEM
+// owner, warps 2..5 = epilogue (one TMEM lane quadrant each).  GEMM view: M = output pixels (128 per tile),
+// N = output channels (BN per tile), K = taps * Cin in 64-wide blocks.  The A operand is never materialised:
+// every filter tap is one TMA box of the NHWC activation tensor, shifted by the tap offset; out-of-bounds rows /
+// columns are zero-filled by TMA, which *is* the convolution's zero padding.
+#include "conv_tc.cuh"
+
+namespace io {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers: 128 / 256 / 512 columns
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + slack for 1024 B alignment
+};
+
+struct TileCoord {
+  int n_img, h0, w0;   // first image / output row / output column of the tile
+  int base_row;        // flat output row of tile row 0
+  int limit;           // rows of the tile that exist (before the m_total clamp)
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int m_tile) {
+  TileCoord t;
+  if (p.mode == CONV_GEMM) {
+    t.n_img = 0; t.h0 = 0; t.w0 = 0;
+    t.base_row = m_tile * BM;
+    t.limit = BM;
+  } else {
+    const int g = m_tile / p.tpg, l = m_tile - g * p.tpg;
+    t.n_img = g * p.bi;
+    if (p.mode == CONV_STEM) {
+      t.h0 = l / p.tpr;
+      t.w0 = (l - t.h0 * p.tpr) * BM;
+      t.limit = min(p.rows_per_tile, p.w_out - t.w0);
+    } else {
+      t.h0 = l * p.bh;
+      t.w0 = 0;
+      t.limit = min(p.rows_per_tile, p.bi * p.hw_out - t.h0 * p.w_out);
+    }
+    t.base_row = t.n_img * p.hw_out + t.h0 * p.w_out + t.w0;
+  }
+  return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.map_a);
+    prefetch_tmap(&p.map_b);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const TileCoord t = tile_coord(p, m_tile);
+        int tap = 0, kb = 0;
+        for (int ki = 0; ki < p.k_iters; ++ki) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], p.a_bytes + C::B_STAGE_BYTES);
+          void* dA = sA + stage * A_STAGE_BYTES;
+          void* dB = sB + stage * C::B_STAGE_BYTES;
+          if (p.mode == CONV_GEMM) {
+            tma_load_2d(dA, &p.map_a, &full[stage], kb * BK, t.base_row);
+          } else if (p.mode == CONV_S1) {
+            const int r = tap / 3, s = tap - r * 3;
+            tma_load_4d(dA, &p.map_a, &full[stage], kb * BK, s - 1, t.h0 + r - 1, t.n_img);
+          } else if (p.mode == CONV_S2) {
+            const int r = tap / p.taps_w, s = tap - r * p.taps_w;
+            const int dr = r - p.pad, ds = s - p.pad;
+            const int ph = dr & 1, pw = ds & 1;
+            tma_load_5d(dA, &p.map_a, &full[stage], pw * p.cin + kb * BK, (ds - pw) / 2, ph, t.h0 + (dr - ph) / 2,
+                        t.n_img);
+          } else {  // CONV_STEM: filter row `tap`, 8 taps x 8 channels per K block
+            tma_load_4d(dA, &p.map_a, &full[stage], 0, t.w0, 2 * t.h0 + tap, t.n_img);
+          }
+          tma_load_2d(dB, &p.map_b, &full[stage], ki * BK, n_tile * BN);
+          if (++kb == p.kpt) { kb = 0; ++tap; }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int ki = 0; ki < p.k_iters; ++ki) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * C::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                      (ki > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot when these MMAs have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete
+      }
+    }
+  } else {
+    // ======================= epilogue (warps 2..5) =======================
+    const int q = warp & 3;  // TMEM lane quadrant accessible to this warp
+    const int r = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const TileCoord t = tile_coord(p, m_tile);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const bool valid = (r < t.limit) && (t.base_row + r < p.m_total);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, v);
+        tmem_ld_wait();
+        int col = n_tile * BN + c0;
+        if (valid && col < p.n_total) {
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col);
+          int row = t.base_row + r;
+          if (col >= p.n_split) { col -= p.n_split; row += p.split_row_off; }
+          const size_t off = static_cast<size_t>(row) * p.ldc + col;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(bias4 + j);
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+          }
+          if (p.residual != nullptr) {
+            const uint4* res = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rr = __ldg(res + j);
+              f[8 * j + 0] += bf16_lo(rr.x); f[8 * j + 1] += bf16_hi(rr.x);
+              f[8 * j + 2] += bf16_lo(rr.y); f[8 * j + 3] += bf16_hi(rr.y);
+              f[8 * j + 4] += bf16_lo(rr.z); f[8 * j + 5] += bf16_hi(rr.z);
+              f[8 * j + 6] += bf16_lo(rr.w); f[8 * j + 7] += bf16_hi(rr.w);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+            o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+            o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+            o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+            dst[j] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int BN>
+static int launch_bn(const ConvParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    IO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_tc_kernel<BN><<<grid, 192, Cfg<BN>::SMEM_BYTES, stream>>>(p);
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
+int conv_tc_launch(const ConvParams& p, int bn_tile, cudaStream_t stream) {
+  if (p.m_tiles <= 0 || p.n_tiles <= 0) return IO_OK;
+  switch (bn_tile) {
+    case 64: return launch_bn<64>(p, stream);
+    case 128: return launch_bn<128>(p, stream);
+    case 256: return launch_bn<256>(p, stream);
+  }
+  set_error("conv_tc_launch: unsupported N tile %d", bn_tile);
+  return IO_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side planning
+// ---------------------------------------------------------------------------------------------------------
+int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, const void* wgt, const float* bias,
+              const void* residual, void* y, int relu) {
+  IO_REQUIRE(d.kernel == 1 || d.kernel == 3, "conv: kernel %d not supported (1 or 3)", d.kernel);
+  IO_REQUIRE(d.stride == 1 || d.stride == 2, "conv: stride %d not supported", d.stride);
+  IO_REQUIRE(d.cin % 64 == 0 && d.cout % 64 == 0, "conv: channels must be multiples of 64 (cin %d cout %d)", d.cin,
+             d.cout);
+  IO_REQUIRE(d.stride == 1 || (d.h % 2 == 0 && d.w % 2 == 0), "conv: stride 2 needs even h, w");
+  IO_REQUIRE(d.b > 0 && d.h > 0 && d.w > 0, "conv: empty input");
+  *p = ConvParams{};
+  const int h_out = d.h / d.stride, w_out = d.w / d.stride;
+  const int ktot = d.kernel * d.kernel * d.cin;
+  p->bias = bias;
+  p->residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p->out = reinterpret_cast<__nv_bfloat16*>(y);
+  p->m_total = d.b * h_out * w_out;
+  p->n_total = d.cout;
+  p->k_iters = ktot / 64;
+  p->kpt = d.cin / 64;
+  p->taps_w = d.kernel;
+  p->pad = d.kernel / 2;
+  p->cin = d.cin;
+  p->w_out = w_out;
+  p->hw_out = h_out * w_out;
+  p->tpr = 1;
+  p->ldc = d.cout;
+  p->n_split = d.cout;
+  p->split_row_off = 0;
+  p->relu = relu;
+  const int bn = d.cout >= 256 ? 256 : d.cout;
+  IO_REQUIRE(d.cout % bn == 0, "conv: cout %d not a multiple of the N tile %d", d.cout, bn);
+  *bn_tile = bn;
+  p->n_tiles = d.cout / bn;
+
+  const uint64_t wdims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d.cout)};
+  const uint64_t wstr[1] = {static_cast<uint64_t>(ktot) * 2};
+  const uint32_t wbox[2] = {64, static_cast<uint32_t>(bn)};
+  int rc = make_tmap_bf16(&p->map_b, wgt, 2, wdims, wstr, wbox, true);
+  if (rc) return rc;
+
+  if (d.kernel == 1 && d.stride == 1) {
+    p->mode = CONV_GEMM;
+    p->rows_per_tile = BM;
+    p->tpg = 1; p->bi = 1; p->bh = 1;
+    p->m_tiles = (p->m_total + BM - 1) / BM;
+    const uint64_t dims[2] = {static_cast<uint64_t>(d.cin), static_cast<uint64_t>(p->m_total)};
+    const uint64_t str[1] = {static_cast<uint64_t>(d.cin) * 2};
+    const uint32_t box[2] = {64, BM};
+    rc = make_tmap_bf16(&p->map_a, x, 2, dims, str, box, true);
+  } else {
+    IO_REQUIRE(w_out <= BM, "conv: output width %d > %d not supported by the spatial tiler", w_out, BM);
+    if (p->hw_out <= BM) {
+      p->bh = h_out;
+      p->bi = BM / p->hw_out;
+      p->tpg = 1;
+      p->m_tiles = (d.b + p->bi - 1) / p->bi;
+    } else {
+      p->bh = BM / w_out;
+      p->bi = 1;
+      p->tpg = (h_out + p->bh - 1) / p->bh;
+      p->m_tiles = d.b * p->tpg;
+    }
+    p->rows_per_tile = p->bi * p->bh * w_out;
+    const uint64_t C = d.cin, W = d.w, H = d.h, B = d.b;
+    if (d.stride == 1) {
+      p->mode = CONV_S1;
+      const uint64_t dims[4] = {C, W, H, B};
+      const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+      const uint32_t box[4] = {64, static_cast<uint32_t>(w_out), static_cast<uint32_t>(p->bh),
+                               static_cast<uint32_t>(p->bi)};
+      rc = make_tmap_bf16(&p->map_a, x, 4, dims, str, box, true);
+    } else {
+      p->mode = CONV_S2;
+      const uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, B};
+      const uint64_t str[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
+      const uint32_t box[5] = {64, static_cast<uint32_t>(w_out), 1, static_cast<uint32_t>(p->bh),
+                               static_cast<uint32_t>(p->bi)};
+      rc = make_tmap_bf16(&p->map_a, x, 5, dims, str, box, true);
+    }
+  }
+  p->a_bytes = p->rows_per_tile * 128;
+  return rc;
+}
+
+int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, const void* wgt, const float* bias,
+              void* y) {
+  IO_REQUIRE(d % 2 == 0 && d >= 32, "stem: input size %d", d);
+  *p = ConvParams{};
+  const int h_out = d / 2, w_out = d / 2;
+  const int64_t pitch = io_pair_tensor_row_pitch(d);
+  const int hp = d + 6;
+  p->bias = bias;
+  p->residual = nullptr;
+  p->out = reinterpret_cast<__nv_bfloat16*>(y);
+  p->mode = CONV_STEM;
+  p->m_total = pairs * h_out * w_out;
+  p->n_total = 128;
+  p->k_iters = 7;
+  p->kpt = 1;
+  p->taps_w = 7;
+  p->pad = 3;
+  p->cin = 8;
+  p->w_out = w_out;
+  p->hw_out = h_out * w_out;
+  p->tpr = (w_out + BM - 1) / BM;
+  p->tpg = h_out * p->tpr;
+  p->bi = 1;
+  p->bh = 1;
+  p->rows_per_tile = w_out < BM ? w_out : BM;
+  p->m_tiles = pairs * p->tpg;
+  p->n_tiles = 1;
+  p->ldc = 64;
+  p->n_split = 64;
+  p->split_row_off = p->m_total;
+  p->relu = 1;
+  p->a_bytes = p->rows_per_tile * 128;
+  *bn_tile = 128;
+  // overlapping-window view of the padded pair tensor: dim0 = 8 pixels x 8 channels starting at padded pixel 2*wo,
+  // dim1 = output column (stride 2 pixels), dim2 = padded input row, dim3 = pair
+  const uint64_t dims[4] = {64, static_cast<uint64_t>(w_out), static_cast<uint64_t>(hp), static_cast<uint64_t>(pairs)};
+  const uint64_t str[3] = {32, static_cast<uint64_t>(pitch) * 16, static_cast<uint64_t>(hp) * pitch * 16};
+  const uint32_t box[4] = {64, static_cast<uint32_t>(p->rows_per_tile), 1, 1};
+  int rc = make_tmap_bf16(&p->map_a, x, 4, dims, str, box, true);
+  if (rc) return rc;
+  const uint64_t wdims[2] = {448, 128};
+  const uint64_t wstr[1] = {448 * 2};
+  const uint32_t wbox[2] = {64, 128};
+  return make_tmap_bf16(&p->map_b, wgt, 2, wdims, wstr, wbox, true);
+}
+
+}  // namespace io
+
+// ---- exported single-conv entry point (per-layer parity tests) ---------------------------------------------
+extern "C" int io_conv_bn_act(const void* x_dev, int b, int h, int w, int cin, const void* w_dev, const float* bias_dev,
+                              const void* residual_dev, int cout, int kernel, int stride, int relu, void* y_dev,
+                              void* stream) {
+  IO_REQUIRE(x_dev && w_dev && bias_dev && y_dev, "io_conv_bn_act: null pointer");
+  io::ConvParams p;
+  int bn = 0;
+  io::ConvDesc d{b, h, w, cin, cout, kernel, stride};
+  int rc = io::conv_plan(&p, &bn, d, x_dev, w_dev, bias_dev, residual_dev, y_dev, relu);
+  if (rc) return rc;
+  return io::conv_tc_launch(p, bn, io::as_stream(stream));
+}

@@ -1,0 +1,54 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (declarations shared by conv_tc.cu and net.cu).
+#pragma once
+#include "common.cuh"
+
+namespace io {
+
+enum ConvMode : int {
+  CONV_GEMM = 0,   // 1x1 stride 1: A is the flat [M, Cin] matrix (2-D tensor map)
+  CONV_S1 = 1,     // 3x3 stride 1 pad 1: A is {C, W, H, N} (4-D), one box per filter tap, OOB = zero padding
+  CONV_S2 = 2,     // k x k stride 2: A is the parity view {2C, W/2, 2, H/2, N} (5-D) of the input
+  CONV_STEM = 3,   // conv1 7x7 stride 2 on the padded 8-channel pair tensor: overlapping-window 4-D map
+};
+
+struct ConvParams {
+  CUtensorMap map_a;
+  CUtensorMap map_b;
+  const float* bias;              // [n_total] fp32 (folded BN shift)
+  const __nv_bfloat16* residual;  // optional, indexed like out
+  __nv_bfloat16* out;             // [rows, ldc] bf16
+  int mode;
+  int m_total;        // valid output rows (pixels over the whole batch)
+  int n_total;        // GEMM N (= Cout, or 2*64 for the two-direction stem)
+  int k_iters;        // number of 64-wide K blocks
+  int kpt;            // K blocks per filter tap (Cin / 64)
+  int taps_w;         // filter width (3 or 1)
+  int pad;            // filter padding (1 or 0)
+  int cin;            // input channels (parity offset in CONV_S2)
+  int a_bytes;        // bytes one A box brings (rows_per_tile * 128)
+  // tile -> output rows
+  int m_tiles, n_tiles;
+  int rows_per_tile;  // <= 128
+  int tpg;            // tiles per image group
+  int bi, bh;         // images / output rows per tile
+  int w_out, hw_out;
+  int tpr;            // CONV_STEM: tiles per output row
+  int ldc;            // output row stride in elements
+  int n_split;        // columns >= n_split go to rows + split_row_off (stem: second direction); else n_total
+  int split_row_off;
+  int relu;
+};
+
+// Launches the persistent kernel for one convolution. bn_tile in {64, 128, 256}.
+int conv_tc_launch(const ConvParams& p, int bn_tile, cudaStream_t stream);
+
+// Fills tile geometry + tensor maps for a conv over NHWC bf16 input [b, h, w, cin] (or the pair tensor for the stem).
+struct ConvDesc {
+  int b, h, w, cin, cout, kernel, stride;
+};
+int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, const void* wgt, const float* bias,
+              const void* residual, void* y, int relu);
+// Stem plan: x is the padded pair tensor [pairs, d+6, pitch, 8]; y is [2*pairs, d/2, d/2, 64] (direction-major).
+int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, const void* wgt, const float* bias, void* y);
+
+}  // namespace io

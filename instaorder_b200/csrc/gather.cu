@@ -1,0 +1,448 @@
+// Pair construction: crop-window geometry (host, float64), bordering test and the fused gather kernels.
+//
+// Replaces, per pair, utils.crop_padding x3 + cv2.resize(INTER_CUBIC) + cv2.resize(INTER_NEAREST) x2 +
+// transform_rgb + 2 H2D copies + torch.cat (reference inference.py:360-375, :141-145; utils/data_utils.py:28-34,
+// :104-124) by ONE kernel that reads the u8 image / masks in HBM and writes the bf16 NHWC pair tensor once.
+//
+// Arithmetic follows OpenCV 4.13's generic (non-IPP) resize exactly (see oracle/oracle.py): 11-bit fixed-point
+// cubic taps (A = -0.75) built with un-fused fp32 operations, integer horizontal pass, fp32 vertical pass in the
+// order 3,2,1,0 without fma, round-half-even, saturate; nearest = floor(dst * (1 / (D / S))) in double.
+#include "common.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace io {
+
+constexpr int GATHER_ROWS = 8;      // output rows per CTA
+constexpr int GATHER_THREADS = 128;
+constexpr int MAX_D = 512;
+
+struct NormLut {
+  uint16_t v[3][256];  // bf16 bits of (u8 / 255 - mean) / std
+};
+
+static inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+static void fill_lut_f32(const float* mean, const float* stdv, float* out) {
+  for (int c = 0; c < 3; ++c)
+    for (int v = 0; v < 256; ++v) {
+      volatile float x = static_cast<float>(v) / 255.0f;  // image / 255.   (fp32, as torch)
+      volatile float y = x - mean[c];                      // Normalize: sub_(mean)
+      out[c * 256 + v] = y / stdv[c];                      //            div_(std)
+    }
+}
+
+// ---- per-axis resampling tables ---------------------------------------------------------------------------
+struct AxisTab {
+  int near;       // nearest source index
+  int first;      // first cubic tap (may be < 0 / > S-4: taps are clamped to the crop)
+  short coef[4];  // 11-bit fixed-point cubic weights
+};
+
+__device__ __forceinline__ AxisTab axis_entry(int dst, int src_len, int dst_len) {
+  AxisTab t;
+  const double inv = __ddiv_rn(static_cast<double>(dst_len), static_cast<double>(src_len));
+  const double scale = __ddiv_rn(1.0, inv);
+  // nearest: cvFloor(x * ifx), clamped
+  int n = static_cast<int>(floor(__dmul_rn(static_cast<double>(dst), scale)));
+  t.near = min(n, src_len - 1);
+  // cubic: fx = (float)((dx + 0.5) * scale - 0.5)
+  float fx = static_cast<float>(__dsub_rn(__dmul_rn(static_cast<double>(dst) + 0.5, scale), 0.5));
+  const float sxf = floorf(fx);
+  const int sx = static_cast<int>(sxf);
+  const float x = __fsub_rn(fx, sxf);
+  const float A = -0.75f;
+  const float xp1 = __fadd_rn(x, 1.0f);
+  const float omx = __fsub_rn(1.0f, x);
+  // coeffs[0] = ((A*(x + 1) - 5*A)*(x + 1) + 8*A)*(x + 1) - 4*A
+  float c0 = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, xp1), __fmul_rn(5.0f, A)), xp1),
+                                            __fmul_rn(8.0f, A)), xp1), __fmul_rn(4.0f, A));
+  // coeffs[1] = ((A + 2)*x - (A + 3))*x*x + 1
+  float c1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.0f), x), __fadd_rn(A, 3.0f)), x), x),
+                       1.0f);
+  // coeffs[2] = ((A + 2)*(1 - x) - (A + 3))*(1 - x)*(1 - x) + 1
+  float c2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.0f), omx), __fadd_rn(A, 3.0f)), omx),
+                                 omx), 1.0f);
+  float c3 = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, c0), c1), c2);
+  const float c[4] = {c0, c1, c2, c3};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int iv = __float2int_rn(__fmul_rn(c[k], 2048.0f));
+    t.coef[k] = static_cast<short>(max(-32768, min(32767, iv)));
+  }
+  t.first = sx - 1;
+  return t;
+}
+
+__device__ __forceinline__ void store_pixel(__nv_bfloat16* dst, float ma, float mb, uint16_t r, uint16_t g,
+                                            uint16_t b) {
+  uint4 o;
+  o.x = pack_bf16(ma, mb);
+  o.y = static_cast<uint32_t>(r) | (static_cast<uint32_t>(g) << 16);
+  o.z = static_cast<uint32_t>(b);
+  o.w = 0u;
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+
+// zero the 3-pixel border (and the pitch padding) that belongs to this CTA's rows
+__device__ __forceinline__ void zero_borders(__nv_bfloat16* out_pair, int d, int pitch, int band, int n_bands,
+                                             int row0, int row1) {
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  const int hp = d + 6;
+  // left / right borders of the band's interior rows
+  const int side = 3 + (pitch - d - 3);
+  for (int i = threadIdx.x; i < (row1 - row0) * side; i += blockDim.x) {
+    const int rr = row0 + i / side, k = i % side;
+    const int col = k < 3 ? k : d + 3 + (k - 3);
+    *reinterpret_cast<uint4*>(out_pair + (static_cast<size_t>(rr + 3) * pitch + col) * 8) = z;
+  }
+  if (band == 0)
+    for (int i = threadIdx.x; i < 3 * pitch; i += blockDim.x)
+      *reinterpret_cast<uint4*>(out_pair + static_cast<size_t>(i) * 8) = z;
+  if (band == n_bands - 1)
+    for (int i = threadIdx.x; i < 3 * pitch; i += blockDim.x)
+      *reinterpret_cast<uint4*>(out_pair + (static_cast<size_t>(hp - 3) * pitch + i) * 8) = z;
+}
+
+__global__ void __launch_bounds__(GATHER_THREADS) gather_patch_kernel(const uint8_t* __restrict__ images,
+                                                                      const uint8_t* __restrict__ masks,
+                                                                      const io_pair_desc* __restrict__ descs, int d,
+                                                                      int pitch, NormLut lut,
+                                                                      __nv_bfloat16* __restrict__ out) {
+  __shared__ AxisTab tab[MAX_D];
+  __shared__ uint16_t slut[3][256];
+  const io_pair_desc ds = descs[blockIdx.y];
+  const int S = ds.s;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) tab[i] = axis_entry(i, S, d);
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) (&slut[0][0])[i] = (&lut.v[0][0])[i];
+  __syncthreads();
+
+  const uint8_t* __restrict__ img = images + ds.image_off;
+  const uint8_t* __restrict__ ma = masks + ds.mask_a_off;
+  const uint8_t* __restrict__ mb = masks + ds.mask_b_off;
+  const int H = ds.h, W = ds.w, X = ds.x, Y = ds.y;
+  __nv_bfloat16* out_pair = out + static_cast<size_t>(blockIdx.y) * (d + 6) * pitch * 8;
+  const int row0 = blockIdx.x * GATHER_ROWS;
+  const int row1 = min(d, row0 + GATHER_ROWS);
+  zero_borders(out_pair, d, pitch, blockIdx.x, gridDim.x, row0, row1);
+  const float kscale = 1.0f / (2048.0f * 2048.0f);
+
+  for (int dy = row0; dy < row1; ++dy) {
+    const AxisTab ty = tab[dy];
+    const int my = Y + ty.near;
+    const bool my_ok = my >= 0 && my < H;
+    int iy[4];
+    bool oky[4];
+    float by[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = min(max(ty.first + k, 0), S - 1);
+      iy[k] = Y + yy;
+      oky[k] = iy[k] >= 0 && iy[k] < H;
+      by[k] = __fmul_rn(static_cast<float>(ty.coef[k]), kscale);
+    }
+    for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
+      const AxisTab tx = tab[dx];
+      // ---- modal masks: nearest
+      const int mx = X + tx.near;
+      float va = 0.0f, vb = 0.0f;
+      if (my_ok && mx >= 0 && mx < W) {
+        const size_t o = static_cast<size_t>(my) * W + mx;
+        va = static_cast<float>(ma[o]);
+        vb = static_cast<float>(mb[o]);
+      }
+      // ---- rgb: bicubic, horizontal (int) then vertical (fp32)
+      int ix[4];
+      bool okx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int xx = min(max(tx.first + j, 0), S - 1);
+        ix[j] = X + xx;
+        okx[j] = ix[j] >= 0 && ix[j] < W;
+      }
+      int hsum[4][3];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        hsum[k][0] = hsum[k][1] = hsum[k][2] = 0;
+        if (oky[k]) {
+          const uint8_t* rowp = img + static_cast<size_t>(iy[k]) * W * 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (okx[j]) {
+              const uint8_t* px = rowp + ix[j] * 3;
+              const int cj = tx.coef[j];
+              hsum[k][0] += static_cast<int>(px[0]) * cj;
+              hsum[k][1] += static_cast<int>(px[1]) * cj;
+              hsum[k][2] += static_cast<int>(px[2]) * cj;
+            }
+          }
+        }
+      }
+      uint16_t rgb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = __fmul_rn(static_cast<float>(hsum[3][c]), by[3]);
+        v = __fadd_rn(__fmul_rn(static_cast<float>(hsum[2][c]), by[2]), v);
+        v = __fadd_rn(__fmul_rn(static_cast<float>(hsum[1][c]), by[1]), v);
+        v = __fadd_rn(__fmul_rn(static_cast<float>(hsum[0][c]), by[0]), v);
+        const int u = min(max(__float2int_rn(v), 0), 255);
+        rgb[c] = slut[c][u];
+      }
+      store_pixel(out_pair + (static_cast<size_t>(dy + 3) * pitch + dx + 3) * 8, va, vb, rgb[0], rgb[1], rgb[2]);
+    }
+  }
+}
+
+// ---- resize mode --------------------------------------------------------------------------------------------
+struct AxisTabF {
+  int first;
+  float coef[4];
+};
+
+__device__ __forceinline__ AxisTabF axis_entry_f(int dst, int src_len, int dst_len) {
+  AxisTabF t;
+  const double inv = __ddiv_rn(static_cast<double>(dst_len), static_cast<double>(src_len));
+  const double scale = __ddiv_rn(1.0, inv);
+  float fx = static_cast<float>(__dsub_rn(__dmul_rn(static_cast<double>(dst) + 0.5, scale), 0.5));
+  const float sxf = floorf(fx);
+  const float x = __fsub_rn(fx, sxf);
+  const float A = -0.75f;
+  const float xp1 = __fadd_rn(x, 1.0f);
+  const float omx = __fsub_rn(1.0f, x);
+  t.coef[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, xp1), __fmul_rn(5.0f, A)), xp1),
+                                            __fmul_rn(8.0f, A)), xp1), __fmul_rn(4.0f, A));
+  t.coef[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.0f), x), __fadd_rn(A, 3.0f)), x), x),
+                        1.0f);
+  t.coef[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.0f), omx), __fadd_rn(A, 3.0f)), omx),
+                                  omx), 1.0f);
+  t.coef[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, t.coef[0]), t.coef[1]), t.coef[2]);
+  t.first = static_cast<int>(sxf) - 1;
+  return t;
+}
+
+struct MeanStd {
+  double mean[3], stdv[3];
+};
+
+// One CTA per output row: image/255. (double) -> cubic with fp32 taps, double accumulation -> normalise -> fp32.
+__global__ void __launch_bounds__(GATHER_THREADS) resize_rgb_kernel(const uint8_t* __restrict__ img, int H, int W, int d,
+                                                                    MeanStd ms, float* __restrict__ plane) {
+  const int dy = blockIdx.x;
+  const AxisTabF ty = axis_entry_f(dy, H, d);
+  for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
+    const AxisTabF tx = axis_entry_f(dx, W, d);
+    double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = min(max(ty.first + k, 0), H - 1);
+      double h[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int xx = min(max(tx.first + j, 0), W - 1);
+        const uint8_t* px = img + (static_cast<size_t>(yy) * W + xx) * 3;
+        const double cj = static_cast<double>(tx.coef[j]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) h[c] += (static_cast<double>(px[c]) / 255.0) * cj;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += h[c] * static_cast<double>(ty.coef[k]);
+    }
+    float* o = plane + (static_cast<size_t>(dy) * d + dx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = static_cast<float>((acc[c] - ms.mean[c]) / ms.stdv[c]);
+  }
+}
+
+__global__ void __launch_bounds__(GATHER_THREADS) gather_resize_kernel(const float* __restrict__ planes,
+                                                                       const uint8_t* __restrict__ masks,
+                                                                       const io_pair_desc* __restrict__ descs, int d,
+                                                                       int pitch, __nv_bfloat16* __restrict__ out) {
+  const io_pair_desc ds = descs[blockIdx.y];
+  const uint8_t* __restrict__ ma = masks + ds.mask_a_off;
+  const uint8_t* __restrict__ mb = masks + ds.mask_b_off;
+  const float* __restrict__ plane = planes + static_cast<size_t>(ds.rgb_slot) * d * d * 3;
+  const int H = ds.h, W = ds.w;
+  __nv_bfloat16* out_pair = out + static_cast<size_t>(blockIdx.y) * (d + 6) * pitch * 8;
+  const int row0 = blockIdx.x * GATHER_ROWS;
+  const int row1 = min(d, row0 + GATHER_ROWS);
+  zero_borders(out_pair, d, pitch, blockIdx.x, gridDim.x, row0, row1);
+  const double sy = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(d), static_cast<double>(H)));
+  const double sx = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(d), static_cast<double>(W)));
+  for (int dy = row0; dy < row1; ++dy) {
+    const int my = min(static_cast<int>(floor(__dmul_rn(static_cast<double>(dy), sy))), H - 1);
+    for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
+      const int mx = min(static_cast<int>(floor(__dmul_rn(static_cast<double>(dx), sx))), W - 1);
+      const size_t o = static_cast<size_t>(my) * W + mx;
+      const float* px = plane + (static_cast<size_t>(dy) * d + dx) * 3;
+      const uint32_t rg = pack_bf16(px[0], px[1]);
+      const uint32_t b = pack_bf16(px[2], 0.0f);
+      store_pixel(out_pair + (static_cast<size_t>(dy + 3) * pitch + dx + 3) * 8, static_cast<float>(ma[o]),
+                  static_cast<float>(mb[o]), static_cast<uint16_t>(rg & 0xFFFF), static_cast<uint16_t>(rg >> 16),
+                  static_cast<uint16_t>(b & 0xFFFF));
+    }
+  }
+}
+
+// ---- bordering ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bordering_kernel(const uint8_t* __restrict__ masks, int H, int W,
+                                                        const int32_t* __restrict__ pairs,
+                                                        uint8_t* __restrict__ flags) {
+  const uint8_t* __restrict__ a = masks + static_cast<size_t>(pairs[2 * blockIdx.x]) * H * W;
+  const uint8_t* __restrict__ b = masks + static_cast<size_t>(pairs[2 * blockIdx.x + 1]) * H * W;
+  int hit = 0;
+  const int total = H * W;
+  for (int i = threadIdx.x; i < total && !hit; i += blockDim.x) {
+    if (b[i] & 1) {
+      const int y = i / W, x = i - y * W;
+      uint8_t m = a[i];
+      if (y > 0) m = max(m, a[i - W]);
+      if (y + 1 < H) m = max(m, a[i + W]);
+      if (x > 0) m = max(m, a[i - 1]);
+      if (x + 1 < W) m = max(m, a[i + 1]);
+      hit |= (m == 1);
+    }
+  }
+  hit = __syncthreads_or(hit);
+  if (threadIdx.x == 0) flags[blockIdx.x] = hit ? 1 : 0;
+}
+
+static int check_d(int d) {
+  IO_REQUIRE(d >= 32 && d <= MAX_D && d % 2 == 0, "input size %d not supported (even, 32..%d)", d, MAX_D);
+  return IO_OK;
+}
+
+}  // namespace io
+
+using namespace io;
+
+extern "C" int io_pair_enumerate(int n, int32_t* out) {
+  IO_REQUIRE(n >= 0 && (out || n < 2), "io_pair_enumerate: bad arguments");
+  int c = 0;
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) {
+      out[2 * c] = i;
+      out[2 * c + 1] = j;
+      ++c;
+    }
+  return c;
+}
+
+static inline double max3(double a, double b, double c) {
+  double m = a;
+  if (b > m) m = b;
+  if (c > m) m = c;
+  return m;
+}
+
+extern "C" int io_expand_bbox(const double* boxes, int n, double enlarge, int32_t* out) {
+  IO_REQUIRE(boxes && out && n >= 0, "io_expand_bbox: bad arguments");
+  for (int k = 0; k < n; ++k) {
+    const double x = boxes[4 * k], y = boxes[4 * k + 1], w = boxes[4 * k + 2], h = boxes[4 * k + 3];
+    const double cx = x + w / 2.0, cy = y + h / 2.0;
+    const double size = max3(sqrt(w * h * enlarge), w * 1.1, h * 1.1);
+    out[4 * k + 0] = static_cast<int32_t>(cx - size / 2.0);  // python int(): truncation toward zero
+    out[4 * k + 1] = static_cast<int32_t>(cy - size / 2.0);
+    out[4 * k + 2] = static_cast<int32_t>(size);
+    out[4 * k + 3] = static_cast<int32_t>(size);
+  }
+  return IO_OK;
+}
+
+extern "C" int io_pair_crop_boxes(const double* boxes, const int32_t* pairs, int p, int32_t* out) {
+  IO_REQUIRE(boxes && pairs && out && p >= 0, "io_pair_crop_boxes: bad arguments");
+  int degenerate = -1;
+  for (int k = 0; k < p; ++k) {
+    const double* a = boxes + 4 * pairs[2 * k];
+    const double* b = boxes + 4 * pairs[2 * k + 1];
+    const double l = a[0] < b[0] ? a[0] : b[0];
+    const double u = a[1] < b[1] ? a[1] : b[1];
+    const double ra = a[0] + a[2], rb = b[0] + b[2];
+    const double ba = a[1] + a[3], bb = b[1] + b[3];
+    const double r = ra > rb ? ra : rb;
+    const double bt = ba > bb ? ba : bb;
+    const double w = r - l, h = bt - u;
+    const double cx = l + w / 2.0, cy = u + h / 2.0;
+    const double size = max3(sqrt(w * h * 2.0), w * 1.1, h * 1.1);
+    out[4 * k + 0] = static_cast<int32_t>(cx - size / 2.0);
+    out[4 * k + 1] = static_cast<int32_t>(cy - size / 2.0);
+    out[4 * k + 2] = static_cast<int32_t>(size);
+    out[4 * k + 3] = static_cast<int32_t>(size);
+    if (out[4 * k + 2] <= 0 && degenerate < 0) degenerate = k;
+  }
+  if (degenerate >= 0) {
+    set_error("pair %d (%d,%d) is degenerate: crop side int(size) == %d (cv2.resize asserts in the reference)",
+              degenerate, pairs[2 * degenerate], pairs[2 * degenerate + 1], out[4 * degenerate + 2]);
+    return IO_ERR_DEGENERATE;
+  }
+  return IO_OK;
+}
+
+extern "C" int64_t io_pair_tensor_row_pitch(int d) { return (static_cast<int64_t>(d) + 6 + 7) / 8 * 8; }
+extern "C" int64_t io_pair_tensor_bytes(int p, int d) {
+  return static_cast<int64_t>(p) * (d + 6) * io_pair_tensor_row_pitch(d) * 8 * 2;
+}
+
+extern "C" int io_normalize_lut(const float* mean, const float* stdv, float* out) {
+  IO_REQUIRE(mean && stdv && out, "io_normalize_lut: null pointer");
+  fill_lut_f32(mean, stdv, out);
+  return IO_OK;
+}
+
+extern "C" int io_pair_bordering(const uint8_t* masks, int n, int h, int w, const int32_t* pairs, int p,
+                                 uint8_t* flags, void* stream) {
+  IO_REQUIRE(masks && pairs && flags && n > 0 && h > 0 && w > 0 && p >= 0, "io_pair_bordering: bad arguments");
+  if (p == 0) return IO_OK;
+  bordering_kernel<<<p, 256, 0, as_stream(stream)>>>(masks, h, w, pairs, flags);
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
+extern "C" int io_pair_gather_patch(const uint8_t* images, const uint8_t* masks, const io_pair_desc* descs, int p,
+                                    int d, const float* mean, const float* stdv, void* out, void* stream) {
+  IO_REQUIRE(images && masks && descs && mean && stdv && out && p >= 0, "io_pair_gather_patch: bad arguments");
+  if (int rc = check_d(d)) return rc;
+  if (p == 0) return IO_OK;
+  float lutf[768];
+  fill_lut_f32(mean, stdv, lutf);
+  NormLut lut;
+  for (int i = 0; i < 768; ++i) (&lut.v[0][0])[i] = f32_to_bf16_rn(lutf[i]);
+  dim3 grid((d + GATHER_ROWS - 1) / GATHER_ROWS, p);
+  gather_patch_kernel<<<grid, GATHER_THREADS, 0, as_stream(stream)>>>(images, masks, descs, d,
+                                                                      static_cast<int>(io_pair_tensor_row_pitch(d)),
+                                                                      lut, reinterpret_cast<__nv_bfloat16*>(out));
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
+extern "C" int io_image_resize_rgb(const uint8_t* image, int h, int w, int d, const float* mean, const float* stdv,
+                                   float* plane, void* stream) {
+  IO_REQUIRE(image && mean && stdv && plane && h > 0 && w > 0, "io_image_resize_rgb: bad arguments");
+  if (int rc = check_d(d)) return rc;
+  MeanStd ms;
+  for (int c = 0; c < 3; ++c) {
+    ms.mean[c] = static_cast<double>(mean[c]);
+    ms.stdv[c] = static_cast<double>(stdv[c]);
+  }
+  resize_rgb_kernel<<<d, GATHER_THREADS, 0, as_stream(stream)>>>(image, h, w, d, ms, plane);
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
+extern "C" int io_pair_gather_resize(const float* planes, const uint8_t* masks, const io_pair_desc* descs, int p,
+                                     int d, void* out, void* stream) {
+  IO_REQUIRE(planes && masks && descs && out && p >= 0, "io_pair_gather_resize: bad arguments");
+  if (int rc = check_d(d)) return rc;
+  if (p == 0) return IO_OK;
+  dim3 grid((d + GATHER_ROWS - 1) / GATHER_ROWS, p);
+  gather_resize_kernel<<<grid, GATHER_THREADS, 0, as_stream(stream)>>>(
+      planes, masks, descs, d, static_cast<int>(io_pair_tensor_row_pitch(d)), reinterpret_cast<__nv_bfloat16*>(out));
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}

@@ -1,0 +1,347 @@
+// io_net_t: the 5-channel ResNet-50 order classifier (reference models/backbone/resnet_cls.py:119-222) as a
+// static plan of tcgen05 implicit-GEMM convolutions over bf16 NHWC activations resident in HBM.
+//
+// Eval-mode BatchNorm is folded into the bf16 GEMM weights + an fp32 bias at load time; ReLU and the residual add
+// run in the convolution epilogues; both directions (A,B) / (B,A) of a pair are produced by ONE stem GEMM with
+// N = 2 x 64 output channels (the second half uses conv1 weights with input channels 0/1 exchanged), so the pair
+// tensor is read once and the swapped input of reference inference.py:145 is never materialised.
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "tail.cuh"
+
+namespace io {
+
+struct ConvW {
+  std::string name;      // e.g. "layer1.0.conv1"
+  std::string bn;        // e.g. "layer1.0.bn1"
+  int cin, cout, k, stride;
+  __nv_bfloat16* w = nullptr;  // [cout][k*k*cin]
+  float* bias = nullptr;       // [cout]
+};
+
+struct Op {
+  enum Kind { STEM, POOL, CONV, TAIL } kind;
+  ConvParams p;
+  int bn_tile = 0;
+  // POOL
+  const void* src = nullptr;
+  void* dst = nullptr;
+  int b = 0, h = 0, w = 0, c = 0;
+};
+
+struct Plan {
+  std::vector<Op> ops;
+  const void* feat = nullptr;
+  int hw_final = 0;
+};
+
+}  // namespace io
+
+struct io_net {
+  int n_heads = 0;
+  int num_classes[2] = {0, 0};
+  int k_total = 0;
+  int d = 0;
+  int max_pairs = 0;
+  int chunk_pairs = 0;
+  bool loaded = false;
+  int last_launches = 0;
+  std::vector<io::ConvW> convs;  // [0] = stem, then the 52 bottleneck convs in execution order
+  __nv_bfloat16* stem_w = nullptr;
+  float* stem_bias = nullptr;
+  float* fc_w = nullptr;
+  float* fc_b = nullptr;
+  __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t buf_elems = 0;
+  std::map<int, std::unique_ptr<io::Plan>> plans;
+};
+
+namespace io {
+
+static uint16_t bf16_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+static void build_conv_list(io_net* net) {
+  net->convs.clear();
+  ConvW stem;
+  stem.name = "conv1"; stem.bn = "bn1"; stem.cin = 5; stem.cout = 64; stem.k = 7; stem.stride = 2;
+  net->convs.push_back(stem);
+  int inpl = 64;
+  const int planes_[4] = {64, 128, 256, 512};
+  const int blocks_[4] = {3, 4, 6, 3};
+  for (int li = 0; li < 4; ++li) {
+    for (int b = 0; b < blocks_[li]; ++b) {
+      const std::string pre = "layer" + std::to_string(li + 1) + "." + std::to_string(b);
+      const int planes = planes_[li];
+      const int stride = (b == 0 && li > 0) ? 2 : 1;
+      ConvW c1{pre + ".conv1", pre + ".bn1", inpl, planes, 1, 1};
+      ConvW c2{pre + ".conv2", pre + ".bn2", planes, planes, 3, stride};
+      ConvW c3{pre + ".conv3", pre + ".bn3", planes, planes * 4, 1, 1};
+      net->convs.push_back(c1);
+      net->convs.push_back(c2);
+      if (b == 0) {
+        ConvW ds{pre + ".downsample.0", pre + ".downsample.1", inpl, planes * 4, 1, stride};
+        net->convs.push_back(ds);
+      }
+      net->convs.push_back(c3);
+      inpl = planes * 4;
+    }
+  }
+}
+
+static int build_plan(io_net* net, int pc, Plan* plan) {
+  const int b = 2 * pc;
+  const int d = net->d;
+  plan->ops.clear();
+  __nv_bfloat16 *X = net->buf[0], *Y = net->buf[1], *T1 = net->buf[2], *T2 = net->buf[3], *DS = net->buf[4];
+  {  // stem (tensor map for the caller's pair tensor is patched per call) + max-pool
+    Op op;
+    op.kind = Op::STEM;
+    plan->ops.push_back(op);
+    Op pool;
+    pool.kind = Op::POOL;
+    pool.src = X; pool.dst = Y; pool.b = b; pool.h = d / 2; pool.w = d / 2; pool.c = 64;
+    plan->ops.push_back(pool);
+  }
+  __nv_bfloat16* cur = Y;
+  __nv_bfloat16* nxt = X;
+  int h = d / 4, w = d / 4;
+  size_t ci = 1;
+  const int blocks_[4] = {3, 4, 6, 3};
+  for (int li = 0; li < 4; ++li) {
+    for (int blk = 0; blk < blocks_[li]; ++blk) {
+      const ConvW& c1 = net->convs[ci++];
+      const ConvW& c2 = net->convs[ci++];
+      const ConvW* ds = (blk == 0) ? &net->convs[ci++] : nullptr;
+      const ConvW& c3 = net->convs[ci++];
+      const int ho = h / c2.stride, wo = w / c2.stride;
+      Op o1; o1.kind = Op::CONV;
+      if (int rc = conv_plan(&o1.p, &o1.bn_tile, ConvDesc{b, h, w, c1.cin, c1.cout, 1, 1}, cur, c1.w, c1.bias, nullptr,
+                             T1, 1)) return rc;
+      plan->ops.push_back(o1);
+      Op o2; o2.kind = Op::CONV;
+      if (int rc = conv_plan(&o2.p, &o2.bn_tile, ConvDesc{b, h, w, c2.cin, c2.cout, 3, c2.stride}, T1, c2.w, c2.bias,
+                             nullptr, T2, 1)) return rc;
+      plan->ops.push_back(o2);
+      const __nv_bfloat16* identity = cur;
+      if (ds) {
+        Op od; od.kind = Op::CONV;
+        if (int rc = conv_plan(&od.p, &od.bn_tile, ConvDesc{b, h, w, ds->cin, ds->cout, 1, ds->stride}, cur, ds->w,
+                               ds->bias, nullptr, DS, 0)) return rc;
+        plan->ops.push_back(od);
+        identity = DS;
+      }
+      Op o3; o3.kind = Op::CONV;
+      if (int rc = conv_plan(&o3.p, &o3.bn_tile, ConvDesc{b, ho, wo, c3.cin, c3.cout, 1, 1}, T2, c3.w, c3.bias, identity,
+                             nxt, 1)) return rc;
+      plan->ops.push_back(o3);
+      std::swap(cur, nxt);
+      h = ho; w = wo;
+    }
+  }
+  plan->feat = cur;
+  plan->hw_final = h * w;
+  return IO_OK;
+}
+
+}  // namespace io
+
+using namespace io;
+
+extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_size, int max_pairs, io_net_t** out) {
+  IO_REQUIRE(num_classes && out, "io_net_create: null pointer");
+  IO_REQUIRE(n_heads == 1 || n_heads == 2, "io_net_create: n_heads must be 1 (fc) or 2 (fc_occ + fc_depth)");
+  IO_REQUIRE(input_size >= 64 && input_size <= 512 && input_size % 32 == 0,
+             "io_net_create: input_size %d (multiple of 32 in [64, 512])", input_size);
+  IO_REQUIRE(max_pairs >= 1, "io_net_create: max_pairs %d", max_pairs);
+  int dev_count = 0;
+  IO_CUDA(cudaGetDeviceCount(&dev_count));
+  std::unique_ptr<io_net> net(new io_net());
+  net->n_heads = n_heads;
+  for (int i = 0; i < n_heads; ++i) {
+    IO_REQUIRE(num_classes[i] >= 1 && num_classes[i] <= 4, "io_net_create: num_classes[%d] = %d", i, num_classes[i]);
+    net->num_classes[i] = num_classes[i];
+    net->k_total += num_classes[i];
+  }
+  net->d = input_size;
+  net->max_pairs = max_pairs;
+  int chunk = 32;
+  if (const char* e = getenv("INSTAORDER_CHUNK_PAIRS")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
+  net->chunk_pairs = std::min(chunk, max_pairs);
+  build_conv_list(net.get());
+  // device weights
+  for (size_t i = 1; i < net->convs.size(); ++i) {
+    ConvW& c = net->convs[i];
+    IO_CUDA(cudaMalloc(&c.w, static_cast<size_t>(c.cout) * c.k * c.k * c.cin * 2));
+    IO_CUDA(cudaMalloc(&c.bias, static_cast<size_t>(c.cout) * 4));
+  }
+  IO_CUDA(cudaMalloc(&net->stem_w, 128 * 448 * 2));
+  IO_CUDA(cudaMalloc(&net->stem_bias, 128 * 4));
+  IO_CUDA(cudaMalloc(&net->fc_w, static_cast<size_t>(net->k_total) * 2048 * 4));
+  IO_CUDA(cudaMalloc(&net->fc_b, static_cast<size_t>(net->k_total) * 4));
+  // activations: 5 buffers of [2*chunk, D/2, D/2, 64] elements (the stem output is the largest tensor per image)
+  net->buf_elems = static_cast<size_t>(2 * net->chunk_pairs) * (input_size / 2) * (input_size / 2) * 64;
+  for (int i = 0; i < 5; ++i) IO_CUDA(cudaMalloc(&net->buf[i], net->buf_elems * 2));
+  *out = net.release();
+  return IO_OK;
+}
+
+extern "C" int io_net_destroy(io_net_t* net) {
+  if (!net) return IO_OK;
+  for (auto& c : net->convs) {
+    cudaFree(c.w);
+    cudaFree(c.bias);
+  }
+  cudaFree(net->stem_w);
+  cudaFree(net->stem_bias);
+  cudaFree(net->fc_w);
+  cudaFree(net->fc_b);
+  for (int i = 0; i < 5; ++i) cudaFree(net->buf[i]);
+  delete net;
+  return IO_OK;
+}
+
+extern "C" int io_net_load_state(io_net_t* net, const char* const* names, const float* const* ptrs,
+                                 const int64_t* numels, int n) {
+  IO_REQUIRE(net && names && ptrs && numels, "io_net_load_state: null pointer");
+  std::map<std::string, std::pair<const float*, int64_t>> sd;
+  for (int i = 0; i < n; ++i) sd[names[i]] = {ptrs[i], numels[i]};
+  auto get = [&](const std::string& key, int64_t numel, const float** out) -> int {
+    auto it = sd.find(key);
+    if (it == sd.end()) {
+      set_error("io_net_load_state: missing key '%s'", key.c_str());
+      return IO_ERR_ARG;
+    }
+    if (it->second.second != numel) {
+      set_error("io_net_load_state: key '%s' has %lld elements, expected %lld", key.c_str(),
+                static_cast<long long>(it->second.second), static_cast<long long>(numel));
+      return IO_ERR_ARG;
+    }
+    *out = it->second.first;
+    return IO_OK;
+  };
+  const double eps = 1e-5;  // nn.BatchNorm2d default
+  for (size_t ci = 0; ci < net->convs.size(); ++ci) {
+    ConvW& c = net->convs[ci];
+    const float *w, *g, *bt, *mu, *var;
+    const int64_t wn = static_cast<int64_t>(c.cout) * c.cin * c.k * c.k;
+    if (int rc = get(c.name + ".weight", wn, &w)) return rc;
+    if (int rc = get(c.bn + ".weight", c.cout, &g)) return rc;
+    if (int rc = get(c.bn + ".bias", c.cout, &bt)) return rc;
+    if (int rc = get(c.bn + ".running_mean", c.cout, &mu)) return rc;
+    if (int rc = get(c.bn + ".running_var", c.cout, &var)) return rc;
+    std::vector<float> scale(c.cout), bias(c.cout);
+    for (int co = 0; co < c.cout; ++co) {
+      const double s = static_cast<double>(g[co]) / sqrt(static_cast<double>(var[co]) + eps);
+      scale[co] = static_cast<float>(s);
+      bias[co] = static_cast<float>(static_cast<double>(bt[co]) - static_cast<double>(mu[co]) * s);
+    }
+    if (ci == 0) {
+      // stem: rows [0,64) = direction (A,B); rows [64,128) = direction (B,A) (input channels 0 and 1 exchanged).
+      // K index = r * 64 + s * 8 + c with s < 7 real taps (+1 zero tap) and c < 5 real channels (+3 zero).
+      std::vector<uint16_t> pk(128 * 448, 0);
+      std::vector<float> b2(128);
+      for (int dir = 0; dir < 2; ++dir)
+        for (int co = 0; co < 64; ++co) {
+          b2[dir * 64 + co] = bias[co];
+          for (int cc = 0; cc < 5; ++cc) {
+            const int src_c = (dir == 1 && cc < 2) ? 1 - cc : cc;
+            for (int r = 0; r < 7; ++r)
+              for (int s = 0; s < 7; ++s) {
+                const float v = w[((static_cast<size_t>(co) * 5 + src_c) * 7 + r) * 7 + s] * scale[co];
+                pk[static_cast<size_t>(dir * 64 + co) * 448 + r * 64 + s * 8 + cc] = bf16_bits(v);
+              }
+          }
+        }
+      IO_CUDA(cudaMemcpy(net->stem_w, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+      IO_CUDA(cudaMemcpy(net->stem_bias, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice));
+    } else {
+      const int kk = c.k * c.k;
+      std::vector<uint16_t> pk(static_cast<size_t>(wn));
+      for (int co = 0; co < c.cout; ++co)
+        for (int cc = 0; cc < c.cin; ++cc)
+          for (int t = 0; t < kk; ++t) {
+            const float v = w[(static_cast<size_t>(co) * c.cin + cc) * kk + t] * scale[co];
+            pk[(static_cast<size_t>(co) * kk + t) * c.cin + cc] = bf16_bits(v);
+          }
+      IO_CUDA(cudaMemcpy(c.w, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+      IO_CUDA(cudaMemcpy(c.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  const char* heads1[1] = {"fc"};
+  const char* heads2[2] = {"fc_occ", "fc_depth"};
+  const char* const* heads = net->n_heads == 1 ? heads1 : heads2;
+  int row = 0;
+  for (int hI = 0; hI < net->n_heads; ++hI) {
+    const float *w, *b;
+    const int k = net->num_classes[hI];
+    if (int rc = get(std::string(heads[hI]) + ".weight", static_cast<int64_t>(k) * 2048, &w)) return rc;
+    if (int rc = get(std::string(heads[hI]) + ".bias", k, &b)) return rc;
+    IO_CUDA(cudaMemcpy(net->fc_w + static_cast<size_t>(row) * 2048, w, static_cast<size_t>(k) * 2048 * 4,
+                       cudaMemcpyHostToDevice));
+    IO_CUDA(cudaMemcpy(net->fc_b + row, b, static_cast<size_t>(k) * 4, cudaMemcpyHostToDevice));
+    row += k;
+  }
+  net->loaded = true;
+  return IO_OK;
+}
+
+extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int p, float* logits, void* stream_) {
+  IO_REQUIRE(net && pair_tensor && logits, "io_net_forward_pairs: null pointer");
+  if (!net->loaded) {
+    set_error("io_net_forward_pairs: no weights loaded (call io_net_load_state first)");
+    return IO_ERR_STATE;
+  }
+  IO_REQUIRE(p >= 0 && p <= net->max_pairs, "io_net_forward_pairs: %d pairs (handle was created for <= %d)", p,
+             net->max_pairs);
+  cudaStream_t stream = as_stream(stream_);
+  net->last_launches = 0;
+  const int64_t pair_bytes = io_pair_tensor_bytes(1, net->d);
+  for (int c0 = 0; c0 < p; c0 += net->chunk_pairs) {
+    const int pc = std::min(net->chunk_pairs, p - c0);
+    auto it = net->plans.find(pc);
+    if (it == net->plans.end()) {
+      std::unique_ptr<Plan> plan(new Plan());
+      if (int rc = build_plan(net, pc, plan.get())) return rc;
+      it = net->plans.emplace(pc, std::move(plan)).first;
+    }
+    Plan& plan = *it->second;
+    for (Op& op : plan.ops) {
+      int rc = IO_OK;
+      switch (op.kind) {
+        case Op::STEM:
+          rc = stem_plan(&op.p, &op.bn_tile, pc, net->d,
+                         reinterpret_cast<const uint8_t*>(pair_tensor) + static_cast<int64_t>(c0) * pair_bytes,
+                         net->stem_w, net->stem_bias, net->buf[0]);
+          if (!rc) rc = conv_tc_launch(op.p, op.bn_tile, stream);
+          break;
+        case Op::POOL:
+          rc = maxpool_launch(op.src, op.dst, op.b, op.h, op.w, op.c, stream);
+          break;
+        case Op::CONV:
+          rc = conv_tc_launch(op.p, op.bn_tile, stream);
+          break;
+        default:
+          break;
+      }
+      if (rc) return rc;
+      ++net->last_launches;
+    }
+    if (int rc = tail_launch(plan.feat, plan.hw_final, pc, net->fc_w, net->fc_b, net->k_total,
+                             logits + static_cast<size_t>(c0) * 2 * net->k_total, stream))
+      return rc;
+    ++net->last_launches;
+  }
+  return IO_OK;
+}
+
+extern "C" int io_net_last_launches(const io_net_t* net) { return net ? net->last_launches : 0; }

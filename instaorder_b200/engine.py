@@ -1,0 +1,375 @@
+"""Host side of the B200 pairwise-order path: batches the instance pairs of many images, stages the u8 images /
+masks through pinned memory, and drives the CUDA kernels behind the C ABI (``include/instaorder_b200.h``).
+
+The reference runs ``inference.py:349-624`` one pair at a time (2 batch-1 forwards + 5 host syncs per pair).  Here a
+*batch* is up to ``max_pairs`` pairs taken from consecutive images; per batch the device runs
+
+    H2D(images, masks, descriptors) -> fused gather -> ResNet-50 (both directions) -> decide + scatter
+
+with no host synchronisation; the order matrices of the whole call come back in one D2H copy at the end.
+PyTorch is used for device memory, pinned staging buffers and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+DATA_MEAN = (0.485, 0.456, 0.406)   # reference utils/data_utils.py:9-10
+DATA_STD = (0.229, 0.224, 0.225)
+
+# algo -> list of (head kind, number of logits, writes 'occ' | 'depth')
+HEADS = {
+    "InstaOrderNet_o": [(_lib.IO_HEAD_OCC, 2, "occ")],
+    "InstaOrderNet_d": [(_lib.IO_HEAD_DEPTH, 3, "depth")],
+    "InstaOrderNet_od": [(_lib.IO_HEAD_OCC, 2, "occ"), (_lib.IO_HEAD_DEPTH, 3, "depth")],
+    "OrderNet": [(_lib.IO_HEAD_ORDERNET, None, "occ")],   # 3 or 4 logits (OrderNet_ext)
+}
+
+
+def heads_for(algo, num_classes):
+    if algo not in HEADS:
+        raise ValueError("method name should be one of %s" % sorted(HEADS))
+    ncs = list(num_classes) if isinstance(num_classes, (list, tuple)) else [int(num_classes)]
+    heads = []
+    for (kind, k, what), nc in zip(HEADS[algo], ncs):
+        k = nc if k is None else k
+        if k != nc:
+            raise ValueError("%s expects %d logits, checkpoint head has %d" % (algo, k, nc))
+        heads.append((kind, k, what))
+    if len(heads) != len(ncs):
+        raise ValueError("%s: num_classes %r does not match its heads" % (algo, num_classes))
+    return heads
+
+
+class Scene:
+    """One image with its instances: the input contract of ``infer_order_sup_*`` (image [H,W,3] u8, inmodal
+    [N,H,W] u8, bboxes [N,4] xywh)."""
+    __slots__ = ("image", "masks", "boxes", "n", "h", "w")
+
+    def __init__(self, image, masks, boxes):
+        self.image = np.ascontiguousarray(image, dtype=np.uint8)
+        self.masks = np.ascontiguousarray(masks, dtype=np.uint8)
+        self.boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 4))
+        self.n, self.h, self.w = self.masks.shape
+        if self.image.shape != (self.h, self.w, 3):
+            raise ValueError("image %r does not match masks %r" % (self.image.shape, self.masks.shape))
+        if self.boxes.shape[0] != self.n:
+            raise ValueError("%d boxes for %d masks" % (self.boxes.shape[0], self.n))
+
+
+def enumerate_pairs(n):
+    out = np.empty((n * (n - 1) // 2, 2), dtype=np.int32)
+    c = _lib.check(_lib.lib().io_pair_enumerate(n, _lib.ptr(out)))
+    assert c == out.shape[0]
+    return out
+
+
+def expand_bbox(bboxes, enlarge_box=3.0):
+    """``Tester.expand_bbox`` (reference tools/test.py:155-163)."""
+    b = np.ascontiguousarray(np.asarray(bboxes, dtype=np.float64).reshape(-1, 4))
+    out = np.empty((b.shape[0], 4), dtype=np.int32)
+    _lib.check(_lib.lib().io_expand_bbox(_lib.ptr(b), b.shape[0], float(enlarge_box), _lib.ptr(out)))
+    return out.astype(np.int64)
+
+
+def pair_crop_boxes(boxes, pairs):
+    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 4))
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32)
+    out = np.empty((pairs.shape[0], 4), dtype=np.int32)
+    _lib.check(_lib.lib().io_pair_crop_boxes(_lib.ptr(b), _lib.ptr(pairs), pairs.shape[0], _lib.ptr(out)))
+    return out
+
+
+class _Slot:
+    """Pinned staging buffers + their device twins for one in-flight batch."""
+
+    def __init__(self, img_bytes, mask_bytes, max_pairs, device):
+        self.h_img = torch.empty(img_bytes, dtype=torch.uint8).pin_memory()
+        self.h_mask = torch.empty(mask_bytes, dtype=torch.uint8).pin_memory()
+        self.h_desc = torch.empty(max_pairs * 48, dtype=torch.uint8).pin_memory()
+        # rows of max_pairs int64: [0] = (i, j) as 2 x int32, [1] = matrix side N as int32, [2] = matrix offset
+        self.h_meta = torch.empty(max_pairs * 4, dtype=torch.int64).pin_memory()
+        self.d_img = torch.empty(img_bytes, dtype=torch.uint8, device=device)
+        self.d_mask = torch.empty(mask_bytes, dtype=torch.uint8, device=device)
+        self.d_desc = torch.empty(max_pairs * 48, dtype=torch.uint8, device=device)
+        self.d_meta = torch.empty(max_pairs * 4, dtype=torch.int64, device=device)
+        self.event = None
+
+
+class OrderEngine:
+    def __init__(self, num_classes, input_size=256, max_pairs=256, device="cuda:0", data_mean=DATA_MEAN,
+                 data_std=DATA_STD, img_bytes=32 << 20, mask_bytes=256 << 20, slots=2):
+        if not torch.cuda.is_available():
+            raise RuntimeError("instaorder_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.ncs = list(num_classes) if isinstance(num_classes, (list, tuple)) else [int(num_classes)]
+        self.k_total = sum(self.ncs)
+        self.d = int(input_size)
+        self.max_pairs = int(max_pairs)
+        self.mean = np.asarray(data_mean, dtype=np.float32)
+        self.std = np.asarray(data_std, dtype=np.float32)
+        ncs = np.asarray(self.ncs, dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(self.lib.io_net_create(_lib.ptr(ncs), len(self.ncs), self.d, self.max_pairs, C.byref(h)))
+        self.net = h
+        self.pair_tensor = torch.zeros(self.lib.io_pair_tensor_bytes(self.max_pairs, self.d), dtype=torch.uint8,
+                                       device=self.device)
+        self.logits = torch.empty((self.max_pairs, 2, self.k_total), dtype=torch.float32, device=self.device)
+        self.margins = torch.empty((2, self.max_pairs), dtype=torch.float32, device=self.device)
+        self._slot_args = (img_bytes, mask_bytes, self.max_pairs, self.device)
+        self._slots = [None] * slots
+        self._slot_i = 0
+        self.gpu_launches = 0   # kernels launched by this engine since creation
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "net", None):
+                self.lib.io_net_destroy(self.net)
+                self.net = None
+        except Exception:
+            pass
+
+    # ---- weights ------------------------------------------------------------------------------------------
+    def load_state_dict(self, sd):
+        """``sd``: a reference ``state_dict`` (keys with or without ``module.``; torch tensors or numpy)."""
+        names, arrs = [], []
+        for k, v in sd.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            k = k[7:] if k.startswith("module.") else k
+            a = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+            names.append(k.encode())
+            arrs.append(np.ascontiguousarray(a, dtype=np.float32))
+        n = len(names)
+        c_names = (C.c_char_p * n)(*names)
+        c_ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        c_numel = (C.c_int64 * n)(*[a.size for a in arrs])
+        _lib.check(self.lib.io_net_load_state(self.net, c_names, c_ptrs, c_numel, n))
+
+    # ---- low-level steps (also used by the tests) ------------------------------------------------------------
+    def _slot(self):
+        i = self._slot_i
+        self._slot_i = (i + 1) % len(self._slots)
+        if self._slots[i] is None:
+            self._slots[i] = _Slot(*self._slot_args)
+        s = self._slots[i]
+        if s.event is not None:
+            s.event.synchronize()   # the previous batch that used these pinned buffers has been consumed
+        return s
+
+    def stage_batch(self, items, mode="patch"):
+        """items: list of (scene, pairs int32[p,2], crops int32[p,4] | None, mat_off, scene_index).
+        Packs images / masks / descriptors into a pinned slot and issues the H2D copies.  Returns (slot, P)."""
+        s = self._slot()
+        img_off = mask_off = 0
+        P = 0
+        desc = np.frombuffer(s.h_desc.numpy(), dtype=_lib.PAIR_DESC_DTYPE)
+        meta = s.h_meta.numpy().reshape(4, self.max_pairs)
+        ij = meta[0:1].view(np.int32).reshape(-1)[: 2 * self.max_pairs].reshape(self.max_pairs, 2)
+        n32 = meta[1:2].view(np.int32).reshape(-1)[: self.max_pairs]
+        himg, hmask = s.h_img.numpy(), s.h_mask.numpy()
+        slot_idx = 0
+        self.resize_jobs = []
+        for (sc, pairs, crops, mat_off, _) in items:
+            p = pairs.shape[0]
+            ib, mb = sc.h * sc.w * 3, sc.n * sc.h * sc.w
+            if img_off + ib > himg.size or mask_off + mb > hmask.size:
+                raise ValueError("staging buffers too small for this batch (image %d B, masks %d B)" % (ib, mb))
+            himg[img_off:img_off + ib] = sc.image.reshape(-1)
+            hmask[mask_off:mask_off + mb] = sc.masks.reshape(-1)
+            d = desc[P:P + p]
+            d["image_off"] = img_off
+            d["mask_a_off"] = mask_off + pairs[:, 0].astype(np.int64) * (sc.h * sc.w)
+            d["mask_b_off"] = mask_off + pairs[:, 1].astype(np.int64) * (sc.h * sc.w)
+            d["h"], d["w"] = sc.h, sc.w
+            if crops is not None:
+                d["x"], d["y"], d["s"] = crops[:, 0], crops[:, 1], crops[:, 2]
+            else:
+                d["x"] = d["y"] = d["s"] = 0
+            d["rgb_slot"] = slot_idx
+            if mode == "resize":
+                self.resize_jobs.append((img_off, sc.h, sc.w, slot_idx))
+                slot_idx += 1
+            ij[P:P + p] = pairs
+            meta[2, P:P + p] = mat_off
+            n32[P:P + p] = sc.n
+            img_off += (ib + 15) // 16 * 16
+            mask_off += (mb + 15) // 16 * 16
+            P += p
+        s.d_img[:img_off].copy_(s.h_img[:img_off], non_blocking=True)
+        s.d_mask[:mask_off].copy_(s.h_mask[:mask_off], non_blocking=True)
+        s.d_desc[:P * 48].copy_(s.h_desc[:P * 48], non_blocking=True)
+        s.d_meta.copy_(s.h_meta, non_blocking=True)
+        self.h2d_bytes += img_off + mask_off + P * 48 + s.h_meta.numel() * 8
+        return s, P
+
+    def gather(self, s, P, mode="patch"):
+        st = _lib.stream_ptr()
+        if mode == "patch":
+            _lib.check(self.lib.io_pair_gather_patch(s.d_img.data_ptr(), s.d_mask.data_ptr(), s.d_desc.data_ptr(), P,
+                                                     self.d, _lib.ptr(self.mean), _lib.ptr(self.std),
+                                                     self.pair_tensor.data_ptr(), st))
+            self.gpu_launches += 1
+        elif mode == "resize":
+            n_img = len(self.resize_jobs)
+            need = n_img * self.d * self.d * 3
+            if getattr(self, "_planes", None) is None or self._planes.numel() < need:
+                self._planes = torch.empty(need, dtype=torch.float32, device=self.device)
+            for (img_off, h, w, slot) in self.resize_jobs:
+                _lib.check(self.lib.io_image_resize_rgb(s.d_img.data_ptr() + img_off, h, w, self.d,
+                                                        _lib.ptr(self.mean), _lib.ptr(self.std),
+                                                        self._planes.data_ptr() + slot * self.d * self.d * 12, st))
+            _lib.check(self.lib.io_pair_gather_resize(self._planes.data_ptr(), s.d_mask.data_ptr(),
+                                                      s.d_desc.data_ptr(), P, self.d, self.pair_tensor.data_ptr(),
+                                                      st))
+            self.gpu_launches += n_img + 1
+        else:
+            raise NotImplementedError("patch_or_image=%r (supported: 'patch', 'resize')" % (mode,))
+
+    def forward(self, P):
+        _lib.check(self.lib.io_net_forward_pairs(self.net, self.pair_tensor.data_ptr(), P, self.logits.data_ptr(),
+                                                 _lib.stream_ptr()))
+        self.gpu_launches += self.lib.io_net_last_launches(self.net)
+
+    def decide(self, s, P, heads, mats):
+        """heads: [(kind, k, 'occ'|'depth')]; mats: dict name -> flat int64 device tensor."""
+        meta = s.d_meta.view(4, self.max_pairs)
+        off = 0
+        for hi, (kind, k, what) in enumerate(heads):
+            _lib.check(self.lib.io_order_decide(self.logits.data_ptr(), P, self.k_total, kind, off, k,
+                                                meta[0].data_ptr(), meta[2].data_ptr(), meta[1].data_ptr(),
+                                                mats[what].data_ptr(), self.margins[hi].data_ptr(),
+                                                _lib.stream_ptr()))
+            off += k
+            self.gpu_launches += 1
+
+    def finish(self, s):
+        s.event = torch.cuda.Event()
+        s.event.record()
+
+    # ---- the batched driver ------------------------------------------------------------------------------
+    def infer_scenes(self, scenes, algo, pairs="all", patch_or_image="patch", return_details=False):
+        """Order matrices for a list of ``Scene``.  Returns a list of dicts with 'occ' / 'depth' int64 [N,N]
+        (+ 'pairs', 'logits', 'margin_occ', 'margin_depth' when ``return_details``)."""
+        heads = heads_for(algo, self.ncs if len(self.ncs) > 1 else self.ncs[0])
+        mode = patch_or_image
+        if mode not in ("patch", "resize"):
+            raise NotImplementedError("patch_or_image=%r (supported: 'patch', 'resize')" % (mode,))
+        # 1. pairs + crop windows per scene (host, float64 -- bit-exact with the reference's geometry)
+        work = []
+        mat_offs = []
+        tot = 0
+        for si, sc in enumerate(scenes):
+            pr = enumerate_pairs(sc.n)
+            if pairs == "nbor" and pr.shape[0]:
+                pr = pr[self.bordering(sc, pr)]
+            elif pairs not in ("all", "nbor"):
+                raise ValueError("pairs must be 'all' or 'nbor'")
+            crops = pair_crop_boxes(sc.boxes, pr) if (mode == "patch" and pr.shape[0]) else None
+            work.append((sc, pr, crops))
+            mat_offs.append(tot)
+            tot += sc.n * sc.n
+        mats = {w: torch.zeros(max(tot, 1), dtype=torch.int64, device=self.device) for (_, _, w) in heads}
+        details = [dict(pairs=w[1], logits=[], margins=[]) for w in work] if return_details else None
+        # 2. batches of <= max_pairs pairs
+        batch, count = [], 0
+
+        def flush():
+            nonlocal batch, count
+            if not batch:
+                return
+            s, P = self.stage_batch(batch, mode)
+            self.gather(s, P, mode)
+            self.forward(P)
+            self.decide(s, P, heads, mats)
+            self.finish(s)
+            if return_details:
+                lg = self.logits[:P].cpu().numpy()
+                mg = self.margins[:, :P].cpu().numpy()
+                self.d2h_bytes += lg.nbytes + mg.nbytes
+                o = 0
+                for (_, pr, _, _, si) in batch:
+                    details[si]["logits"].append(lg[o:o + pr.shape[0]])
+                    details[si]["margins"].append(mg[:, o:o + pr.shape[0]])
+                    o += pr.shape[0]
+            batch, count = [], 0
+
+        for si, (sc, pr, crops) in enumerate(work):
+            o = 0
+            while o < pr.shape[0]:
+                take = min(pr.shape[0] - o, self.max_pairs - count)
+                if take == 0:
+                    flush()
+                    continue
+                batch.append((sc, pr[o:o + take], None if crops is None else crops[o:o + take], mat_offs[si], si))
+                count += take
+                o += take
+                if count == self.max_pairs:
+                    flush()
+        flush()
+        # 3. one D2H for every matrix of the call
+        host = {w: m.cpu().numpy() for w, m in mats.items()}
+        self.d2h_bytes += sum(v.nbytes for v in host.values())
+        out = []
+        for si, sc in enumerate(scenes):
+            r = {}
+            for w, m in host.items():
+                r[w] = m[mat_offs[si]:mat_offs[si] + sc.n * sc.n].reshape(sc.n, sc.n).copy()
+            if return_details:
+                d = details[si]
+                r["pairs"] = d["pairs"]
+                r["logits"] = np.concatenate(d["logits"]) if d["logits"] else np.zeros((0, 2, self.k_total), np.float32)
+                mg = np.concatenate(d["margins"], axis=1) if d["margins"] else np.zeros((2, 0), np.float32)
+                for hi, (_, _, w) in enumerate(heads):
+                    r["margin_" + w] = mg[hi]
+            out.append(r)
+        return out
+
+    def bordering(self, sc, pairs):
+        """``bordering`` (reference inference.py:691-696) for every candidate pair of one scene -> bool[p]."""
+        m = torch.from_numpy(sc.masks).to(self.device)
+        pr = torch.from_numpy(np.ascontiguousarray(pairs, dtype=np.int32)).to(self.device)
+        flags = torch.empty(pairs.shape[0], dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.io_pair_bordering(m.data_ptr(), sc.n, sc.h, sc.w, pr.data_ptr(), pairs.shape[0],
+                                              flags.data_ptr(), _lib.stream_ptr()))
+        self.gpu_launches += 1
+        self.h2d_bytes += m.numel() + pr.numel() * 4
+        self.d2h_bytes += flags.numel()
+        return flags.cpu().numpy().astype(bool)
+
+
+# ---- metrics -----------------------------------------------------------------------------------------------
+def _pack_mats(mats, device):
+    ns = np.array([m.shape[0] for m in mats], dtype=np.int32)
+    offs = np.concatenate([[0], np.cumsum(ns.astype(np.int64) ** 2)[:-1]]).astype(np.int64)
+    flat = np.concatenate([np.asarray(m, dtype=np.int64).reshape(-1) for m in mats]) if len(mats) else \
+        np.zeros(0, np.int64)
+    return torch.from_numpy(flat).to(device), torch.from_numpy(offs).to(device), torch.from_numpy(ns).to(device)
+
+
+def metrics_prf(orders, gts, zd, device="cuda:0"):
+    """Batched ``eval_order_recall_precision_f1`` (reference inference.py:794-802) -> float64 [B, 3]."""
+    o, off, ns = _pack_mats(orders, device)
+    g, _, _ = _pack_mats(gts, device)
+    out = torch.empty((len(orders), 3), dtype=torch.float64, device=device)
+    _lib.check(_lib.lib().io_metrics_prf(o.data_ptr(), g.data_ptr(), off.data_ptr(), ns.data_ptr(), len(orders),
+                                         int(zd), out.data_ptr(), _lib.stream_ptr()))
+    return out.cpu().numpy()
+
+
+def metrics_whdr(orders, gt_orders, gt_overlaps, gt_counts, device="cuda:0"):
+    """Batched ``eval_depth_order_whdr`` (reference inference.py:764-791) -> float64 [B, 9]."""
+    o, off, ns = _pack_mats(orders, device)
+    g, _, _ = _pack_mats(gt_orders, device)
+    v, _, _ = _pack_mats(gt_overlaps, device)
+    c, _, _ = _pack_mats(gt_counts, device)
+    out = torch.empty((len(orders), 9), dtype=torch.float64, device=device)
+    _lib.check(_lib.lib().io_metrics_whdr(o.data_ptr(), g.data_ptr(), v.data_ptr(), c.data_ptr(), off.data_ptr(),
+                                          ns.data_ptr(), len(orders), out.data_ptr(), _lib.stream_ptr()))
+    return out.cpu().numpy()

@@ -1,0 +1,69 @@
+"""Drop-in replacements for the pairwise-order entry points of the reference's ``inference.py``.
+
+Same names, argument order and return types as the reference (file:line cited per function); the work is done by
+``OrderEngine`` (CUDA kernels behind ``libinstaorder_b200.so``).  ``model`` is one of the wrappers in
+``instaorder_b200.models`` (same constructor / ``load_state`` as the reference's ``models.*``).
+"""
+import collections
+
+import numpy as np
+
+from . import engine as _engine
+
+WHDR_KEYS = ["%s_%s" % (o, e) for o in ("ovlX", "ovlO", "ovlOX") for e in ("eq", "neq", "all")]
+
+
+def _run(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size):
+    eng = model.engine_for(input_size)
+    sc = _engine.Scene(image, inmodal, bboxes)
+    return eng.infer_scenes([sc], method, pairs=pairs, patch_or_image=patch_or_image)[0]
+
+
+def infer_order_sup_occ(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size=256, use_rgb=True):
+    """reference inference.py:439-512 -> int [N,N] occlusion order matrix."""
+    if method not in ("OrderNet", "InstaOrderNet_o"):
+        print("method name should be one of {OrderNet or InstaOrderNet_o}")   # reference :503-505
+        return
+    if not use_rgb:
+        raise NotImplementedError("use_rgb=False (2-channel nets): no shipped config uses it")
+    return _run(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size)["occ"]
+
+
+def infer_order_sup_depth(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size,
+                          disp_select_method, use_rgb=True):
+    """reference inference.py:515-624 -> (int [N,N] depth order matrix, disp_clipped=None)."""
+    if method != "InstaOrderNet_d":
+        if method in ("midas_pretrained", "InstaDepthNet_d", "InstaDepthNet_od"):
+            raise NotImplementedError("%s is outside the pairwise-order hot path (SURVEY.md section 8f)" % method)
+        print("method name should be one of {InstaOrderNet_d or midas_pretrained}")   # reference :608-610
+        return
+    if not use_rgb:
+        raise NotImplementedError("use_rgb=False (2-channel nets): no shipped config uses it")
+    return _run(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size)["depth"], None
+
+
+def infer_order_sup_occ_depth(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size,
+                              disp_select_method):
+    """reference inference.py:349-436 -> (occ_order, depth_order)."""
+    if method != "InstaOrderNet_od":
+        raise NotImplementedError("%s is outside the pairwise-order hot path (SURVEY.md section 8f)" % method)
+    r = _run(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size)
+    return r["occ"], r["depth"]
+
+
+def eval_order_recall_precision_f1(order_matrix, gt_order_matrix, zd):
+    """reference inference.py:794-802 -> (recall, precision, f1) x100, python floats."""
+    if not np.any(np.asarray(gt_order_matrix) != -1):
+        raise ValueError("Found empty input array (no entry with gt != -1)")   # sklearn raises in the reference
+    r = _engine.metrics_prf([order_matrix], [gt_order_matrix], zd)[0]
+    return float(r[0]), float(r[1]), float(r[2])
+
+
+def eval_depth_order_whdr(order_matrix, gt_order_ovl_count):
+    """reference inference.py:764-791 -> defaultdict(list) with the nine '{ovl}_{eq}' keys."""
+    gt, ovl, cnt = gt_order_ovl_count
+    r = _engine.metrics_whdr([order_matrix], [gt], [ovl], [cnt])[0]
+    out = collections.defaultdict(list)
+    for k, v in zip(WHDR_KEYS, r):
+        out[k].append(-1 if v == -1.0 else float(v))
+    return out

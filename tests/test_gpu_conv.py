@@ -1,0 +1,63 @@
+"""Per-layer parity of the tcgen05 implicit-GEMM convolution against a torch fp32 reference of the same op
+(floating point: tolerance = bf16 output rounding, 2^-8 relative, + accumulation-order noise)."""
+import pytest
+import torch
+
+from instaorder_b200 import _lib
+import gpu_util as U
+
+pytestmark = pytest.mark.gpu
+
+# (B, H, W, Cin, Cout, k, stride, residual, relu)  -- every ResNet-50 layer family at 256^2, plus ragged batches
+CASES = [
+    (4, 64, 64, 64, 64, 1, 1, False, True),      # layer1 conv1: K = 64 (one K block), N tile 64
+    (2, 64, 64, 64, 256, 1, 1, True, True),      # layer1 conv3 + residual, N tile 256
+    (2, 64, 64, 256, 128, 1, 1, False, True),    # layer2.0 conv1, N tile 128
+    (3, 64, 64, 64, 64, 3, 1, False, True),      # layer1 conv2: 3x3 s1, 2 rows x 64 per tile
+    (3, 32, 32, 128, 128, 3, 1, False, True),    # layer2 conv2: 4 rows x 32
+    (3, 16, 16, 256, 256, 3, 1, False, True),    # layer3 conv2: 8 rows x 16
+    (5, 8, 8, 512, 512, 3, 1, False, True),      # layer4 conv2: 2 images per tile, odd batch
+    (2, 64, 64, 128, 128, 3, 2, False, True),    # layer2.0 conv2: 3x3 s2
+    (3, 32, 32, 256, 256, 3, 2, False, True),    # layer3.0 conv2
+    (4, 16, 16, 512, 512, 3, 2, False, True),    # layer4.0 conv2
+    (2, 64, 64, 256, 512, 1, 2, False, False),   # layer2.0 downsample: 1x1 s2, no relu
+    (3, 16, 16, 1024, 2048, 1, 2, False, False), # layer4.0 downsample
+    (6, 8, 8, 2048, 512, 1, 1, False, True),     # layer4 conv1: K = 2048
+    (6, 8, 8, 512, 2048, 1, 1, True, True),      # layer4 conv3 + residual
+    (1, 64, 64, 64, 64, 1, 1, False, False),     # single image
+    (37, 8, 8, 512, 2048, 1, 1, True, True),     # M = 2368 (not a multiple of 128) -> row guard
+    (2, 96, 96, 64, 64, 3, 1, False, True),      # 384^2 geometry: 96-wide rows, 1 row per tile (96 of 128 rows)
+    (2, 24, 24, 256, 256, 3, 1, False, True),    # 384^2 layer3: 5 rows x 24 per tile, partial last tile
+    (2, 12, 12, 512, 512, 3, 1, False, True),    # 384^2 layer4: 10 rows x 12
+    (2, 48, 48, 128, 128, 3, 2, False, True),    # 384^2 s2: 24 x 24 out
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B%d_%dx%d_%d-%d_k%ds%d%s%s" % (
+    c[0], c[1], c[2], c[3], c[4], c[5], c[6], "_res" if c[7] else "", "_relu" if c[8] else ""))
+def test_conv_bn_act(case):
+    B, H, W, Cin, Cout, k, stride, use_res, relu = case
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H + Cin + Cout + k + stride)
+    dev = "cuda"
+    x = torch.randn((B, H, W, Cin), generator=g, device=dev).to(torch.bfloat16).contiguous()
+    w = (torch.randn((Cout, Cin, k, k), generator=g, device=dev) * (1.0 / (Cin * k * k) ** 0.5))
+    w = w.to(torch.bfloat16).float()
+    bias = torch.randn((Cout,), generator=g, device=dev)
+    Ho, Wo = H // stride, W // stride
+    res = torch.randn((B, Ho, Wo, Cout), generator=g, device=dev).to(torch.bfloat16).contiguous() if use_res else None
+    y = torch.full((B, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+    wp = U.pack_weight(w)
+    rc = _lib.lib().io_conv_bn_act(x.data_ptr(), B, H, W, Cin, wp.data_ptr(), bias.data_ptr(),
+                                   res.data_ptr() if use_res else None, Cout, k, stride, int(relu), y.data_ptr(),
+                                   _lib.stream_ptr())
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    ref = U.conv_reference(x, w, None, bias, res, stride, relu)
+    got = y.float()
+    assert torch.isfinite(got).all(), "unwritten / non-finite outputs: %d" % int((~torch.isfinite(got)).sum())
+    err = (got - ref).abs()
+    tol = 1e-2 + 1e-2 * ref.abs()
+    bad = err > tol
+    assert not bad.any(), "max err %.4g at %s (ref %.4g got %.4g), %d bad" % (
+        float(err.max()), tuple(int(v) for v in torch.nonzero(bad)[0]), float(ref[bad][0]), float(got[bad][0]),
+        int(bad.sum()))

@@ -1,0 +1,101 @@
+"""End-to-end parity through the reference-facing API: order matrices identical to the *reference's* on every
+pair whose decision margin exceeds 1e-3, logits within 2e-2 absolute of the reference's fp32 logits
+(BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from instaorder_b200 import engine, inference, models
+from oracle import calib, gen_golden
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-2
+
+
+def make_model(case, golden_dir):
+    c = gen_golden.CASES[case]
+    params = dict(algo=c["algo"], backbone_arch="resnet50_cls",
+                  backbone_param=dict(in_channels=5, num_classes=c["num_classes"]), optim="SGD", lr=1e-4,
+                  weight_decay=1e-4, use_rgb=True, max_pairs=32)
+    m = models.__dict__[c["algo"]](params, dist_model=False)
+    m.load_state_dict(calib.load_calibrated(gen_golden.calib_path(case), c["wseed"], 5, c["num_classes"]))
+    m.switch_to("eval")
+    return m
+
+
+@pytest.mark.parametrize("case", ["c1_o", "c2_od", "c3_ordernet", "c2_d", "c3_ordernet_ext", "c2_od_resize"])
+def test_order_matrices_match_reference(golden_dir, case):
+    c = gen_golden.CASES[case]
+    z = np.load(os.path.join(golden_dir, "order_%s.npz" % case))
+    image, masks, boxes = gen_golden.build_scene(case)
+    bexp = engine.expand_bbox(boxes, 3.0)
+    mode = c.get("patch_or_image", "patch")
+    D = c.get("input_size", 256)
+    model = make_model(case, golden_dir)
+    # details (logits, margins) through the engine ...
+    eng = model.engine_for(D)
+    r = eng.infer_scenes([engine.Scene(image, masks, bexp)], c["algo"], "all", mode, return_details=True)[0]
+    heads = engine.heads_for(c["algo"], c["num_classes"])
+    off = 0
+    for h, (_, k, what) in enumerate(heads):
+        ref = z["logits%d" % h]
+        got = r["logits"][:, :, off:off + k]
+        err = np.abs(got - ref).max()
+        assert err < LOGIT_TOL, "%s head %d: max |logit - reference| = %.4f" % (case, h, err)
+        off += k
+    N = masks.shape[0]
+    for what in ("occ", "depth"):
+        if what not in r:
+            continue
+        mg = np.full((N, N), np.inf)
+        for (i, j), m in zip(r["pairs"], r["margin_" + what]):
+            mg[i, j] = mg[j, i] = m
+        ok = mg > 1e-3
+        assert ok.sum() >= 0.8 * N * (N - 1)
+        assert np.array_equal(r[what][ok], z[what][ok]), (case, what)
+    # ... and the drop-in functions return the same matrices with the reference's signature / types
+    if c["algo"] == "InstaOrderNet_od":
+        occ, depth = inference.infer_order_sup_occ_depth(model, image, masks, bexp, "all", c["algo"], mode, D, "")
+        assert np.array_equal(occ, r["occ"]) and np.array_equal(depth, r["depth"])
+        assert occ.dtype == np.int64 and occ.shape == (N, N)
+    elif c["algo"] == "InstaOrderNet_d":
+        depth, disp = inference.infer_order_sup_depth(model, image, masks, bexp, "all", c["algo"], mode, D, "")
+        assert disp is None and np.array_equal(depth, r["depth"])
+    else:
+        occ = inference.infer_order_sup_occ(model, image, masks, bexp, "all", c["algo"], mode, D)
+        assert np.array_equal(occ, r["occ"])
+
+
+def test_nbor_pairs_and_multi_image_batching(golden_dir):
+    """pairs='nbor' skips non-bordering pairs (their entries stay 0); batching several images / splitting one
+    image over several batches gives the same matrices as one image at a time."""
+    case = "c2_od"
+    c = gen_golden.CASES[case]
+    model = make_model(case, golden_dir)
+    eng = model.engine_for(256)
+    from instaorder_b200 import synth
+    from oracle import oracle as O
+    rng = np.random.RandomState(21)
+    scenes = []
+    for n in (2, 9, 3, 7):           # 1 + 36 + 3 + 21 pairs with max_pairs = 32 -> images split across batches
+        img, masks, boxes = synth.make_scene(rng, 200, 260, n, wh_range=((20, 120), (20, 100)))
+        scenes.append(engine.Scene(img, masks, engine.expand_bbox(boxes, 3.0)))
+    together = eng.infer_scenes(scenes, c["algo"], "all", "patch")
+    for sc, r in zip(scenes, together):
+        alone = eng.infer_scenes([sc], c["algo"], "all", "patch")[0]
+        assert np.array_equal(alone["occ"], r["occ"]) and np.array_equal(alone["depth"], r["depth"])
+    sc = scenes[1]
+    nb = eng.infer_scenes([sc], c["algo"], "nbor", "patch")[0]
+    full = together[1]
+    for i in range(sc.n):
+        for j in range(i + 1, sc.n):
+            if O.bordering(sc.masks[i], sc.masks[j]):
+                assert nb["occ"][i, j] == full["occ"][i, j] and nb["depth"][i, j] == full["depth"][i, j]
+                assert nb["occ"][j, i] == full["occ"][j, i] and nb["depth"][j, i] == full["depth"][j, i]
+            else:
+                assert nb["occ"][i, j] == 0 and nb["occ"][j, i] == 0 and nb["depth"][i, j] == 0
+    # empty / single-instance images are legal and give empty / 1x1 zero matrices
+    e = eng.infer_scenes([engine.Scene(scenes[0].image, scenes[0].masks[:1], scenes[0].boxes[:1])], c["algo"])[0]
+    assert e["occ"].shape == (1, 1) and e["occ"][0, 0] == 0
