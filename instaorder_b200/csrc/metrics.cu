@@ -92,29 +92,53 @@ __device__ __forceinline__ void add2(double2& a, const double2 b) { a.x += b.x; 
 
 // numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src: @TYPE@_pairwise_sum), applied to both
 // streams at once: n < 8 sequential; n <= 128 eight interleaved accumulators; else split at n/2 rounded down to 8.
-__device__ double2 pairwise(TriGen& g, int n) {
+__device__ double2 pairwise_leaf(TriGen& g, int n) {
   if (n < 8) {
     double2 r = make_double2(0.0, 0.0);
     for (int i = 0; i < n; ++i) add2(r, g.next());
     return r;
   }
-  if (n <= 128) {
-    double2 r[8];
-    for (int k = 0; k < 8; ++k) r[k] = g.next();
-    int i;
-    for (i = 8; i < n - (n % 8); i += 8)
-      for (int k = 0; k < 8; ++k) add2(r[k], g.next());
-    double2 res;
-    res.x = ((r[0].x + r[1].x) + (r[2].x + r[3].x)) + ((r[4].x + r[5].x) + (r[6].x + r[7].x));
-    res.y = ((r[0].y + r[1].y) + (r[2].y + r[3].y)) + ((r[4].y + r[5].y) + (r[6].y + r[7].y));
-    for (; i < n; ++i) add2(res, g.next());
-    return res;
+  double2 r[8];
+  for (int k = 0; k < 8; ++k) r[k] = g.next();
+  int i;
+  for (i = 8; i < n - (n % 8); i += 8)
+    for (int k = 0; k < 8; ++k) add2(r[k], g.next());
+  double2 res;
+  res.x = ((r[0].x + r[1].x) + (r[2].x + r[3].x)) + ((r[4].x + r[5].x) + (r[6].x + r[7].x));
+  res.y = ((r[0].y + r[1].y) + (r[2].y + r[3].y)) + ((r[4].y + r[5].y) + (r[6].y + r[7].y));
+  for (; i < n; ++i) add2(res, g.next());
+  return res;
+}
+
+// the recursion of pairwise_sum unrolled onto an explicit stack (device call stacks are tiny)
+__device__ double2 pairwise(TriGen& g, int n) {
+  struct Frame { int n; int stage; double2 left; };
+  Frame st[32];
+  int sp = 0;
+  st[sp++] = Frame{n, 0, make_double2(0.0, 0.0)};
+  double2 ret = make_double2(0.0, 0.0);
+  while (sp > 0) {
+    Frame& f = st[sp - 1];
+    if (f.n <= 128) {
+      ret = pairwise_leaf(g, f.n);
+      --sp;
+      continue;
+    }
+    int n2 = f.n / 2;
+    n2 -= n2 % 8;
+    if (f.stage == 0) {
+      f.stage = 1;
+      st[sp++] = Frame{n2, 0, make_double2(0.0, 0.0)};
+    } else if (f.stage == 1) {
+      f.left = ret;
+      f.stage = 2;
+      st[sp++] = Frame{f.n - n2, 0, make_double2(0.0, 0.0)};
+    } else {
+      ret = make_double2(f.left.x + ret.x, f.left.y + ret.y);
+      --sp;
+    }
   }
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  const double2 a = pairwise(g, n2);
-  const double2 b = pairwise(g, n - n2);
-  return make_double2(a.x + b.x, a.y + b.y);
+  return ret;
 }
 
 // one thread per (image, key)

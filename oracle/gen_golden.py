@@ -32,7 +32,7 @@ CASES = {
                         wh_range=((20, 200), (20, 150))), expand=True, float_boxes=False),
     "c2_d": dict(algo="InstaOrderNet_d", num_classes=3, wseed=3, scene=dict(seed=11, H=375, W=500, N=5),
                  expand=True, float_boxes=True),
-    "c2_od_resize": dict(algo="InstaOrderNet_od", num_classes=[2, 3], wseed=0, scene=dict(seed=6, H=333, W=500, N=4),
+    "c2_od_resize": dict(algo="InstaOrderNet_od", num_classes=[2, 3], wseed=5, scene=dict(seed=6, H=333, W=500, N=4),
                          expand=True, float_boxes=True, patch_or_image="resize", input_size=384),
     "c3_ordernet_ext": dict(algo="OrderNet", num_classes=4, wseed=4, scene=dict(seed=13, H=375, W=1242, N=4,
                             wh_range=((20, 200), (20, 150))), expand=True, float_boxes=False),
@@ -81,7 +81,7 @@ def gen_calib():
             continue
         done.add(p)
         sd = synth.random_state_dict(c["wseed"], 5, c["num_classes"])
-        changed = calib.calibrate(sd)
+        changed = calib.calibrate(sd, D=c.get("input_size", 256), mode=c.get("patch_or_image", "patch"))
         np.savez_compressed(p, **changed)
         print("wrote", p, sum(v.size for v in changed.values()), "floats")
 

@@ -264,6 +264,54 @@ def resnet50_forward(sd, x, prefix="module.", eps=1e-5, bn_override=None, return
         return out
 
 
+def resnet50_forward_bf16(sd, x, prefix="module.", eps=1e-5):
+    """The same network evaluated with *ideal* bf16 storage: BN folded into bf16 weights (fp32 bias), every stored
+    activation rounded to bf16, fp32 accumulation -- the arithmetic contract of the CUDA path.  Used to
+    separate kernel bugs (CUDA vs this, tight tolerance) from bf16-vs-fp32 sensitivity (this vs resnet50_forward)."""
+    import torch
+    import torch.nn.functional as F
+
+    def r(t):
+        return t.to(torch.bfloat16).float()
+
+    def g(k):
+        v = sd[prefix + k]
+        return v if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v))
+
+    def fold(conv, bn):
+        s = (g(bn + ".weight").double() / torch.sqrt(g(bn + ".running_var").double() + eps))
+        w = r((g(conv + ".weight") * s.float()[:, None, None, None]))
+        b = (g(bn + ".bias").double() - g(bn + ".running_mean").double() * s).float()
+        return w, b[None, :, None, None]
+
+    with torch.no_grad():
+        x = x if isinstance(x, torch.Tensor) else torch.from_numpy(x)
+        w, b = fold("conv1", "bn1")
+        t = r(F.relu(F.conv2d(r(x), w, stride=2, padding=3) + b))
+        t = F.max_pool2d(t, 3, 2, 1)
+        for li, blocks in enumerate((3, 4, 6, 3), start=1):
+            for blk in range(blocks):
+                p = "layer%d.%d" % (li, blk)
+                stride = 2 if (blk == 0 and li > 1) else 1
+                idt = t
+                w, b = fold(p + ".conv1", p + ".bn1")
+                o = r(F.relu(F.conv2d(t, w) + b))
+                w, b = fold(p + ".conv2", p + ".bn2")
+                o = r(F.relu(F.conv2d(o, w, stride=stride, padding=1) + b))
+                w, b = fold(p + ".conv3", p + ".bn3")
+                o = F.conv2d(o, w) + b
+                if blk == 0:
+                    w, b = fold(p + ".downsample.0", p + ".downsample.1")
+                    idt = r(F.conv2d(t, w, stride=stride) + b)
+                t = r(F.relu(o + idt))
+        feat = torch.flatten(F.adaptive_avg_pool2d(t, 1), 1)
+        out = {}
+        for head in ("fc", "fc_occ", "fc_depth"):
+            if (prefix + head + ".weight") in sd:
+                out[head] = F.linear(feat, g(head + ".weight"), g(head + ".bias")).numpy()
+        return out
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # H -- heads / decisions / order matrices
 # ----------------------------------------------------------------------------------------------------------------
