@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""Benchmark of the pairwise-order hot path (BASELINE.json metric: instance pairs/s, InstaOrderNet^od, 256^2, bf16).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path, one process per GPU (torchrun for N>1)
+    python bench.py --impl reference ...                      # the reference algorithm on the box's host cores
+
+One *step* = one pass of the hot path (fused gather -> 5-ch ResNet-50, both directions -> decide + scatter) over
+one batch of 256 instance pairs cut from synthetic COCO-shaped images (10 instances -> 45 pairs / image, patch 256).
+`value`  : whole-job pairs/s with the u8 images / masks / pair descriptors already resident in HBM.
+`e2e`    : the same metric through the public API (`OrderEngine.infer_scenes`) from HOST numpy buffers: pinned staging,
+           H2D copies and the D2H read of the order matrices are inside the timed region.
+`roofline`: the tensor-core convolution kernel (conv_tc_kernel), algorithmic FLOPs / CUDA-event time per launch.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 21.764e9          # 2 x 10.882 GFLOP (conv + FC, 2*MAC) @256^2
+PAIRS_PER_STEP = 256
+ALGO = "InstaOrderNet_od"
+NUM_CLASSES = [2, 3]
+D = 256
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            j = json.load(f)
+        return dict(bf16=j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1590.0)), hbm=j.get("hbm_gbs", 6650.0),
+                    source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(bf16=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # clocks under load = upper half of the samples (the sampler also sees idle gaps)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return dict(sm_mhz=float(np.median(load)) if load else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def make_scenes(seed, n_images):
+    from instaorder_b200 import engine, synth
+    out = []
+    for image, masks, boxes in synth.coco_scene_stream(seed, n_images, N=10):
+        out.append(engine.Scene(image, masks, engine.expand_bbox(boxes, 3.0)))
+    return out
+
+
+def cpu_port_pairs_per_s(n_pairs, threads=None):
+    """The oracle port (= the reference algorithm: per-pair cv2-equivalent crops, fp32 torch-CPU ResNet-50 on both
+    directions, decisions) timed on the host cores for a bounded sample of the same workload."""
+    import torch
+    from instaorder_b200 import synth
+    from oracle import oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    rng = np.random.RandomState(1234)
+    sd = synth.random_state_dict(0, 5, NUM_CLASSES)
+    image, masks, boxes = next(synth.coco_scene_stream(99, 1, N=10))
+    bexp = O.expand_bbox(boxes, 3.0)
+    # restrict to n_pairs pairs by dropping instances: k instances -> k(k-1)/2 pairs
+    k = 2
+    while k * (k - 1) // 2 < n_pairs and k < 10:
+        k += 1
+    m, b = masks[:k], bexp[:k]
+    O.infer_order(sd, image, m[:2], b[:2], "all", ALGO, "patch", D)          # warm-up (1 pair)
+    t0 = time.perf_counter()
+    r = O.infer_order(sd, image, m, b, "all", ALGO, "patch", D, chunk=8)
+    dt = time.perf_counter() - t0
+    return len(r["pairs"]) / dt, len(r["pairs"]), dt, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's algorithm on the host cores (the reference itself is Python and lives at
+    /root/reference, which does not exist on the GPU box; oracle/oracle.py is its restatement, pinned against it by
+    tests/test_oracle_golden.py).  Rank 0 only; other ranks exit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    steps, warmup = args.steps, args.warmup
+    sample_pairs = 10                                           # 5 instances -> 10 pairs per step
+    vals = []
+    for s in range(warmup + steps):
+        v, n, dt, threads = cpu_port_pairs_per_s(sample_pairs)
+        if s >= warmup:
+            vals.append((n, dt))
+    pairs = sum(n for n, _ in vals)
+    secs = sum(dt for _, dt in vals)
+    value = pairs / secs
+    line = dict(impl="reference", metric="instance pairs/s (InstaOrderNet^od, 256^2)", value=value, unit="pairs/s",
+                n_gpus=args.gpus, steps=steps, warmup=warmup, ms_per_step=1000.0 * secs / max(len(vals), 1),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="C2: COCO-shaped 10-instance images, patch 256^2, InstaOrderNet^od; "
+                                     "bounded sample of %d pairs per step on host cores" % sample_pairs),
+                cpu_baseline=dict(value=value, unit="pairs/s", cores=threads, kind="port",
+                                  sample="%d pairs/step x %d steps, batched fp32 torch-CPU forward" % (sample_pairs, steps)),
+                e2e=dict(value=value, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=28)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from instaorder_b200 import _lib, engine, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    # ---- workload: every rank owns its own images (weak scaling: images are sharded, no data-path collective)
+    n_batches = 8                                    # distinct resident batches, rotated so inputs never sit in L2
+    n_images = (n_batches * PAIRS_PER_STEP) // 45 + 2
+    scenes = make_scenes(1000 + rank, n_images)
+    eng = engine.OrderEngine(NUM_CLASSES, D, max_pairs=PAIRS_PER_STEP, device=dev)
+    eng.load_state_dict(synth.random_state_dict(0, 5, NUM_CLASSES))
+    heads = engine.heads_for(ALGO, NUM_CLASSES)
+    batches, mat_elems = eng.make_batches(scenes, PAIRS_PER_STEP)
+    batches = batches[:n_batches]
+    resident = [eng.upload_resident(b, mat_elems) for b in batches]
+    input_bytes = sum(r.input_bytes for r in resident)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------------------
+    for i in range(args.warmup):
+        eng.run_resident(resident[i % len(resident)], heads)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.gpu_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        eng.run_resident(resident[i % len(resident)], heads)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.gpu_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps * PAIRS_PER_STEP / (ms / 1000.0)
+
+    # ---- per-kernel events (separate pass, so the events do not perturb the number above) -------------------
+    _lib.check(eng.lib.io_net_profile(eng.net, 1))
+    conv_ms = conv_flops = tot_ms = 0.0
+    n_conv = 0
+    prof_steps = min(args.steps, 4)
+    for i in range(prof_steps):
+        eng.run_resident(resident[i % len(resident)], heads)
+        torch.cuda.synchronize()
+        mx = 4096
+        pms = np.zeros(mx, np.float32); kind = np.zeros(mx, np.int32); fl = np.zeros(mx, np.float64)
+        n = _lib.check(eng.lib.io_net_profile_read(eng.net, _lib.ptr(pms), _lib.ptr(kind), _lib.ptr(fl), mx))
+        sel = (kind[:n] == 0) | (kind[:n] == 2)
+        conv_ms += float(pms[:n][sel].sum()); conv_flops += float(fl[:n][sel].sum()); n_conv += int(sel.sum())
+        tot_ms += float(pms[:n].sum())
+    _lib.check(eng.lib.io_net_profile(eng.net, 0))
+    peaks = measured_peaks()
+    achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+
+    # ---- end to end through the public API (host numpy -> pinned -> H2D -> ... -> D2H matrices) ---------------
+    per_step_scenes = []
+    o = 0
+    for i in range(args.warmup + args.steps):
+        # the public API takes whole images: an e2e step = 17 images = 765 pairs = 3 engine batches (256+256+253)
+        per_step_scenes.append([scenes[(o + k) % len(scenes)] for k in range(17)])
+        o += 17
+    for i in range(args.warmup):
+        eng.infer_scenes(per_step_scenes[i], ALGO, "all", "patch")
+    sync_all()
+    h0, d0 = eng.h2d_bytes, eng.d2h_bytes
+    t0 = time.perf_counter()
+    pairs_e2e = 0
+    for i in range(args.warmup, args.warmup + args.steps):
+        r = eng.infer_scenes(per_step_scenes[i], ALGO, "all", "patch")
+        pairs_e2e += sum(s.n * (s.n - 1) // 2 for s in per_step_scenes[i])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = world * pairs_e2e / dt
+    h2d = (eng.h2d_bytes - h0) / args.steps
+    d2h = (eng.d2h_bytes - d0) / args.steps
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, n, cdt, threads = cpu_port_pairs_per_s(args.cpu_sample_pairs)
+            cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
+                       sample="%d pairs of one C2 image (%.1f s): oracle port of inference.py patch path + fp32 "
+                              "torch-CPU ResNet-50, batched 16 forwards" % (n, cdt))
+        line = dict(
+            metric="instance pairs/s (InstaOrderNet^od, 256^2, bf16)", value=value, unit="pairs/s", n_gpus=world,
+            steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
+            scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+            config=dict(workload="C2: synthetic COCO-val-shaped images, 10 instances -> 45 pairs/image, %d pairs per "
+                                 "step, patch 256^2, InstaOrderNet^od heads [2,3], random-init weights" % PAIRS_PER_STEP,
+                        pairs_per_step=PAIRS_PER_STEP, parallelism="images sharded over %d GPU(s), no collective" % world,
+                        l2="inputs rotate over %d resident batches (%.0f MB) and each step streams >10 GB of "
+                           "activations, i.e. >> 126 MB L2" % (len(resident), input_bytes / 1e6)),
+            e2e=dict(value=e2e_value, unit="pairs/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                     pairs_per_step=pairs_e2e // args.steps),
+            gpu_launches=launches,
+            clocks=clocks,
+            roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
+                          frac=achieved / peaks["bf16"], traffic=None, kernel="conv_tc_kernel (53 launches per "
+                          "32-pair chunk)", launches_timed=n_conv, avg_launch_ms=conv_ms / max(n_conv, 1),
+                          conv_share_of_step=conv_ms / tot_ms if tot_ms else None, peak_source=peaks["source"],
+                          step_frac=value / world * FLOP_PER_PAIR / 1e12 / peaks["bf16"]),
+            cpu_baseline=cpu,
+        )
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -128,6 +128,14 @@ IO_API int io_net_forward_pairs(io_net_t* net, const void* pair_tensor_dev, int 
 /* number of kernel launches the last io_net_forward_pairs issued (bench.py's gpu_launches) */
 IO_API int io_net_last_launches(const io_net_t* net);
 
+/* Optional per-kernel timing for bench.py's roofline: when enabled, io_net_forward_pairs brackets every launch
+ * with CUDA events on the launching stream.  io_net_profile_read (after the caller synchronised the stream)
+ * returns the number of launches of the last forward and fills ms_host[i] (duration), kind_host[i]
+ * (0 stem conv, 1 max-pool, 2 bottleneck conv, 3 pool+FC tail) and flop_host[i] (algorithmic 2*MAC of the launch:
+ * real taps / channels only, no padding) for i < max_n. */
+IO_API int io_net_profile(io_net_t* net, int enable);
+IO_API int io_net_profile_read(io_net_t* net, float* ms_host, int32_t* kind_host, double* flop_host, int max_n);
+
 /* H1-H5: probabilities, direction average, decision and scatter into the per-image order matrices.
  * logits_dev[P][2][K]; head_kind/head_off/head_k select the columns of one head.
  * pair_ij_dev[2 P]; mat_off_dev[P] = element offset of the pair's image matrix inside mat_dev (int64, row stride

@@ -27,6 +27,7 @@ struct Op {
   enum Kind { STEM, POOL, CONV, TAIL } kind;
   ConvParams p;
   int bn_tile = 0;
+  double flops = 0.0;  // algorithmic 2*MAC of this launch
   // POOL
   const void* src = nullptr;
   void* dst = nullptr;
@@ -58,6 +59,10 @@ struct io_net {
   __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t buf_elems = 0;
   std::map<int, std::unique_ptr<io::Plan>> plans;
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;       // 2 per launch
+  std::vector<int> prof_kind;
+  std::vector<double> prof_flops;
 };
 
 namespace io {
@@ -106,6 +111,7 @@ static int build_plan(io_net* net, int pc, Plan* plan) {
   {  // stem (tensor map for the caller's pair tensor is patched per call) + max-pool
     Op op;
     op.kind = Op::STEM;
+    op.flops = 2.0 * b * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
     plan->ops.push_back(op);
     Op pool;
     pool.kind = Op::POOL;
@@ -127,22 +133,26 @@ static int build_plan(io_net* net, int pc, Plan* plan) {
       Op o1; o1.kind = Op::CONV;
       if (int rc = conv_plan(&o1.p, &o1.bn_tile, ConvDesc{b, h, w, c1.cin, c1.cout, 1, 1}, cur, c1.w, c1.bias, nullptr,
                              T1, 1)) return rc;
+      o1.flops = 2.0 * b * h * w * c1.cin * c1.cout;
       plan->ops.push_back(o1);
       Op o2; o2.kind = Op::CONV;
       if (int rc = conv_plan(&o2.p, &o2.bn_tile, ConvDesc{b, h, w, c2.cin, c2.cout, 3, c2.stride}, T1, c2.w, c2.bias,
                              nullptr, T2, 1)) return rc;
+      o2.flops = 2.0 * b * ho * wo * 9.0 * c2.cin * c2.cout;
       plan->ops.push_back(o2);
       const __nv_bfloat16* identity = cur;
       if (ds) {
         Op od; od.kind = Op::CONV;
         if (int rc = conv_plan(&od.p, &od.bn_tile, ConvDesc{b, h, w, ds->cin, ds->cout, 1, ds->stride}, cur, ds->w,
                                ds->bias, nullptr, DS, 0)) return rc;
+        od.flops = 2.0 * b * ho * wo * ds->cin * ds->cout;
         plan->ops.push_back(od);
         identity = DS;
       }
       Op o3; o3.kind = Op::CONV;
       if (int rc = conv_plan(&o3.p, &o3.bn_tile, ConvDesc{b, ho, wo, c3.cin, c3.cout, 1, 1}, T2, c3.w, c3.bias, identity,
                              nxt, 1)) return rc;
+      o3.flops = 2.0 * b * ho * wo * c3.cin * c3.cout;
       plan->ops.push_back(o3);
       std::swap(cur, nxt);
       h = ho; w = wo;
@@ -206,6 +216,7 @@ extern "C" int io_net_destroy(io_net_t* net) {
   cudaFree(net->fc_w);
   cudaFree(net->fc_b);
   for (int i = 0; i < 5; ++i) cudaFree(net->buf[i]);
+  for (cudaEvent_t e : net->ev) cudaEventDestroy(e);
   delete net;
   return IO_OK;
 }
@@ -305,6 +316,23 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
              net->max_pairs);
   cudaStream_t stream = as_stream(stream_);
   net->last_launches = 0;
+  net->prof_kind.clear();
+  net->prof_flops.clear();
+  auto mark = [&](int kind, double flops, bool begin) -> int {
+    if (!net->profile) return IO_OK;
+    const size_t idx = 2 * net->prof_kind.size() + (begin ? 0 : 1);
+    while (net->ev.size() <= idx) {
+      cudaEvent_t e;
+      IO_CUDA(cudaEventCreate(&e));
+      net->ev.push_back(e);
+    }
+    IO_CUDA(cudaEventRecord(net->ev[idx], stream));
+    if (!begin) {
+      net->prof_kind.push_back(kind);
+      net->prof_flops.push_back(flops);
+    }
+    return IO_OK;
+  };
   const int64_t pair_bytes = io_pair_tensor_bytes(1, net->d);
   for (int c0 = 0; c0 < p; c0 += net->chunk_pairs) {
     const int pc = std::min(net->chunk_pairs, p - c0);
@@ -316,7 +344,8 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
     }
     Plan& plan = *it->second;
     for (Op& op : plan.ops) {
-      int rc = IO_OK;
+      int rc = mark(static_cast<int>(op.kind), op.flops, true);
+      if (rc) return rc;
       switch (op.kind) {
         case Op::STEM:
           rc = stem_plan(&op.p, &op.bn_tile, pc, net->d,
@@ -334,14 +363,34 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
           break;
       }
       if (rc) return rc;
+      if ((rc = mark(static_cast<int>(op.kind), op.flops, false))) return rc;
       ++net->last_launches;
     }
+    if (int rc = mark(3, 2.0 * 2 * pc * 2048.0 * net->k_total, true)) return rc;
     if (int rc = tail_launch(plan.feat, plan.hw_final, pc, net->fc_w, net->fc_b, net->k_total,
                              logits + static_cast<size_t>(c0) * 2 * net->k_total, stream))
       return rc;
+    if (int rc = mark(3, 2.0 * 2 * pc * 2048.0 * net->k_total, false)) return rc;
     ++net->last_launches;
   }
   return IO_OK;
+}
+
+extern "C" int io_net_profile(io_net_t* net, int enable) {
+  IO_REQUIRE(net, "io_net_profile: null handle");
+  net->profile = enable != 0;
+  return IO_OK;
+}
+
+extern "C" int io_net_profile_read(io_net_t* net, float* ms, int32_t* kind, double* flop, int max_n) {
+  IO_REQUIRE(net && ms && kind && flop, "io_net_profile_read: null pointer");
+  const int n = static_cast<int>(net->prof_kind.size());
+  for (int i = 0; i < n && i < max_n; ++i) {
+    IO_CUDA(cudaEventElapsedTime(&ms[i], net->ev[2 * i], net->ev[2 * i + 1]));
+    kind[i] = net->prof_kind[i];
+    flop[i] = net->prof_flops[i];
+  }
+  return n;
 }
 
 extern "C" int io_net_last_launches(const io_net_t* net) { return net ? net->last_launches : 0; }
