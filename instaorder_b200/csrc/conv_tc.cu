@@ -21,10 +21,16 @@ template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers: 128 / 256 / 512 columns
+  // epilogue staging: per epilogue warp, BN/64 regions of 32 rows x 64 columns bf16 (4 KB, 128B-swizzled).  A
+  // region first receives the residual tile (TMA load), is overwritten in place with the result, and is then
+  // TMA-stored -- every global access of the epilogue is a full 128-byte line.
+  static constexpr int EPI_REGION_BYTES = 32 * 128;
+  static constexpr int EPI_WARP_BYTES = (BN / 64) * EPI_REGION_BYTES;
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + slack for 1024 B alignment
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + 1024 B alignment slack
 };
 
 struct TileCoord {
@@ -51,7 +57,9 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int m_tile)
       t.w0 = 0;
       t.limit = min(p.rows_per_tile, p.bi * p.hw_out - t.h0 * p.w_out);
     }
-    t.base_row = t.n_img * p.hw_out + t.h0 * p.w_out + t.w0;
+    // the stem writes image 2n (direction A,B) and image 2n+1 (direction B,A; columns >= n_split)
+    const int img_out = p.mode == CONV_STEM ? 2 * t.n_img : t.n_img;
+    t.base_row = img_out * p.hw_out + t.h0 * p.w_out + t.w0;
   }
   return t;
 }
@@ -63,11 +71,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* sEpi = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rbar = tempty + 2;  // one residual barrier per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -75,6 +85,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.map_a);
     prefetch_tmap(&p.map_b);
+    prefetch_tmap(&p.map_out);
+    if (p.residual != nullptr) prefetch_tmap(&p.map_res);
+    for (int i = 0; i < 4; ++i) mbar_init(&rbar[i], 1);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -160,28 +173,51 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     }
   } else {
     // ======================= epilogue (warps 2..5) =======================
-    const int q = warp & 3;  // TMEM lane quadrant accessible to this warp
+    const int q = warp & 3;  // TMEM lane quadrant accessible to this warp: tile rows 32q .. 32q+31
     const int r = q * 32 + lane;
+    uint8_t* stage_base = sEpi + q * C::EPI_WARP_BYTES;
+    uint64_t* my_rbar = &rbar[q];
+    uint32_t rphase = 0;
+    const bool has_res = p.residual != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       const TileCoord t = tile_coord(p, m_tile);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const bool valid = (r < t.limit) && (t.base_row + r < p.m_total);
+      const int row0 = t.base_row + q * 32;                    // first output row of this warp's slab
+      // whole slab inside the tile -> TMA path (rows past the end of the tensor are clipped by TMA);
+      // slab cut by the tile's row limit (384^2 geometries) -> per-thread path with a row guard
+      const bool slab_full = (q * 32 + 32 <= t.limit) && (row0 < p.m_total);
+      const bool slab_part = !slab_full && (q * 32 < t.limit) && (row0 < p.m_total);
+      const bool valid = slab_part && (r < t.limit) && (t.base_row + r < p.m_total);
+      const int col_base = n_tile * BN;
+
+      // previous tile's stores must have finished reading the staging regions before they are refilled
+      if (lane == 0) {
+        tma_store_wait_read();
+        if (slab_full && has_res) {
+          mbar_expect_tx(my_rbar, C::EPI_WARP_BYTES);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(stage_base + j * C::EPI_REGION_BYTES, &p.map_res, my_rbar, col_base + j * 64, row0);
+        }
+      }
+      __syncwarp();
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if (slab_full && has_res) {
+        mbar_wait(my_rbar, rphase);
+        rphase ^= 1;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, v);
         tmem_ld_wait();
-        int col = n_tile * BN + c0;
-        if (valid && col < p.n_total) {
+        int col = col_base + c0;
+        if (col < p.n_total && (slab_full || valid)) {
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col);
-          int row = t.base_row + r;
-          if (col >= p.n_split) { col -= p.n_split; row += p.split_row_off; }
-          const size_t off = static_cast<size_t>(row) * p.ldc + col;
           float f[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -191,30 +227,72 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
             f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
             f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
           }
-          if (p.residual != nullptr) {
-            const uint4* res = reinterpret_cast<const uint4*>(p.residual + off);
+          if (slab_full) {
+            // staging region of this 64-column group; row `lane`, 16-byte chunks XOR-swizzled by (row & 7)
+            uint8_t* region = stage_base + (c0 >> 6) * C::EPI_REGION_BYTES + lane * 128;
+            const int kbase = (c0 & 32) >> 3;  // first 16-byte chunk of this 32-column half: 0 or 4
+            if (has_res) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(region + (((kbase + j) ^ (lane & 7)) << 4));
+                f[8 * j + 0] += bf16_lo(rr.x); f[8 * j + 1] += bf16_hi(rr.x);
+                f[8 * j + 2] += bf16_lo(rr.y); f[8 * j + 3] += bf16_hi(rr.y);
+                f[8 * j + 4] += bf16_lo(rr.z); f[8 * j + 5] += bf16_hi(rr.z);
+                f[8 * j + 6] += bf16_lo(rr.w); f[8 * j + 7] += bf16_hi(rr.w);
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 rr = __ldg(res + j);
-              f[8 * j + 0] += bf16_lo(rr.x); f[8 * j + 1] += bf16_hi(rr.x);
-              f[8 * j + 2] += bf16_lo(rr.y); f[8 * j + 3] += bf16_hi(rr.y);
-              f[8 * j + 4] += bf16_lo(rr.z); f[8 * j + 5] += bf16_hi(rr.z);
-              f[8 * j + 6] += bf16_lo(rr.w); f[8 * j + 7] += bf16_hi(rr.w);
+              uint4 o;
+              o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+              *reinterpret_cast<uint4*>(region + (((kbase + j) ^ (lane & 7)) << 4)) = o;
             }
-          }
-          if (p.relu) {
+            if (c0 & 32) {  // second half written: the 64-column region is complete -> one TMA store
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                int scol = col_base + (c0 & ~63), srow = row0;
+                if (scol >= p.n_split) { scol -= p.n_split; srow += p.split_row_off; }
+                tma_store_2d(&p.map_out, stage_base + (c0 >> 6) * C::EPI_REGION_BYTES, scol, srow);
+                tma_store_commit();
+              }
+            }
+          } else {
+            int row = t.base_row + r;
+            if (col >= p.n_split) { col -= p.n_split; row += p.split_row_off; }
+            const size_t off = static_cast<size_t>(row) * p.ldc + col;
+            if (has_res) {
+              const uint4* res = reinterpret_cast<const uint4*>(p.residual + off);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(p.out + off);
+              for (int j = 0; j < 4; ++j) {
+                const uint4 rr = __ldg(res + j);
+                f[8 * j + 0] += bf16_lo(rr.x); f[8 * j + 1] += bf16_hi(rr.x);
+                f[8 * j + 2] += bf16_lo(rr.y); f[8 * j + 3] += bf16_hi(rr.y);
+                f[8 * j + 4] += bf16_lo(rr.z); f[8 * j + 5] += bf16_hi(rr.z);
+                f[8 * j + 6] += bf16_lo(rr.w); f[8 * j + 7] += bf16_hi(rr.w);
+              }
+            }
+            if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
-            o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-            o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-            o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
-            dst[j] = o;
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+              dst[j] = o;
+            }
           }
         }
       }
@@ -222,6 +300,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -258,6 +337,16 @@ int conv_tc_launch(const ConvParams& p, int bn_tile, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------------
 // host-side planning
 // ---------------------------------------------------------------------------------------------------------
+static int make_out_maps(ConvParams* p, int rows_total) {
+  const uint64_t dims[2] = {static_cast<uint64_t>(p->ldc), static_cast<uint64_t>(rows_total)};
+  const uint64_t str[1] = {static_cast<uint64_t>(p->ldc) * 2};
+  const uint32_t box[2] = {64, 32};
+  int rc = make_tmap_bf16(&p->map_out, p->out, 2, dims, str, box, true);
+  if (rc) return rc;
+  if (p->residual != nullptr) rc = make_tmap_bf16(&p->map_res, p->residual, 2, dims, str, box, true);
+  return rc;
+}
+
 int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, const void* wgt, const float* bias,
               const void* residual, void* y, int relu) {
   IO_REQUIRE(d.kernel == 1 || d.kernel == 3, "conv: kernel %d not supported (1 or 3)", d.kernel);
@@ -338,7 +427,8 @@ int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, con
     }
   }
   p->a_bytes = p->rows_per_tile * 128;
-  return rc;
+  if (rc) return rc;
+  return make_out_maps(p, p->m_total);
 }
 
 int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, const void* wgt, const float* bias,
@@ -352,7 +442,7 @@ int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, cons
   p->residual = nullptr;
   p->out = reinterpret_cast<__nv_bfloat16*>(y);
   p->mode = CONV_STEM;
-  p->m_total = pairs * h_out * w_out;
+  p->m_total = 2 * pairs * h_out * w_out;  // output rows (both directions, pair-major interleaved)
   p->n_total = 128;
   p->k_iters = 7;
   p->kpt = 1;
@@ -370,7 +460,7 @@ int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, cons
   p->n_tiles = 1;
   p->ldc = 64;
   p->n_split = 64;
-  p->split_row_off = p->m_total;
+  p->split_row_off = p->hw_out;
   p->relu = 1;
   p->a_bytes = p->rows_per_tile * 128;
   *bn_tile = 128;
@@ -384,7 +474,9 @@ int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, cons
   const uint64_t wdims[2] = {448, 128};
   const uint64_t wstr[1] = {448 * 2};
   const uint32_t wbox[2] = {64, 128};
-  return make_tmap_bf16(&p->map_b, wgt, 2, wdims, wstr, wbox, true);
+  rc = make_tmap_bf16(&p->map_b, wgt, 2, wdims, wstr, wbox, true);
+  if (rc) return rc;
+  return make_out_maps(p, p->m_total);
 }
 
 }  // namespace io

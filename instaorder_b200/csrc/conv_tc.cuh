@@ -14,6 +14,8 @@ enum ConvMode : int {
 struct ConvParams {
   CUtensorMap map_a;
   CUtensorMap map_b;
+  CUtensorMap map_out;  // [rows, ldc] bf16 output, box 64 columns x 32 rows, 128B swizzle (epilogue TMA store)
+  CUtensorMap map_res;  // same geometry over the residual tensor (valid only if residual != nullptr)
   const float* bias;              // [n_total] fp32 (folded BN shift)
   const __nv_bfloat16* residual;  // optional, indexed like out
   __nv_bfloat16* out;             // [rows, ldc] bf16
@@ -48,7 +50,7 @@ struct ConvDesc {
 };
 int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, const void* wgt, const float* bias,
               const void* residual, void* y, int relu);
-// Stem plan: x is the padded pair tensor [pairs, d+6, pitch, 8]; y is [2*pairs, d/2, d/2, 64] (direction-major).
+// Stem plan: x is the padded pair tensor [pairs, d+6, pitch, 8]; y is [2*pairs, d/2, d/2, 64] (image 2p + dir).
 int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, const void* wgt, const float* bias, void* y);
 
 }  // namespace io

@@ -48,7 +48,6 @@ struct io_net {
   int k_total = 0;
   int d = 0;
   int max_pairs = 0;
-  int chunk_pairs = 0;
   bool loaded = false;
   int last_launches = 0;
   std::vector<io::ConvW> convs;  // [0] = stem, then the 52 bottleneck convs in execution order
@@ -56,9 +55,14 @@ struct io_net {
   float* stem_bias = nullptr;
   float* fc_w = nullptr;
   float* fc_b = nullptr;
-  __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t buf_elems = 0;
-  std::map<int, std::unique_ptr<io::Plan>> plans;
+  // phase A (stem .. layer2) works on sub-chunks of chunk_a pairs so that its large activations stay in L2;
+  // phase B (layer3, layer4, tail) runs over chunk_b pairs at once so that its small GEMMs fill all SMs.
+  int chunk_a = 0, chunk_b = 0;
+  __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase A: X, Y, T1, T2, DS
+  __nv_bfloat16* bufb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase B: X, Y, T1, T2, DS
+  __nv_bfloat16* big = nullptr;                                            // layer2 output of a whole B chunk
+  std::map<std::pair<int, int>, std::unique_ptr<io::Plan>> plans_a;        // (pairs, first pair inside the B chunk)
+  std::map<int, std::unique_ptr<io::Plan>> plans_b;
   bool profile = false;
   std::vector<cudaEvent_t> ev;       // 2 per launch
   std::vector<int> prof_kind;
@@ -103,35 +107,28 @@ static void build_conv_list(io_net* net) {
   }
 }
 
-static int build_plan(io_net* net, int pc, Plan* plan) {
-  const int b = 2 * pc;
-  const int d = net->d;
-  plan->ops.clear();
-  __nv_bfloat16 *X = net->buf[0], *Y = net->buf[1], *T1 = net->buf[2], *T2 = net->buf[3], *DS = net->buf[4];
-  {  // stem (tensor map for the caller's pair tensor is patched per call) + max-pool
-    Op op;
-    op.kind = Op::STEM;
-    op.flops = 2.0 * b * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
-    plan->ops.push_back(op);
-    Op pool;
-    pool.kind = Op::POOL;
-    pool.src = X; pool.dst = Y; pool.b = b; pool.h = d / 2; pool.w = d / 2; pool.c = 64;
-    plan->ops.push_back(pool);
-  }
-  __nv_bfloat16* cur = Y;
-  __nv_bfloat16* nxt = X;
-  int h = d / 4, w = d / 4;
-  size_t ci = 1;
+// Appends the bottlenecks of layers [l0, l1) for `b` images whose input [b, h, w, C] is `src`.  Block outputs
+// ping-pong between P0 and P1 (`src` may be one of them or a read-only third buffer); the very last output goes
+// to `final_dst` if given.
+static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_io, int* w_io,
+                        const __nv_bfloat16* src, __nv_bfloat16* P0, __nv_bfloat16* P1, __nv_bfloat16* T1,
+                        __nv_bfloat16* T2, __nv_bfloat16* DS, __nv_bfloat16* final_dst,
+                        const __nv_bfloat16** out_ptr) {
   const int blocks_[4] = {3, 4, 6, 3};
-  for (int li = 0; li < 4; ++li) {
+  size_t ci = 1;
+  for (int li = 0; li < l0; ++li) ci += 3 * blocks_[li] + 1;
+  int h = *h_io, w = *w_io;
+  for (int li = l0; li < l1; ++li) {
     for (int blk = 0; blk < blocks_[li]; ++blk) {
       const ConvW& c1 = net->convs[ci++];
       const ConvW& c2 = net->convs[ci++];
       const ConvW* ds = (blk == 0) ? &net->convs[ci++] : nullptr;
       const ConvW& c3 = net->convs[ci++];
       const int ho = h / c2.stride, wo = w / c2.stride;
+      const bool last = (li == l1 - 1) && (blk == blocks_[li] - 1);
+      __nv_bfloat16* dst = (last && final_dst) ? final_dst : (src == P0 ? P1 : P0);
       Op o1; o1.kind = Op::CONV;
-      if (int rc = conv_plan(&o1.p, &o1.bn_tile, ConvDesc{b, h, w, c1.cin, c1.cout, 1, 1}, cur, c1.w, c1.bias, nullptr,
+      if (int rc = conv_plan(&o1.p, &o1.bn_tile, ConvDesc{b, h, w, c1.cin, c1.cout, 1, 1}, src, c1.w, c1.bias, nullptr,
                              T1, 1)) return rc;
       o1.flops = 2.0 * b * h * w * c1.cin * c1.cout;
       plan->ops.push_back(o1);
@@ -140,10 +137,10 @@ static int build_plan(io_net* net, int pc, Plan* plan) {
                              nullptr, T2, 1)) return rc;
       o2.flops = 2.0 * b * ho * wo * 9.0 * c2.cin * c2.cout;
       plan->ops.push_back(o2);
-      const __nv_bfloat16* identity = cur;
+      const __nv_bfloat16* identity = src;
       if (ds) {
         Op od; od.kind = Op::CONV;
-        if (int rc = conv_plan(&od.p, &od.bn_tile, ConvDesc{b, h, w, ds->cin, ds->cout, 1, ds->stride}, cur, ds->w,
+        if (int rc = conv_plan(&od.p, &od.bn_tile, ConvDesc{b, h, w, ds->cin, ds->cout, 1, ds->stride}, src, ds->w,
                                ds->bias, nullptr, DS, 0)) return rc;
         od.flops = 2.0 * b * ho * wo * ds->cin * ds->cout;
         plan->ops.push_back(od);
@@ -151,16 +148,48 @@ static int build_plan(io_net* net, int pc, Plan* plan) {
       }
       Op o3; o3.kind = Op::CONV;
       if (int rc = conv_plan(&o3.p, &o3.bn_tile, ConvDesc{b, ho, wo, c3.cin, c3.cout, 1, 1}, T2, c3.w, c3.bias, identity,
-                             nxt, 1)) return rc;
+                             dst, 1)) return rc;
       o3.flops = 2.0 * b * ho * wo * c3.cin * c3.cout;
       plan->ops.push_back(o3);
-      std::swap(cur, nxt);
+      src = dst;  // the next block reads what was just written
       h = ho; w = wo;
     }
   }
-  plan->feat = cur;
-  plan->hw_final = h * w;
+  *h_io = h; *w_io = w;
+  *out_ptr = src;
   return IO_OK;
+}
+
+// phase A: stem + max-pool + layer1 + layer2 for `pa` pairs; layer2's output goes to `dst` ([2*pa, D/8, D/8, 512])
+static int build_plan_a(io_net* net, int pa, __nv_bfloat16* dst, Plan* plan) {
+  const int b = 2 * pa, d = net->d;
+  plan->ops.clear();
+  __nv_bfloat16 *X = net->buf[0], *Y = net->buf[1];
+  Op op;
+  op.kind = Op::STEM;   // its tensor maps are rebuilt per call (the pair tensor belongs to the caller)
+  op.flops = 2.0 * b * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
+  plan->ops.push_back(op);
+  Op pool;
+  pool.kind = Op::POOL;
+  pool.src = X; pool.dst = Y; pool.b = b; pool.h = d / 2; pool.w = d / 2; pool.c = 64;
+  plan->ops.push_back(pool);
+  int h = d / 4, w = d / 4;
+  const __nv_bfloat16* out = nullptr;
+  return build_blocks(net, plan, 0, 2, b, &h, &w, Y, X, Y, net->buf[2], net->buf[3], net->buf[4], dst, &out);
+}
+
+// phase B: layer3 + layer4 for `pb` pairs reading the big layer2-output buffer
+static int build_plan_b(io_net* net, int pb, Plan* plan) {
+  const int b = 2 * pb, d = net->d;
+  plan->ops.clear();
+  int h = d / 8, w = d / 8;
+  const __nv_bfloat16* out = nullptr;
+  // the first block reads `big` (kept intact) and writes bufb[0]; afterwards bufb[0] / bufb[1] ping-pong
+  int rc = build_blocks(net, plan, 2, 4, b, &h, &w, net->big, net->bufb[0], net->bufb[1], net->bufb[2], net->bufb[3],
+                        net->bufb[4], nullptr, &out);
+  plan->feat = out;
+  plan->hw_final = h * w;
+  return rc;
 }
 
 }  // namespace io
@@ -184,9 +213,11 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
   }
   net->d = input_size;
   net->max_pairs = max_pairs;
-  int chunk = 32;
-  if (const char* e = getenv("INSTAORDER_CHUNK_PAIRS")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
-  net->chunk_pairs = std::min(chunk, max_pairs);
+  int chunk_a = 16, chunk_b = 128;
+  if (const char* e = getenv("INSTAORDER_CHUNK_A")) chunk_a = atoi(e) > 0 ? atoi(e) : chunk_a;
+  if (const char* e = getenv("INSTAORDER_CHUNK_B")) chunk_b = atoi(e) > 0 ? atoi(e) : chunk_b;
+  net->chunk_b = std::min(chunk_b, max_pairs);
+  net->chunk_a = std::min(chunk_a, net->chunk_b);
   build_conv_list(net.get());
   // device weights
   for (size_t i = 1; i < net->convs.size(); ++i) {
@@ -198,9 +229,14 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
   IO_CUDA(cudaMalloc(&net->stem_bias, 128 * 4));
   IO_CUDA(cudaMalloc(&net->fc_w, static_cast<size_t>(net->k_total) * 2048 * 4));
   IO_CUDA(cudaMalloc(&net->fc_b, static_cast<size_t>(net->k_total) * 4));
-  // activations: 5 buffers of [2*chunk, D/2, D/2, 64] elements (the stem output is the largest tensor per image)
-  net->buf_elems = static_cast<size_t>(2 * net->chunk_pairs) * (input_size / 2) * (input_size / 2) * 64;
-  for (int i = 0; i < 5; ++i) IO_CUDA(cudaMalloc(&net->buf[i], net->buf_elems * 2));
+  // phase A activations: 5 buffers of [2*chunk_a, D/2, D/2, 64] elements (the stem output is the largest tensor per
+  // image); phase B: 5 buffers of [2*chunk_b, D/8, D/8, 256] (layer3.0 conv1 output) + `big` [2*chunk_b, D/8, D/8, 512]
+  const size_t d = input_size;
+  const size_t ea = static_cast<size_t>(2 * net->chunk_a) * (d / 2) * (d / 2) * 64;
+  const size_t eb = static_cast<size_t>(2 * net->chunk_b) * (d / 8) * (d / 8) * 256;
+  for (int i = 0; i < 5; ++i) IO_CUDA(cudaMalloc(&net->buf[i], ea * 2));
+  for (int i = 0; i < 5; ++i) IO_CUDA(cudaMalloc(&net->bufb[i], eb * 2));
+  IO_CUDA(cudaMalloc(&net->big, eb * 2 * 2));
   *out = net.release();
   return IO_OK;
 }
@@ -216,6 +252,8 @@ extern "C" int io_net_destroy(io_net_t* net) {
   cudaFree(net->fc_w);
   cudaFree(net->fc_b);
   for (int i = 0; i < 5; ++i) cudaFree(net->buf[i]);
+  for (int i = 0; i < 5; ++i) cudaFree(net->bufb[i]);
+  cudaFree(net->big);
   for (cudaEvent_t e : net->ev) cudaEventDestroy(e);
   delete net;
   return IO_OK;
@@ -334,23 +372,14 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
     return IO_OK;
   };
   const int64_t pair_bytes = io_pair_tensor_bytes(1, net->d);
-  for (int c0 = 0; c0 < p; c0 += net->chunk_pairs) {
-    const int pc = std::min(net->chunk_pairs, p - c0);
-    auto it = net->plans.find(pc);
-    if (it == net->plans.end()) {
-      std::unique_ptr<Plan> plan(new Plan());
-      if (int rc = build_plan(net, pc, plan.get())) return rc;
-      it = net->plans.emplace(pc, std::move(plan)).first;
-    }
-    Plan& plan = *it->second;
+  const size_t l2_elems_per_pair = static_cast<size_t>(2) * (net->d / 8) * (net->d / 8) * 512;
+  auto run_ops = [&](Plan& plan, const uint8_t* pair_ptr, int pa) -> int {
     for (Op& op : plan.ops) {
       int rc = mark(static_cast<int>(op.kind), op.flops, true);
       if (rc) return rc;
       switch (op.kind) {
         case Op::STEM:
-          rc = stem_plan(&op.p, &op.bn_tile, pc, net->d,
-                         reinterpret_cast<const uint8_t*>(pair_tensor) + static_cast<int64_t>(c0) * pair_bytes,
-                         net->stem_w, net->stem_bias, net->buf[0]);
+          rc = stem_plan(&op.p, &op.bn_tile, pa, net->d, pair_ptr, net->stem_w, net->stem_bias, net->buf[0]);
           if (!rc) rc = conv_tc_launch(op.p, op.bn_tile, stream);
           break;
         case Op::POOL:
@@ -366,11 +395,35 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
       if ((rc = mark(static_cast<int>(op.kind), op.flops, false))) return rc;
       ++net->last_launches;
     }
-    if (int rc = mark(3, 2.0 * 2 * pc * 2048.0 * net->k_total, true)) return rc;
-    if (int rc = tail_launch(plan.feat, plan.hw_final, pc, net->fc_w, net->fc_b, net->k_total,
-                             logits + static_cast<size_t>(c0) * 2 * net->k_total, stream))
+    return IO_OK;
+  };
+  for (int b0 = 0; b0 < p; b0 += net->chunk_b) {
+    const int pb = std::min(net->chunk_b, p - b0);
+    for (int a0 = 0; a0 < pb; a0 += net->chunk_a) {
+      const int pa = std::min(net->chunk_a, pb - a0);
+      auto key = std::make_pair(pa, a0);
+      auto it = net->plans_a.find(key);
+      if (it == net->plans_a.end()) {
+        std::unique_ptr<Plan> plan(new Plan());
+        if (int rc = build_plan_a(net, pa, net->big + static_cast<size_t>(a0) * l2_elems_per_pair, plan.get())) return rc;
+        it = net->plans_a.emplace(key, std::move(plan)).first;
+      }
+      const uint8_t* pair_ptr = reinterpret_cast<const uint8_t*>(pair_tensor) + static_cast<int64_t>(b0 + a0) * pair_bytes;
+      if (int rc = run_ops(*it->second, pair_ptr, pa)) return rc;
+    }
+    auto itb = net->plans_b.find(pb);
+    if (itb == net->plans_b.end()) {
+      std::unique_ptr<Plan> plan(new Plan());
+      if (int rc = build_plan_b(net, pb, plan.get())) return rc;
+      itb = net->plans_b.emplace(pb, std::move(plan)).first;
+    }
+    Plan& planb = *itb->second;
+    if (int rc = run_ops(planb, nullptr, pb)) return rc;
+    if (int rc = mark(3, 2.0 * 2 * pb * 2048.0 * net->k_total, true)) return rc;
+    if (int rc = tail_launch(planb.feat, planb.hw_final, pb, net->fc_w, net->fc_b, net->k_total,
+                             logits + static_cast<size_t>(b0) * 2 * net->k_total, stream))
       return rc;
-    if (int rc = mark(3, 2.0 * 2 * pc * 2048.0 * net->k_total, false)) return rc;
+    if (int rc = mark(3, 2.0 * 2 * pb * 2048.0 * net->k_total, false)) return rc;
     ++net->last_launches;
   }
   return IO_OK;

@@ -56,7 +56,7 @@ int maxpool_launch(const void* x, void* y, int b, int h, int w, int c, cudaStrea
 }
 
 // ---- AdaptiveAvgPool2d(1) + flatten + Linear head(s) (resnet_cls.py:214-221) ----------------------------------
-// feat: [2P, HW, 2048] bf16, image p = direction (A,B) of pair p, image P + p = direction (B,A).
+// feat: [2P, HW, 2048] bf16, image 2p = direction (A,B) of pair p, image 2p + 1 = direction (B,A).
 // logits: [P][2][K] fp32.  One CTA per image, 256 threads x 8 channels.
 constexpr int TAIL_C = 2048;
 constexpr int TAIL_MAXK = 8;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) tail_kernel(const uint4* __restrict__ fea
                                                    const float* __restrict__ fcw, const float* __restrict__ fcb,
                                                    int k_total, float* __restrict__ logits) {
   const int img = blockIdx.x;
-  const int pair = img % pairs, dir = img / pairs;
+  const int pair = img >> 1, dir = img & 1;
   const int t = threadIdx.x;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const uint4* p = feat + static_cast<size_t>(img) * hw * (TAIL_C / 8) + t;
