@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -158,7 +158,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -231,7 +231,7 @@ def main():
         torch.cuda.synchronize()
         mx = 4096
         pms = np.zeros(mx, np.float32); kind = np.zeros(mx, np.int32); fl = np.zeros(mx, np.float64)
-        n = _lib.check(eng.lib.io_net_profile_read(eng.net, _lib.ptr(pms), _lib.ptr(kind), _lib.ptr(fl), mx))
+        n = _lib.check(eng.lib.io_net_profile_read(eng.net, _lib.ptr(pms), _lib.ptr(kind), _lib.ptr(fl), None, None, mx))
         sel = (kind[:n] == 0) | (kind[:n] == 2)
         conv_ms += float(pms[:n][sel].sum()); conv_flops += float(fl[:n][sel].sum()); n_conv += int(sel.sum())
         tot_ms += float(pms[:n].sum())

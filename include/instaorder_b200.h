@@ -131,10 +131,12 @@ IO_API int io_net_last_launches(const io_net_t* net);
 /* Optional per-kernel timing for bench.py's roofline: when enabled, io_net_forward_pairs brackets every launch
  * with CUDA events on the launching stream.  io_net_profile_read (after the caller synchronised the stream)
  * returns the number of launches of the last forward and fills ms_host[i] (duration), kind_host[i]
- * (0 stem conv, 1 max-pool, 2 bottleneck conv, 3 pool+FC tail) and flop_host[i] (algorithmic 2*MAC of the launch:
- * real taps / channels only, no padding) for i < max_n. */
+ * (0 stem conv, 1 max-pool, 2 bottleneck conv, 3 pool+FC tail), flop_host[i] (algorithmic 2*MAC of the launch:
+ * real taps / channels only, no padding) and, if non-null, bytes_host[i] (algorithmic HBM bytes) and tag_host[i]
+ * (layer * 100 + block * 10 + conv index; 1 = stem, 2 = max-pool) for i < max_n. */
 IO_API int io_net_profile(io_net_t* net, int enable);
-IO_API int io_net_profile_read(io_net_t* net, float* ms_host, int32_t* kind_host, double* flop_host, int max_n);
+IO_API int io_net_profile_read(io_net_t* net, float* ms_host, int32_t* kind_host, double* flop_host,
+                               double* bytes_host, int32_t* tag_host, int max_n);
 
 /* H1-H5: probabilities, direction average, decision and scatter into the per-image order matrices.
  * logits_dev[P][2][K]; head_kind/head_off/head_k select the columns of one head.

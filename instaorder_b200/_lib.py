@@ -49,7 +49,7 @@ _SIGS = {
     "io_net_forward_pairs": (_i, [_vp, _vp, _i, _vp, _vp]),
     "io_net_last_launches": (_i, [_vp]),
     "io_net_profile": (_i, [_vp, _i]),
-    "io_net_profile_read": (_i, [_vp, _vp, _vp, _vp, _i]),
+    "io_net_profile_read": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "io_order_decide": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "io_conv_bn_act": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "io_metrics_prf": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),

@@ -28,6 +28,8 @@ struct Op {
   ConvParams p;
   int bn_tile = 0;
   double flops = 0.0;  // algorithmic 2*MAC of this launch
+  double bytes = 0.0;  // algorithmic HBM bytes of this launch (activations in + out + residual + weights)
+  int tag = 0;         // layer*100 + block*10 + conv index (profiling label)
   // POOL
   const void* src = nullptr;
   void* dst = nullptr;
@@ -67,6 +69,8 @@ struct io_net {
   std::vector<cudaEvent_t> ev;       // 2 per launch
   std::vector<int> prof_kind;
   std::vector<double> prof_flops;
+  std::vector<double> prof_bytes;
+  std::vector<int> prof_tag;
 };
 
 namespace io {
@@ -131,11 +135,15 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       if (int rc = conv_plan(&o1.p, &o1.bn_tile, ConvDesc{b, h, w, c1.cin, c1.cout, 1, 1}, src, c1.w, c1.bias, nullptr,
                              T1, 1)) return rc;
       o1.flops = 2.0 * b * h * w * c1.cin * c1.cout;
+      o1.bytes = 2.0 * b * h * w * (c1.cin + c1.cout) + 2.0 * c1.cin * c1.cout;
+      o1.tag = (li + 1) * 100 + blk * 10 + 1;
       plan->ops.push_back(o1);
       Op o2; o2.kind = Op::CONV;
       if (int rc = conv_plan(&o2.p, &o2.bn_tile, ConvDesc{b, h, w, c2.cin, c2.cout, 3, c2.stride}, T1, c2.w, c2.bias,
                              nullptr, T2, 1)) return rc;
       o2.flops = 2.0 * b * ho * wo * 9.0 * c2.cin * c2.cout;
+      o2.bytes = 2.0 * b * (h * w * c2.cin + ho * wo * c2.cout) + 18.0 * c2.cin * c2.cout;
+      o2.tag = (li + 1) * 100 + blk * 10 + 2;
       plan->ops.push_back(o2);
       const __nv_bfloat16* identity = src;
       if (ds) {
@@ -143,6 +151,8 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
         if (int rc = conv_plan(&od.p, &od.bn_tile, ConvDesc{b, h, w, ds->cin, ds->cout, 1, ds->stride}, src, ds->w,
                                ds->bias, nullptr, DS, 0)) return rc;
         od.flops = 2.0 * b * ho * wo * ds->cin * ds->cout;
+        od.bytes = 2.0 * b * (h * w * ds->cin + ho * wo * ds->cout) + 2.0 * ds->cin * ds->cout;
+        od.tag = (li + 1) * 100 + blk * 10 + 4;
         plan->ops.push_back(od);
         identity = DS;
       }
@@ -150,6 +160,8 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       if (int rc = conv_plan(&o3.p, &o3.bn_tile, ConvDesc{b, ho, wo, c3.cin, c3.cout, 1, 1}, T2, c3.w, c3.bias, identity,
                              dst, 1)) return rc;
       o3.flops = 2.0 * b * ho * wo * c3.cin * c3.cout;
+      o3.bytes = 2.0 * b * ho * wo * (c3.cin + 2 * c3.cout) + 2.0 * c3.cin * c3.cout;
+      o3.tag = (li + 1) * 100 + blk * 10 + 3;
       plan->ops.push_back(o3);
       src = dst;  // the next block reads what was just written
       h = ho; w = wo;
@@ -168,10 +180,14 @@ static int build_plan_a(io_net* net, int pa, __nv_bfloat16* dst, Plan* plan) {
   Op op;
   op.kind = Op::STEM;   // its tensor maps are rebuilt per call (the pair tensor belongs to the caller)
   op.flops = 2.0 * b * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
+  op.bytes = static_cast<double>(io_pair_tensor_bytes(pa, d)) + 2.0 * b * (d / 2) * (d / 2) * 64;
+  op.tag = 1;
   plan->ops.push_back(op);
   Op pool;
   pool.kind = Op::POOL;
   pool.src = X; pool.dst = Y; pool.b = b; pool.h = d / 2; pool.w = d / 2; pool.c = 64;
+  pool.bytes = 2.0 * b * (d / 2) * (d / 2) * 64 * 1.25;
+  pool.tag = 2;
   plan->ops.push_back(pool);
   int h = d / 4, w = d / 4;
   const __nv_bfloat16* out = nullptr;
@@ -213,7 +229,7 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
   }
   net->d = input_size;
   net->max_pairs = max_pairs;
-  int chunk_a = 16, chunk_b = 128;
+  int chunk_a = 128, chunk_b = 256;
   if (const char* e = getenv("INSTAORDER_CHUNK_A")) chunk_a = atoi(e) > 0 ? atoi(e) : chunk_a;
   if (const char* e = getenv("INSTAORDER_CHUNK_B")) chunk_b = atoi(e) > 0 ? atoi(e) : chunk_b;
   net->chunk_b = std::min(chunk_b, max_pairs);
@@ -356,7 +372,9 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
   net->last_launches = 0;
   net->prof_kind.clear();
   net->prof_flops.clear();
-  auto mark = [&](int kind, double flops, bool begin) -> int {
+  net->prof_bytes.clear();
+  net->prof_tag.clear();
+  auto mark = [&](int kind, double flops, bool begin, double bytes = 0.0, int tag = 0) -> int {
     if (!net->profile) return IO_OK;
     const size_t idx = 2 * net->prof_kind.size() + (begin ? 0 : 1);
     while (net->ev.size() <= idx) {
@@ -368,6 +386,8 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
     if (!begin) {
       net->prof_kind.push_back(kind);
       net->prof_flops.push_back(flops);
+      net->prof_bytes.push_back(bytes);
+      net->prof_tag.push_back(tag);
     }
     return IO_OK;
   };
@@ -392,7 +412,7 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
           break;
       }
       if (rc) return rc;
-      if ((rc = mark(static_cast<int>(op.kind), op.flops, false))) return rc;
+      if ((rc = mark(static_cast<int>(op.kind), op.flops, false, op.bytes, op.tag))) return rc;
       ++net->last_launches;
     }
     return IO_OK;
@@ -435,13 +455,16 @@ extern "C" int io_net_profile(io_net_t* net, int enable) {
   return IO_OK;
 }
 
-extern "C" int io_net_profile_read(io_net_t* net, float* ms, int32_t* kind, double* flop, int max_n) {
+extern "C" int io_net_profile_read(io_net_t* net, float* ms, int32_t* kind, double* flop, double* bytes, int32_t* tag,
+                                   int max_n) {
   IO_REQUIRE(net && ms && kind && flop, "io_net_profile_read: null pointer");
   const int n = static_cast<int>(net->prof_kind.size());
   for (int i = 0; i < n && i < max_n; ++i) {
     IO_CUDA(cudaEventElapsedTime(&ms[i], net->ev[2 * i], net->ev[2 * i + 1]));
     kind[i] = net->prof_kind[i];
     flop[i] = net->prof_flops[i];
+    if (bytes) bytes[i] = net->prof_bytes[i];
+    if (tag) tag[i] = net->prof_tag[i];
   }
   return n;
 }
