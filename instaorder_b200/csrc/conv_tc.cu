@@ -21,16 +21,20 @@ template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers: 128 / 256 / 512 columns
   // epilogue staging: per epilogue warp, BN/64 regions of 32 rows x 64 columns bf16 (4 KB, 128B-swizzled).  A
   // region first receives the residual tile (TMA load), is overwritten in place with the result, and is then
   // TMA-stored -- every global access of the epilogue is a full 128-byte line.
   static constexpr int EPI_REGION_BYTES = 32 * 128;
   static constexpr int EPI_WARP_BYTES = (BN / 64) * EPI_REGION_BYTES;
-  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  // two staging sets (alternating per tile) where shared memory allows, so that a tile's stores / next tile's
+  // residual loads never wait for each other; N = 256 has room for one set only
+  static constexpr int EPI_SETS = (BN == 256) ? 1 : 2;
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES * EPI_SETS;
+  static constexpr int BIAS_BYTES = (BN == 256) ? 8192 : 512;  // whole bias vector of the layer (<= 2048 / 128 floats)
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + 1024 B alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES + 1024;  // + align slack
 };
 
 struct TileCoord {
@@ -72,12 +76,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
   uint8_t* sEpi = smem + C::STAGES * C::STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES);
+  float* sBias = reinterpret_cast<float*>(sEpi + C::EPI_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES + C::BIAS_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* rbar = tempty + 2;  // one residual barrier per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 4);
+  uint64_t* rbar = tempty + 2;  // one residual barrier per epilogue warp and staging set
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     prefetch_tmap(&p.map_b);
     prefetch_tmap(&p.map_out);
     if (p.residual != nullptr) prefetch_tmap(&p.map_res);
-    for (int i = 0; i < 4; ++i) mbar_init(&rbar[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -102,6 +107,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) sBias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -175,9 +181,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     // ======================= epilogue (warps 2..5) =======================
     const int q = warp & 3;  // TMEM lane quadrant accessible to this warp: tile rows 32q .. 32q+31
     const int r = q * 32 + lane;
-    uint8_t* stage_base = sEpi + q * C::EPI_WARP_BYTES;
-    uint64_t* my_rbar = &rbar[q];
-    uint32_t rphase = 0;
+    uint32_t rphase[2] = {0, 0};
     const bool has_res = p.residual != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -185,6 +189,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       const TileCoord t = tile_coord(p, m_tile);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int set = (C::EPI_SETS == 2) ? (it & 1) : 0;
+      uint8_t* stage_base = sEpi + (set * 4 + q) * C::EPI_WARP_BYTES;
+      uint64_t* my_rbar = &rbar[set * 4 + q];
       const int row0 = t.base_row + q * 32;                    // first output row of this warp's slab
       // whole slab inside the tile -> TMA path (rows past the end of the tensor are clipped by TMA);
       // slab cut by the tile's row limit (384^2 geometries) -> per-thread path with a row guard
@@ -193,9 +200,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       const bool valid = slab_part && (r < t.limit) && (t.base_row + r < p.m_total);
       const int col_base = n_tile * BN;
 
-      // previous tile's stores must have finished reading the staging regions before they are refilled
+      // the stores that last used this staging set must have finished reading it before it is refilled:
+      // with two sets those are everything but the previous tile's BN/64 store groups
       if (lane == 0) {
-        tma_store_wait_read();
+        tma_store_wait_read<(C::EPI_SETS == 2) ? (BN / 64) : 0>();
         if (slab_full && has_res) {
           mbar_expect_tx(my_rbar, C::EPI_WARP_BYTES);
 #pragma unroll
@@ -207,30 +215,37 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (slab_full && has_res) {
-        mbar_wait(my_rbar, rphase);
-        rphase ^= 1;
+        mbar_wait(my_rbar, rphase[set]);
+        rphase[set] ^= 1;
       }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, v);
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        uint32_t v[2][32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
+        tmem_ld32(taddr, v[0]);
+        tmem_ld32(taddr + 32, v[1]);
         tmem_ld_wait();
-        int col = col_base + c0;
-        if (col < p.n_total && (slab_full || valid)) {
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + col);
+        if (col_base + c0 >= p.n_total || !(slab_full || valid)) {
+          if (lane == 0) tma_store_commit();  // empty group: keeps "BN/64 groups per tile" for wait_group.read
+          continue;
+        }
+        uint8_t* region = stage_base + (c0 >> 6) * C::EPI_REGION_BYTES + lane * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          int col = col_base + c0 + half * 32;
+          const float4* bias4 = reinterpret_cast<const float4*>(sBias + col);
           float f[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(bias4 + j);
-            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+            const float4 b = bias4[j];
+            f[4 * j + 0] = __uint_as_float(v[half][4 * j + 0]) + b.x;
+            f[4 * j + 1] = __uint_as_float(v[half][4 * j + 1]) + b.y;
+            f[4 * j + 2] = __uint_as_float(v[half][4 * j + 2]) + b.z;
+            f[4 * j + 3] = __uint_as_float(v[half][4 * j + 3]) + b.w;
           }
           if (slab_full) {
-            // staging region of this 64-column group; row `lane`, 16-byte chunks XOR-swizzled by (row & 7)
-            uint8_t* region = stage_base + (c0 >> 6) * C::EPI_REGION_BYTES + lane * 128;
-            const int kbase = (c0 & 32) >> 3;  // first 16-byte chunk of this 32-column half: 0 or 4
+            // row `lane` of the 64-column staging region; 16-byte chunks XOR-swizzled by (row & 7)
+            const int kbase = half * 4;
             if (has_res) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -253,16 +268,6 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
               o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
               o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
               *reinterpret_cast<uint4*>(region + (((kbase + j) ^ (lane & 7)) << 4)) = o;
-            }
-            if (c0 & 32) {  // second half written: the 64-column region is complete -> one TMA store
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                int scol = col_base + (c0 & ~63), srow = row0;
-                if (scol >= p.n_split) { scol -= p.n_split; srow += p.split_row_off; }
-                tma_store_2d(&p.map_out, stage_base + (c0 >> 6) * C::EPI_REGION_BYTES, scol, srow);
-                tma_store_commit();
-              }
             }
           } else {
             int row = t.base_row + r;
@@ -294,6 +299,18 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
               dst[j] = o;
             }
           }
+        }
+        if (slab_full) {  // the 64-column region is complete -> one TMA store
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            int scol = col_base + c0, srow = row0;
+            if (scol >= p.n_split) { scol -= p.n_split; srow += p.split_row_off; }
+            tma_store_2d(&p.map_out, stage_base + (c0 >> 6) * C::EPI_REGION_BYTES, scol, srow);
+            tma_store_commit();
+          }
+        } else if (lane == 0) {
+          tma_store_commit();
         }
       }
       tc_fence_before();
