@@ -108,8 +108,12 @@ def cpu_port_pairs_per_s(n_pairs, threads=None):
     import torch
     from instaorder_b200 import synth
     from oracle import oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    if threads is None:      # every host core this process may use (torchrun pins OMP_NUM_THREADS=1 by default)
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     rng = np.random.RandomState(1234)
     sd = synth.random_state_dict(0, 5, NUM_CLASSES)
     image, masks, boxes = next(synth.coco_scene_stream(99, 1, N=10))
