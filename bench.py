@@ -242,6 +242,12 @@ def main():
     _lib.check(eng.lib.io_net_profile(eng.net, 0))
     peaks = measured_peaks()
     achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+    # DRAM traffic of the conv kernel per launch, from the committed ncu capture of this command (profiles/)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if os.path.isfile(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
 
     # ---- end to end through the public API (host numpy -> pinned -> H2D -> ... -> D2H matrices) ---------------
     per_step_scenes = []
@@ -290,8 +296,8 @@ def main():
             gpu_launches=launches,
             clocks=clocks,
             roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
-                          frac=achieved / peaks["bf16"], traffic=None, kernel="conv_tc_kernel (53 launches per "
-                          "32-pair chunk)", launches_timed=n_conv, avg_launch_ms=conv_ms / max(n_conv, 1),
+                          frac=achieved / peaks["bf16"], traffic=traffic, kernel="conv_tc_kernel (all "
+                          "53 conv layers)", launches_timed=n_conv, avg_launch_ms=conv_ms / max(n_conv, 1),
                           conv_share_of_step=conv_ms / tot_ms if tot_ms else None, peak_source=peaks["source"],
                           step_frac=value / world * FLOP_PER_PAIR / 1e12 / peaks["bf16"]),
             cpu_baseline=cpu,

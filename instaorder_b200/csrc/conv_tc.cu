@@ -107,10 +107,14 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) sBias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) sBias[i] = p.bias[i];  // weights: not produced upstream
+  // Programmatic dependent launch: let the next convolution's CTAs start their prologue on SMs this grid has
+  // already vacated, and do not touch activations before the previous grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
@@ -335,8 +339,17 @@ static int launch_bn(const ConvParams& p, cudaStream_t stream) {
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_tc_kernel<BN><<<grid, 192, Cfg<BN>::SMEM_BYTES, stream>>>(p);
-  IO_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IO_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN>, p));
   return IO_OK;
 }
 

@@ -95,7 +95,8 @@ class _Slot:
         self.d_mask = torch.empty(mask_bytes, dtype=torch.uint8, device=device)
         self.d_desc = torch.empty(max_pairs * 48, dtype=torch.uint8, device=device)
         self.d_meta = torch.empty(max_pairs * 4, dtype=torch.int64, device=device)
-        self.event = None
+        self.event = None        # compute that consumed the device buffers has finished
+        self.copied = None       # H2D copies out of the pinned buffers have finished
 
 
 class _Resident:
@@ -128,6 +129,7 @@ class OrderEngine:
         self._slot_args = (img_bytes, mask_bytes, self.max_pairs, self.device)
         self._slots = [None] * slots
         self._slot_i = 0
+        self.copy_stream = torch.cuda.Stream(device=self.device)   # H2D of batch k+1 overlaps compute of batch k
         self.gpu_launches = 0   # kernels launched by this engine since creation
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -164,8 +166,8 @@ class OrderEngine:
         if self._slots[i] is None:
             self._slots[i] = _Slot(*self._slot_args)
         s = self._slots[i]
-        if s.event is not None:
-            s.event.synchronize()   # the previous batch that used these pinned buffers has been consumed
+        if s.copied is not None:
+            s.copied.synchronize()  # the pinned buffers have been read by the previous H2D that used this slot
         return s
 
     def stage_batch(self, items, mode="patch"):
@@ -207,10 +209,17 @@ class OrderEngine:
             img_off += (ib + 15) // 16 * 16
             mask_off += (mb + 15) // 16 * 16
             P += p
-        s.d_img[:img_off].copy_(s.h_img[:img_off], non_blocking=True)
-        s.d_mask[:mask_off].copy_(s.h_mask[:mask_off], non_blocking=True)
-        s.d_desc[:P * 48].copy_(s.h_desc[:P * 48], non_blocking=True)
-        s.d_meta.copy_(s.h_meta, non_blocking=True)
+        compute = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            if s.event is not None:
+                self.copy_stream.wait_event(s.event)   # kernels of the batch that last used these device buffers
+            s.d_img[:img_off].copy_(s.h_img[:img_off], non_blocking=True)
+            s.d_mask[:mask_off].copy_(s.h_mask[:mask_off], non_blocking=True)
+            s.d_desc[:P * 48].copy_(s.h_desc[:P * 48], non_blocking=True)
+            s.d_meta.copy_(s.h_meta, non_blocking=True)
+            s.copied = torch.cuda.Event()
+            s.copied.record(self.copy_stream)
+        compute.wait_event(s.copied)
         self.h2d_bytes += img_off + mask_off + P * 48 + s.h_meta.numel() * 8
         return s, P
 
