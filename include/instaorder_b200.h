@@ -154,6 +154,14 @@ IO_API int io_order_decide(const float* logits_dev, int p, int k_total, int head
 IO_API int io_conv_bn_act(const void* x_dev, int b, int h, int w, int cin, const void* w_dev, const float* bias_dev,
                    const void* residual_dev, int cout, int kernel, int stride, int relu, void* y_dev, void* stream);
 
+/* conv3 (1x1, cmid -> 4*cmid, + residual + ReLU -> y) of one bottleneck fused with conv1 (1x1, 4*cmid -> n2, + ReLU
+ * -> y2) of the next one (resnet_cls.py:107-116 then :99-101): the block output is written once and consumed from
+ * shared memory by the second GEMM.  x_dev: [rows][cmid], w3_dev: [4*cmid][cmid], w1n_dev: [n2][4*cmid], all bf16;
+ * cmid in {64, 128, 256}, n2 in {64, 128, 256}.  Exported for the parity test. */
+IO_API int io_conv_fused_pair(const void* x_dev, int rows, int cmid, const void* w3_dev, const float* bias3_dev,
+                              const void* residual_dev, void* y_dev, const void* w1n_dev, const float* bias1n_dev,
+                              int n2, void* y2_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------ */
 /* M -- metrics, batched over images                                                                             */
 /* ------------------------------------------------------------------------------------------------------------ */

@@ -52,6 +52,7 @@ _SIGS = {
     "io_net_profile_read": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "io_order_decide": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "io_conv_bn_act": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "io_conv_fused_pair": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "io_metrics_prf": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "io_metrics_whdr": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
 }

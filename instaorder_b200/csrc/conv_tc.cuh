@@ -41,6 +41,18 @@ struct ConvParams {
   int relu;
 };
 
+// conv3 (+ residual + ReLU) of one bottleneck fused with conv1 (+ ReLU) of the next one (conv_fused.cu)
+struct FusedParams {
+  ConvParams c;          // the conv3 GEMM: CONV_GEMM mode, N tile 256, residual required
+  CUtensorMap map_b2;    // next conv1 weights [n2][n_total] bf16, box 64 x n2
+  CUtensorMap map_out2;  // next block's T1 [rows][n2] bf16, box 64 x 32
+  const float* bias2;
+  int n2;
+};
+int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, const void* w3, const float* bias3,
+                    const void* residual, void* y, const void* w1n, const float* bias1n, void* y2);
+int conv_fused_launch(const FusedParams& fp, cudaStream_t stream);
+
 // Launches the persistent kernel for one convolution. bn_tile in {64, 128, 256}.
 int conv_tc_launch(const ConvParams& p, int bn_tile, cudaStream_t stream);
 

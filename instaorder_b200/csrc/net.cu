@@ -24,8 +24,9 @@ struct ConvW {
 };
 
 struct Op {
-  enum Kind { STEM, POOL, CONV, TAIL } kind;
+  enum Kind { STEM, POOL, CONV, TAIL, FUSED } kind;
   ConvParams p;
+  FusedParams fp;
   int bn_tile = 0;
   double flops = 0.0;  // algorithmic 2*MAC of this launch
   double bytes = 0.0;  // algorithmic HBM bytes of this launch (activations in + out + residual + weights)
@@ -60,6 +61,7 @@ struct io_net {
   // phase A (stem .. layer2) works on sub-chunks of chunk_a pairs so that its large activations stay in L2;
   // phase B (layer3, layer4, tail) runs over chunk_b pairs at once so that its small GEMMs fill all SMs.
   int chunk_a = 0, chunk_b = 0;
+  bool fuse = true;   // conv3 -> next conv1 back-to-back GEMM fusion (INSTAORDER_FUSE=0 disables)
   __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase A: X, Y, T1, T2, DS
   __nv_bfloat16* bufb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase B: X, Y, T1, T2, DS
   __nv_bfloat16* big = nullptr;                                            // layer2 output of a whole B chunk
@@ -122,6 +124,7 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
   size_t ci = 1;
   for (int li = 0; li < l0; ++li) ci += 3 * blocks_[li] + 1;
   int h = *h_io, w = *w_io;
+  bool t1_ready = false;   // the previous block's fused conv3 already produced this block's conv1 output
   for (int li = l0; li < l1; ++li) {
     for (int blk = 0; blk < blocks_[li]; ++blk) {
       const ConvW& c1 = net->convs[ci++];
@@ -131,13 +134,16 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       const int ho = h / c2.stride, wo = w / c2.stride;
       const bool last = (li == l1 - 1) && (blk == blocks_[li] - 1);
       __nv_bfloat16* dst = (last && final_dst) ? final_dst : (src == P0 ? P1 : P0);
-      Op o1; o1.kind = Op::CONV;
-      if (int rc = conv_plan(&o1.p, &o1.bn_tile, ConvDesc{b, h, w, c1.cin, c1.cout, 1, 1}, src, c1.w, c1.bias, nullptr,
-                             T1, 1)) return rc;
-      o1.flops = 2.0 * b * h * w * c1.cin * c1.cout;
-      o1.bytes = 2.0 * b * h * w * (c1.cin + c1.cout) + 2.0 * c1.cin * c1.cout;
-      o1.tag = (li + 1) * 100 + blk * 10 + 1;
-      plan->ops.push_back(o1);
+      if (!t1_ready) {
+        Op o1; o1.kind = Op::CONV;
+        if (int rc = conv_plan(&o1.p, &o1.bn_tile, ConvDesc{b, h, w, c1.cin, c1.cout, 1, 1}, src, c1.w, c1.bias,
+                               nullptr, T1, 1)) return rc;
+        o1.flops = 2.0 * b * h * w * c1.cin * c1.cout;
+        o1.bytes = 2.0 * b * h * w * (c1.cin + c1.cout) + 2.0 * c1.cin * c1.cout;
+        o1.tag = (li + 1) * 100 + blk * 10 + 1;
+        plan->ops.push_back(o1);
+      }
+      t1_ready = false;
       Op o2; o2.kind = Op::CONV;
       if (int rc = conv_plan(&o2.p, &o2.bn_tile, ConvDesc{b, h, w, c2.cin, c2.cout, 3, c2.stride}, T1, c2.w, c2.bias,
                              nullptr, T2, 1)) return rc;
@@ -156,13 +162,26 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
         plan->ops.push_back(od);
         identity = DS;
       }
-      Op o3; o3.kind = Op::CONV;
-      if (int rc = conv_plan(&o3.p, &o3.bn_tile, ConvDesc{b, ho, wo, c3.cin, c3.cout, 1, 1}, T2, c3.w, c3.bias, identity,
-                             dst, 1)) return rc;
-      o3.flops = 2.0 * b * ho * wo * c3.cin * c3.cout;
-      o3.bytes = 2.0 * b * ho * wo * (c3.cin + 2 * c3.cout) + 2.0 * c3.cin * c3.cout;
-      o3.tag = (li + 1) * 100 + blk * 10 + 3;
-      plan->ops.push_back(o3);
+      const bool fuse_next = net->fuse && (blk + 1 < blocks_[li]) && c3.cout <= 1024;
+      if (fuse_next) {
+        const ConvW& n1 = net->convs[ci];   // next block's conv1 (no downsample in blocks >= 1)
+        Op of; of.kind = Op::FUSED;
+        if (int rc = conv_fused_plan(&of.fp, b * ho * wo, c3.cin, n1.cout, T2, c3.w, c3.bias, identity, dst, n1.w,
+                                     n1.bias, T1)) return rc;
+        of.flops = 2.0 * b * ho * wo * (static_cast<double>(c3.cin) * c3.cout + static_cast<double>(n1.cin) * n1.cout);
+        of.bytes = 2.0 * b * ho * wo * (c3.cin + 2 * c3.cout + n1.cout) + 2.0 * c3.cin * c3.cout + 2.0 * n1.cin * n1.cout;
+        of.tag = (li + 1) * 100 + blk * 10 + 5;
+        plan->ops.push_back(of);
+        t1_ready = true;
+      } else {
+        Op o3; o3.kind = Op::CONV;
+        if (int rc = conv_plan(&o3.p, &o3.bn_tile, ConvDesc{b, ho, wo, c3.cin, c3.cout, 1, 1}, T2, c3.w, c3.bias,
+                               identity, dst, 1)) return rc;
+        o3.flops = 2.0 * b * ho * wo * c3.cin * c3.cout;
+        o3.bytes = 2.0 * b * ho * wo * (c3.cin + 2 * c3.cout) + 2.0 * c3.cin * c3.cout;
+        o3.tag = (li + 1) * 100 + blk * 10 + 3;
+        plan->ops.push_back(o3);
+      }
       src = dst;  // the next block reads what was just written
       h = ho; w = wo;
     }
@@ -232,6 +251,7 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
   int chunk_a = 128, chunk_b = 256;
   if (const char* e = getenv("INSTAORDER_CHUNK_A")) chunk_a = atoi(e) > 0 ? atoi(e) : chunk_a;
   if (const char* e = getenv("INSTAORDER_CHUNK_B")) chunk_b = atoi(e) > 0 ? atoi(e) : chunk_b;
+  if (const char* e = getenv("INSTAORDER_FUSE")) net->fuse = atoi(e) != 0;
   net->chunk_b = std::min(chunk_b, max_pairs);
   net->chunk_a = std::min(chunk_a, net->chunk_b);
   build_conv_list(net.get());
@@ -407,6 +427,9 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
           break;
         case Op::CONV:
           rc = conv_tc_launch(op.p, op.bn_tile, stream);
+          break;
+        case Op::FUSED:
+          rc = conv_fused_launch(op.fp, stream);
           break;
         default:
           break;

@@ -61,3 +61,36 @@ def test_conv_bn_act(case):
     assert not bad.any(), "max err %.4g at %s (ref %.4g got %.4g), %d bad" % (
         float(err.max()), tuple(int(v) for v in torch.nonzero(bad)[0]), float(ref[bad][0]), float(got[bad][0]),
         int(bad.sum()))
+
+
+# (rows, cmid, n2): layer1 / layer2 / layer3 bottleneck pairs + a ragged row count (row guard by TMA clipping)
+FUSED_CASES = [(2 * 64 * 64, 64, 64), (3 * 32 * 32, 128, 128), (5 * 16 * 16, 256, 256), (1000, 64, 64),
+               (148 * 128 * 2 + 77, 128, 128)]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: "rows%d_c%d_n%d" % c)
+def test_conv_fused_pair(case):
+    """conv3 + residual + ReLU fused with the next block's conv1 + ReLU (back-to-back GEMM) vs two torch GEMMs."""
+    rows, cmid, n2 = case
+    n1 = 4 * cmid
+    g = torch.Generator(device="cuda").manual_seed(rows + cmid)
+    dev = "cuda"
+    x = torch.randn((rows, cmid), generator=g, device=dev).to(torch.bfloat16)
+    w3 = (torch.randn((n1, cmid), generator=g, device=dev) / cmid ** 0.5).to(torch.bfloat16)
+    b3 = torch.randn((n1,), generator=g, device=dev)
+    res = torch.randn((rows, n1), generator=g, device=dev).to(torch.bfloat16)
+    w1 = (torch.randn((n2, n1), generator=g, device=dev) / n1 ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn((n2,), generator=g, device=dev)
+    y = torch.full((rows, n1), float("nan"), device=dev, dtype=torch.bfloat16)
+    y2 = torch.full((rows, n2), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().io_conv_fused_pair(x.data_ptr(), rows, cmid, w3.data_ptr(), b3.data_ptr(), res.data_ptr(),
+                                             y.data_ptr(), w1.data_ptr(), b1.data_ptr(), n2, y2.data_ptr(),
+                                             _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.relu(x.float() @ w3.float().t() + b3 + res.float())
+    ref2 = torch.relu(ref.to(torch.bfloat16).float() @ w1.float().t() + b1)
+    for got, want, name in ((y.float(), ref, "y"), (y2.float(), ref2, "y2")):
+        assert torch.isfinite(got).all(), "%s: %d unwritten outputs" % (name, int((~torch.isfinite(got)).sum()))
+        err = (got - want).abs()
+        tol = 1.5e-2 + 1e-2 * want.abs()
+        assert not (err > tol).any(), "%s: max err %.4g, %d bad" % (name, float(err.max()), int((err > tol).sum()))
