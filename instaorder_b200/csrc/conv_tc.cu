@@ -27,13 +27,16 @@ struct Cfg {
   // region first receives the residual tile (TMA load), is overwritten in place with the result, and is then
   // TMA-stored -- every global access of the epilogue is a full 128-byte line.
   static constexpr int EPI_REGION_BYTES = 32 * 128;
-  static constexpr int EPI_WARP_BYTES = (BN / 64) * EPI_REGION_BYTES;
-  // two staging sets (alternating per tile) where shared memory allows, so that a tile's stores / next tile's
-  // residual loads never wait for each other; N = 256 has room for one set only
-  static constexpr int EPI_SETS = (BN == 256) ? 1 : 2;
-  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES * EPI_SETS;
+  // 8 epilogue warps (two per TMEM lane quadrant, splitting the 64-column groups between them) so that every SM
+  // sub-partition has two warps to hide tcgen05.ld / shared-memory / barrier latencies; N = 64 uses 4 of them.
+  // Every warp owns two staging slots: for N = 256 its two column groups of the tile, otherwise one group with
+  // the slot alternating per tile -- so a slot is refilled two store-commits after it was last stored from.
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int GROUPS = BN / 64;
+  static constexpr int ACTIVE_EPI_WARPS = (GROUPS == 1) ? 4 : 8;
+  static constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_REGION_BYTES;
   static constexpr int BIAS_BYTES = (BN == 256) ? 8192 : 512;  // whole bias vector of the layer (<= 2048 / 128 floats)
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;  // up to 6+6+2+2+16 mbarriers + the TMEM base slot
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES + 1024;  // + align slack
 };
 
@@ -69,7 +72,7 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int m_tile)
 }
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -81,8 +84,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* rbar = tempty + 2;  // one residual barrier per epilogue warp and staging set
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 8);
+  uint64_t* rbar = tempty + 2;  // residual tile landed: one barrier per epilogue warp and staging slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,14 +95,14 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     prefetch_tmap(&p.map_b);
     prefetch_tmap(&p.map_out);
     if (p.residual != nullptr) prefetch_tmap(&p.map_res);
-    for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&rbar[i], 1);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty[i], C::ACTIVE_EPI_WARPS);  // one arrival per participating epilogue warp
     }
     fence_barrier_init();
   }
@@ -182,146 +185,160 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       }
     }
   } else {
-    // ======================= epilogue (warps 2..5) =======================
-    const int q = warp & 3;  // TMEM lane quadrant accessible to this warp: tile rows 32q .. 32q+31
+    // ======================= epilogue (warps 2..9) =======================
+    const int e = warp - 2;      // epilogue warp index
+    const int q = warp & 3;      // TMEM lane quadrant accessible to this warp: tile rows 32q .. 32q+31
+    const int hsel = e >> 2;     // which of the quadrant's two warps: owns column groups hsel, hsel + 2
     const int r = q * 32 + lane;
-    uint32_t rphase[2] = {0, 0};
     const bool has_res = p.residual != nullptr;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-      const TileCoord t = tile_coord(p, m_tile);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int set = (C::EPI_SETS == 2) ? (it & 1) : 0;
-      uint8_t* stage_base = sEpi + (set * 4 + q) * C::EPI_WARP_BYTES;
-      uint64_t* my_rbar = &rbar[set * 4 + q];
-      const int row0 = t.base_row + q * 32;                    // first output row of this warp's slab
-      // whole slab inside the tile -> TMA path (rows past the end of the tensor are clipped by TMA);
-      // slab cut by the tile's row limit (384^2 geometries) -> per-thread path with a row guard
-      const bool slab_full = (q * 32 + 32 <= t.limit) && (row0 < p.m_total);
-      const bool slab_part = !slab_full && (q * 32 < t.limit) && (row0 < p.m_total);
-      const bool valid = slab_part && (r < t.limit) && (t.base_row + r < p.m_total);
-      const int col_base = n_tile * BN;
+    constexpr int MY_GROUPS = (C::GROUPS + 1) / 2;     // 1 (N = 64, 128) or 2 (N = 256)
+    if (hsel < C::GROUPS) {
+      uint8_t* my_stage = sEpi + e * 2 * C::EPI_REGION_BYTES;
+      uint64_t* my_rbar = &rbar[e * 2];
+      uint32_t rphase[2] = {0, 0};
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const TileCoord t = tile_coord(p, m_tile);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int row0 = t.base_row + q * 32;                    // first output row of this warp's slab
+        // whole slab inside the tile -> TMA path (rows past the end of the tensor are clipped by TMA);
+        // slab cut by the tile's row limit (384^2 geometries) -> per-thread path with a row guard
+        const bool slab_full = (q * 32 + 32 <= t.limit) && (row0 < p.m_total);
+        const bool slab_part = !slab_full && (q * 32 < t.limit) && (row0 < p.m_total);
+        const bool valid = slab_part && (r < t.limit) && (t.base_row + r < p.m_total);
+        const int col_base = n_tile * BN;
 
-      // the stores that last used this staging set must have finished reading it before it is refilled:
-      // with two sets those are everything but the previous tile's BN/64 store groups
-      if (lane == 0) {
-        tma_store_wait_read<(C::EPI_SETS == 2) ? (BN / 64) : 0>();
-        if (slab_full && has_res) {
-          mbar_expect_tx(my_rbar, C::EPI_WARP_BYTES);
+        // residual prefetch: a slot may be refilled once the store that last read it has finished reading
+        if (slab_full && has_res && lane == 0) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(stage_base + j * C::EPI_REGION_BYTES, &p.map_res, my_rbar, col_base + j * 64, row0);
+          for (int i = 0; i < MY_GROUPS; ++i) {
+            const int slot = (MY_GROUPS == 2) ? i : (it & 1);
+            const int g = hsel + 2 * i;
+            if (MY_GROUPS == 2 && i == 1) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            mbar_expect_tx(&my_rbar[slot], C::EPI_REGION_BYTES);
+            tma_load_2d(my_stage + slot * C::EPI_REGION_BYTES, &p.map_res, &my_rbar[slot], col_base + g * 64, row0);
+          }
         }
-      }
-      __syncwarp();
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      if (slab_full && has_res) {
-        mbar_wait(my_rbar, rphase[set]);
-        rphase[set] ^= 1;
-      }
+        __syncwarp();
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 64) {
-        uint32_t v[2][32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
-        tmem_ld32(taddr, v[0]);
-        tmem_ld32(taddr + 32, v[1]);
-        tmem_ld_wait();
-        if (col_base + c0 >= p.n_total || !(slab_full || valid)) {
-          if (lane == 0) tma_store_commit();  // empty group: keeps "BN/64 groups per tile" for wait_group.read
-          continue;
-        }
-        uint8_t* region = stage_base + (c0 >> 6) * C::EPI_REGION_BYTES + lane * 128;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          int col = col_base + c0 + half * 32;
-          const float4* bias4 = reinterpret_cast<const float4*>(sBias + col);
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = bias4[j];
-            f[4 * j + 0] = __uint_as_float(v[half][4 * j + 0]) + b.x;
-            f[4 * j + 1] = __uint_as_float(v[half][4 * j + 1]) + b.y;
-            f[4 * j + 2] = __uint_as_float(v[half][4 * j + 2]) + b.z;
-            f[4 * j + 3] = __uint_as_float(v[half][4 * j + 3]) + b.w;
+        for (int i = 0; i < MY_GROUPS; ++i) {
+          const int slot = (MY_GROUPS == 2) ? i : (it & 1);
+          const int c0 = (hsel + 2 * i) * 64;
+          uint32_t v[2][32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
+          tmem_ld32(taddr, v[0]);
+          tmem_ld32(taddr + 32, v[1]);
+          tmem_ld_wait();
+          if (i == MY_GROUPS - 1) {   // accumulator fully read by this warp: hand it back to the MMA warp early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
           }
+          if (col_base + c0 >= p.n_total || !(slab_full || valid)) {
+            if (lane == 0) tma_store_commit();  // empty group: keeps one store-commit per group for wait_group.read
+            continue;
+          }
+          uint8_t* region = my_stage + slot * C::EPI_REGION_BYTES;
+          uint8_t* rowp = region + lane * 128;
           if (slab_full) {
-            // row `lane` of the 64-column staging region; 16-byte chunks XOR-swizzled by (row & 7)
-            const int kbase = half * 4;
             if (has_res) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(region + (((kbase + j) ^ (lane & 7)) << 4));
-                f[8 * j + 0] += bf16_lo(rr.x); f[8 * j + 1] += bf16_hi(rr.x);
-                f[8 * j + 2] += bf16_lo(rr.y); f[8 * j + 3] += bf16_hi(rr.y);
-                f[8 * j + 4] += bf16_lo(rr.z); f[8 * j + 5] += bf16_hi(rr.z);
-                f[8 * j + 6] += bf16_lo(rr.w); f[8 * j + 7] += bf16_hi(rr.w);
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
-              o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
-              *reinterpret_cast<uint4*>(region + (((kbase + j) ^ (lane & 7)) << 4)) = o;
-            }
-          } else {
-            int row = t.base_row + r;
-            if (col >= p.n_split) { col -= p.n_split; row += p.split_row_off; }
-            const size_t off = static_cast<size_t>(row) * p.ldc + col;
-            if (has_res) {
-              const uint4* res = reinterpret_cast<const uint4*>(p.residual + off);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 rr = __ldg(res + j);
-                f[8 * j + 0] += bf16_lo(rr.x); f[8 * j + 1] += bf16_hi(rr.x);
-                f[8 * j + 2] += bf16_lo(rr.y); f[8 * j + 3] += bf16_hi(rr.y);
-                f[8 * j + 4] += bf16_lo(rr.z); f[8 * j + 5] += bf16_hi(rr.z);
-                f[8 * j + 6] += bf16_lo(rr.w); f[8 * j + 7] += bf16_hi(rr.w);
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(p.out + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
-              o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
-              dst[j] = o;
+              mbar_wait(&my_rbar[slot], rphase[slot]);
+              rphase[slot] ^= 1;
+            } else {
+              if (lane == 0) tma_store_wait_read<1>();   // the store that last used this slot has read it
+              __syncwarp();
             }
           }
-        }
-        if (slab_full) {  // the 64-column region is complete -> one TMA store
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            int scol = col_base + c0, srow = row0;
-            if (scol >= p.n_split) { scol -= p.n_split; srow += p.split_row_off; }
-            tma_store_2d(&p.map_out, stage_base + (c0 >> 6) * C::EPI_REGION_BYTES, scol, srow);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            int col = col_base + c0 + half * 32;
+            const float4* bias4 = reinterpret_cast<const float4*>(sBias + col);
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = bias4[j];
+              f[4 * j + 0] = __uint_as_float(v[half][4 * j + 0]) + b.x;
+              f[4 * j + 1] = __uint_as_float(v[half][4 * j + 1]) + b.y;
+              f[4 * j + 2] = __uint_as_float(v[half][4 * j + 2]) + b.z;
+              f[4 * j + 3] = __uint_as_float(v[half][4 * j + 3]) + b.w;
+            }
+            if (slab_full) {
+              // row `lane` of the 64-column staging region; 16-byte chunks XOR-swizzled by (row & 7)
+              const int kbase = half * 4;
+              if (has_res) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((kbase + j) ^ (lane & 7)) << 4));
+                  f[8 * j + 0] += bf16_lo(rr.x); f[8 * j + 1] += bf16_hi(rr.x);
+                  f[8 * j + 2] += bf16_lo(rr.y); f[8 * j + 3] += bf16_hi(rr.y);
+                  f[8 * j + 4] += bf16_lo(rr.z); f[8 * j + 5] += bf16_hi(rr.z);
+                  f[8 * j + 6] += bf16_lo(rr.w); f[8 * j + 7] += bf16_hi(rr.w);
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+                *reinterpret_cast<uint4*>(rowp + (((kbase + j) ^ (lane & 7)) << 4)) = o;
+              }
+            } else {
+              int row = t.base_row + r;
+              if (col >= p.n_split) { col -= p.n_split; row += p.split_row_off; }
+              const size_t off = static_cast<size_t>(row) * p.ldc + col;
+              if (has_res) {
+                const uint4* res = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 rr = __ldg(res + j);
+                  f[8 * j + 0] += bf16_lo(rr.x); f[8 * j + 1] += bf16_hi(rr.x);
+                  f[8 * j + 2] += bf16_lo(rr.y); f[8 * j + 3] += bf16_hi(rr.y);
+                  f[8 * j + 4] += bf16_lo(rr.z); f[8 * j + 5] += bf16_hi(rr.z);
+                  f[8 * j + 6] += bf16_lo(rr.w); f[8 * j + 7] += bf16_hi(rr.w);
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+                dst[j] = o;
+              }
+            }
+          }
+          if (slab_full) {  // the 64-column region is complete -> one TMA store
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              int scol = col_base + c0, srow = row0;
+              if (scol >= p.n_split) { scol -= p.n_split; srow += p.split_row_off; }
+              tma_store_2d(&p.map_out, region, scol, srow);
+              tma_store_commit();
+            }
+          } else if (lane == 0) {
             tma_store_commit();
           }
-        } else if (lane == 0) {
-          tma_store_commit();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) tma_store_wait_all();
     }
-    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -341,7 +358,7 @@ static int launch_bn(const ConvParams& p, cudaStream_t stream) {
   const int grid = tiles < num_sms() ? tiles : num_sms();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

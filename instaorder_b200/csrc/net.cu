@@ -61,7 +61,7 @@ struct io_net {
   // phase A (stem .. layer2) works on sub-chunks of chunk_a pairs so that its large activations stay in L2;
   // phase B (layer3, layer4, tail) runs over chunk_b pairs at once so that its small GEMMs fill all SMs.
   int chunk_a = 0, chunk_b = 0;
-  bool fuse = true;   // conv3 -> next conv1 back-to-back GEMM fusion (INSTAORDER_FUSE=0 disables)
+  bool fuse = false;  // conv3 -> next conv1 back-to-back GEMM fusion (INSTAORDER_FUSE=1 enables; parity-tested, not yet faster)
   __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase A: X, Y, T1, T2, DS
   __nv_bfloat16* bufb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase B: X, Y, T1, T2, DS
   __nv_bfloat16* big = nullptr;                                            // layer2 output of a whole B chunk
