@@ -99,6 +99,11 @@ IO_API int io_image_resize_rgb(const uint8_t* image_dev, int h, int w, int d, co
 IO_API int io_pair_gather_resize(const float* rgb_planes_dev, const uint8_t* masks_dev, const io_pair_desc* descs_dev,
                           int p, int d, void* out_dev, void* stream);
 
+/* Collated dataset tensors (rgb [B,3,D,D], modal1 / modal2 [B,1,D,D], fp32 NCHW, device) -> pair tensor: the
+ * torch.cat([modal1, modal2, rgb], 1) of models/supervised_order.py:52 for validation / arbitrary `model.model(x)`. */
+IO_API int io_pair_pack_nchw(const float* rgb_dev, const float* modal1_dev, const float* modal2_dev, int b, int d,
+                             void* out_dev, void* stream);
+
 /* (u8 / 255 - mean) / std in fp32 exactly as torchvision computes it; out_host[3 * 256].  Host only. */
 IO_API int io_normalize_lut(const float* mean_host, const float* std_host, float* out_host);
 
@@ -161,6 +166,17 @@ IO_API int io_conv_bn_act(const void* x_dev, int b, int h, int w, int cin, const
 IO_API int io_conv_fused_pair(const void* x_dev, int rows, int cmid, const void* w3_dev, const float* bias3_dev,
                               const void* residual_dev, void* y_dev, const void* w1n_dev, const float* bias1n_dev,
                               int n2, void* y2_dev, void* stream);
+
+/* Validation losses (forward only) -- models/supervised_order.py:60-81 (^od), :397-411 (^d), :465-479 (OrderNet),
+ * :518-533 (^o), including the swapped-direction labels of set_input and the reference's softmax-then-CrossEntropy
+ * / sigmoid-then-BCELoss quirks.  logits_dev[n][2][k_total]; occ_off >= 0 selects a 2-logit sigmoid head with
+ * occ_target_dev[n][2] fp32; class_off >= 0 selects a class_k-way softmax head with class_target_dev[n] int64.
+ * is_overlap_dev (optional, int64[n]) switches on the overlap / distinct weighting of ^od.  out_dev[3] fp32 =
+ * (loss / world_size, occlusion loss, class loss). */
+IO_API int io_loss_forward(const float* logits_dev, int n, int k_total, int occ_off, int class_off, int class_k,
+                           const float* occ_target_dev, const int64_t* class_target_dev,
+                           const int64_t* is_overlap_dev, float overlap_w, float distinct_w, int world_size,
+                           float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------ */
 /* M -- metrics, batched over images                                                                             */

@@ -290,6 +290,33 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_resize_kernel(const flo
   }
 }
 
+// ---- pack: training / validation batches arrive as the reference's collated tensors ---------------------------
+// rgb [B,3,D,D], modal1 [B,1,D,D], modal2 [B,1,D,D] fp32 NCHW (what Dataset.__getitem__ + default collate produce,
+// reference datasets/*_order_dataset.py) -> pair tensor, i.e. torch.cat([modal1, modal2, rgb], 1) of
+// models/supervised_order.py:52 in the stem's layout.
+__global__ void __launch_bounds__(GATHER_THREADS) pack_nchw_kernel(const float* __restrict__ rgb,
+                                                                   const float* __restrict__ m1,
+                                                                   const float* __restrict__ m2, int d, int pitch,
+                                                                   __nv_bfloat16* __restrict__ out) {
+  const int b = blockIdx.y;
+  __nv_bfloat16* out_pair = out + static_cast<size_t>(b) * (d + 6) * pitch * 8;
+  const int row0 = blockIdx.x * GATHER_ROWS;
+  const int row1 = min(d, row0 + GATHER_ROWS);
+  zero_borders(out_pair, d, pitch, blockIdx.x, gridDim.x, row0, row1);
+  const size_t plane = static_cast<size_t>(d) * d;
+  for (int dy = row0; dy < row1; ++dy) {
+    for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
+      const size_t o = static_cast<size_t>(dy) * d + dx;
+      const float* px = rgb + static_cast<size_t>(b) * 3 * plane + o;
+      const uint32_t rg = pack_bf16(px[0], px[plane]);
+      const uint32_t bb = pack_bf16(px[2 * plane], 0.0f);
+      store_pixel(out_pair + (static_cast<size_t>(dy + 3) * pitch + dx + 3) * 8, m1[b * plane + o], m2[b * plane + o],
+                  static_cast<uint16_t>(rg & 0xFFFF), static_cast<uint16_t>(rg >> 16),
+                  static_cast<uint16_t>(bb & 0xFFFF));
+    }
+  }
+}
+
 // ---- bordering ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bordering_kernel(const uint8_t* __restrict__ masks, int H, int W,
                                                         const int32_t* __restrict__ pairs,
@@ -417,6 +444,19 @@ extern "C" int io_pair_gather_patch(const uint8_t* images, const uint8_t* masks,
   gather_patch_kernel<<<grid, GATHER_THREADS, 0, as_stream(stream)>>>(images, masks, descs, d,
                                                                       static_cast<int>(io_pair_tensor_row_pitch(d)),
                                                                       lut, reinterpret_cast<__nv_bfloat16*>(out));
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
+extern "C" int io_pair_pack_nchw(const float* rgb, const float* m1, const float* m2, int b, int d, void* out,
+                                 void* stream) {
+  IO_REQUIRE(rgb && m1 && m2 && out && b >= 0, "io_pair_pack_nchw: bad arguments");
+  if (int rc = check_d(d)) return rc;
+  if (b == 0) return IO_OK;
+  dim3 grid((d + GATHER_ROWS - 1) / GATHER_ROWS, b);
+  pack_nchw_kernel<<<grid, GATHER_THREADS, 0, as_stream(stream)>>>(rgb, m1, m2, d,
+                                                                   static_cast<int>(io_pair_tensor_row_pitch(d)),
+                                                                   reinterpret_cast<__nv_bfloat16*>(out));
   IO_CUDA(cudaGetLastError());
   return IO_OK;
 }

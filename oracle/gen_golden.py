@@ -216,10 +216,67 @@ def gen_geometry(ns):
     print("wrote", p)
 
 
+def val_batch(seed, algo, num_classes, B=6, D=256):
+    """C4-style synthetic collated batch: normal rgb, blob masks, random labels."""
+    rng = np.random.RandomState(seed)
+    rgb = rng.standard_normal((B, 3, D, D)).astype(np.float32)
+    m = np.zeros((B, 2, D, D), dtype=np.float32)
+    for b in range(B):
+        for c in range(2):
+            x0, y0 = rng.randint(0, D // 2, size=2)
+            w, h = rng.randint(D // 8, D // 2, size=2)
+            m[b, c, y0:y0 + h, x0:x0 + w] = 1.0
+    out = dict(rgb=rgb, modal1=m[:, 0:1].copy(), modal2=m[:, 1:2].copy())
+    if algo in ("InstaOrderNet_od", "InstaOrderNet_d"):
+        out["depth_order"] = rng.randint(0, 3, size=B).astype(np.int64)
+        out["count"] = rng.randint(2, 4, size=B).astype(np.int64)
+        out["is_overlap"] = (rng.rand(B) < 0.4).astype(np.int64)
+    if algo == "InstaOrderNet_od":
+        out["occ_order"] = (rng.rand(B, 2) < 0.3).astype(np.float32)
+    elif algo == "InstaOrderNet_o":
+        out["occ_order"] = (rng.rand(B, 2) < 0.3).astype(np.float32)
+    elif algo == "OrderNet":
+        out["occ_order"] = rng.randint(0, int(num_classes), size=B).astype(np.int64)
+    return out
+
+
+VAL_CASES = {"c2_od": 31, "c1_o": 32, "c2_d": 33, "c3_ordernet": 34, "c3_ordernet_ext": 35}
+
+
+def gen_losses(ns):
+    """Reference set_input + forward_only (validation loss) and model.model(x) logits on synthetic batches."""
+    import torch
+    rec = {}
+    for case, seed in VAL_CASES.items():
+        c = CASES[case]
+        sd = calib.load_calibrated(calib_path(case), c["wseed"], 5, c["num_classes"])
+        model = make_reference_model(ns, c["algo"], c["num_classes"], sd)
+        model.params["overlap_weight"], model.params["distinct_weight"] = 1.5, 0.5
+        batch = val_batch(seed, c["algo"], c["num_classes"])
+        model.set_input(**{k: torch.from_numpy(v) for k, v in batch.items()})
+        r = model.forward_only()
+        log, loss = r if isinstance(r, tuple) else ({}, r)
+        rec[case + "_loss"] = np.float32(loss["loss"].item())
+        for k, v in log.items():
+            rec[case + "_" + k] = np.float32(v.item())
+        with torch.no_grad():
+            x = torch.cat([torch.from_numpy(batch["modal1"]), torch.from_numpy(batch["modal2"]),
+                           torch.from_numpy(batch["rgb"])], dim=1)
+            y = model.model(x)
+            y2 = model.model(x[:, [1, 0, 2, 3, 4]])
+        y = torch.cat(y, dim=1) if isinstance(y, tuple) else y
+        y2 = torch.cat(y2, dim=1) if isinstance(y2, tuple) else y2
+        rec[case + "_logits"] = torch.stack([y, y2], dim=1).numpy().astype(np.float32)     # [B, 2, K]
+        print(case, {k: float(v) for k, v in rec.items() if k.startswith(case) and not k.endswith("logits")})
+    p = os.path.join(GOLDEN, "val_losses.npz")
+    np.savez_compressed(p, **rec)
+    print("wrote", p)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ns = ref_shim.load()
-    what = sys.argv[1:] or ["calib", "geometry", "metrics", "order"]
+    what = sys.argv[1:] or ["calib", "geometry", "metrics", "order", "losses"]
     if "calib" in what:
         gen_calib()
     if "geometry" in what:
@@ -228,6 +285,8 @@ def main():
         gen_metrics(ns)
     if "order" in what:
         gen_order(ns)
+    if "losses" in what:
+        gen_losses(ns)
 
 
 if __name__ == "__main__":
