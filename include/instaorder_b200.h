@@ -67,6 +67,12 @@ IO_API int io_pair_crop_boxes(const double* boxes_host, const int32_t* pairs_hos
 IO_API int io_pair_bordering(const uint8_t* masks_dev, int n, int h, int w, const int32_t* pairs_dev, int p,
                       uint8_t* flags_dev, void* stream);
 
+/* infer_gt_order(), inference.py:719-739 (KINS has no order annotation; tools/test.py:129,417-418 derives it from the
+ * modal / amodal masks): for every pair (i < j) that borders, compares |modal_i & amodal_j| with |modal_j & amodal_i|.
+ * modal_dev / amodal_dev: [N, H, W] u8; mat_dev: [N, N] int64, zero-initialised by the caller. */
+IO_API int io_infer_gt_order(const uint8_t* modal_dev, const uint8_t* amodal_dev, int n, int h, int w,
+                             const int32_t* pairs_dev, int p, int64_t* mat_dev, void* stream);
+
 /* One record per pair for the fused gather.  Offsets are in bytes from the base pointers passed to the call. */
 typedef struct io_pair_desc {
   int64_t image_off;  /* start of the pair's H x W x 3 u8 image                         */
@@ -96,6 +102,13 @@ IO_API int io_pair_gather_patch(const uint8_t* images_dev, const uint8_t* masks_
  * rgb_planes_dev[slot][d][d][3]; step 2, per pair: nearest-resized masks + the image's plane -> pair tensor. */
 IO_API int io_image_resize_rgb(const uint8_t* image_dev, int h, int w, int d, const float* mean_host, const float* std_host,
                         float* rgb_plane_dev, void* stream);
+/* `image` mode rgb (inference.py:377-393): zero-pad to the centred max(h, w) square, cv2.INTER_LINEAR (8-bit generic
+ * path, bit-exact) to d x d, transform_rgb -> fp32 plane [d][d][3].  lut_scratch_dev: 768 floats of device scratch.
+ * The pairs are then assembled by io_pair_gather_resize with desc.s = max(h, w), desc.x = (s - w) / 2,
+ * desc.y = (s - h) / 2 (nearest over the padded square; s = 0 selects the plain `resize` mode). */
+IO_API int io_image_square_linear_rgb(const uint8_t* image_dev, int h, int w, int d, const float* mean_host,
+                                      const float* std_host, float* lut_scratch_dev, float* rgb_plane_dev,
+                                      void* stream);
 IO_API int io_pair_gather_resize(const float* rgb_planes_dev, const uint8_t* masks_dev, const io_pair_desc* descs_dev,
                           int p, int d, void* out_dev, void* stream);
 

@@ -37,10 +37,12 @@ _SIGS = {
     "io_expand_bbox": (_i, [_vp, _i, C.c_double, _vp]),
     "io_pair_crop_boxes": (_i, [_vp, _vp, _i, _vp]),
     "io_pair_bordering": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "io_infer_gt_order": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "io_pair_tensor_row_pitch": (_i64, [_i]),
     "io_pair_tensor_bytes": (_i64, [_i, _i]),
     "io_pair_gather_patch": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "io_image_resize_rgb": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "io_image_square_linear_rgb": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "io_pair_gather_resize": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "io_normalize_lut": (_i, [_vp, _vp, _vp]),
     "io_net_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),

@@ -260,6 +260,73 @@ __global__ void __launch_bounds__(GATHER_THREADS) resize_rgb_kernel(const uint8_
   }
 }
 
+// ---- image mode (reference inference.py:377-393): zero-pad to a centred max(H,W) square, cv2.INTER_LINEAR (8-bit
+// generic path, bit-exact: 11-bit weights, integer horizontal pass, (((b0*(S0>>4))>>16)+((b1*(S1>>4))>>16)+2)>>2
+// vertical pass), transform_rgb -> fp32 plane [d][d][3] shared by all pairs of the image.
+struct LinTab {
+  int idx;     // first tap (clamped); second tap = idx + 1
+  int a0, a1;  // weights (a1 unused when single)
+  int single;
+};
+
+__device__ __forceinline__ LinTab linear_entry(int dst, int src_len, int dst_len, bool horizontal) {
+  LinTab t;
+  const double inv = __ddiv_rn(static_cast<double>(dst_len), static_cast<double>(src_len));
+  const double scale = __ddiv_rn(1.0, inv);
+  float fx = static_cast<float>(__dsub_rn(__dmul_rn(static_cast<double>(dst) + 0.5, scale), 0.5));
+  const float sxf = floorf(fx);
+  int sx = static_cast<int>(sxf);
+  fx = __fsub_rn(fx, sxf);
+  t.single = 0;
+  if (horizontal) {
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= src_len - 1) { fx = 0.f; sx = src_len - 1; }
+    t.single = (sx + 1 >= src_len);
+  }
+  t.idx = sx;
+  t.a0 = max(-32768, min(32767, __float2int_rn(__fmul_rn(__fsub_rn(1.0f, fx), 2048.0f))));
+  t.a1 = max(-32768, min(32767, __float2int_rn(__fmul_rn(fx, 2048.0f))));
+  return t;
+}
+
+struct LutF {
+  float v[3][256];
+};
+
+__global__ void __launch_bounds__(GATHER_THREADS) square_linear_rgb_kernel(const uint8_t* __restrict__ img, int H, int W,
+                                                                           int d, const float* __restrict__ lut,
+                                                                           float* __restrict__ plane) {
+  const int S = max(H, W);
+  const int left = (S - W) / 2, top = (S - H) / 2;
+  const int dy = blockIdx.x;
+  const LinTab ty = linear_entry(dy, S, d, false);
+  const int r0 = min(max(ty.idx, 0), S - 1) - top, r1 = min(max(ty.idx + 1, 0), S - 1) - top;
+  const bool ok0 = r0 >= 0 && r0 < H, ok1 = r1 >= 0 && r1 < H;
+  for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
+    const LinTab tx = linear_entry(dx, S, d, true);
+    const int c0 = tx.idx - left, c1 = tx.idx + 1 - left;
+    const bool okc0 = c0 >= 0 && c0 < W, okc1 = !tx.single && c1 >= 0 && c1 < W;
+    float* o = plane + (static_cast<size_t>(dy) * d + dx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int h0, h1;
+      {
+        const int p0 = (ok0 && okc0) ? img[(static_cast<size_t>(r0) * W + c0) * 3 + c] : 0;
+        const int p1 = (ok0 && okc1) ? img[(static_cast<size_t>(r0) * W + c1) * 3 + c] : 0;
+        h0 = tx.single ? p0 * 2048 : p0 * tx.a0 + p1 * tx.a1;
+      }
+      {
+        const int p0 = (ok1 && okc0) ? img[(static_cast<size_t>(r1) * W + c0) * 3 + c] : 0;
+        const int p1 = (ok1 && okc1) ? img[(static_cast<size_t>(r1) * W + c1) * 3 + c] : 0;
+        h1 = tx.single ? p0 * 2048 : p0 * tx.a0 + p1 * tx.a1;
+      }
+      int v = (((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      v = min(max(v, 0), 255);
+      o[c] = lut[c * 256 + v];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(GATHER_THREADS) gather_resize_kernel(const float* __restrict__ planes,
                                                                        const uint8_t* __restrict__ masks,
                                                                        const io_pair_desc* __restrict__ descs, int d,
@@ -273,18 +340,27 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_resize_kernel(const flo
   const int row0 = blockIdx.x * GATHER_ROWS;
   const int row1 = min(d, row0 + GATHER_ROWS);
   zero_borders(out_pair, d, pitch, blockIdx.x, gridDim.x, row0, row1);
-  const double sy = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(d), static_cast<double>(H)));
-  const double sx = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(d), static_cast<double>(W)));
+  // resize mode: nearest over the H x W image; image mode (ds.s > 0): nearest over the centred ds.s-square whose
+  // image window starts at (ds.x, ds.y); pixels of the zero padding read as 0
+  const int SH = ds.s > 0 ? ds.s : H, SW = ds.s > 0 ? ds.s : W;
+  const int left = ds.s > 0 ? ds.x : 0, top = ds.s > 0 ? ds.y : 0;
+  const double sy = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(d), static_cast<double>(SH)));
+  const double sx = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(d), static_cast<double>(SW)));
   for (int dy = row0; dy < row1; ++dy) {
-    const int my = min(static_cast<int>(floor(__dmul_rn(static_cast<double>(dy), sy))), H - 1);
+    const int my = min(static_cast<int>(floor(__dmul_rn(static_cast<double>(dy), sy))), SH - 1) - top;
     for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
-      const int mx = min(static_cast<int>(floor(__dmul_rn(static_cast<double>(dx), sx))), W - 1);
-      const size_t o = static_cast<size_t>(my) * W + mx;
+      const int mx = min(static_cast<int>(floor(__dmul_rn(static_cast<double>(dx), sx))), SW - 1) - left;
+      float va = 0.f, vb = 0.f;
+      if (my >= 0 && my < H && mx >= 0 && mx < W) {
+        const size_t o = static_cast<size_t>(my) * W + mx;
+        va = static_cast<float>(ma[o]);
+        vb = static_cast<float>(mb[o]);
+      }
       const float* px = plane + (static_cast<size_t>(dy) * d + dx) * 3;
       const uint32_t rg = pack_bf16(px[0], px[1]);
       const uint32_t b = pack_bf16(px[2], 0.0f);
-      store_pixel(out_pair + (static_cast<size_t>(dy + 3) * pitch + dx + 3) * 8, static_cast<float>(ma[o]),
-                  static_cast<float>(mb[o]), static_cast<uint16_t>(rg & 0xFFFF), static_cast<uint16_t>(rg >> 16),
+      store_pixel(out_pair + (static_cast<size_t>(dy + 3) * pitch + dx + 3) * 8, va, vb,
+                  static_cast<uint16_t>(rg & 0xFFFF), static_cast<uint16_t>(rg >> 16),
                   static_cast<uint16_t>(b & 0xFFFF));
     }
   }
@@ -338,6 +414,53 @@ __global__ void __launch_bounds__(256) bordering_kernel(const uint8_t* __restric
   }
   hit = __syncthreads_or(hit);
   if (threadIdx.x == 0) flags[blockIdx.x] = hit ? 1 : 0;
+}
+
+// ---- infer_gt_order (reference inference.py:719-739): KINS ground-truth occlusion order from modal / amodal masks --
+// one CTA per pair (i < j): skipped unless bordering(i, j); occ_ij = |modal_i == 1 & amodal_j == 1| and vice versa;
+// both zero -> no order; occ_ij >= occ_ji -> gt[i,j] = 1, gt[j,i] = 0, else the reverse.
+__global__ void __launch_bounds__(256) gt_order_kernel(const uint8_t* __restrict__ modal,
+                                                       const uint8_t* __restrict__ amodal, int n, int H, int W,
+                                                       const int32_t* __restrict__ pairs, int64_t* __restrict__ mat) {
+  const int i = pairs[2 * blockIdx.x], j = pairs[2 * blockIdx.x + 1];
+  const size_t hw = static_cast<size_t>(H) * W;
+  const uint8_t* __restrict__ a = modal + i * hw;
+  const uint8_t* __restrict__ b = modal + j * hw;
+  const uint8_t* __restrict__ aa = amodal + i * hw;
+  const uint8_t* __restrict__ ab = amodal + j * hw;
+  int hit = 0, cij = 0, cji = 0;
+  const int total = H * W;
+  for (int k = threadIdx.x; k < total; k += blockDim.x) {
+    const uint8_t av = a[k], bv = b[k];
+    if (bv & 1) {
+      const int y = k / W, x = k - y * W;
+      uint8_t m = av;
+      if (y > 0) m = max(m, a[k - W]);
+      if (y + 1 < H) m = max(m, a[k + W]);
+      if (x > 0) m = max(m, a[k - 1]);
+      if (x + 1 < W) m = max(m, a[k + 1]);
+      hit |= (m == 1);
+    }
+    cij += (av == 1) & (ab[k] == 1);
+    cji += (bv == 1) & (aa[k] == 1);
+  }
+  hit = __syncthreads_or(hit);
+  __shared__ int red[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    cij += __shfl_xor_sync(0xffffffffu, cij, o);
+    cji += __shfl_xor_sync(0xffffffffu, cji, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = cij; red[1][threadIdx.x >> 5] = cji; }
+  __syncthreads();
+  if (threadIdx.x == 0 && hit) {
+    int sij = 0, sji = 0;
+    for (int w = 0; w < 8; ++w) { sij += red[0][w]; sji += red[1][w]; }
+    if (sij != 0 || sji != 0) {
+      const bool i_over = sij >= sji;
+      mat[static_cast<size_t>(i) * n + j] = i_over ? 1 : 0;
+      mat[static_cast<size_t>(j) * n + i] = i_over ? 0 : 1;
+    }
+  }
 }
 
 static int check_d(int d) {
@@ -431,6 +554,15 @@ extern "C" int io_pair_bordering(const uint8_t* masks, int n, int h, int w, cons
   return IO_OK;
 }
 
+extern "C" int io_infer_gt_order(const uint8_t* modal, const uint8_t* amodal, int n, int h, int w, const int32_t* pairs,
+                                 int p, int64_t* mat, void* stream) {
+  IO_REQUIRE(modal && amodal && pairs && mat && n > 0 && h > 0 && w > 0 && p >= 0, "io_infer_gt_order: bad arguments");
+  if (p == 0) return IO_OK;
+  gt_order_kernel<<<p, 256, 0, as_stream(stream)>>>(modal, amodal, n, h, w, pairs, mat);
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
 extern "C" int io_pair_gather_patch(const uint8_t* images, const uint8_t* masks, const io_pair_desc* descs, int p,
                                     int d, const float* mean, const float* stdv, void* out, void* stream) {
   IO_REQUIRE(images && masks && descs && mean && stdv && out && p >= 0, "io_pair_gather_patch: bad arguments");
@@ -471,6 +603,20 @@ extern "C" int io_image_resize_rgb(const uint8_t* image, int h, int w, int d, co
     ms.stdv[c] = static_cast<double>(stdv[c]);
   }
   resize_rgb_kernel<<<d, GATHER_THREADS, 0, as_stream(stream)>>>(image, h, w, d, ms, plane);
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
+extern "C" int io_image_square_linear_rgb(const uint8_t* image, int h, int w, int d, const float* mean, const float* stdv,
+                                          float* lut_dev_scratch, float* plane, void* stream) {
+  IO_REQUIRE(image && mean && stdv && lut_dev_scratch && plane && h > 0 && w > 0,
+             "io_image_square_linear_rgb: bad arguments");
+  if (int rc = check_d(d)) return rc;
+  float lutf[768];
+  fill_lut_f32(mean, stdv, lutf);
+  IO_CUDA(cudaMemcpyAsync(lut_dev_scratch, lutf, sizeof(lutf), cudaMemcpyHostToDevice, as_stream(stream)));
+  IO_CUDA(cudaStreamSynchronize(as_stream(stream)));   // lutf lives on this stack frame
+  square_linear_rgb_kernel<<<d, GATHER_THREADS, 0, as_stream(stream)>>>(image, h, w, d, lut_dev_scratch, plane);
   IO_CUDA(cudaGetLastError());
   return IO_OK;
 }

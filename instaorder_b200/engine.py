@@ -197,10 +197,13 @@ class OrderEngine:
             d["h"], d["w"] = sc.h, sc.w
             if crops is not None:
                 d["x"], d["y"], d["s"] = crops[:, 0], crops[:, 1], crops[:, 2]
+            elif mode == "image":      # centred zero-padded square, reference inference.py:378-382
+                sq = max(sc.h, sc.w)
+                d["x"], d["y"], d["s"] = (sq - sc.w) // 2, (sq - sc.h) // 2, sq
             else:
                 d["x"] = d["y"] = d["s"] = 0
             d["rgb_slot"] = slot_idx
-            if mode == "resize":
+            if mode in ("resize", "image"):
                 self.resize_jobs.append((img_off, sc.h, sc.w, slot_idx))
                 slot_idx += 1
             ij[P:P + p] = pairs
@@ -230,21 +233,27 @@ class OrderEngine:
                                                      self.d, _lib.ptr(self.mean), _lib.ptr(self.std),
                                                      self.pair_tensor.data_ptr(), st))
             self.gpu_launches += 1
-        elif mode == "resize":
+        elif mode in ("resize", "image"):
             n_img = len(self.resize_jobs)
             need = n_img * self.d * self.d * 3
             if getattr(self, "_planes", None) is None or self._planes.numel() < need:
                 self._planes = torch.empty(need, dtype=torch.float32, device=self.device)
+                self._lut_scratch = torch.empty(768, dtype=torch.float32, device=self.device)
             for (img_off, h, w, slot) in self.resize_jobs:
-                _lib.check(self.lib.io_image_resize_rgb(s.d_img.data_ptr() + img_off, h, w, self.d,
-                                                        _lib.ptr(self.mean), _lib.ptr(self.std),
-                                                        self._planes.data_ptr() + slot * self.d * self.d * 12, st))
+                dst = self._planes.data_ptr() + slot * self.d * self.d * 12
+                if mode == "resize":
+                    _lib.check(self.lib.io_image_resize_rgb(s.d_img.data_ptr() + img_off, h, w, self.d,
+                                                            _lib.ptr(self.mean), _lib.ptr(self.std), dst, st))
+                else:
+                    _lib.check(self.lib.io_image_square_linear_rgb(s.d_img.data_ptr() + img_off, h, w, self.d,
+                                                                   _lib.ptr(self.mean), _lib.ptr(self.std),
+                                                                   self._lut_scratch.data_ptr(), dst, st))
             _lib.check(self.lib.io_pair_gather_resize(self._planes.data_ptr(), s.d_mask.data_ptr(),
                                                       s.d_desc.data_ptr(), P, self.d, self.pair_tensor.data_ptr(),
                                                       st))
             self.gpu_launches += n_img + 1
         else:
-            raise NotImplementedError("patch_or_image=%r (supported: 'patch', 'resize')" % (mode,))
+            raise NotImplementedError("patch_or_image=%r (supported: 'patch', 'resize', 'image')" % (mode,))
 
     def forward(self, P):
         _lib.check(self.lib.io_net_forward_pairs(self.net, self.pair_tensor.data_ptr(), P, self.logits.data_ptr(),
@@ -273,8 +282,9 @@ class OrderEngine:
         (+ 'pairs', 'logits', 'margin_occ', 'margin_depth' when ``return_details``)."""
         heads = heads_for(algo, self.ncs if len(self.ncs) > 1 else self.ncs[0])
         mode = patch_or_image
-        if mode not in ("patch", "resize"):
-            raise NotImplementedError("patch_or_image=%r (supported: 'patch', 'resize')" % (mode,))
+        if mode not in ("patch", "resize", "image"):
+            raise NotImplementedError("patch_or_image=%r (supported: 'patch', 'resize', 'image'; 'orig' needs "
+                                      "non-square network inputs)" % (mode,))
         # 1. pairs + crop windows per scene (host, float64 -- bit-exact with the reference's geometry)
         work = []
         mat_offs = []

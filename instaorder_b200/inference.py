@@ -51,6 +51,23 @@ def infer_order_sup_occ_depth(model, image, inmodal, bboxes, pairs, method, patc
     return r["occ"], r["depth"]
 
 
+def infer_gt_order(inmodal, amodal):
+    """reference inference.py:719-739 -> int [N,N] ground-truth occlusion order (KINS)."""
+    import torch
+    from . import _lib
+    inmodal = np.ascontiguousarray(inmodal, dtype=np.uint8)
+    amodal = np.ascontiguousarray(amodal, dtype=np.uint8)
+    n, h, w = inmodal.shape
+    pairs = _engine.enumerate_pairs(n)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mat = torch.zeros((n, n), dtype=torch.int64, device=dev)
+    if pairs.shape[0]:
+        m, a, pr = (torch.from_numpy(x).to(dev) for x in (inmodal, amodal, pairs))
+        _lib.check(_lib.lib().io_infer_gt_order(m.data_ptr(), a.data_ptr(), n, h, w, pr.data_ptr(), pairs.shape[0],
+                                                mat.data_ptr(), _lib.stream_ptr()))
+    return mat.cpu().numpy()
+
+
 def eval_order_recall_precision_f1(order_matrix, gt_order_matrix, zd):
     """reference inference.py:794-802 -> (recall, precision, f1) x100, python floats."""
     if not np.any(np.asarray(gt_order_matrix) != -1):

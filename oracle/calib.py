@@ -23,11 +23,15 @@ def calib_inputs(seed=123, n_scenes=6, D=256, mode="patch"):
         H, W = synth.COCO_SHAPES[int(rng.randint(0, len(synth.COCO_SHAPES)))]
         image, masks, boxes = synth.make_scene(rng, H, W, 4)
         boxes = O.expand_bbox(boxes, 3.0)
-        rgb_whole = O.resize_mode_rgb(image, D) if mode == "resize" else None
+        rgb_whole = O.resize_mode_rgb(image, D) if mode == "resize" else \
+            (O.image_mode_rgb(image, D) if mode == "image" else None)
         for (i, j) in O.enumerate_pairs(4):
             if mode == "patch":
                 rgb, mi, mj, _ = O.pair_patch(image, masks, boxes, i, j, D)
                 x = O.pair_tensor(rgb, mi, mj)
+            elif mode == "image":
+                x = np.concatenate([O.image_mode_mask(masks[i], D)[None].astype(np.float32),
+                                    O.image_mode_mask(masks[j], D)[None].astype(np.float32), rgb_whole])
             else:
                 x = np.concatenate([O.resize_mode_mask(masks[i], D)[None].astype(np.float32),
                                     O.resize_mode_mask(masks[j], D)[None].astype(np.float32), rgb_whole])

@@ -34,6 +34,8 @@ CASES = {
                  expand=True, float_boxes=True),
     "c2_od_resize": dict(algo="InstaOrderNet_od", num_classes=[2, 3], wseed=5, scene=dict(seed=6, H=333, W=500, N=4),
                          expand=True, float_boxes=True, patch_or_image="resize", input_size=384),
+    "c1_o_image": dict(algo="InstaOrderNet_o", num_classes=2, wseed=6, scene=dict(seed=17, H=375, W=500, N=5),
+                       expand=True, float_boxes=False, patch_or_image="image", input_size=256),
     "c3_ordernet_ext": dict(algo="OrderNet", num_classes=4, wseed=4, scene=dict(seed=13, H=375, W=1242, N=4,
                             wh_range=((20, 200), (20, 150))), expand=True, float_boxes=False),
 }
@@ -179,6 +181,36 @@ def gen_metrics(ns):
     print("wrote", p)
 
 
+def kins_scene(seed, n=7, H=96, W=160):
+    """Modal / amodal masks: amodal = modal plus a dilated halo, so neighbouring instances overlap in amodal space."""
+    rng = np.random.RandomState(seed)
+    _, modal, _ = synth.make_scene(rng, H, W, n, wh_range=((15, 70), (15, 50)))
+    # later instances are drawn on top: remove their pixels from earlier modal masks (a real occlusion pattern)
+    for i in range(n):
+        for j in range(i + 1, n):
+            modal[i] &= ~modal[j] & 1
+    amodal = modal.copy()
+    for i in range(n):
+        a = amodal[i]
+        for _ in range(int(rng.randint(0, 6))):
+            d = a.copy()
+            d[1:] |= a[:-1]; d[:-1] |= a[1:]; d[:, 1:] |= a[:, :-1]; d[:, :-1] |= a[:, 1:]
+            a = d
+        amodal[i] = a
+    return modal, amodal
+
+
+def gen_gt_order(ns):
+    recs = {}
+    for t, seed in enumerate((3, 4, 5)):
+        modal, amodal = kins_scene(seed)
+        recs["gt%d" % t] = ns.inference.infer_gt_order(modal, amodal).astype(np.int64)
+        recs["seed%d" % t] = seed
+    p = os.path.join(GOLDEN, "gt_order.npz")
+    np.savez_compressed(p, **recs)
+    print("wrote", p, [int(recs["gt%d" % t].sum()) for t in range(3)])
+
+
 def gen_geometry(ns):
     """Crop geometry + crop_padding + cv2 resizes on hand-picked and random edge cases, from the reference's own
     utils.combine_bbox / utils.crop_padding / inference.resize_mask and cv2 (IPP off, see ref_shim)."""
@@ -276,7 +308,7 @@ def gen_losses(ns):
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ns = ref_shim.load()
-    what = sys.argv[1:] or ["calib", "geometry", "metrics", "order", "losses"]
+    what = sys.argv[1:] or ["calib", "geometry", "metrics", "order", "losses", "gt"]
     if "calib" in what:
         gen_calib()
     if "geometry" in what:
@@ -287,6 +319,8 @@ def main():
         gen_order(ns)
     if "losses" in what:
         gen_losses(ns)
+    if "gt" in what:
+        gen_gt_order(ns)
 
 
 if __name__ == "__main__":

@@ -213,6 +213,68 @@ def resize_mode_rgb(image, input_size):
     return np.ascontiguousarray(out.transpose(2, 0, 1)).astype(np.float32)
 
 
+def linear_taps_fixed(src_len, dst_len):
+    """cv2 INTER_LINEAR taps for 8-bit images (OpenCV 4.13 resize.cpp): (first index, 11-bit weights a0, a1,
+    single-tap flag).  sx < 0 -> (0, fx = 0); sx >= src_len - 1 -> (src_len - 1, fx = 0); when the second tap would
+    fall outside, only the first is used with weight 2048."""
+    f32 = np.float32
+    inv = np.float64(dst_len) / np.float64(src_len)
+    scale = np.float64(1.0) / inv
+    d = np.arange(dst_len, dtype=np.float64)
+    fx = ((d + 0.5) * scale - 0.5).astype(f32)
+    sx = np.floor(fx).astype(np.int32)
+    fx = (fx - sx.astype(f32)).astype(f32)
+    neg = sx < 0
+    fx = np.where(neg, f32(0), fx); sx = np.where(neg, 0, sx)
+    hi = sx >= src_len - 1
+    fx = np.where(hi, f32(0), fx); sx = np.where(hi, src_len - 1, sx)
+    a0 = np.clip(np.rint((f32(1) - fx) * f32(2048)), -32768, 32767).astype(np.int64)
+    a1 = np.clip(np.rint(fx * f32(2048)), -32768, 32767).astype(np.int64)
+    return sx, a0, a1, (sx + 1 >= src_len)
+
+
+def resize_linear_u8(src, dw, dh):
+    """cv2.resize(src_u8, (dw, dh), interpolation=cv2.INTER_LINEAR), generic path, bit-exact:
+    HResizeLinear<uchar,int,short> then VResizeLinear: (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2."""
+    f32 = np.float32
+    Hs, Ws = src.shape[:2]
+    s3 = src.reshape(Hs, Ws, -1).astype(np.int64)
+    sx, a0, a1, one = linear_taps_fixed(Ws, dw)
+    sx1 = np.minimum(sx + 1, Ws - 1)
+    h = np.where(one[None, :, None], s3[:, sx, :] * 2048, s3[:, sx, :] * a0[None, :, None] + s3[:, sx1, :] * a1[None, :, None])
+    inv = np.float64(dh) / np.float64(Hs)
+    scale = np.float64(1.0) / inv
+    fy = ((np.arange(dh, dtype=np.float64) + 0.5) * scale - 0.5).astype(f32)
+    sy = np.floor(fy).astype(np.int32)
+    fy = (fy - sy.astype(f32)).astype(f32)
+    b0 = np.clip(np.rint((f32(1) - fy) * f32(2048)), -32768, 32767).astype(np.int64)
+    b1 = np.clip(np.rint(fy * f32(2048)), -32768, 32767).astype(np.int64)
+    S0 = h[np.clip(sy, 0, Hs - 1)]
+    S1 = h[np.clip(sy + 1, 0, Hs - 1)]
+    out = (((b0[:, None, None] * (S0 >> 4)) >> 16) + ((b1[:, None, None] * (S1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8).reshape((dh, dw) + src.shape[2:])
+
+
+def pad_square(a):
+    """inference.py:377-391 -- zero-pad to a centred max(H, W) square."""
+    hh, ww = a.shape[:2]
+    s = int(max(hh, ww))
+    left, top = (s - ww) // 2, (s - hh) // 2
+    out = np.zeros((s, s) + a.shape[2:], dtype=a.dtype)
+    out[top:top + hh, left:left + ww] = a
+    return out
+
+
+def image_mode_rgb(image, input_size):
+    """``image`` mode rgb, inference.py:390-393: padded square -> INTER_LINEAR (u8) -> transform_rgb; CHW fp32."""
+    return transform_rgb(resize_linear_u8(pad_square(image), input_size, input_size))
+
+
+def image_mode_mask(mask, input_size):
+    """inference.py:383-388."""
+    return resize_nearest(pad_square(mask), input_size, input_size)
+
+
 def resize_mode_mask(mask, input_size):
     """inference.py:398-399 -- whole-image nearest resize of a modal mask."""
     return resize_nearest(mask, input_size, input_size)
@@ -384,7 +446,8 @@ def infer_order(sd, image, inmodal, bboxes, pairs="all", method="InstaOrderNet_o
     depth = np.zeros((N, N), dtype=np.int64)
     m_occ = np.full((N, N), np.inf)
     m_depth = np.full((N, N), np.inf)
-    rgb_whole = resize_mode_rgb(image, input_size) if patch_or_image == "resize" else None
+    rgb_whole = resize_mode_rgb(image, input_size) if patch_or_image == "resize" else \
+        (image_mode_rgb(image, input_size) if patch_or_image == "image" else None)
     logits = {}
     for c0 in range(0, len(plist), chunk):
         xs = []
@@ -395,6 +458,10 @@ def infer_order(sd, image, inmodal, bboxes, pairs="all", method="InstaOrderNet_o
             elif patch_or_image == "resize":
                 mi = resize_mode_mask(inmodal[i], input_size).astype(np.float32)
                 mj = resize_mode_mask(inmodal[j], input_size).astype(np.float32)
+                x = np.concatenate([mi[None], mj[None], rgb_whole], axis=0)
+            elif patch_or_image == "image":
+                mi = image_mode_mask(inmodal[i], input_size).astype(np.float32)
+                mj = image_mode_mask(inmodal[j], input_size).astype(np.float32)
                 x = np.concatenate([mi[None], mj[None], rgb_whole], axis=0)
             else:
                 raise NotImplementedError(patch_or_image)
@@ -426,6 +493,25 @@ def infer_order(sd, image, inmodal, bboxes, pairs="all", method="InstaOrderNet_o
             else:
                 raise ValueError(method)
     return dict(occ=occ, depth=depth, margin_occ=m_occ, margin_depth=m_depth, logits=logits, pairs=plist)
+
+
+def infer_gt_order(inmodal, amodal):
+    """inference.py:719-739 (M4)."""
+    n = inmodal.shape[0]
+    gt = np.zeros((n, n), dtype=np.int64)
+    for i in range(n):
+        for j in range(i + 1, n):
+            if not bordering(inmodal[i], inmodal[j]):
+                continue
+            oij = int(((inmodal[i] == 1) & (amodal[j] == 1)).sum())
+            oji = int(((inmodal[j] == 1) & (amodal[i] == 1)).sum())
+            if oij == 0 and oji == 0:
+                continue
+            if oij >= oji:
+                gt[i, j], gt[j, i] = 1, 0
+            else:
+                gt[i, j], gt[j, i] = 0, 1
+    return gt
 
 
 # ----------------------------------------------------------------------------------------------------------------

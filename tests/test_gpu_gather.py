@@ -112,3 +112,19 @@ def test_bordering_kernel():
     want = np.array([O.bordering(masks[i], masks[j]) for i, j in pr])
     assert np.array_equal(got, want)
     assert want.any() and not want.all()
+
+
+def test_gather_image_mode(golden_dir):
+    """`image` mode: padded-square INTER_LINEAR rgb (bit-exact) + nearest masks over the padded square."""
+    case = "c1_o_image"
+    z = np.load(os.path.join(golden_dir, "order_%s.npz" % case))
+    scene = gen_golden.build_scene(case)
+    bexp = engine.expand_bbox(scene[2], 3.0)
+    pr, _, inner, raw = run_gather(scene, bexp, 256, mode="image")
+    for k in range(pr.shape[0]):
+        assert gen_golden.digest(inner[k, :2].astype(np.uint8)) == z["mask_digest"][k], k
+    k = int(z["full_idx"][0])
+    assert np.array_equal(inner[k], U.f32_to_bf16_rn(z["full_x"][0]))
+    want = U.f32_to_bf16_rn(O.image_mode_rgb(scene[0], 256))
+    for k in range(pr.shape[0]):
+        assert np.array_equal(inner[k, 2:], want)

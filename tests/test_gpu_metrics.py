@@ -46,3 +46,12 @@ def test_metrics_large_batch_vs_oracle():
     want = np.array([[float(O.eval_depth_order_whdr(p, (g, v, c))[k][0]) for k in O.WHDR_KEYS]
                      for p, g, v, c in zip(dps, gds, ovs, cns)])
     assert np.array_equal(got, want)
+
+
+def test_infer_gt_order_matches_reference(golden_dir):
+    from oracle import gen_golden
+    z = np.load(os.path.join(golden_dir, "gt_order.npz"))
+    for t in range(3):
+        modal, amodal = gen_golden.kins_scene(int(z["seed%d" % t]))
+        got = inference.infer_gt_order(modal, amodal)
+        assert got.dtype == np.int64 and np.array_equal(got, z["gt%d" % t])

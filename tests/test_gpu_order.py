@@ -26,7 +26,8 @@ def make_model(case, golden_dir):
     return m
 
 
-@pytest.mark.parametrize("case", ["c1_o", "c2_od", "c3_ordernet", "c2_d", "c3_ordernet_ext", "c2_od_resize"])
+@pytest.mark.parametrize("case", ["c1_o", "c2_od", "c3_ordernet", "c2_d", "c3_ordernet_ext", "c2_od_resize",
+                                  "c1_o_image"])
 def test_order_matrices_match_reference(golden_dir, case):
     c = gen_golden.CASES[case]
     z = np.load(os.path.join(golden_dir, "order_%s.npz" % case))

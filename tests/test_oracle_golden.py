@@ -33,7 +33,8 @@ def test_metrics_golden(golden_dir):
         assert np.array_equal(got, z["whdr"][t]), t
 
 
-@pytest.mark.parametrize("case", ["c1_o", "c2_od", "c3_ordernet", "c2_d", "c3_ordernet_ext", "c2_od_resize"])
+@pytest.mark.parametrize("case", ["c1_o", "c2_od", "c3_ordernet", "c2_d", "c3_ordernet_ext", "c2_od_resize",
+                                  "c1_o_image"])
 def test_order_golden(golden_dir, case):
     c = gen_golden.CASES[case]
     z = np.load(os.path.join(golden_dir, "order_%s.npz" % case))
@@ -45,11 +46,16 @@ def test_order_golden(golden_dir, case):
     N = masks.shape[0]
     plist = O.enumerate_pairs(N)
     # gather: masks bit-exact for every pair, rgb fp32 tensor bit-exact (patch) / 1e-5 (resize: float64 cubic)
-    rgb_whole = O.resize_mode_rgb(image, D) if mode == "resize" else None
+    rgb_whole = O.resize_mode_rgb(image, D) if mode == "resize" else \
+        (O.image_mode_rgb(image, D) if mode == "image" else None)
     for k, (i, j) in enumerate(plist):
         if mode == "patch":
             rgb, mi, mj, _ = O.pair_patch(image, masks, bexp, i, j, D)
             x = O.pair_tensor(rgb, mi, mj)
+            assert gen_golden.digest(x[2:]) == z["rgb_digest"][k], (case, k)
+        elif mode == "image":
+            x = np.concatenate([O.image_mode_mask(masks[i], D)[None].astype(np.float32),
+                                O.image_mode_mask(masks[j], D)[None].astype(np.float32), rgb_whole])
             assert gen_golden.digest(x[2:]) == z["rgb_digest"][k], (case, k)
         else:
             x = np.concatenate([O.resize_mode_mask(masks[i], D)[None].astype(np.float32),
@@ -58,7 +64,7 @@ def test_order_golden(golden_dir, case):
         if k in list(z["full_idx"]):
             ref = z["full_x"][list(z["full_idx"]).index(k)]
             assert np.array_equal(x[:2], ref[:2])
-            if mode == "patch":
+            if mode in ("patch", "image"):
                 assert np.array_equal(x, ref)
             else:
                 assert np.abs(x - ref).max() < 2e-5
@@ -90,3 +96,11 @@ def test_bordering_matches_definition():
     assert not O.bordering(a, b)
     a[:] = 0; a[0, 0] = 1; b[:] = 0; b[0, 1] = 1
     assert O.bordering(a, b)
+
+
+def test_gt_order_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "gt_order.npz"))
+    for t in range(3):
+        modal, amodal = gen_golden.kins_scene(int(z["seed%d" % t]))
+        assert np.array_equal(O.infer_gt_order(modal, amodal), z["gt%d" % t])
+        assert z["gt%d" % t].sum() > 0
