@@ -36,8 +36,10 @@ struct Cfg {
   static constexpr int ACTIVE_EPI_WARPS = (GROUPS == 1) ? 4 : 8;
   static constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_REGION_BYTES;
   static constexpr int BIAS_BYTES = (BN == 256) ? 8192 : 512;  // whole bias vector of the layer (<= 2048 / 128 floats)
-  static constexpr int BAR_BYTES = 512;  // up to 6+6+2+2+16 mbarriers + the TMEM base slot
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES + 1024;  // + align slack
+  static constexpr int BAR_BYTES = 512;  // up to 8+8+2+2+16+1 mbarriers + the TMEM base slot
+  static constexpr int FIXED_BYTES = EPI_BYTES + BIAS_BYTES + BAR_BYTES + 1024;  // + 1024 B alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
+  static constexpr int MAX_SMEM = 232448;  // 227 KB
 };
 
 struct TileCoord {
@@ -76,16 +78,19 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_stages = p.stages;
+  const bool b_res = p.b_resident != 0;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;
-  uint8_t* sEpi = smem + C::STAGES * C::STAGE_BYTES;
+  uint8_t* sB = smem + n_stages * A_STAGE_BYTES;   // ring slots, or the resident [k_iters][BN x 64] weights
+  uint8_t* sEpi = sB + (b_res ? p.k_iters : n_stages) * C::B_STAGE_BYTES;
   float* sBias = reinterpret_cast<float*>(sEpi + C::EPI_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES + C::BIAS_BYTES);
-  uint64_t* empty = full + C::STAGES;
-  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* empty = full + 8;
+  uint64_t* tfull = empty + 8;
   uint64_t* tempty = tfull + 2;
   uint64_t* rbar = tempty + 2;  // residual tile landed: one barrier per epilogue warp and staging slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 16);
+  uint64_t* bres_full = rbar + 16;  // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,10 +101,11 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     prefetch_tmap(&p.map_out);
     if (p.residual != nullptr) prefetch_tmap(&p.map_res);
     for (int i = 0; i < 16; ++i) mbar_init(&rbar[i], 1);
-    for (int i = 0; i < C::STAGES; ++i) {
+    for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
+    mbar_init(bres_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], C::ACTIVE_EPI_WARPS);  // one arrival per participating epilogue warp
@@ -126,13 +132,36 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (b_res && blockIdx.x < total_tiles) {   // weights of the whole layer, once
+        mbar_expect_tx(bres_full, p.k_iters * C::B_STAGE_BYTES);
+        for (int ki = 0; ki < p.k_iters; ++ki)
+          tma_load_2d(sB + ki * C::B_STAGE_BYTES, &p.map_b, bres_full, ki * BK, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         const TileCoord t = tile_coord(p, m_tile);
+        // The ring holds less than one tile of K blocks for the small-channel layers, so the first touch of a
+        // tile's activations would expose a full DRAM latency per tile: pull the NEXT tile's rows into L2 now.
+        if (p.prefetch && tile + static_cast<int>(gridDim.x) < total_tiles) {
+          const int nm = (tile + static_cast<int>(gridDim.x)) / p.n_tiles;
+          if (nm != m_tile) {
+            const TileCoord nx = tile_coord(p, nm);
+            if (p.mode == CONV_GEMM) {
+              for (int b = 0; b < p.kpt; ++b) tma_prefetch_2d(&p.map_a, b * BK, nx.base_row);
+            } else if (p.mode == CONV_S1) {
+              for (int b = 0; b < p.kpt; ++b) {
+                tma_prefetch_4d(&p.map_a, b * BK, 0, nx.h0 - 1, nx.n_img);   // taps r = 0 and r = 2 cover every
+                tma_prefetch_4d(&p.map_a, b * BK, 0, nx.h0 + 1, nx.n_img);   // input row the tile needs
+              }
+            } else if (p.mode == CONV_STEM) {
+              for (int r = 0; r < 7; ++r) tma_prefetch_4d(&p.map_a, 0, nx.w0, 2 * nx.h0 + r, nx.n_img);
+            }
+          }
+        }
         int tap = 0, kb = 0;
         for (int ki = 0; ki < p.k_iters; ++ki) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], p.a_bytes + C::B_STAGE_BYTES);
+          mbar_expect_tx(&full[stage], p.a_bytes + (b_res ? 0 : C::B_STAGE_BYTES));
           void* dA = sA + stage * A_STAGE_BYTES;
           void* dB = sB + stage * C::B_STAGE_BYTES;
           if (p.mode == CONV_GEMM) {
@@ -149,9 +178,9 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           } else {  // CONV_STEM: filter row `tap`, 8 taps x 8 channels per K block
             tma_load_4d(dA, &p.map_a, &full[stage], 0, t.w0, 2 * t.h0 + tap, t.n_img);
           }
-          tma_load_2d(dB, &p.map_b, &full[stage], ki * BK, n_tile * BN);
+          if (!b_res) tma_load_2d(dB, &p.map_b, &full[stage], ki * BK, n_tile * BN);
           if (++kb == p.kpt) { kb = 0; ++tap; }
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -162,6 +191,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (b_res && blockIdx.x < total_tiles) {
+        mbar_wait(bres_full, 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -172,14 +205,14 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * C::B_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + (b_res ? ki : stage) * C::B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                       (ki > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the smem slot when these MMAs have read it
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);  // accumulator complete
       }
@@ -351,15 +384,17 @@ static int launch_bn(const ConvParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     IO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg<BN>::SMEM_BYTES));
+                                 Cfg<BN>::MAX_SMEM));
     attr_set = true;
   }
+  IO_REQUIRE(p.stages >= 2 && p.stages <= 8 && p.smem_bytes <= Cfg<BN>::MAX_SMEM, "conv: bad smem plan (%d stages, %d B)",
+             p.stages, p.smem_bytes);
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(320);
-  cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = p.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -384,6 +419,45 @@ int conv_tc_launch(const ConvParams& p, int bn_tile, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------------
 // host-side planning
 // ---------------------------------------------------------------------------------------------------------
+// ring depth / weight residency for a planned convolution (bn = N tile)
+template <int BN>
+static void plan_smem_t(ConvParams* p, bool allow_resident) {
+  using C = Cfg<BN>;
+  const int bres = p->k_iters * C::B_STAGE_BYTES;
+  p->b_resident = 0;
+  p->stages = C::STAGES;
+  if (allow_resident && p->n_tiles == 1) {
+    const int room = C::MAX_SMEM - C::FIXED_BYTES - bres;
+    const int st = room / A_STAGE_BYTES;
+    if (st >= 3) {
+      p->b_resident = 1;
+      p->stages = st > 8 ? 8 : st;
+    }
+  }
+  p->smem_bytes = p->b_resident ? bres + p->stages * A_STAGE_BYTES + C::FIXED_BYTES
+                                : p->stages * C::STAGE_BYTES + C::FIXED_BYTES;
+}
+
+static void plan_prefetch(ConvParams* p) {
+  static const bool allow = []() {
+    const char* e = getenv("INSTAORDER_L2_PREFETCH");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  // worthwhile when a tile has few K blocks (the ring then covers less than a tile); never for stride-2 views
+  p->prefetch = (allow && p->mode != CONV_S2 && p->k_iters <= 18) ? 1 : 0;
+}
+
+static void plan_smem(ConvParams* p, int bn) {
+  plan_prefetch(p);
+  static const bool allow = []() {
+    const char* e = getenv("INSTAORDER_WEIGHT_STATIONARY");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  if (bn == 64) plan_smem_t<64>(p, allow);
+  else if (bn == 128) plan_smem_t<128>(p, allow);
+  else plan_smem_t<256>(p, allow);
+}
+
 static int make_out_maps(ConvParams* p, int rows_total) {
   const uint64_t dims[2] = {static_cast<uint64_t>(p->ldc), static_cast<uint64_t>(rows_total)};
   const uint64_t str[1] = {static_cast<uint64_t>(p->ldc) * 2};
@@ -475,6 +549,7 @@ int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, con
   }
   p->a_bytes = p->rows_per_tile * 128;
   if (rc) return rc;
+  plan_smem(p, bn);
   return make_out_maps(p, p->m_total);
 }
 
@@ -523,6 +598,7 @@ int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, cons
   const uint32_t wbox[2] = {64, 128};
   rc = make_tmap_bf16(&p->map_b, wgt, 2, wdims, wstr, wbox, true);
   if (rc) return rc;
+  plan_smem(p, 128);
   return make_out_maps(p, p->m_total);
 }
 

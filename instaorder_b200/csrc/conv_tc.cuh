@@ -39,6 +39,12 @@ struct ConvParams {
   int n_split;        // columns >= n_split go to rows + split_row_off (stem: second direction); else n_total
   int split_row_off;
   int relu;
+  // weight-stationary mode: when the layer has a single N tile and all its K blocks of weights fit in shared memory
+  // they are loaded once per CTA and only the activation tiles stream through the ring
+  int prefetch;       // producer pulls the next tile's activation rows into L2 one tile ahead
+  int b_resident;
+  int stages;         // ring depth (runtime: depends on how much shared memory the resident weights take)
+  int smem_bytes;     // dynamic shared memory of the launch
 };
 
 // conv3 (+ residual + ReLU) of one bottleneck fused with conv1 (+ ReLU) of the next one (conv_fused.cu)
