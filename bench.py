@@ -236,7 +236,7 @@ def main():
         mx = 4096
         pms = np.zeros(mx, np.float32); kind = np.zeros(mx, np.int32); fl = np.zeros(mx, np.float64)
         n = _lib.check(eng.lib.io_net_profile_read(eng.net, _lib.ptr(pms), _lib.ptr(kind), _lib.ptr(fl), None, None, mx))
-        sel = (kind[:n] == 0) | (kind[:n] == 2) | (kind[:n] == 4)
+        sel = (kind[:n] == 0) | (kind[:n] == 2) | (kind[:n] >= 4)
         conv_ms += float(pms[:n][sel].sum()); conv_flops += float(fl[:n][sel].sum()); n_conv += int(sel.sum())
         tot_ms += float(pms[:n].sum())
     _lib.check(eng.lib.io_net_profile(eng.net, 0))

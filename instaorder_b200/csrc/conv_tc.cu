@@ -612,6 +612,11 @@ extern "C" int io_conv_bn_act(const void* x_dev, int b, int h, int w, int cin, c
   io::ConvParams p;
   int bn = 0;
   io::ConvDesc d{b, h, w, cin, cout, kernel, stride};
+  if (residual_dev == nullptr && io::tn_enabled() && io::conv_tn_supported(d)) {
+    io::TnParams tp;
+    if (int rc = io::conv_tn_plan(&tp, d, x_dev, w_dev, bias_dev, y_dev, relu)) return rc;
+    return io::conv_tn_launch(tp, io::as_stream(stream));
+  }
   int rc = io::conv_plan(&p, &bn, d, x_dev, w_dev, bias_dev, residual_dev, y_dev, relu);
   if (rc) return rc;
   return io::conv_tc_launch(p, bn, io::as_stream(stream));

@@ -11,6 +11,10 @@ enum ConvMode : int {
   CONV_STEM = 3,   // conv1 7x7 stride 2 on the padded 8-channel pair tensor: overlapping-window 4-D map
 };
 
+struct ConvDesc {
+  int b, h, w, cin, cout, kernel, stride;
+};
+
 struct ConvParams {
   CUtensorMap map_a;
   CUtensorMap map_b;
@@ -59,13 +63,27 @@ int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, 
                     const void* residual, void* y, const void* w1n, const float* bias1n, void* y2);
 int conv_fused_launch(const FusedParams& fp, cudaStream_t stream);
 
+// Transposed kernel (conv_tn.cu): 128 output channels on the MMA's M side, 256 pixels on its N side
+struct TnParams {
+  CUtensorMap map_w;    // weights [128][Ktot] bf16, box 64 x 128
+  CUtensorMap map_x;    // activation view (as in ConvParams::map_a) with 256-pixel boxes (128 for the stem)
+  CUtensorMap map_out;  // [rows][ldc] bf16, box 64 x 32
+  const float* bias;
+  int mode, k_iters, kpt, taps_w, pad, cin;
+  int tiles, tpi, bh, w_out, hw_out;
+  int ldc, n_split, split_row_off, relu;
+};
+bool conv_tn_supported(const ConvDesc& d);
+int conv_tn_plan(TnParams* p, const ConvDesc& d, const void* x, const void* wgt, const float* bias, void* y, int relu);
+bool stem_tn_supported(int d);
+int stem_tn_plan(TnParams* p, int pairs, int d, const void* x, const void* wgt, const float* bias, void* y);
+int conv_tn_launch(const TnParams& p, cudaStream_t stream);
+bool tn_enabled();
+
 // Launches the persistent kernel for one convolution. bn_tile in {64, 128, 256}.
 int conv_tc_launch(const ConvParams& p, int bn_tile, cudaStream_t stream);
 
 // Fills tile geometry + tensor maps for a conv over NHWC bf16 input [b, h, w, cin] (or the pair tensor for the stem).
-struct ConvDesc {
-  int b, h, w, cin, cout, kernel, stride;
-};
 int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, const void* wgt, const float* bias,
               const void* residual, void* y, int relu);
 // Stem plan: x is the padded pair tensor [pairs, d+6, pitch, 8]; y is [2*pairs, d/2, d/2, 64] (image 2p + dir).

@@ -24,9 +24,10 @@ struct ConvW {
 };
 
 struct Op {
-  enum Kind { STEM, POOL, CONV, TAIL, FUSED } kind;
+  enum Kind { STEM, POOL, CONV, TAIL, FUSED, CONV_TN, STEM_TN } kind;
   ConvParams p;
   FusedParams fp;
+  TnParams tp;
   int bn_tile = 0;
   double flops = 0.0;  // algorithmic 2*MAC of this launch
   double bytes = 0.0;  // algorithmic HBM bytes of this launch (activations in + out + residual + weights)
@@ -145,8 +146,13 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       }
       t1_ready = false;
       Op o2; o2.kind = Op::CONV;
-      if (int rc = conv_plan(&o2.p, &o2.bn_tile, ConvDesc{b, h, w, c2.cin, c2.cout, 3, c2.stride}, T1, c2.w, c2.bias,
-                             nullptr, T2, 1)) return rc;
+      const ConvDesc d2{b, h, w, c2.cin, c2.cout, 3, c2.stride};
+      if (tn_enabled() && conv_tn_supported(d2)) {
+        o2.kind = Op::CONV_TN;
+        if (int rc = conv_tn_plan(&o2.tp, d2, T1, c2.w, c2.bias, T2, 1)) return rc;
+      } else if (int rc = conv_plan(&o2.p, &o2.bn_tile, d2, T1, c2.w, c2.bias, nullptr, T2, 1)) {
+        return rc;
+      }
       o2.flops = 2.0 * b * ho * wo * 9.0 * c2.cin * c2.cout;
       o2.bytes = 2.0 * b * (h * w * c2.cin + ho * wo * c2.cout) + 18.0 * c2.cin * c2.cout;
       o2.tag = (li + 1) * 100 + blk * 10 + 2;
@@ -197,7 +203,8 @@ static int build_plan_a(io_net* net, int pa, __nv_bfloat16* dst, Plan* plan) {
   plan->ops.clear();
   __nv_bfloat16 *X = net->buf[0], *Y = net->buf[1];
   Op op;
-  op.kind = Op::STEM;   // its tensor maps are rebuilt per call (the pair tensor belongs to the caller)
+  op.kind = (tn_enabled() && stem_tn_supported(d)) ? Op::STEM_TN : Op::STEM;   // maps are rebuilt per call (the
+                                                                               // pair tensor belongs to the caller)
   op.flops = 2.0 * b * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
   op.bytes = static_cast<double>(io_pair_tensor_bytes(pa, d)) + 2.0 * b * (d / 2) * (d / 2) * 64;
   op.tag = 1;
@@ -430,6 +437,13 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
           break;
         case Op::FUSED:
           rc = conv_fused_launch(op.fp, stream);
+          break;
+        case Op::CONV_TN:
+          rc = conv_tn_launch(op.tp, stream);
+          break;
+        case Op::STEM_TN:
+          rc = stem_tn_plan(&op.tp, pa, net->d, pair_ptr, net->stem_w, net->stem_bias, net->buf[0]);
+          if (!rc) rc = conv_tn_launch(op.tp, stream);
           break;
         default:
           break;
