@@ -69,6 +69,7 @@ struct TnParams {
   CUtensorMap map_x;    // activation view (as in ConvParams::map_a) with 256-pixel boxes (128 for the stem)
   CUtensorMap map_out;  // [rows][ldc] bf16, box 64 x 32
   const float* bias;
+  int ch;               // 128 or 64 output channels (MMA M)
   int mode, k_iters, kpt, taps_w, pad, cin;
   int tiles, tpi, bh, w_out, hw_out;
   int ldc, n_split, split_row_off, relu;

@@ -18,16 +18,21 @@ namespace io {
 namespace {
 constexpr int BK = 64;
 constexpr int PX = 256;                       // pixels per tile (MMA N)
-constexpr int CH = 128;                       // channels (MMA M)
-constexpr int W_STAGE_BYTES = CH * BK * 2;    // 16 KB
 constexpr int X_STAGE_BYTES = PX * BK * 2;    // 32 KB
-constexpr int STAGE_BYTES = W_STAGE_BYTES + X_STAGE_BYTES;
 constexpr int STAGES = 3;
 constexpr int REGION_BYTES = 32 * 128;        // 32 pixels x 64 channels bf16, 128B-swizzled
-constexpr int EPI_BYTES = 16 * REGION_BYTES;  // 4 warp pairs x 4 slots
+constexpr int EPI_BYTES = 16 * REGION_BYTES;  // 4 slots per epilogue warp group
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 512 + BAR_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
+
+// CH = channels on the MMA's M side: 128, or 64 (M = 64: the accumulator then occupies lanes 0-15 of each of the
+// four TMEM lane quadrants -- row m lives in lane (m % 16) + 32 * (m / 16), cute/atom/mma_traits_sm100.hpp tmem_frg)
+template <int CH>
+struct TnCfg {
+  static constexpr int W_STAGE_BYTES = CH * BK * 2;   // 16 KB / 8 KB
+  static constexpr int STAGE_BYTES = W_STAGE_BYTES + X_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 512 + BAR_BYTES + 1024;
+};
 
 struct TileTn {
   int n_img, h0, base_row;
@@ -51,7 +56,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 }
 }  // namespace
 
+template <int CH>
 __global__ void __launch_bounds__(320, 1) conv_tn_kernel(const __grid_constant__ TnParams p) {
+  constexpr int W_STAGE_BYTES = TnCfg<CH>::W_STAGE_BYTES;
+  constexpr int STAGE_BYTES = TnCfg<CH>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
@@ -157,13 +165,18 @@ __global__ void __launch_bounds__(320, 1) conv_tn_kernel(const __grid_constant__
   } else {
     // ======================= epilogue (warps 2..9): transpose D^T -> NHWC =======================
     const int e = warp - 2;
-    const int q = warp & 3;             // TMEM lane quadrant = channels 32q .. 32q+31
+    const int q = warp & 3;             // TMEM lane quadrant
     const int hsel = e >> 2;            // pixel half of the tile: pixels 128*hsel .. 128*hsel+127
-    const int chalf = q >> 1;           // 64-channel group this warp contributes to
-    const int pair = hsel * 2 + chalf;  // the two warps (q even / odd) that fill one staging region
-    const bool leader = (q & 1) == 0 && lane == 0;
-    const int cl = (q & 1) * 32 + lane; // channel inside the 64-channel group
-    const float my_bias = sBias[q * 32 + lane];
+    // CH = 128: quadrant q holds channels 32q..32q+31; the two warps (q even / odd) of a pixel half fill one
+    //           64-channel staging region.  CH = 64: quadrant q holds channels 16q..16q+15 in its lanes 0..15; the
+    //           four warps of a pixel half fill one region.
+    const int chalf = (CH == 128) ? (q >> 1) : 0;
+    const int pair = (CH == 128) ? hsel * 2 + chalf : hsel;
+    constexpr int GROUP_THREADS = (CH == 128) ? 64 : 128;
+    const bool leader = ((CH == 128) ? (q & 1) == 0 : q == 0) && lane == 0;
+    const bool lane_on = (CH == 128) || lane < 16;
+    const int cl = (CH == 128) ? (q & 1) * 32 + lane : q * 16 + (lane & 15);  // channel inside the 64-channel group
+    const float my_bias = sBias[(CH == 128) ? q * 32 + lane : q * 16 + (lane & 15)];
     uint8_t* my_slots = sEpi + pair * 4 * REGION_BYTES;
     const int chunk_off = ((cl >> 3) << 4), sub_off = (cl & 7) * 2;
     int it = 0;
@@ -185,18 +198,20 @@ __global__ void __launch_bounds__(320, 1) conv_tn_kernel(const __grid_constant__
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
         if (leader) tma_store_wait_read<3>();       // the store that last read this slot (previous tile) is done
-        named_bar_sync(1 + pair, 64);
+        named_bar_sync(1 + pair, GROUP_THREADS);
         uint8_t* region = my_slots + c * REGION_BYTES;
+        if (lane_on) {
 #pragma unroll
-        for (int px = 0; px < 32; ++px) {
-          float f = __uint_as_float(v[px]) + my_bias;
-          if (p.relu) f = fmaxf(f, 0.0f);
-          const __nv_bfloat16 h = __float2bfloat16_rn(f);
-          // row = pixel, 16-byte chunks XOR-swizzled by (row & 7); px is a compile-time constant after unrolling
-          *reinterpret_cast<__nv_bfloat16*>(region + px * 128 + (chunk_off ^ ((px & 7) << 4)) + sub_off) = h;
+          for (int px = 0; px < 32; ++px) {
+            float f = __uint_as_float(v[px]) + my_bias;
+            if (p.relu) f = fmaxf(f, 0.0f);
+            const __nv_bfloat16 h = __float2bfloat16_rn(f);
+            // row = pixel, 16-byte chunks XOR-swizzled by (row & 7); px is a compile-time constant after unrolling
+            *reinterpret_cast<__nv_bfloat16*>(region + px * 128 + (chunk_off ^ ((px & 7) << 4)) + sub_off) = h;
+          }
         }
         fence_proxy_async();
-        named_bar_sync(1 + pair, 64);
+        named_bar_sync(1 + pair, GROUP_THREADS);
         if (leader) {
           int scol = chalf * 64, srow = t.base_row + px0;
           if (scol >= p.n_split) { scol -= p.n_split; srow += p.split_row_off; }
@@ -213,10 +228,19 @@ __global__ void __launch_bounds__(320, 1) conv_tn_kernel(const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+template <int CH>
+static int conv_tn_launch_t(const TnParams& p, cudaStream_t stream);
+
 int conv_tn_launch(const TnParams& p, cudaStream_t stream) {
+  return p.ch == 64 ? conv_tn_launch_t<64>(p, stream) : conv_tn_launch_t<128>(p, stream);
+}
+
+template <int CH>
+static int conv_tn_launch_t(const TnParams& p, cudaStream_t stream) {
+  constexpr int SMEM_BYTES = TnCfg<CH>::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    IO_CUDA(cudaFuncSetAttribute(conv_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IO_CUDA(cudaFuncSetAttribute(conv_tn_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   if (p.tiles <= 0) return IO_OK;
@@ -231,7 +255,7 @@ int conv_tn_launch(const TnParams& p, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IO_CUDA(cudaLaunchKernelEx(&cfg, conv_tn_kernel, p));
+  IO_CUDA(cudaLaunchKernelEx(&cfg, conv_tn_kernel<CH>, p));
   return IO_OK;
 }
 
@@ -243,10 +267,10 @@ bool tn_enabled() {
   return on;
 }
 
-// true when the transposed kernel can run this convolution: 3x3 (stride 1 or 2) with exactly 128 output channels
+// true when the transposed kernel can run this convolution: 3x3 (stride 1 or 2) with 128 or 64 output channels
 // whose output is tiled by whole 256-pixel tiles of full rows
 bool conv_tn_supported(const ConvDesc& d) {
-  if (d.kernel != 3 || d.cout != CH || d.cin % 64 != 0) return false;
+  if (d.kernel != 3 || (d.cout != 128 && d.cout != 64) || d.cin % 64 != 0) return false;
   const int h_out = d.h / d.stride, w_out = d.w / d.stride;
   if (w_out > PX || PX % w_out != 0) return false;
   const int bh = PX / w_out;
@@ -270,15 +294,17 @@ int conv_tn_plan(TnParams* p, const ConvDesc& d, const void* x, const void* wgt,
   p->tiles = d.b * p->tpi;
   p->w_out = w_out;
   p->hw_out = h_out * w_out;
+  const int CH = d.cout;
+  p->ch = CH;
   p->ldc = CH;
   p->n_split = CH;
   p->split_row_off = 0;
   p->relu = relu;
   int rc;
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(ktot), CH};
+    const uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(CH)};
     const uint64_t str[1] = {static_cast<uint64_t>(ktot) * 2};
-    const uint32_t box[2] = {64, CH};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(CH)};
     if ((rc = make_tmap_bf16(&p->map_w, wgt, 2, dims, str, box, true))) return rc;
   }
   const uint64_t C = d.cin, W = d.w, H = d.h, B = d.b;
@@ -294,8 +320,8 @@ int conv_tn_plan(TnParams* p, const ConvDesc& d, const void* x, const void* wgt,
     rc = make_tmap_bf16(&p->map_x, x, 5, dims, str, box, true);
   }
   if (rc) return rc;
-  const uint64_t odims[2] = {CH, static_cast<uint64_t>(d.b) * p->hw_out};
-  const uint64_t ostr[1] = {CH * 2};
+  const uint64_t odims[2] = {static_cast<uint64_t>(CH), static_cast<uint64_t>(d.b) * p->hw_out};
+  const uint64_t ostr[1] = {static_cast<uint64_t>(CH) * 2};
   const uint32_t obox[2] = {64, 32};
   return make_tmap_bf16(&p->map_out, y, 2, odims, ostr, obox, true);
 }
@@ -309,6 +335,8 @@ int stem_tn_plan(TnParams* p, int pairs, int d, const void* x, const void* wgt, 
   const int h_out = d / 2, w_out = d / 2;
   const int64_t pitch = io_pair_tensor_row_pitch(d);
   const int hp = d + 6;
+  constexpr int CH = 128;
+  p->ch = CH;
   p->bias = bias;
   p->mode = CONV_STEM;
   p->k_iters = 7;
