@@ -167,6 +167,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-pairs", type=int, default=28)
+    ap.add_argument("--mode", default="patch256", choices=["patch256", "resize384"],
+                    help="patch256 = the BASELINE.json metric (default); resize384 = the shipped InstaOrderNet^od "
+                         "config (whole image -> 384^2), reported as a second row in DESIGN.md")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -174,6 +177,10 @@ def main():
     import torch
     import torch.distributed as dist
     from instaorder_b200 import _lib, engine, synth
+    global D, FLOP_PER_PAIR
+    gmode = "patch"
+    if args.mode == "resize384":
+        D, FLOP_PER_PAIR, gmode = 384, 48.970e9, "resize"
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -191,9 +198,9 @@ def main():
     eng = engine.OrderEngine(NUM_CLASSES, D, max_pairs=PAIRS_PER_STEP, device=dev)
     eng.load_state_dict(synth.random_state_dict(0, 5, NUM_CLASSES))
     heads = engine.heads_for(ALGO, NUM_CLASSES)
-    batches, mat_elems = eng.make_batches(scenes, PAIRS_PER_STEP)
+    batches, mat_elems = eng.make_batches(scenes, PAIRS_PER_STEP, gmode)
     batches = batches[:n_batches]
-    resident = [eng.upload_resident(b, mat_elems) for b in batches]
+    resident = [eng.upload_resident(b, mat_elems, gmode) for b in batches]
     input_bytes = sum(r.input_bytes for r in resident)
 
     def sync_all():
@@ -204,7 +211,7 @@ def main():
 
     # ---- device-resident timing ---------------------------------------------------------------------------
     for i in range(args.warmup):
-        eng.run_resident(resident[i % len(resident)], heads)
+        eng.run_resident(resident[i % len(resident)], heads, gmode)
     sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -213,7 +220,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        eng.run_resident(resident[i % len(resident)], heads)
+        eng.run_resident(resident[i % len(resident)], heads, gmode)
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -231,7 +238,7 @@ def main():
     n_conv = 0
     prof_steps = min(args.steps, 4)
     for i in range(prof_steps):
-        eng.run_resident(resident[i % len(resident)], heads)
+        eng.run_resident(resident[i % len(resident)], heads, gmode)
         torch.cuda.synchronize()
         mx = 4096
         pms = np.zeros(mx, np.float32); kind = np.zeros(mx, np.int32); fl = np.zeros(mx, np.float64)
@@ -257,13 +264,13 @@ def main():
         per_step_scenes.append([scenes[(o + k) % len(scenes)] for k in range(17)])
         o += 17
     for i in range(args.warmup):
-        eng.infer_scenes(per_step_scenes[i], ALGO, "all", "patch")
+        eng.infer_scenes(per_step_scenes[i], ALGO, "all", gmode)
     sync_all()
     h0, d0 = eng.h2d_bytes, eng.d2h_bytes
     t0 = time.perf_counter()
     pairs_e2e = 0
     for i in range(args.warmup, args.warmup + args.steps):
-        r = eng.infer_scenes(per_step_scenes[i], ALGO, "all", "patch")
+        r = eng.infer_scenes(per_step_scenes[i], ALGO, "all", gmode)
         pairs_e2e += sum(s.n * (s.n - 1) // 2 for s in per_step_scenes[i])
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
@@ -283,11 +290,12 @@ def main():
                        sample="%d pairs of one C2 image (%.1f s): oracle port of inference.py patch path + fp32 "
                               "torch-CPU ResNet-50, batched 16 forwards" % (n, cdt))
         line = dict(
-            metric="instance pairs/s (InstaOrderNet^od, 256^2, bf16)", value=value, unit="pairs/s", n_gpus=world,
+            metric="instance pairs/s (InstaOrderNet^od, %s, bf16)" % ("256^2" if gmode == "patch" else "resize 384^2"),
+            value=value, unit="pairs/s", n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
             scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
             config=dict(workload="C2: synthetic COCO-val-shaped images, 10 instances -> 45 pairs/image, %d pairs per "
-                                 "step, patch 256^2, InstaOrderNet^od heads [2,3], random-init weights" % PAIRS_PER_STEP,
+                                 "step, %s, InstaOrderNet^od heads [2,3], random-init weights" % (PAIRS_PER_STEP, "patch 256^2" if gmode == "patch" else "resize 384^2 (shipped config)"),
                         pairs_per_step=PAIRS_PER_STEP, parallelism="images sharded over %d GPU(s), no collective" % world,
                         l2="inputs rotate over %d resident batches (%.0f MB) and each step streams >10 GB of "
                            "activations, i.e. >> 126 MB L2" % (len(resident), input_bytes / 1e6)),
