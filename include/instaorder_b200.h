@@ -192,6 +192,92 @@ IO_API int io_loss_forward(const float* logits_dev, int n, int k_total, int occ_
                            float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------ */
+/* T -- training step: models/supervised_order.py:83-95 (^od), :413-438 (^d), :481-493 (OrderNet), :535-548 (^o)   */
+/* ------------------------------------------------------------------------------------------------------------ */
+
+typedef struct io_train io_train_t;
+
+/* One handle = one model replica with a fixed per-rank batch of `batch_pairs` pairs at `input_size`^2 (workspace for
+ * all saved activations is allocated by io_train_bind: ~120 MB per pair at 256^2).  num_classes / n_heads as
+ * io_net_create. */
+IO_API int io_train_create(const int32_t* num_classes, int n_heads, int input_size, int batch_pairs, io_train_t** out);
+IO_API int io_train_destroy(io_train_t* t);
+
+/* Flat buffers.  Parameters, gradients and optimiser state are flat fp32 arrays of io_train_param_count() elements
+ * owned by the CALLER (torch tensors); BatchNorm running_mean / running_var live in a second flat array of
+ * io_train_stat_count() elements.  The segment table maps them to the reference's state_dict names (without the
+ * `module.` prefix): buffer_out = 0 (parameter buffer) or 1 (statistics buffer), offset_out in elements, and
+ * dims4_out = {cout, kh, kw, cin} for a convolution weight -- stored tap-major / channel-minor, i.e. the reference
+ * tensor [cout, cin, kh, kw] permuted (0, 2, 3, 1) -- or {n, 0, 0, 0} / {rows, cols, 0, 0} for tensors kept in
+ * the reference's own layout (BN weight / bias / running stats, FC weight / bias).  Segments are 64-element
+ * aligned; the gaps stay zero.  Because the optimisers are element-wise, momentum / Adam buffers use the same table
+ * (utils/common_utils.py:128-149 resume path). */
+IO_API int64_t io_train_param_count(const io_train_t* t);
+IO_API int64_t io_train_stat_count(const io_train_t* t);
+IO_API int io_train_num_segments(const io_train_t* t);
+IO_API int io_train_segment(const io_train_t* t, int i, char* name_out, int name_cap, int32_t* buffer_out,
+                            int64_t* offset_out, int32_t* dims4_out);
+IO_API int io_train_bind(io_train_t* t, float* params_dev, float* grads_dev, float* stats_dev);
+/* Refreshes the bf16 GEMM copies of the weights from the fp32 masters (after loading / editing params_dev). */
+IO_API int io_train_sync_weights(io_train_t* t, void* stream);
+
+/* forward (both directions, train-mode BatchNorm: batch statistics per direction, running statistics updated once
+ * per direction as the reference's two forward passes do) + loss (+ backward into grads_dev, which is zeroed first).
+ * pair_tensor_dev: [batch_pairs] pair tensor (io_pair_pack_nchw / io_pair_gather_*).  Heads and targets as
+ * io_loss_forward (the swapped-direction labels of set_input are derived inside).  out_losses_dev[3] fp32 =
+ * (loss / world_size, occlusion loss, class loss).  The gradient all-reduce (utils/distributed_utils.py:27-31) is
+ * the caller's: ONE all-reduce of grads_dev. */
+IO_API int io_train_forward_backward(io_train_t* t, const void* pair_tensor_dev, int occ_off, int class_off, int class_k,
+                                     const float* occ_target_dev, const int64_t* class_target_dev,
+                                     const int64_t* is_overlap_dev, float overlap_w, float distinct_w, int world_size,
+                                     float* out_losses_dev, int run_backward, void* stream);
+/* torch.optim.SGD(lr, momentum, weight_decay) / torch.optim.Adam(lr, betas, eps) over the bound flat buffers
+ * (models/single_stage_model.py:34-42), fused with the refresh of the bf16 GEMM weights. */
+IO_API int io_train_sgd_step(io_train_t* t, float* momentum_buf_dev, float lr, float momentum, float weight_decay,
+                             int first_step, void* stream);
+IO_API int io_train_adam_step(io_train_t* t, float* m_dev, float* v_dev, float lr, float beta1, float beta2, float eps,
+                              int step, void* stream);
+/* logits of the last forward: device pointer to [2][batch_pairs][K] fp32 ([direction][pair]) */
+IO_API const float* io_train_logits(const io_train_t* t);
+IO_API int io_train_last_launches(const io_train_t* t);
+/* per-launch CUDA-event timing as io_net_profile; kind: 0 conv forward, 1 data gradient, 2 weight gradient,
+ * 3 element-wise / reduction, 4 loss */
+IO_API int io_train_profile(io_train_t* t, int enable);
+IO_API int io_train_profile_read(io_train_t* t, float* ms_host, int32_t* kind_host, double* flop_host,
+                                 double* bytes_host, int32_t* tag_host, int max_n);
+
+/* The same optimiser kernels on arbitrary flat buffers (w_bf16_dev optional: first n_bf16 elements re-cast). */
+IO_API int io_optim_sgd(float* w_dev, const float* g_dev, float* buf_dev, int64_t n, float lr, float momentum,
+                        float weight_decay, int first_step, void* w_bf16_dev, int64_t n_bf16, void* stream);
+IO_API int io_optim_adam(float* w_dev, const float* g_dev, float* m_dev, float* v_dev, int64_t n, float lr, float beta1,
+                         float beta2, float eps, int step, void* w_bf16_dev, int64_t n_bf16, void* stream);
+
+/* Building blocks of the training step, exported for the per-kernel parity tests (NHWC bf16 tensors).
+ * io_conv_wgrad: dw_dev[cout][k*k*cin] fp32 += weight gradient of conv(x[b,h,w,cin]; k, stride, pad k/2) given
+ *   dy[b,h/stride,w/stride,cout].  io_conv_dgrad: dx[b,h,w,cin] = data gradient of the stride-1 convolution given
+ *   dy[b,h,w,cout] and the forward weights w_dev[cout][k*k*cin] bf16 (+ residual).  io_stem_wgrad: packed
+ *   two-direction stem gradient [128][448] fp32 from the pair tensor and dy[2][pairs][d/2][d/2][64]. */
+IO_API int io_conv_wgrad(const void* x_dev, int b, int h, int w, int cin, const void* dy_dev, int cout, int kernel,
+                         int stride, float* dw_dev, void* stream);
+IO_API int io_conv_dgrad(const void* dy_dev, int b, int h, int w, int cin, int cout, int kernel, const void* w_dev,
+                         const float* zero_bias_dev, const void* residual_dev, void* dx_dev, void* stream);
+IO_API int io_stem_wgrad(const void* pair_tensor_dev, int pairs, int d, const void* dy_dev, float* dw_scratch_dev,
+                         void* stream);
+/* train-mode BatchNorm over [groups][rows][c] (+ residual) (+ ReLU) and its backward; save_dev = 4 x [groups][c] fp32
+ * (scale, shift, mean, invstd), scratch_dev = [groups][2][c] doubles. */
+IO_API int io_bn_train_forward(const void* y_dev, const void* residual_dev, void* a_dev, int groups, int rows, int c,
+                               const float* gamma_dev, const float* beta_dev, float eps, float momentum,
+                               float* running_mean_dev, float* running_var_dev, float* save_dev, double* scratch_dev,
+                               int relu, void* stream);
+IO_API int io_bn_train_backward(const void* da_dev, const void* a_dev, const void* y_dev, void* dy_dev, void* g_out_dev,
+                                int groups, int rows, int c, const float* gamma_dev, const float* save_dev,
+                                double* scratch_dev, int relu, float* dgamma_dev, float* dbeta_dev, void* stream);
+/* nn.MaxPool2d(3, 2, 1) with arg-max (idx_dev: one byte per output element) and, if dy_dev / dx_dev are given, its
+ * backward */
+IO_API int io_maxpool_train(const void* x_dev, void* y_dev, uint8_t* idx_dev, const void* dy_dev, void* dx_dev, int b,
+                            int h, int w, int c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------ */
 /* M -- metrics, batched over images                                                                             */
 /* ------------------------------------------------------------------------------------------------------------ */
 

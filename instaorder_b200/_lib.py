@@ -60,6 +60,32 @@ _SIGS = {
     "io_metrics_prf": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "io_metrics_whdr": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
 }
+_f = C.c_float
+_SIGS.update({
+    "io_train_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "io_train_destroy": (_i, [_vp]),
+    "io_train_param_count": (_i64, [_vp]),
+    "io_train_stat_count": (_i64, [_vp]),
+    "io_train_num_segments": (_i, [_vp]),
+    "io_train_segment": (_i, [_vp, _i, C.c_char_p, _i, _vp, _vp, _vp]),
+    "io_train_bind": (_i, [_vp, _vp, _vp, _vp]),
+    "io_train_sync_weights": (_i, [_vp, _vp]),
+    "io_train_forward_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _i, _vp, _i, _vp]),
+    "io_train_sgd_step": (_i, [_vp, _vp, _f, _f, _f, _i, _vp]),
+    "io_train_adam_step": (_i, [_vp, _vp, _vp, _f, _f, _f, _f, _i, _vp]),
+    "io_train_logits": (_vp, [_vp]),
+    "io_train_last_launches": (_i, [_vp]),
+    "io_train_profile": (_i, [_vp, _i]),
+    "io_train_profile_read": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "io_optim_sgd": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _i, _vp, _i64, _vp]),
+    "io_optim_adam": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _vp, _i64, _vp]),
+    "io_conv_wgrad": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "io_conv_dgrad": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "io_stem_wgrad": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "io_bn_train_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    "io_bn_train_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "io_maxpool_train": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+})
 # io_net_load_state takes (net, names, ptrs, numels, n)
 _SIGS["io_net_load_state"] = (_i, [_vp, _vp, _vp, _vp, _i])
 

@@ -3,6 +3,7 @@
 
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace io {
 
@@ -28,6 +29,19 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+int mn_lbo() {
+  static const int v = env_int("INSTAORDER_MN_LBO", 8192);
+  return v;
+}
+int mn_sbo() {
+  static const int v = env_int("INSTAORDER_MN_SBO", 1024);
+  return v;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -30,6 +30,10 @@ int cuda_fail(cudaError_t e, const char* what);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 int num_sms();
+// byte distances of the MN-major operand descriptors (defaults 8192 / 1024; INSTAORDER_MN_LBO / _SBO override them
+// for bring-up experiments)
+int mn_lbo();
+int mn_sbo();
 
 // ---- TMA descriptors (driver entry point resolved at run time; no link-time libcuda dependency) -----------
 // dims / strides innermost first; strides_bytes[i] is the byte stride of dim i+1 (rank-1 entries).
@@ -187,6 +191,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
   return d;
 }
+// MN-major, 128-byte-swizzled operand (the GEMM's M or N index is the contiguous one in memory: activations
+// [pixel][channel] contracted over pixels, forward weights [cout][cin] contracted over cout).  Canonical layout
+// (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>, in 16-byte units):
+//   Swizzle<3,4,3> o ((8, n), (8, k)) : ((1, LBO), (8, SBO))
+// i.e. one K index = one 128-byte row of 64 MN elements, 8 K rows = one 1024-byte swizzle atom (exactly what a
+// 128B-swizzled TMA box {64 elements, R rows} writes), SBO = 1024 B between 8-row K groups, LBO = byte distance
+// between consecutive 64-element MN slabs (here: one TMA box per slab).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                       uint32_t sbo_bytes = 1024) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t UMMA_A_MN = 1u << 15;  // InstrDescriptor::a_major_
+constexpr uint32_t UMMA_B_MN = 1u << 16;  // InstrDescriptor::b_major_
 // kind::f16 instruction descriptor (InstrDescriptor in mma_sm100_desc.hpp): D=f32, A=B=bf16, both K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |

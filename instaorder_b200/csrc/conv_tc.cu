@@ -67,7 +67,7 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int m_tile)
       t.limit = min(p.rows_per_tile, p.bi * p.hw_out - t.h0 * p.w_out);
     }
     // the stem writes image 2n (direction A,B) and image 2n+1 (direction B,A; columns >= n_split)
-    const int img_out = p.mode == CONV_STEM ? 2 * t.n_img : t.n_img;
+    const int img_out = p.mode == CONV_STEM ? p.img_mul * t.n_img : t.n_img;
     t.base_row = img_out * p.hw_out + t.h0 * p.w_out + t.w0;
   }
   return t;
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
             tma_load_2d(dA, &p.map_a, &full[stage], kb * BK, t.base_row);
           } else if (p.mode == CONV_S1) {
             const int r = tap / 3, s = tap - r * 3;
-            tma_load_4d(dA, &p.map_a, &full[stage], kb * BK, s - 1, t.h0 + r - 1, t.n_img);
+            if (p.flip) tma_load_4d(dA, &p.map_a, &full[stage], kb * BK, 1 - s, t.h0 + 1 - r, t.n_img);
+            else tma_load_4d(dA, &p.map_a, &full[stage], kb * BK, s - 1, t.h0 + r - 1, t.n_img);
           } else if (p.mode == CONV_S2) {
             const int r = tap / p.taps_w, s = tap - r * p.taps_w;
             const int dr = r - p.pad, ds = s - p.pad;
@@ -178,7 +179,14 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           } else {  // CONV_STEM: filter row `tap`, 8 taps x 8 channels per K block
             tma_load_4d(dA, &p.map_a, &full[stage], 0, t.w0, 2 * t.h0 + tap, t.n_img);
           }
-          if (!b_res) tma_load_2d(dB, &p.map_b, &full[stage], ki * BK, n_tile * BN);
+          if (p.b_mn) {   // forward weights as MN-major slabs: {64 input channels (N)} x {64 output channels (K)}
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(static_cast<uint8_t*>(dB) + j * 8192, &p.map_b, &full[stage],
+                          tap * p.b_tap_cols + n_tile * BN + j * 64, kb * BK);
+          } else if (!b_res) {
+            tma_load_2d(dB, &p.map_b, &full[stage], ki * BK, n_tile * BN);
+          }
           if (++kb == p.kpt) { kb = 0; ++tap; }
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = umma_idesc_bf16(BM, BN) | (p.b_mn ? UMMA_B_MN : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -206,10 +214,16 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + (b_res ? ki : stage) * C::B_STAGE_BYTES);
+          if (p.b_mn) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                      (ki > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_mn_sw128(b_addr + k * 2048, p.mn_lbo, p.mn_sbo), idesc,
+                        (ki > 0 || k > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                        (ki > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the smem slot when these MMAs have read it
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -583,6 +597,7 @@ int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, cons
   p->ldc = 64;
   p->n_split = 64;
   p->split_row_off = p->hw_out;
+  p->img_mul = 2;
   p->relu = 1;
   p->a_bytes = p->rows_per_tile * 128;
   *bn_tile = 128;
@@ -600,6 +615,34 @@ int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, cons
   if (rc) return rc;
   plan_smem(p, 128);
   return make_out_maps(p, p->m_total);
+}
+
+int dgrad_plan(ConvParams* p, int* bn_tile, int b, int h, int w, int cin_f, int cout_f, int kernel, const void* dy,
+               const void* wgt_f, const float* zero_bias, const void* residual, void* dx) {
+  // the data gradient is itself a stride-1 convolution dy[cout_f] -> dx[cin_f]; plan it as such (the weight map
+  // built from the dummy K-major view is replaced below)
+  int rc = conv_plan(p, bn_tile, ConvDesc{b, h, w, cout_f, cin_f, kernel, 1}, dy, wgt_f, zero_bias, residual, dx, 0);
+  if (rc) return rc;
+  const uint64_t kk = static_cast<uint64_t>(kernel) * kernel;
+  const uint64_t wdims[2] = {kk * cin_f, static_cast<uint64_t>(cout_f)};
+  const uint64_t wstr[1] = {kk * cin_f * 2};
+  const uint32_t wbox[2] = {64, 64};
+  rc = make_tmap_bf16(&p->map_b, wgt_f, 2, wdims, wstr, wbox, true);
+  if (rc) return rc;
+  p->b_mn = 1;
+  p->mn_lbo = mn_lbo();
+  p->mn_sbo = mn_sbo();
+  p->flip = kernel == 3 ? 1 : 0;
+  p->b_tap_cols = cin_f;
+  if (p->b_resident) {   // weight residency assumes the K-major layout: fall back to the streaming ring
+    p->b_resident = 0;
+    const int bn = *bn_tile;
+    p->stages = bn == 256 ? Cfg<256>::STAGES : (bn == 128 ? Cfg<128>::STAGES : Cfg<64>::STAGES);
+    const int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+    const int fixed = bn == 256 ? Cfg<256>::FIXED_BYTES : (bn == 128 ? Cfg<128>::FIXED_BYTES : Cfg<64>::FIXED_BYTES);
+    p->smem_bytes = p->stages * stage_bytes + fixed;
+  }
+  return IO_OK;
 }
 
 }  // namespace io

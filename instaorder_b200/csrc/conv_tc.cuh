@@ -49,6 +49,13 @@ struct ConvParams {
   int b_resident;
   int stages;         // ring depth (runtime: depends on how much shared memory the resident weights take)
   int smem_bytes;     // dynamic shared memory of the launch
+  // training (data-gradient) mode: B = the FORWARD weights [Cout_f][taps * Cin_f] used as an MN-major operand
+  // (K = Cout_f rows, N = Cin_f contiguous), filter taps visited mirrored (tap offsets negated) -- dgrad_plan()
+  int b_mn;           // 1: B boxes are {64 n, 64 k} MN-major slabs of 8 KB, UMMA b_major = MN
+  int flip;           // 1: activation box of tap (r, s) is shifted by (1 - r, 1 - s) instead of (r - 1, s - 1)
+  int mn_lbo, mn_sbo; // b_mn: descriptor byte offsets (8192 / 1024)
+  int b_tap_cols;     // b_mn: columns per filter tap in the weight matrix (= Cin_f)
+  int img_mul;        // CONV_STEM: output image of pair n, direction 0 is img_mul * n (2 = interleaved, 1 = [dir][pair])
 };
 
 // conv3 (+ residual + ReLU) of one bottleneck fused with conv1 (+ ReLU) of the next one (conv_fused.cu)
@@ -73,6 +80,7 @@ struct TnParams {
   int mode, k_iters, kpt, taps_w, pad, cin;
   int tiles, tpi, bh, w_out, hw_out;
   int ldc, n_split, split_row_off, relu;
+  int img_mul;          // CONV_STEM: output image of pair n, direction 0 (2 = interleaved 2n + dir, 1 = [dir][pair])
 };
 bool conv_tn_supported(const ConvDesc& d);
 int conv_tn_plan(TnParams* p, const ConvDesc& d, const void* x, const void* wgt, const float* bias, void* y, int relu);
@@ -89,5 +97,9 @@ int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, con
               const void* residual, void* y, int relu);
 // Stem plan: x is the padded pair tensor [pairs, d+6, pitch, 8]; y is [2*pairs, d/2, d/2, 64] (image 2p + dir).
 int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, const void* wgt, const float* bias, void* y);
+// Data gradient of a stride-1 convolution (1x1 or 3x3 pad 1) as a convolution over dy [b, h, w, cout_f] with the
+// forward weights wgt_f [cout_f][k*k*cin_f] read MN-major and the taps mirrored; dx [b, h, w, cin_f] (+ residual).
+int dgrad_plan(ConvParams* p, int* bn_tile, int b, int h, int w, int cin_f, int cout_f, int kernel, const void* dy,
+               const void* wgt_f, const float* zero_bias, const void* residual, void* dx);
 
 }  // namespace io

@@ -45,7 +45,7 @@ __device__ __forceinline__ TileTn tile_tn(const TnParams& p, int t) {
   } else {
     r.n_img = t / p.tpi;
     r.h0 = (t - r.n_img * p.tpi) * p.bh;
-    const int img_out = p.mode == CONV_STEM ? 2 * r.n_img : r.n_img;
+    const int img_out = p.mode == CONV_STEM ? p.img_mul * r.n_img : r.n_img;
     r.base_row = img_out * p.hw_out + r.h0 * p.w_out;
   }
   return r;
@@ -352,6 +352,7 @@ int stem_tn_plan(TnParams* p, int pairs, int d, const void* x, const void* wgt, 
   p->ldc = 64;
   p->n_split = 64;
   p->split_row_off = p->hw_out;
+  p->img_mul = 2;
   p->relu = 1;
   int rc;
   {

@@ -1,0 +1,647 @@
+// io_train_t: one training step (forward in train mode + loss + backward) of the 5-channel ResNet-50 order
+// classifiers as a static list of launches over bf16 NHWC activations resident in HBM.
+//
+// Replaces InstaOrderNet_od / _d / _o / OrderNet `.step()` up to (not including) the gradient all-reduce and the
+// optimiser update (reference models/supervised_order.py:83-95, 413-438, 481-493, 535-548): two forward passes
+// (A,B) and (B,A) in train-mode BatchNorm -- two separate BN batches, running statistics updated twice --, the loss
+// of :60-81, and `loss.backward()`.
+//
+// Both directions run through every launch together as image groups [direction][pair]; only the BatchNorm statistics
+// are per group.  Convolutions (forward and data gradient) are the tcgen05 implicit-GEMM kernels of conv_tc.cu /
+// conv_tn.cu with un-folded bf16 weights; the data gradient reads the SAME weight matrix as an MN-major operand with
+// mirrored taps; weight gradients are wgrad.cu.  fp32 master parameters, gradients and optimiser state live in flat
+// caller-owned buffers (GEMM layout [cout][kh][kw][cin] per convolution; the segment table maps them to the
+// reference's state_dict names), so the data-parallel all-reduce (utils/distributed_utils.py:27-31) is ONE NCCL
+// call on the flat gradient buffer.
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "train.cuh"
+#include "tail.cuh"
+
+namespace io {
+
+int loss_train_launch(const float* logits, int n, int k_total, int occ_off, int cls_off, int cls_k,
+                      const float* occ_target, const int64_t* class_target, const int64_t* is_overlap,
+                      float overlap_w, float distinct_w, int world_size, float* out, float* dlogits,
+                      cudaStream_t stream);
+int cast_bf16_launch(const float* w, void* w16, int64_t n, cudaStream_t stream);
+int stem_pack_launch(const float* w, void* pk, cudaStream_t stream);
+int stem_unpack_grad_launch(const float* scratch, float* dw, cudaStream_t stream);
+
+struct Segment {
+  std::string name;
+  int buffer;        // 0 = parameter / gradient flat buffer, 1 = statistics (running_mean / running_var) buffer
+  int64_t offset;
+  int dims[4];       // conv weight: {cout, kh, kw, cin} (GEMM layout; reference layout is [cout, cin, kh, kw]);
+                     // everything else: {n, 0, 0, 0} or {rows, cols, 0, 0} in the reference's own layout
+};
+
+struct Unit {        // one convolution + BatchNorm
+  std::string conv, bn;
+  int cin, cout, k, stride;
+  int h_in, w_in, h_out, w_out;
+  int64_t w_off, g_off, b_off;   // parameter offsets (weight, BN gamma, BN beta)
+  int64_t rm_off, rv_off;        // statistics offsets
+  __nv_bfloat16* y = nullptr;    // raw convolution output [imgs, h_out, w_out, cout]
+  __nv_bfloat16* a = nullptr;    // activation after BN (+ residual) (+ ReLU)
+  float* bnws = nullptr;         // scale, shift, mean, invstd: 4 x [2][cout]
+  float *scale, *shift, *mean, *invstd;
+};
+
+struct TOp {
+  std::function<int(cudaStream_t)> run;
+  int kind;        // 0 conv fwd, 1 dgrad, 2 wgrad, 3 element-wise / reduction, 4 other
+  double flops, bytes;
+  int tag;
+};
+
+}  // namespace io
+
+struct io_train {
+  int n_heads = 0;
+  int num_classes[2] = {0, 0};
+  int k_total = 0;
+  int d = 0;
+  int pairs = 0, imgs = 0;
+  std::vector<io::Unit> units;          // [0] = stem, then execution order (conv1, conv2, [downsample], conv3)
+  std::vector<io::Segment> segs;
+  int64_t n_params = 0, n_stats = 0;
+  int64_t fc_w_off = 0, fc_b_off = 0;
+  // caller-owned
+  float* params = nullptr;
+  float* grads = nullptr;
+  float* stats = nullptr;
+  // library-owned
+  __nv_bfloat16* w16 = nullptr;         // bf16 copy of the flat parameter buffer (same offsets)
+  __nv_bfloat16* stem_pk = nullptr;     // [128][448] packed two-direction stem weights
+  float* stem_scratch = nullptr;        // [128][448] stem wgrad accumulator
+  float* zero_bias = nullptr;           // [2048] zeros
+  double* red = nullptr;                // [2][2][2048] reduction scratch
+  uint8_t* pool_idx = nullptr;
+  __nv_bfloat16* pool_out = nullptr;
+  float* pooled = nullptr;              // [imgs][2048]
+  float* logits = nullptr;              // [imgs][k]
+  float* dlogits = nullptr;
+  __nv_bfloat16* gbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // GA, GG, GY, GT, GD, GZ
+  std::vector<void*> allocs;
+  std::vector<io::TOp> fwd, bwd;
+  bool built = false;
+  bool weights_synced = false;
+  // per-step inputs referenced by the op closures
+  const void* pair_tensor = nullptr;
+  int occ_off = -1, cls_off = -1, cls_k = 0;
+  const float* occ_target = nullptr;
+  const int64_t* class_target = nullptr;
+  const int64_t* is_overlap = nullptr;
+  float overlap_w = 1.f, distinct_w = 1.f;
+  int world_size = 1;
+  float* out_losses = nullptr;
+  int last_launches = 0;
+  // profiling
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> prof_kind, prof_tag;
+  std::vector<double> prof_flops, prof_bytes;
+};
+
+namespace io {
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static void build_units(io_train* t) {
+  auto add_seg = [&](const std::string& name, int buffer, int64_t numel, int d0, int d1, int d2, int d3) -> int64_t {
+    int64_t& n = buffer == 0 ? t->n_params : t->n_stats;
+    const int64_t off = n;
+    t->segs.push_back(Segment{name, buffer, off, {d0, d1, d2, d3}});
+    n = align_up(n + numel, 64);
+    return off;
+  };
+  auto add_unit = [&](const std::string& conv, const std::string& bn, int cin, int cout, int k, int stride, int h_in,
+                      int w_in) {
+    Unit u;
+    u.conv = conv; u.bn = bn; u.cin = cin; u.cout = cout; u.k = k; u.stride = stride;
+    u.h_in = h_in; u.w_in = w_in; u.h_out = h_in / stride; u.w_out = w_in / stride;
+    u.w_off = add_seg(conv + ".weight", 0, static_cast<int64_t>(cout) * k * k * cin, cout, k, k, cin);
+    u.g_off = add_seg(bn + ".weight", 0, cout, cout, 0, 0, 0);
+    u.b_off = add_seg(bn + ".bias", 0, cout, cout, 0, 0, 0);
+    u.rm_off = add_seg(bn + ".running_mean", 1, cout, cout, 0, 0, 0);
+    u.rv_off = add_seg(bn + ".running_var", 1, cout, cout, 0, 0, 0);
+    t->units.push_back(u);
+  };
+  const int d = t->d;
+  add_unit("conv1", "bn1", 5, 64, 7, 2, d, d);
+  int inpl = 64, h = d / 4;
+  const int planes_[4] = {64, 128, 256, 512};
+  const int blocks_[4] = {3, 4, 6, 3};
+  for (int li = 0; li < 4; ++li)
+    for (int b = 0; b < blocks_[li]; ++b) {
+      const std::string pre = "layer" + std::to_string(li + 1) + "." + std::to_string(b);
+      const int planes = planes_[li];
+      const int stride = (b == 0 && li > 0) ? 2 : 1;
+      add_unit(pre + ".conv1", pre + ".bn1", inpl, planes, 1, 1, h, h);
+      add_unit(pre + ".conv2", pre + ".bn2", planes, planes, 3, stride, h, h);
+      if (b == 0) add_unit(pre + ".downsample.0", pre + ".downsample.1", inpl, planes * 4, 1, stride, h, h);
+      add_unit(pre + ".conv3", pre + ".bn3", planes, planes * 4, 1, 1, h / stride, h / stride);
+      inpl = planes * 4;
+      h /= stride;
+    }
+  const char* heads1[1] = {"fc"};
+  const char* heads2[2] = {"fc_occ", "fc_depth"};
+  const char* const* heads = t->n_heads == 1 ? heads1 : heads2;
+  // the FC heads are stored as one [k_total][2048] matrix + [k_total] bias (rows in head order): the two segments of
+  // a head are consecutive slices of them
+  t->fc_w_off = t->n_params;
+  int row = 0;
+  for (int hI = 0; hI < t->n_heads; ++hI) {
+    const int k = t->num_classes[hI];
+    t->segs.push_back(Segment{std::string(heads[hI]) + ".weight", 0, t->fc_w_off + static_cast<int64_t>(row) * 2048,
+                              {k, 2048, 0, 0}});
+    row += k;
+  }
+  t->n_params = align_up(t->fc_w_off + static_cast<int64_t>(t->k_total) * 2048, 64);
+  t->fc_b_off = t->n_params;
+  row = 0;
+  for (int hI = 0; hI < t->n_heads; ++hI) {
+    const int k = t->num_classes[hI];
+    t->segs.push_back(Segment{std::string(heads[hI]) + ".bias", 0, t->fc_b_off + row, {k, 0, 0, 0}});
+    row += k;
+  }
+  t->n_params = align_up(t->fc_b_off + t->k_total, 64);
+}
+
+template <typename T>
+static int dev_alloc(io_train* t, T** p, size_t count) {
+  void* q = nullptr;
+  IO_CUDA(cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
+  t->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return IO_OK;
+}
+
+// ---- op builders ------------------------------------------------------------------------------------------------
+static void push(std::vector<TOp>& v, int kind, double flops, double bytes, int tag,
+                 std::function<int(cudaStream_t)> f) {
+  v.push_back(TOp{std::move(f), kind, flops, bytes, tag});
+}
+
+// forward convolution of unit u over `x` -> u.y (raw, no bias / ReLU)
+static int add_conv_fwd(io_train* t, const Unit& u, const __nv_bfloat16* x, int tag) {
+  const ConvDesc d{t->imgs, u.h_in, u.w_in, u.cin, u.cout, u.k, u.stride};
+  const void* w = t->w16 + u.w_off;
+  const double flops = 2.0 * t->imgs * u.h_out * u.w_out * u.k * u.k * static_cast<double>(u.cin) * u.cout;
+  const double bytes = 2.0 * t->imgs * (static_cast<double>(u.h_in) * u.w_in * u.cin + u.h_out * u.w_out * u.cout);
+  if (tn_enabled() && conv_tn_supported(d)) {
+    TnParams tp;
+    if (int rc = conv_tn_plan(&tp, d, x, w, t->zero_bias, u.y, 0)) return rc;
+    push(t->fwd, 0, flops, bytes, tag, [tp](cudaStream_t s) { return conv_tn_launch(tp, s); });
+  } else {
+    ConvParams p;
+    int bn = 0;
+    if (int rc = conv_plan(&p, &bn, d, x, w, t->zero_bias, nullptr, u.y, 0)) return rc;
+    push(t->fwd, 0, flops, bytes, tag, [p, bn](cudaStream_t s) { return conv_tc_launch(p, bn, s); });
+  }
+  return IO_OK;
+}
+
+// train-mode BN of unit u: statistics of u.y per direction group, then a = [relu](bn(y) [+ residual])
+static void add_bn_fwd(io_train* t, Unit& u, const __nv_bfloat16* residual, int relu, int tag) {
+  const int rows = t->pairs * u.h_out * u.w_out, c = u.cout;
+  const double act = 2.0 * 2 * rows * c;
+  Unit* up = &u;
+  push(t->fwd, 3, 0, act, tag, [t, up, rows, c](cudaStream_t s) -> int {
+    IO_CUDA(cudaMemsetAsync(t->red, 0, sizeof(double) * 2 * 2 * c, s));
+    if (int rc = bn_stats_launch(up->y, 2, rows, c, t->red, s)) return rc;
+    return bn_finalize_launch(t->red, 2, rows, c, t->params + up->g_off, t->params + up->b_off, 1e-5f, 0.1f, up->scale,
+                              up->shift, up->mean, up->invstd, t->stats + up->rm_off, t->stats + up->rv_off, s);
+  });
+  push(t->fwd, 3, 0, act * (residual ? 3.0 : 2.0), tag, [up, residual, rows, c, relu](cudaStream_t s) {
+    return bn_apply_launch(up->y, residual, up->a, 2, rows, c, up->scale, up->shift, relu, s);
+  });
+}
+
+// backward through BN (+ ReLU) of unit u: da -> dy (and the masked gradient g if g_out), BN parameter gradients
+static void add_bn_bwd(io_train* t, Unit& u, const __nv_bfloat16* da, __nv_bfloat16* dy, __nv_bfloat16* g_out,
+                       int relu, int tag) {
+  const int rows = t->pairs * u.h_out * u.w_out, c = u.cout;
+  const double act = 2.0 * 2 * rows * c;
+  Unit* up = &u;
+  push(t->bwd, 3, 0, act * (relu ? 3.0 : 2.0), tag, [t, up, da, rows, c, relu](cudaStream_t s) -> int {
+    IO_CUDA(cudaMemsetAsync(t->red, 0, sizeof(double) * 2 * 2 * c, s));
+    return bn_bwd_reduce_launch(da, up->a, up->y, 2, rows, c, up->mean, up->invstd, relu, t->red, s);
+  });
+  push(t->bwd, 3, 0, act * ((relu ? 3.0 : 2.0) + 1.0 + (g_out ? 1.0 : 0.0)), tag,
+       [t, up, da, dy, g_out, rows, c, relu](cudaStream_t s) {
+         return bn_bwd_apply_launch(da, up->a, up->y, dy, g_out, 2, rows, c, t->params + up->g_off, up->mean,
+                                    up->invstd, t->red, relu, t->grads + up->g_off, t->grads + up->b_off, s);
+       });
+}
+
+static int add_wgrad(io_train* t, const Unit& u, const __nv_bfloat16* x, const __nv_bfloat16* dy, int tag) {
+  WgradParams p;
+  // the plan needs the final gradient pointer, which is bound later: keep the offset and patch at launch
+  if (int rc = wgrad_plan(&p, ConvDesc{t->imgs, u.h_in, u.w_in, u.cin, u.cout, u.k, u.stride}, x, dy, nullptr))
+    return rc;
+  const int64_t off = u.w_off;
+  const double bytes = 2.0 * t->imgs * (static_cast<double>(u.h_in) * u.w_in * u.cin + u.h_out * u.w_out * u.cout) +
+                       4.0 * u.cout * u.k * u.k * u.cin;
+  push(t->bwd, 2, p.flops, bytes, tag, [t, p, off](cudaStream_t s) {
+    WgradParams q = p;
+    q.dw = t->grads + off;
+    return wgrad_launch(q, s);
+  });
+  return IO_OK;
+}
+
+// data gradient of a stride-1 convolution (1x1 or 3x3) of unit u: dx = conv^T(dy) (+ residual)
+static int add_dgrad(io_train* t, const Unit& u, int h, int w, const __nv_bfloat16* dy, const __nv_bfloat16* residual,
+                     __nv_bfloat16* dx, int tag) {
+  ConvParams p;
+  int bn = 0;
+  if (int rc = dgrad_plan(&p, &bn, t->imgs, h, w, u.cin, u.cout, u.k, dy, t->w16 + u.w_off, t->zero_bias, residual, dx))
+    return rc;
+  const double flops = 2.0 * t->imgs * h * w * u.k * u.k * static_cast<double>(u.cin) * u.cout;
+  const double bytes = 2.0 * t->imgs * h * w * (static_cast<double>(u.cin) * (residual ? 2 : 1) + u.cout);
+  push(t->bwd, 1, flops, bytes, tag, [p, bn](cudaStream_t s) { return conv_tc_launch(p, bn, s); });
+  return IO_OK;
+}
+
+static int build_graph(io_train* t) {
+  const int I = t->imgs, d = t->d;
+  // ---- buffers ----
+  size_t max_act = static_cast<size_t>(d / 2) * (d / 2) * 64;   // stem output per image
+  size_t max_z = 0;
+  for (Unit& u : t->units) {
+    const size_t out = static_cast<size_t>(u.h_out) * u.w_out * u.cout;
+    if (out > max_act) max_act = out;
+    if (u.k == 3 && u.stride == 2) max_z = std::max(max_z, static_cast<size_t>(u.h_in) * u.w_in * u.cout);
+    if (int rc = dev_alloc(t, &u.y, out * I)) return rc;
+    if (int rc = dev_alloc(t, &u.a, out * I)) return rc;
+    if (int rc = dev_alloc(t, &u.bnws, static_cast<size_t>(8) * u.cout)) return rc;
+    u.scale = u.bnws; u.shift = u.bnws + 2 * u.cout; u.mean = u.bnws + 4 * u.cout; u.invstd = u.bnws + 6 * u.cout;
+  }
+  for (int i = 0; i < 5; ++i)
+    if (int rc = dev_alloc(t, &t->gbuf[i], max_act * I)) return rc;
+  if (int rc = dev_alloc(t, &t->gbuf[5], max_z * I)) return rc;
+  if (int rc = dev_alloc(t, &t->w16, static_cast<size_t>(t->n_params))) return rc;
+  if (int rc = dev_alloc(t, &t->stem_pk, 128 * 448)) return rc;
+  if (int rc = dev_alloc(t, &t->stem_scratch, 128 * 448)) return rc;
+  if (int rc = dev_alloc(t, &t->zero_bias, 2048)) return rc;
+  IO_CUDA(cudaMemset(t->zero_bias, 0, 2048 * sizeof(float)));
+  if (int rc = dev_alloc(t, &t->red, 2 * 2 * 2048)) return rc;
+  const size_t pool_el = static_cast<size_t>(I) * (d / 4) * (d / 4) * 64;
+  if (int rc = dev_alloc(t, &t->pool_idx, pool_el)) return rc;
+  if (int rc = dev_alloc(t, &t->pool_out, pool_el)) return rc;
+  if (int rc = dev_alloc(t, &t->pooled, static_cast<size_t>(I) * 2048)) return rc;
+  if (int rc = dev_alloc(t, &t->logits, static_cast<size_t>(I) * t->k_total)) return rc;
+  if (int rc = dev_alloc(t, &t->dlogits, static_cast<size_t>(I) * t->k_total)) return rc;
+  __nv_bfloat16 *GA = t->gbuf[0], *GG = t->gbuf[1], *GY = t->gbuf[2], *GT = t->gbuf[3], *GD = t->gbuf[4],
+                *GZ = t->gbuf[5];
+
+  // ---- forward ----
+  Unit& stem = t->units[0];
+  {
+    const double flops = 2.0 * I * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
+    const double bytes = static_cast<double>(io_pair_tensor_bytes(t->pairs, d)) + 2.0 * I * (d / 2) * (d / 2) * 64;
+    Unit* sp = &stem;
+    push(t->fwd, 0, flops, bytes, 1, [t, sp](cudaStream_t s) -> int {
+      const int hw = (t->d / 2) * (t->d / 2);
+      if (tn_enabled() && stem_tn_supported(t->d)) {
+        TnParams tp;
+        if (int rc = stem_tn_plan(&tp, t->pairs, t->d, t->pair_tensor, t->stem_pk, t->zero_bias, sp->y)) return rc;
+        tp.img_mul = 1; tp.split_row_off = t->pairs * hw; tp.relu = 0;
+        return conv_tn_launch(tp, s);
+      }
+      ConvParams p;
+      int bn = 0;
+      if (int rc = stem_plan(&p, &bn, t->pairs, t->d, t->pair_tensor, t->stem_pk, t->zero_bias, sp->y)) return rc;
+      p.img_mul = 1; p.split_row_off = t->pairs * hw; p.relu = 0;
+      return conv_tc_launch(p, bn, s);
+    });
+  }
+  add_bn_fwd(t, stem, nullptr, 1, 1);
+  Unit* stem_p = &stem;
+  push(t->fwd, 3, 0, 2.0 * I * (d / 2) * (d / 2) * 64 * 1.25 + pool_el, 2, [t, stem_p](cudaStream_t s) {
+    return maxpool_fwd_idx_launch(stem_p->a, t->pool_out, t->pool_idx, t->imgs, t->d / 2, t->d / 2, 64, s);
+  });
+  const int blocks_[4] = {3, 4, 6, 3};
+  struct Blk { int c1, c2, ds, c3; const __nv_bfloat16* x; int tag; };
+  std::vector<Blk> blks;
+  size_t ui = 1;
+  const __nv_bfloat16* X = t->pool_out;
+  for (int li = 0; li < 4; ++li)
+    for (int b = 0; b < blocks_[li]; ++b) {
+      Blk k;
+      k.c1 = static_cast<int>(ui++);
+      k.c2 = static_cast<int>(ui++);
+      k.ds = (b == 0) ? static_cast<int>(ui++) : -1;
+      k.c3 = static_cast<int>(ui++);
+      k.x = X;
+      k.tag = (li + 1) * 100 + b * 10;
+      Unit &u1 = t->units[k.c1], &u2 = t->units[k.c2], &u3 = t->units[k.c3];
+      if (int rc = add_conv_fwd(t, u1, X, k.tag + 1)) return rc;
+      add_bn_fwd(t, u1, nullptr, 1, k.tag + 1);
+      if (int rc = add_conv_fwd(t, u2, u1.a, k.tag + 2)) return rc;
+      add_bn_fwd(t, u2, nullptr, 1, k.tag + 2);
+      if (int rc = add_conv_fwd(t, u3, u2.a, k.tag + 3)) return rc;
+      const __nv_bfloat16* identity = X;
+      if (k.ds >= 0) {
+        Unit& ud = t->units[k.ds];
+        if (int rc = add_conv_fwd(t, ud, X, k.tag + 4)) return rc;
+        add_bn_fwd(t, ud, nullptr, 0, k.tag + 4);
+        identity = ud.a;
+      }
+      add_bn_fwd(t, u3, identity, 1, k.tag + 3);
+      X = u3.a;
+      blks.push_back(k);
+    }
+  const Unit& last = t->units.back();
+  const int hw_final = last.h_out * last.w_out;
+  push(t->fwd, 3, 2.0 * I * 2048.0 * t->k_total, 2.0 * I * hw_final * 2048, 3, [t, X, hw_final](cudaStream_t s) {
+    return pool_fc_fwd_launch(X, hw_final, t->imgs, t->params + t->fc_w_off, t->params + t->fc_b_off, t->k_total,
+                              t->pooled, t->logits, s);
+  });
+  push(t->fwd, 4, 0, 0, 4, [t](cudaStream_t s) {
+    return loss_train_launch(t->logits, t->pairs, t->k_total, t->occ_off, t->cls_off, t->cls_k, t->occ_target,
+                             t->class_target, t->is_overlap, t->overlap_w, t->distinct_w, t->world_size,
+                             t->out_losses, t->dlogits, s);
+  });
+
+  // ---- backward ----
+  push(t->bwd, 3, 2.0 * I * 2048.0 * t->k_total * 2, 2.0 * I * hw_final * 2048, 3, [t, GA, hw_final](cudaStream_t s) {
+    return pool_fc_bwd_launch(t->dlogits, t->pooled, t->params + t->fc_w_off, hw_final, t->imgs, t->k_total,
+                              t->grads + t->fc_w_off, t->grads + t->fc_b_off, GA, s);
+  });
+  for (int bi = static_cast<int>(blks.size()) - 1; bi >= 0; --bi) {
+    const Blk& k = blks[bi];
+    Unit &u1 = t->units[k.c1], &u2 = t->units[k.c2], &u3 = t->units[k.c3];
+    // out = relu(bn3(conv3(a2)) + identity):  GA = d out  ->  GY = d y3, GG = masked gradient (identity branch)
+    add_bn_bwd(t, u3, GA, GY, GG, 1, k.tag + 3);
+    if (int rc = add_wgrad(t, u3, u2.a, GY, k.tag + 3)) return rc;
+    if (int rc = add_dgrad(t, u3, u3.h_out, u3.w_out, GY, nullptr, GT, k.tag + 3)) return rc;   // GT = d a2
+    add_bn_bwd(t, u2, GT, GY, nullptr, 1, k.tag + 2);                                          // GY = d y2
+    if (int rc = add_wgrad(t, u2, u1.a, GY, k.tag + 2)) return rc;
+    if (u2.stride == 1) {
+      if (int rc = add_dgrad(t, u2, u2.h_in, u2.w_in, GY, nullptr, GT, k.tag + 2)) return rc;  // GT = d a1
+    } else {
+      const int ho = u2.h_out, wo = u2.w_out, c = u2.cout;
+      push(t->bwd, 3, 0, 2.0 * I * ho * wo * c * 5.0, k.tag + 2, [t, GY, GZ, ho, wo, c](cudaStream_t s) {
+        return upsample2_zero_launch(GY, GZ, t->imgs, ho, wo, c, s);
+      });
+      if (int rc = add_dgrad(t, u2, u2.h_in, u2.w_in, GZ, nullptr, GT, k.tag + 2)) return rc;
+    }
+    add_bn_bwd(t, u1, GT, GY, nullptr, 1, k.tag + 1);                                          // GY = d y1
+    if (int rc = add_wgrad(t, u1, k.x, GY, k.tag + 1)) return rc;
+    if (k.ds < 0) {
+      if (int rc = add_dgrad(t, u1, u1.h_in, u1.w_in, GY, GG, GA, k.tag + 1)) return rc;       // GA = d x
+    } else {
+      Unit& ud = t->units[k.ds];
+      add_bn_bwd(t, ud, GG, GD, nullptr, 0, k.tag + 4);                                        // GD = d y_ds
+      if (int rc = add_wgrad(t, ud, k.x, GD, k.tag + 4)) return rc;
+      if (int rc = add_dgrad(t, ud, ud.h_out, ud.w_out, GD, nullptr, GG, k.tag + 4)) return rc;  // GG = low-res d x
+      if (ud.stride == 1) {
+        if (int rc = add_dgrad(t, u1, u1.h_in, u1.w_in, GY, GG, GA, k.tag + 1)) return rc;
+      } else {
+        if (int rc = add_dgrad(t, u1, u1.h_in, u1.w_in, GY, nullptr, GA, k.tag + 1)) return rc;
+        const int ho = ud.h_out, wo = ud.w_out, c = ud.cin;
+        push(t->bwd, 3, 0, 2.0 * I * ho * wo * c * 3.0, k.tag + 4, [t, GG, GA, ho, wo, c](cudaStream_t s) {
+          return scatter_add2_launch(GG, GA, t->imgs, ho, wo, c, s);
+        });
+      }
+    }
+  }
+  // max-pool, stem BN + ReLU, stem weight gradient
+  push(t->bwd, 3, 0, 2.0 * I * (d / 2) * (d / 2) * 64 * 2.0, 2, [t, GA, GT](cudaStream_t s) {
+    return maxpool_bwd_launch(GA, t->pool_idx, GT, t->imgs, t->d / 2, t->d / 2, 64, s);
+  });
+  add_bn_bwd(t, stem, GT, GY, nullptr, 1, 1);
+  {
+    const double flops = 2.0 * I * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
+    const double bytes = static_cast<double>(io_pair_tensor_bytes(t->pairs, d)) + 2.0 * I * (d / 2) * (d / 2) * 64;
+    const int64_t off = stem.w_off;
+    push(t->bwd, 2, flops, bytes, 1, [t, GY, off](cudaStream_t s) -> int {
+      IO_CUDA(cudaMemsetAsync(t->stem_scratch, 0, sizeof(float) * 128 * 448, s));
+      WgradParams p;
+      if (int rc = stem_wgrad_plan(&p, t->pairs, t->d, t->pair_tensor, GY, t->stem_scratch)) return rc;
+      if (int rc = wgrad_launch(p, s)) return rc;
+      return stem_unpack_grad_launch(t->stem_scratch, t->grads + off, s);
+    });
+  }
+  t->built = true;
+  return IO_OK;
+}
+
+static int run_ops(io_train* t, std::vector<TOp>& ops, cudaStream_t stream) {
+  for (TOp& op : ops) {
+    size_t idx = 0;
+    if (t->profile) {
+      idx = 2 * t->prof_kind.size();
+      while (t->ev.size() <= idx + 1) {
+        cudaEvent_t e;
+        IO_CUDA(cudaEventCreate(&e));
+        t->ev.push_back(e);
+      }
+      IO_CUDA(cudaEventRecord(t->ev[idx], stream));
+    }
+    if (int rc = op.run(stream)) return rc;
+    if (t->profile) {
+      IO_CUDA(cudaEventRecord(t->ev[idx + 1], stream));
+      t->prof_kind.push_back(op.kind);
+      t->prof_tag.push_back(op.tag);
+      t->prof_flops.push_back(op.flops);
+      t->prof_bytes.push_back(op.bytes);
+    }
+    ++t->last_launches;
+  }
+  return IO_OK;
+}
+
+}  // namespace io
+
+using namespace io;
+
+extern "C" int io_train_create(const int32_t* num_classes, int n_heads, int input_size, int batch_pairs,
+                               io_train_t** out) {
+  IO_REQUIRE(num_classes && out, "io_train_create: null pointer");
+  IO_REQUIRE(n_heads == 1 || n_heads == 2, "io_train_create: n_heads must be 1 or 2");
+  IO_REQUIRE(input_size >= 64 && input_size <= 512 && input_size % 32 == 0, "io_train_create: input_size %d",
+             input_size);
+  IO_REQUIRE(batch_pairs >= 1 && batch_pairs <= 1024, "io_train_create: batch_pairs %d", batch_pairs);
+  int dev_count = 0;
+  IO_CUDA(cudaGetDeviceCount(&dev_count));
+  std::unique_ptr<io_train> t(new io_train());
+  t->n_heads = n_heads;
+  for (int i = 0; i < n_heads; ++i) {
+    IO_REQUIRE(num_classes[i] >= 1 && num_classes[i] <= 4, "io_train_create: num_classes[%d] = %d", i, num_classes[i]);
+    t->num_classes[i] = num_classes[i];
+    t->k_total += num_classes[i];
+  }
+  t->d = input_size;
+  t->pairs = batch_pairs;
+  t->imgs = 2 * batch_pairs;
+  build_units(t.get());
+  *out = t.release();
+  return IO_OK;
+}
+
+extern "C" int io_train_destroy(io_train_t* t) {
+  if (!t) return IO_OK;
+  for (void* p : t->allocs) cudaFree(p);
+  for (cudaEvent_t e : t->ev) cudaEventDestroy(e);
+  delete t;
+  return IO_OK;
+}
+
+extern "C" int64_t io_train_param_count(const io_train_t* t) { return t ? t->n_params : 0; }
+extern "C" int64_t io_train_stat_count(const io_train_t* t) { return t ? t->n_stats : 0; }
+extern "C" int io_train_num_segments(const io_train_t* t) { return t ? static_cast<int>(t->segs.size()) : 0; }
+
+extern "C" int io_train_segment(const io_train_t* t, int i, char* name, int name_cap, int32_t* buffer, int64_t* offset,
+                                int32_t* dims4) {
+  IO_REQUIRE(t && name && buffer && offset && dims4, "io_train_segment: null pointer");
+  IO_REQUIRE(i >= 0 && i < static_cast<int>(t->segs.size()), "io_train_segment: index %d", i);
+  const Segment& s = t->segs[i];
+  snprintf(name, static_cast<size_t>(name_cap), "%s", s.name.c_str());
+  *buffer = s.buffer;
+  *offset = s.offset;
+  for (int k = 0; k < 4; ++k) dims4[k] = s.dims[k];
+  return IO_OK;
+}
+
+extern "C" int io_train_bind(io_train_t* t, float* params_dev, float* grads_dev, float* stats_dev) {
+  IO_REQUIRE(t && params_dev && grads_dev && stats_dev, "io_train_bind: null pointer");
+  t->params = params_dev;
+  t->grads = grads_dev;
+  t->stats = stats_dev;
+  t->weights_synced = false;
+  if (!t->built) return build_graph(t);
+  return IO_OK;
+}
+
+extern "C" int io_train_sync_weights(io_train_t* t, void* stream) {
+  IO_REQUIRE(t && t->params, "io_train_sync_weights: bind the parameter buffers first");
+  if (int rc = cast_bf16_launch(t->params, t->w16, t->n_params, as_stream(stream))) return rc;
+  if (int rc = stem_pack_launch(t->params + t->units[0].w_off, t->stem_pk, as_stream(stream))) return rc;
+  t->weights_synced = true;
+  return IO_OK;
+}
+
+extern "C" int io_train_forward_backward(io_train_t* t, const void* pair_tensor_dev, int occ_off, int class_off,
+                                         int class_k, const float* occ_target_dev, const int64_t* class_target_dev,
+                                         const int64_t* is_overlap_dev, float overlap_w, float distinct_w,
+                                         int world_size, float* out_losses_dev, int run_backward, void* stream_) {
+  IO_REQUIRE(t && pair_tensor_dev && out_losses_dev, "io_train_forward_backward: null pointer");
+  if (!t->built || !t->params) {
+    set_error("io_train_forward_backward: call io_train_bind first");
+    return IO_ERR_STATE;
+  }
+  if (!t->weights_synced) {
+    set_error("io_train_forward_backward: call io_train_sync_weights after loading / changing the parameters");
+    return IO_ERR_STATE;
+  }
+  IO_REQUIRE(occ_off < 0 || (occ_target_dev && occ_off + 2 <= t->k_total), "io_train_forward_backward: occlusion head");
+  IO_REQUIRE(class_off < 0 || (class_target_dev && class_k >= 2 && class_k <= 4 && class_off + class_k <= t->k_total),
+             "io_train_forward_backward: class head");
+  IO_REQUIRE(world_size >= 1, "io_train_forward_backward: world_size");
+  cudaStream_t stream = as_stream(stream_);
+  t->pair_tensor = pair_tensor_dev;
+  t->occ_off = occ_off; t->cls_off = class_off; t->cls_k = class_k;
+  t->occ_target = occ_target_dev; t->class_target = class_target_dev; t->is_overlap = is_overlap_dev;
+  t->overlap_w = overlap_w; t->distinct_w = distinct_w; t->world_size = world_size;
+  t->out_losses = out_losses_dev;
+  t->last_launches = 0;
+  t->prof_kind.clear(); t->prof_tag.clear(); t->prof_flops.clear(); t->prof_bytes.clear();
+  if (int rc = run_ops(t, t->fwd, stream)) return rc;
+  if (run_backward) {
+    IO_CUDA(cudaMemsetAsync(t->grads, 0, sizeof(float) * t->n_params, stream));
+    if (int rc = run_ops(t, t->bwd, stream)) return rc;
+  }
+  return IO_OK;
+}
+
+extern "C" int io_train_sgd_step(io_train_t* t, float* momentum_buf_dev, float lr, float momentum, float weight_decay,
+                                 int first_step, void* stream) {
+  IO_REQUIRE(t && t->params && momentum_buf_dev, "io_train_sgd_step: bind the buffers first");
+  if (int rc = io_optim_sgd(t->params, t->grads, momentum_buf_dev, t->n_params, lr, momentum, weight_decay, first_step,
+                            t->w16, t->n_params, stream))
+    return rc;
+  return stem_pack_launch(t->params + t->units[0].w_off, t->stem_pk, as_stream(stream));
+}
+
+extern "C" int io_train_adam_step(io_train_t* t, float* m_dev, float* v_dev, float lr, float beta1, float beta2,
+                                  float eps, int step, void* stream) {
+  IO_REQUIRE(t && t->params && m_dev && v_dev, "io_train_adam_step: bind the buffers first");
+  if (int rc = io_optim_adam(t->params, t->grads, m_dev, v_dev, t->n_params, lr, beta1, beta2, eps, step, t->w16,
+                             t->n_params, stream))
+    return rc;
+  return stem_pack_launch(t->params + t->units[0].w_off, t->stem_pk, as_stream(stream));
+}
+
+extern "C" const float* io_train_logits(const io_train_t* t) { return t ? t->logits : nullptr; }
+extern "C" int io_train_last_launches(const io_train_t* t) { return t ? t->last_launches : 0; }
+
+extern "C" int io_train_profile(io_train_t* t, int enable) {
+  IO_REQUIRE(t, "io_train_profile: null handle");
+  t->profile = enable != 0;
+  return IO_OK;
+}
+
+extern "C" int io_train_profile_read(io_train_t* t, float* ms, int32_t* kind, double* flop, double* bytes, int32_t* tag,
+                                     int max_n) {
+  IO_REQUIRE(t && ms && kind && flop, "io_train_profile_read: null pointer");
+  const int n = static_cast<int>(t->prof_kind.size());
+  for (int i = 0; i < n && i < max_n; ++i) {
+    IO_CUDA(cudaEventElapsedTime(&ms[i], t->ev[2 * i], t->ev[2 * i + 1]));
+    kind[i] = t->prof_kind[i];
+    flop[i] = t->prof_flops[i];
+    if (bytes) bytes[i] = t->prof_bytes[i];
+    if (tag) tag[i] = t->prof_tag[i];
+  }
+  return n;
+}
+
+// ---- exported single kernels for the per-kernel parity tests ------------------------------------------------
+extern "C" int io_bn_train_forward(const void* y_dev, const void* residual_dev, void* a_dev, int groups, int rows, int c,
+                                   const float* gamma_dev, const float* beta_dev, float eps, float momentum,
+                                   float* running_mean_dev, float* running_var_dev, float* save_dev,
+                                   double* scratch_dev, int relu, void* stream_) {
+  // save_dev: 4 x [groups][c] fp32 (scale, shift, mean, invstd); scratch_dev: [groups][2][c] doubles
+  IO_REQUIRE(y_dev && a_dev && gamma_dev && beta_dev && running_mean_dev && running_var_dev && save_dev && scratch_dev,
+             "io_bn_train_forward: null pointer");
+  cudaStream_t s = as_stream(stream_);
+  const size_t gc = static_cast<size_t>(groups) * c;
+  IO_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(double) * 2 * gc, s));
+  if (int rc = bn_stats_launch(y_dev, groups, rows, c, scratch_dev, s)) return rc;
+  if (int rc = bn_finalize_launch(scratch_dev, groups, rows, c, gamma_dev, beta_dev, eps, momentum, save_dev,
+                                  save_dev + gc, save_dev + 2 * gc, save_dev + 3 * gc, running_mean_dev,
+                                  running_var_dev, s))
+    return rc;
+  return bn_apply_launch(y_dev, residual_dev, a_dev, groups, rows, c, save_dev, save_dev + gc, relu, s);
+}
+
+extern "C" int io_bn_train_backward(const void* da_dev, const void* a_dev, const void* y_dev, void* dy_dev,
+                                    void* g_out_dev, int groups, int rows, int c, const float* gamma_dev,
+                                    const float* save_dev, double* scratch_dev, int relu, float* dgamma_dev,
+                                    float* dbeta_dev, void* stream_) {
+  IO_REQUIRE(da_dev && y_dev && dy_dev && gamma_dev && save_dev && scratch_dev && dgamma_dev && dbeta_dev,
+             "io_bn_train_backward: null pointer");
+  IO_REQUIRE(!relu || a_dev, "io_bn_train_backward: relu needs the activation");
+  cudaStream_t s = as_stream(stream_);
+  const size_t gc = static_cast<size_t>(groups) * c;
+  IO_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(double) * 2 * gc, s));
+  if (int rc = bn_bwd_reduce_launch(da_dev, a_dev, y_dev, groups, rows, c, save_dev + 2 * gc, save_dev + 3 * gc, relu,
+                                    scratch_dev, s))
+    return rc;
+  return bn_bwd_apply_launch(da_dev, a_dev, y_dev, dy_dev, g_out_dev, groups, rows, c, gamma_dev, save_dev + 2 * gc,
+                             save_dev + 3 * gc, scratch_dev, relu, dgamma_dev, dbeta_dev, s);
+}
+
+extern "C" int io_maxpool_train(const void* x_dev, void* y_dev, uint8_t* idx_dev, const void* dy_dev, void* dx_dev,
+                                int b, int h, int w, int c, void* stream_) {
+  IO_REQUIRE(x_dev && y_dev && idx_dev, "io_maxpool_train: null pointer");
+  if (int rc = maxpool_fwd_idx_launch(x_dev, y_dev, idx_dev, b, h, w, c, as_stream(stream_))) return rc;
+  if (dy_dev && dx_dev) return maxpool_bwd_launch(dy_dev, idx_dev, dx_dev, b, h, w, c, as_stream(stream_));
+  return IO_OK;
+}

@@ -1,0 +1,71 @@
+// Training step of the order networks (reference models/supervised_order.py:83-95 `step`, train-mode
+// models/backbone/resnet_cls.py:75-222): declarations shared by wgrad.cu, train_ew.cu and train.cu.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace io {
+
+// ---- weight gradient on tcgen05 (wgrad.cu) ------------------------------------------------------------------
+// dW[cout][tap][cin] += sum over output pixels of dy[pixel][cout] * x[pixel shifted by tap][cin]: a GEMM whose
+// contraction index is the PIXEL, so both operands are consumed MN-major straight from their NHWC tensors.
+struct WgradParams {
+  CUtensorMap map_dy;   // [rows_out][cout] bf16, box {64 channels, kp rows}
+  CUtensorMap map_x;    // forward-input view of the convolution (as ConvParams::map_a) with kp-pixel boxes
+  float* dw;            // [cout][ldw] fp32, accumulated with red.global.add (zero it first)
+  int mode;             // ConvMode of the forward convolution
+  int cout;             // GEMM M (128 for the two-direction stem)
+  int cin;              // GEMM N per filter tap (64 = 8 taps x 8 channels for the stem); also the S2 parity offset
+  int taps, taps_w, pad;
+  int ldw;
+  int m_tiles, n_tiles, bn;
+  int a_slabs;          // 64-channel slabs loaded per A stage (1 when cout == 64: upper accumulator rows unused)
+  int a_split_rows;     // stem: slab j = channels [0,64) of rows + j * a_split_rows (direction j); 0 = plain
+  int kblocks, ksplit, kp;
+  int wseg, bh, bi, bpr, bpi;   // K-block geometry: box {wseg, bh, bi} pixels, blocks per row / per image
+  int stages, smem_bytes;
+  int mn_lbo, mn_sbo;
+  double flops;
+};
+int wgrad_plan(WgradParams* p, const ConvDesc& d, const void* x, const void* dy, float* dw);
+// x = pair tensor [pairs, d+6, pitch, 8]; dy = [2][pairs][d/2][d/2][64] ([direction][pair] image order);
+// dw_scratch = [128][448] fp32 in the packed stem-GEMM layout (rows 64.. = swapped-direction weights)
+int stem_wgrad_plan(WgradParams* p, int pairs, int d, const void* x, const void* dy, float* dw_scratch);
+int wgrad_launch(const WgradParams& p, cudaStream_t stream);
+
+// ---- element-wise / reduction kernels (train_ew.cu) ---------------------------------------------------------
+// All activations NHWC bf16 viewed as [groups][rows][c]; BatchNorm statistics are per (group, channel): the two
+// directions of a training step are two separate forward passes in the reference (two BN batches).
+// stats: sums[g][0][c] = sum x, sums[g][1][c] = sum x^2 (double, zeroed by the caller)
+int bn_stats_launch(const void* y, int groups, int rows, int c, double* sums, cudaStream_t stream);
+// mean / biased var -> scale = gamma * invstd, shift = beta - mean * scale (fp32 [g][c] each), saves mean & invstd,
+// updates running_mean / running_var (momentum 0.1, unbiased variance) once per group in group order
+int bn_finalize_launch(const double* sums, int groups, int rows, int c, const float* gamma, const float* beta,
+                       float eps, float momentum, float* scale, float* shift, float* mean, float* invstd,
+                       float* running_mean, float* running_var, cudaStream_t stream);
+// a = [relu](y * scale + shift [+ residual])
+int bn_apply_launch(const void* y, const void* residual, void* a, int groups, int rows, int c, const float* scale,
+                    const float* shift, int relu, cudaStream_t stream);
+// backward of a = [relu](bn(y) [+ residual]):  g = da * (a > 0 if relu);  red[g][0][c] = sum g, red[g][1][c] =
+// sum g * xhat (double, zeroed by caller)
+int bn_bwd_reduce_launch(const void* da, const void* a, const void* y, int groups, int rows, int c, const float* mean,
+                         const float* invstd, int relu, double* red, cudaStream_t stream);
+// dy = gamma * invstd * (g - sum_g / M - xhat * sum_gx / M)  (bf16);  if g_out != nullptr also writes g (the
+// gradient flowing into the residual branch);  accumulates dgamma += sum_gx, dbeta += sum_g into the flat grads
+int bn_bwd_apply_launch(const void* da, const void* a, const void* y, void* dy, void* g_out, int groups, int rows,
+                        int c, const float* gamma, const float* mean, const float* invstd, const double* red,
+                        int relu, float* dgamma, float* dbeta, cudaStream_t stream);
+// max-pool 3x3 s2 p1 forward with arg-max (first maximum in window scan order) and its backward
+int maxpool_fwd_idx_launch(const void* x, void* y, uint8_t* idx, int b, int h, int w, int c, cudaStream_t stream);
+int maxpool_bwd_launch(const void* dy, const uint8_t* idx, void* dx, int b, int h, int w, int c, cudaStream_t stream);
+// zero-insertion up-sampling of a stride-2 gradient: z[n, 2i, 2j, :] = dy[n, i, j, :], zero elsewhere
+int upsample2_zero_launch(const void* dy, void* z, int b, int ho, int wo, int c, cudaStream_t stream);
+// dx[n, 2i, 2j, :] += d[n, i, j, :]   (data gradient of the stride-2 1x1 downsample convolution)
+int scatter_add2_launch(const void* d, void* dx, int b, int ho, int wo, int c, cudaStream_t stream);
+// average pool + FC heads: pooled [imgs][2048] fp32 (saved), logits [imgs][k] fp32
+int pool_fc_fwd_launch(const void* feat, int hw, int imgs, const float* fcw, const float* fcb, int k_total,
+                       float* pooled, float* logits, cudaStream_t stream);
+// dW_fc[k][2048] += dlogits^T pooled, db += sum dlogits, dfeat[img][hw][2048] = (dlogits W_fc) / hw  (bf16)
+int pool_fc_bwd_launch(const float* dlogits, const float* pooled, const float* fcw, int hw, int imgs, int k_total,
+                       float* dfcw, float* dfcb, void* dfeat, cudaStream_t stream);
+
+}  // namespace io
