@@ -237,8 +237,14 @@ IO_API int io_train_sgd_step(io_train_t* t, float* momentum_buf_dev, float lr, f
                              int first_step, void* stream);
 IO_API int io_train_adam_step(io_train_t* t, float* m_dev, float* v_dev, float lr, float beta1, float beta2, float eps,
                               int step, void* stream);
-/* logits of the last forward: device pointer to [2][batch_pairs][K] fp32 ([direction][pair]) */
-IO_API const float* io_train_logits(const io_train_t* t);
+/* logits of the last forward, copied (device to device) into out_dev[2][batch_pairs][K] fp32 ([direction][pair]) */
+IO_API int io_train_read_logits(const io_train_t* t, float* out_dev, void* stream);
+/* Saved tensors of the last forward (layer-by-layer parity tests): conv_name = reference module name ("conv1",
+ * "layer3.2.conv2", "layer2.0.downsample.0"), which = 0: raw convolution output, 1: activation after BN (+ residual)
+ * (+ ReLU); bf16 [2 * batch_pairs, h, w, c] in [direction][pair] image order.  numel_out receives the element count
+ * (out_dev may be NULL to query it). */
+IO_API int io_train_read_activation(const io_train_t* t, const char* conv_name, int which, void* out_dev,
+                                    int64_t* numel_out, void* stream);
 IO_API int io_train_last_launches(const io_train_t* t);
 /* per-launch CUDA-event timing as io_net_profile; kind: 0 conv forward, 1 data gradient, 2 weight gradient,
  * 3 element-wise / reduction, 4 loss */

@@ -73,7 +73,8 @@ _SIGS.update({
     "io_train_forward_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _i, _vp, _i, _vp]),
     "io_train_sgd_step": (_i, [_vp, _vp, _f, _f, _f, _i, _vp]),
     "io_train_adam_step": (_i, [_vp, _vp, _vp, _f, _f, _f, _f, _i, _vp]),
-    "io_train_logits": (_vp, [_vp]),
+    "io_train_read_logits": (_i, [_vp, _vp, _vp]),
+    "io_train_read_activation": (_i, [_vp, C.c_char_p, _i, _vp, _vp, _vp]),
     "io_train_last_launches": (_i, [_vp]),
     "io_train_profile": (_i, [_vp, _i]),
     "io_train_profile_read": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),

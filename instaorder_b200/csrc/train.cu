@@ -579,7 +579,27 @@ extern "C" int io_train_adam_step(io_train_t* t, float* m_dev, float* v_dev, flo
   return stem_pack_launch(t->params + t->units[0].w_off, t->stem_pk, as_stream(stream));
 }
 
-extern "C" const float* io_train_logits(const io_train_t* t) { return t ? t->logits : nullptr; }
+extern "C" int io_train_read_logits(const io_train_t* t, float* out_dev, void* stream) {
+  IO_REQUIRE(t && out_dev && t->logits, "io_train_read_logits: null pointer / handle not bound");
+  IO_CUDA(cudaMemcpyAsync(out_dev, t->logits, sizeof(float) * t->imgs * t->k_total, cudaMemcpyDeviceToDevice,
+                          as_stream(stream)));
+  return IO_OK;
+}
+extern "C" int io_train_read_activation(const io_train_t* t, const char* conv_name, int which, void* out_dev,
+                                        int64_t* numel_out, void* stream) {
+  IO_REQUIRE(t && conv_name && numel_out && t->built, "io_train_read_activation: null pointer / handle not bound");
+  for (const Unit& u : t->units) {
+    if (u.conv != conv_name) continue;
+    const int64_t n = static_cast<int64_t>(t->imgs) * u.h_out * u.w_out * u.cout;
+    *numel_out = n;
+    if (out_dev)
+      IO_CUDA(cudaMemcpyAsync(out_dev, which == 0 ? u.y : u.a, n * 2, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return IO_OK;
+  }
+  set_error("io_train_read_activation: no convolution named '%s'", conv_name);
+  return IO_ERR_ARG;
+}
+
 extern "C" int io_train_last_launches(const io_train_t* t) { return t ? t->last_launches : 0; }
 
 extern "C" int io_train_profile(io_train_t* t, int enable) {

@@ -1,10 +1,10 @@
 """Model wrappers with the reference's names and constructor (``models.__dict__[algo](params, load_pretrain,
 dist_model)``, reference models/supervised_order.py:18-95, 370-548 and models/single_stage_model.py:11-78).
 
-Round 1 covers the inference / validation surface: ``load_state`` / ``load_pretrain`` / ``save_state`` (reference
-``.pth.tar`` layout), ``switch_to``, ``model(x)``, ``set_input`` + ``forward_only`` (validation losses, reference
-trainer.py:218-266) and the engine handle used by ``instaorder_b200.inference``.  ``step`` (training) raises
-NotImplementedError until the backward kernels land (scope table).
+Covers ``load_state`` / ``load_pretrain`` / ``save_state`` (reference ``.pth.tar`` layout incl. the optimiser state),
+``switch_to``, ``model(x)``, ``set_input`` + ``forward_only`` (validation losses, reference trainer.py:218-266),
+``step()`` (training: train-mode BN forward of both directions, loss, backward, ONE flat gradient all-reduce,
+fused SGD / Adam) and the engine handle used by ``instaorder_b200.inference``.
 """
 import os
 
@@ -13,6 +13,7 @@ import torch
 
 from . import _lib
 from .engine import OrderEngine
+from .training import FlatOptim, TrainEngine
 
 __all__ = ["InstaOrderNet_o", "InstaOrderNet_d", "InstaOrderNet_od", "OrderNet"]
 
@@ -33,6 +34,16 @@ class _OrderModel(object):
             raise Exception("No such optimizer: {}".format(params["optim"]))   # single_stage_model.py:44
         self.num_classes = bp.get("num_classes", 2)
         self.world_size = 1
+        self.dist_model = bool(dist_model)
+        if dist_model:                                   # single_stage_model.py:28-30
+            import torch.distributed as dist
+            self.world_size = dist.get_world_size()
+        if params.get("optim", "SGD") == "SGD":          # single_stage_model.py:34-42
+            self.optim = FlatOptim("SGD", params.get("lr", 1e-4), weight_decay=params.get("weight_decay", 0.0))
+        else:
+            self.optim = FlatOptim("Adam", params.get("lr", 1e-4), beta1=params.get("beta1", 0.9))
+        self._trainer = None        # TrainEngine, created by the first step() (batch size / input size known then)
+        self._train_dirty = False   # the TrainEngine holds newer weights than self._state / the eval engines
         self.max_pairs = int(params.get("max_pairs", 256))
         self.device = params.get("device", "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0")))
         self._engines = {}
@@ -57,6 +68,19 @@ class _OrderModel(object):
         self._state = sd
         for e in self._engines.values():
             e.load_state_dict(sd)
+        if self._trainer is not None:
+            self._trainer.load_state_dict(sd)
+        self._train_dirty = False
+
+    def _sync_from_trainer(self):
+        """After training steps the fp32 masters live in the TrainEngine: export them (reference layout) for the
+        eval-mode engines and for save_state."""
+        if self._trainer is not None and self._train_dirty:
+            sd = self._trainer.state_dict()
+            self._state = sd
+            for e in self._engines.values():
+                e.load_state_dict(sd)
+            self._train_dirty = False
 
     def load_state(self, path, Iter=None, resume=False):
         """reference models/single_stage_model.py:54-61 + utils/common_utils.py:128-149."""
@@ -66,25 +90,62 @@ class _OrderModel(object):
             raise Exception("=> no checkpoint found at '{}'".format(path))
         ckpt = torch.load(path, map_location="cpu", weights_only=False)
         self.load_state_dict(ckpt["state_dict"])
+        if resume and ckpt.get("optimizer"):              # utils/common_utils.py:143-147
+            self.optim.load_state_dict(ckpt["optimizer"])
         return ckpt["step"]
 
     def load_pretrain(self, load_path):
         self.load_state(load_path)
 
     def save_state(self, path, Iter):
-        """reference models/single_stage_model.py:66-72 -- same file name and dict layout.  (No optimiser state
-        exists before the training step is built; an empty dict is stored in its place.)"""
+        """reference models/single_stage_model.py:66-72 -- same file name and dict layout
+        ({'step', 'state_dict' with the ``module.`` prefix, 'optimizer'})."""
+        self._sync_from_trainer()
         if self._state is None:
             raise RuntimeError("no weights to save")
         path = os.path.join(path, "ckpt_iter_{}.pth.tar".format(Iter))
         sd = {(k if k.startswith("module.") else "module." + k): torch.as_tensor(np.asarray(v))
               for k, v in self._state.items()}
-        torch.save({"step": Iter, "state_dict": sd, "optimizer": {}}, path)
+        torch.save({"step": Iter, "state_dict": sd, "optimizer": self.optim.state_dict()}, path)
 
     def switch_to(self, phase):
-        if phase == "train":
-            raise NotImplementedError("training mode is not built yet (round 1 = inference / validation path)")
+        """single_stage_model.py:74-78.  'eval' after training refreshes the eval-mode (folded-BN) engines."""
+        if phase != "train":
+            self._sync_from_trainer()
         self.phase = phase
+
+    # ---- training step (reference models/supervised_order.py:83-95, 413-438, 481-493, 535-548) ----------------
+    def _train_engine(self, batch, input_size):
+        t = self._trainer
+        if t is not None and (t.batch_pairs != batch or t.input_size != input_size):
+            raise RuntimeError("the training engine was built for batches of [%d, %d^2]; got [%d, %d^2] "
+                               "(the reference's DistributedGivenIterationSampler only yields full batches)" %
+                               (t.batch_pairs, t.input_size, batch, input_size))
+        if t is None:
+            if self._state is None:
+                raise RuntimeError("no weights loaded: call load_state()/load_state_dict() first")
+            t = TrainEngine(self.num_classes, input_size, batch, self.device)
+            t.load_state_dict(self._state)
+            if self.dist_model:
+                t.broadcast_params()                      # DistModule.__init__, utils/distributed_utils.py:17-24
+            self.optim.attach(t)
+            self._trainer = t
+        return t
+
+    def _step(self, occ_off, class_off, class_k, occ_target, class_target, is_overlap):
+        if self.phase != "train":
+            raise RuntimeError("step() needs switch_to('train')")
+        t = self._train_engine(int(self.rgb.shape[0]), int(self.rgb.shape[-1]))
+        t.pack_inputs(self.rgb, self.modal1, self.modal2)
+        losses = t.forward_backward(occ_off, class_off, class_k, occ_target, class_target, is_overlap,
+                                    float(self.params.get("overlap_weight", 1.0)),
+                                    float(self.params.get("distinct_weight", 1.0)), self.world_size)
+        out = losses.clone()
+        self.optim.zero_grad()
+        t.all_reduce_grads()                              # utils.average_gradients
+        self.optim.step()
+        self._train_dirty = True
+        return out
 
     # ---- model(x): eval-mode forward of an arbitrary [B,5,D,D] batch (reference resnet_cls.py:203-222) ------
     @property
@@ -94,6 +155,7 @@ class _OrderModel(object):
     def _forward_batch(self, rgb, modal1, modal2):
         """logits [B, 2, K] fp32 (both directions) for collated fp32 NCHW tensors on the device."""
         D = int(rgb.shape[-1])
+        self._sync_from_trainer()
         eng = self.engine_for(D)
         dev = eng.device
         rgb = rgb.to(dev, torch.float32).contiguous()
@@ -126,7 +188,7 @@ class _OrderModel(object):
         return out
 
     def step(self):
-        raise NotImplementedError("training step is not built yet (round 1 = inference / validation path)")
+        raise NotImplementedError
 
 
 class _ModelCallable(object):
@@ -171,6 +233,9 @@ class InstaOrderNet_o(_OrderModel):
             return {}
         return {}, {"loss": self._loss(lg, 0, -1, 0, self.occ_order1, None, None)[0]}
 
+    def step(self):                                                               # supervised_order.py:535-548
+        return {"loss": self._step(0, -1, 0, self.occ_order1, None, None)[0]}
+
 
 class InstaOrderNet_d(_OrderModel):
     algo = "InstaOrderNet_d"
@@ -187,6 +252,9 @@ class InstaOrderNet_d(_OrderModel):
         if not ret_loss:
             return {}
         return {}, {"loss": self._loss(lg, -1, 0, 3, None, self.depth_order1, None)[0]}
+
+    def step(self):                                           # supervised_order.py:413-438 (overlap / distinct weights)
+        return {"loss": self._step(-1, 0, 3, None, self.depth_order1, self.is_overlap)[0]}
 
 
 class InstaOrderNet_od(_OrderModel):
@@ -207,6 +275,10 @@ class InstaOrderNet_od(_OrderModel):
         out = self._loss(lg, 0, 2, 3, self.occ_order1, self.depth_order1, self.is_overlap)
         return {"loss_occ": out[1], "loss_depth": out[2]}, {"loss": out[0]}
 
+    def step(self):                                                               # supervised_order.py:83-95
+        out = self._step(0, 2, 3, self.occ_order1, self.depth_order1, self.is_overlap)
+        return {"loss_occ": out[1], "loss_depth": out[2]}, {"loss": out[0]}
+
 
 class OrderNet(_OrderModel):
     algo = "OrderNet"
@@ -222,3 +294,6 @@ class OrderNet(_OrderModel):
             return {}
         k = self.num_classes
         return {}, {"loss": self._loss(lg, -1, 0, int(k), None, self.occ_order1, None)[0]}
+
+    def step(self):                                                               # supervised_order.py:481-493
+        return {"loss": self._step(-1, 0, int(self.num_classes), None, self.occ_order1, None)[0]}
