@@ -270,14 +270,15 @@ IO_API int io_conv_dgrad(const void* dy_dev, int b, int h, int w, int cin, int c
 IO_API int io_stem_wgrad(const void* pair_tensor_dev, int pairs, int d, const void* dy_dev, float* dw_scratch_dev,
                          void* stream);
 /* train-mode BatchNorm over [groups][rows][c] (+ residual) (+ ReLU) and its backward; save_dev = 4 x [groups][c] fp32
- * (scale, shift, mean, invstd), scratch_dev = [groups][2][c] doubles. */
+ * (scale, shift, mean, invstd), scratch_dev = [groups][2][c] doubles.  Backward mask_mode: 0 = no ReLU, 1 = ReLU mask
+ * from the stored activation a_dev (needed when a residual was added), 2 = mask recomputed from y_dev (a_dev unused). */
 IO_API int io_bn_train_forward(const void* y_dev, const void* residual_dev, void* a_dev, int groups, int rows, int c,
                                const float* gamma_dev, const float* beta_dev, float eps, float momentum,
                                float* running_mean_dev, float* running_var_dev, float* save_dev, double* scratch_dev,
                                int relu, void* stream);
 IO_API int io_bn_train_backward(const void* da_dev, const void* a_dev, const void* y_dev, void* dy_dev, void* g_out_dev,
                                 int groups, int rows, int c, const float* gamma_dev, const float* save_dev,
-                                double* scratch_dev, int relu, float* dgamma_dev, float* dbeta_dev, void* stream);
+                                double* scratch_dev, int mask_mode, float* dgamma_dev, float* dbeta_dev, void* stream);
 /* nn.MaxPool2d(3, 2, 1) with arg-max (idx_dev: one byte per output element) and, if dy_dev / dx_dev are given, its
  * backward */
 IO_API int io_maxpool_train(const void* x_dev, void* y_dev, uint8_t* idx_dev, const void* dy_dev, void* dx_dev, int b,

@@ -47,8 +47,7 @@ struct Unit {        // one convolution + BatchNorm
   int64_t rm_off, rv_off;        // statistics offsets
   __nv_bfloat16* y = nullptr;    // raw convolution output [imgs, h_out, w_out, cout]
   __nv_bfloat16* a = nullptr;    // activation after BN (+ residual) (+ ReLU)
-  float* bnws = nullptr;         // scale, shift, mean, invstd: 4 x [2][cout]
-  float *scale, *shift, *mean, *invstd;
+  float* save = nullptr;         // [4][2][cout]: scale, shift, mean, invstd of the last forward (per direction)
 };
 
 struct TOp {
@@ -79,7 +78,9 @@ struct io_train {
   __nv_bfloat16* stem_pk = nullptr;     // [128][448] packed two-direction stem weights
   float* stem_scratch = nullptr;        // [128][448] stem wgrad accumulator
   float* zero_bias = nullptr;           // [2048] zeros
-  double* red = nullptr;                // [2][2][2048] reduction scratch
+  double* red[2] = {nullptr, nullptr};  // two [2][2][2048] reduction scratch buffers used alternately: the apply
+                                        // kernel of BatchNorm i clears the buffer BatchNorm i + 1 accumulates into
+  int red_sel = 0;                      // build-time cursor
   uint8_t* pool_idx = nullptr;
   __nv_bfloat16* pool_out = nullptr;
   float* pooled = nullptr;              // [imgs][2048]
@@ -211,31 +212,36 @@ static void add_bn_fwd(io_train* t, Unit& u, const __nv_bfloat16* residual, int 
   const int rows = t->pairs * u.h_out * u.w_out, c = u.cout;
   const double act = 2.0 * 2 * rows * c;
   Unit* up = &u;
-  push(t->fwd, 3, 0, act, tag, [t, up, rows, c](cudaStream_t s) -> int {
-    IO_CUDA(cudaMemsetAsync(t->red, 0, sizeof(double) * 2 * 2 * c, s));
-    if (int rc = bn_stats_launch(up->y, 2, rows, c, t->red, s)) return rc;
-    return bn_finalize_launch(t->red, 2, rows, c, t->params + up->g_off, t->params + up->b_off, 1e-5f, 0.1f, up->scale,
-                              up->shift, up->mean, up->invstd, t->stats + up->rm_off, t->stats + up->rv_off, s);
+  double* mine = t->red[t->red_sel];
+  double* next = t->red[t->red_sel ^ 1];
+  t->red_sel ^= 1;
+  push(t->fwd, 3, 0, act, tag, [up, rows, c, mine](cudaStream_t s) {
+    return bn_stats_launch(up->y, 2, rows, c, mine, s);
   });
-  push(t->fwd, 3, 0, act * (residual ? 3.0 : 2.0), tag, [up, residual, rows, c, relu](cudaStream_t s) {
-    return bn_apply_launch(up->y, residual, up->a, 2, rows, c, up->scale, up->shift, relu, s);
+  push(t->fwd, 3, 0, act * (residual ? 3.0 : 2.0), tag, [t, up, residual, rows, c, relu, mine, next](cudaStream_t s) {
+    return bn_apply_launch(up->y, residual, up->a, 2, rows, c, mine, t->params + up->g_off, t->params + up->b_off,
+                           1e-5f, 0.1f, up->save, t->stats + up->rm_off, t->stats + up->rv_off, next, relu, s);
   });
 }
 
-// backward through BN (+ ReLU) of unit u: da -> dy (and the masked gradient g if g_out), BN parameter gradients
+// backward through BN (+ ReLU) of unit u: da -> dy (and the masked gradient g if g_out), BN parameter gradients.
+// mask_mode: 0 none, 1 from the stored activation (residual blocks), 2 recomputed from y
 static void add_bn_bwd(io_train* t, Unit& u, const __nv_bfloat16* da, __nv_bfloat16* dy, __nv_bfloat16* g_out,
-                       int relu, int tag) {
+                       int mask_mode, int tag) {
   const int rows = t->pairs * u.h_out * u.w_out, c = u.cout;
   const double act = 2.0 * 2 * rows * c;
+  const double reads = mask_mode == 1 ? 3.0 : 2.0;
   Unit* up = &u;
-  push(t->bwd, 3, 0, act * (relu ? 3.0 : 2.0), tag, [t, up, da, rows, c, relu](cudaStream_t s) -> int {
-    IO_CUDA(cudaMemsetAsync(t->red, 0, sizeof(double) * 2 * 2 * c, s));
-    return bn_bwd_reduce_launch(da, up->a, up->y, 2, rows, c, up->mean, up->invstd, relu, t->red, s);
+  double* mine = t->red[t->red_sel];
+  double* next = t->red[t->red_sel ^ 1];
+  t->red_sel ^= 1;
+  push(t->bwd, 3, 0, act * reads, tag, [up, da, rows, c, mask_mode, mine](cudaStream_t s) {
+    return bn_bwd_reduce_launch(da, up->a, up->y, 2, rows, c, up->save, mask_mode, mine, s);
   });
-  push(t->bwd, 3, 0, act * ((relu ? 3.0 : 2.0) + 1.0 + (g_out ? 1.0 : 0.0)), tag,
-       [t, up, da, dy, g_out, rows, c, relu](cudaStream_t s) {
-         return bn_bwd_apply_launch(da, up->a, up->y, dy, g_out, 2, rows, c, t->params + up->g_off, up->mean,
-                                    up->invstd, t->red, relu, t->grads + up->g_off, t->grads + up->b_off, s);
+  push(t->bwd, 3, 0, act * (reads + 1.0 + (g_out ? 1.0 : 0.0)), tag,
+       [t, up, da, dy, g_out, rows, c, mask_mode, mine, next](cudaStream_t s) {
+         return bn_bwd_apply_launch(da, up->a, up->y, dy, g_out, 2, rows, c, t->params + up->g_off, up->save, mine,
+                                    mask_mode, t->grads + up->g_off, t->grads + up->b_off, next, s);
        });
 }
 
@@ -279,8 +285,7 @@ static int build_graph(io_train* t) {
     if (u.k == 3 && u.stride == 2) max_z = std::max(max_z, static_cast<size_t>(u.h_in) * u.w_in * u.cout);
     if (int rc = dev_alloc(t, &u.y, out * I)) return rc;
     if (int rc = dev_alloc(t, &u.a, out * I)) return rc;
-    if (int rc = dev_alloc(t, &u.bnws, static_cast<size_t>(8) * u.cout)) return rc;
-    u.scale = u.bnws; u.shift = u.bnws + 2 * u.cout; u.mean = u.bnws + 4 * u.cout; u.invstd = u.bnws + 6 * u.cout;
+    if (int rc = dev_alloc(t, &u.save, static_cast<size_t>(8) * u.cout)) return rc;
   }
   for (int i = 0; i < 5; ++i)
     if (int rc = dev_alloc(t, &t->gbuf[i], max_act * I)) return rc;
@@ -290,7 +295,10 @@ static int build_graph(io_train* t) {
   if (int rc = dev_alloc(t, &t->stem_scratch, 128 * 448)) return rc;
   if (int rc = dev_alloc(t, &t->zero_bias, 2048)) return rc;
   IO_CUDA(cudaMemset(t->zero_bias, 0, 2048 * sizeof(float)));
-  if (int rc = dev_alloc(t, &t->red, 2 * 2 * 2048)) return rc;
+  for (int i = 0; i < 2; ++i) {
+    if (int rc = dev_alloc(t, &t->red[i], 2 * 2 * 2048)) return rc;
+    IO_CUDA(cudaMemset(t->red[i], 0, sizeof(double) * 2 * 2 * 2048));
+  }
   const size_t pool_el = static_cast<size_t>(I) * (d / 4) * (d / 4) * 64;
   if (int rc = dev_alloc(t, &t->pool_idx, pool_el)) return rc;
   if (int rc = dev_alloc(t, &t->pool_out, pool_el)) return rc;
@@ -378,10 +386,10 @@ static int build_graph(io_train* t) {
     const Blk& k = blks[bi];
     Unit &u1 = t->units[k.c1], &u2 = t->units[k.c2], &u3 = t->units[k.c3];
     // out = relu(bn3(conv3(a2)) + identity):  GA = d out  ->  GY = d y3, GG = masked gradient (identity branch)
-    add_bn_bwd(t, u3, GA, GY, GG, 1, k.tag + 3);
+    add_bn_bwd(t, u3, GA, GY, GG, 1, k.tag + 3);   // mask from the stored block output
     if (int rc = add_wgrad(t, u3, u2.a, GY, k.tag + 3)) return rc;
     if (int rc = add_dgrad(t, u3, u3.h_out, u3.w_out, GY, nullptr, GT, k.tag + 3)) return rc;   // GT = d a2
-    add_bn_bwd(t, u2, GT, GY, nullptr, 1, k.tag + 2);                                          // GY = d y2
+    add_bn_bwd(t, u2, GT, GY, nullptr, 2, k.tag + 2);                                          // GY = d y2
     if (int rc = add_wgrad(t, u2, u1.a, GY, k.tag + 2)) return rc;
     if (u2.stride == 1) {
       if (int rc = add_dgrad(t, u2, u2.h_in, u2.w_in, GY, nullptr, GT, k.tag + 2)) return rc;  // GT = d a1
@@ -392,7 +400,7 @@ static int build_graph(io_train* t) {
       });
       if (int rc = add_dgrad(t, u2, u2.h_in, u2.w_in, GZ, nullptr, GT, k.tag + 2)) return rc;
     }
-    add_bn_bwd(t, u1, GT, GY, nullptr, 1, k.tag + 1);                                          // GY = d y1
+    add_bn_bwd(t, u1, GT, GY, nullptr, 2, k.tag + 1);                                          // GY = d y1
     if (int rc = add_wgrad(t, u1, k.x, GY, k.tag + 1)) return rc;
     if (k.ds < 0) {
       if (int rc = add_dgrad(t, u1, u1.h_in, u1.w_in, GY, GG, GA, k.tag + 1)) return rc;       // GA = d x
@@ -416,7 +424,7 @@ static int build_graph(io_train* t) {
   push(t->bwd, 3, 0, 2.0 * I * (d / 2) * (d / 2) * 64 * 2.0, 2, [t, GA, GT](cudaStream_t s) {
     return maxpool_bwd_launch(GA, t->pool_idx, GT, t->imgs, t->d / 2, t->d / 2, 64, s);
   });
-  add_bn_bwd(t, stem, GT, GY, nullptr, 1, 1);
+  add_bn_bwd(t, stem, GT, GY, nullptr, 2, 1);
   {
     const double flops = 2.0 * I * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
     const double bytes = static_cast<double>(io_pair_tensor_bytes(t->pairs, d)) + 2.0 * I * (d / 2) * (d / 2) * 64;
@@ -634,28 +642,25 @@ extern "C" int io_bn_train_forward(const void* y_dev, const void* residual_dev, 
   const size_t gc = static_cast<size_t>(groups) * c;
   IO_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(double) * 2 * gc, s));
   if (int rc = bn_stats_launch(y_dev, groups, rows, c, scratch_dev, s)) return rc;
-  if (int rc = bn_finalize_launch(scratch_dev, groups, rows, c, gamma_dev, beta_dev, eps, momentum, save_dev,
-                                  save_dev + gc, save_dev + 2 * gc, save_dev + 3 * gc, running_mean_dev,
-                                  running_var_dev, s))
-    return rc;
-  return bn_apply_launch(y_dev, residual_dev, a_dev, groups, rows, c, save_dev, save_dev + gc, relu, s);
+  return bn_apply_launch(y_dev, residual_dev, a_dev, groups, rows, c, scratch_dev, gamma_dev, beta_dev, eps, momentum,
+                         save_dev, running_mean_dev, running_var_dev, nullptr, relu, s);
 }
 
 extern "C" int io_bn_train_backward(const void* da_dev, const void* a_dev, const void* y_dev, void* dy_dev,
                                     void* g_out_dev, int groups, int rows, int c, const float* gamma_dev,
-                                    const float* save_dev, double* scratch_dev, int relu, float* dgamma_dev,
+                                    const float* save_dev, double* scratch_dev, int mask_mode, float* dgamma_dev,
                                     float* dbeta_dev, void* stream_) {
   IO_REQUIRE(da_dev && y_dev && dy_dev && gamma_dev && save_dev && scratch_dev && dgamma_dev && dbeta_dev,
              "io_bn_train_backward: null pointer");
-  IO_REQUIRE(!relu || a_dev, "io_bn_train_backward: relu needs the activation");
+  IO_REQUIRE(mask_mode >= 0 && mask_mode <= 2 && (mask_mode != 1 || a_dev),
+             "io_bn_train_backward: mask_mode %d (1 needs the activation)", mask_mode);
   cudaStream_t s = as_stream(stream_);
   const size_t gc = static_cast<size_t>(groups) * c;
   IO_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(double) * 2 * gc, s));
-  if (int rc = bn_bwd_reduce_launch(da_dev, a_dev, y_dev, groups, rows, c, save_dev + 2 * gc, save_dev + 3 * gc, relu,
-                                    scratch_dev, s))
+  if (int rc = bn_bwd_reduce_launch(da_dev, a_dev, y_dev, groups, rows, c, save_dev, mask_mode, scratch_dev, s))
     return rc;
-  return bn_bwd_apply_launch(da_dev, a_dev, y_dev, dy_dev, g_out_dev, groups, rows, c, gamma_dev, save_dev + 2 * gc,
-                             save_dev + 3 * gc, scratch_dev, relu, dgamma_dev, dbeta_dev, s);
+  return bn_bwd_apply_launch(da_dev, a_dev, y_dev, dy_dev, g_out_dev, groups, rows, c, gamma_dev, save_dev,
+                             scratch_dev, mask_mode, dgamma_dev, dbeta_dev, nullptr, s);
 }
 
 extern "C" int io_maxpool_train(const void* x_dev, void* y_dev, uint8_t* idx_dev, const void* dy_dev, void* dx_dev,

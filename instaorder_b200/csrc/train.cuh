@@ -18,6 +18,14 @@ struct WgradParams {
   int taps, taps_w, pad;
   int ldw;
   int m_tiles, n_tiles, bn;
+  // filter taps handled by one work item: when cin <= 128 several taps share one accumulator tile (N = ntaps * cin
+  // <= 256), so the dy tile is loaded -- and the M = 128 side of the MMA paid for -- once per group instead of once
+  // per tap
+  int ngroups;
+  int g_tap0[9], g_ntaps[9];
+  int max_b_slabs;      // B slabs per stage (largest group)
+  int acc_cols;         // TMEM columns of one accumulator (largest group's N)
+  int tmem_cols;        // allocation: 2 accumulators, power of two
   int a_slabs;          // 64-channel slabs loaded per A stage (1 when cout == 64: upper accumulator rows unused)
   int a_split_rows;     // stem: slab j = channels [0,64) of rows + j * a_split_rows (direction j); 0 = plain
   int kblocks, ksplit, kp;
@@ -35,25 +43,25 @@ int wgrad_launch(const WgradParams& p, cudaStream_t stream);
 // ---- element-wise / reduction kernels (train_ew.cu) ---------------------------------------------------------
 // All activations NHWC bf16 viewed as [groups][rows][c]; BatchNorm statistics are per (group, channel): the two
 // directions of a training step are two separate forward passes in the reference (two BN batches).
-// stats: sums[g][0][c] = sum x, sums[g][1][c] = sum x^2 (double, zeroed by the caller)
+// stats: sums[g][0][c] = sum x, sums[g][1][c] = sum x^2 (double, must be zero on entry)
 int bn_stats_launch(const void* y, int groups, int rows, int c, double* sums, cudaStream_t stream);
-// mean / biased var -> scale = gamma * invstd, shift = beta - mean * scale (fp32 [g][c] each), saves mean & invstd,
-// updates running_mean / running_var (momentum 0.1, unbiased variance) once per group in group order
-int bn_finalize_launch(const double* sums, int groups, int rows, int c, const float* gamma, const float* beta,
-                       float eps, float momentum, float* scale, float* shift, float* mean, float* invstd,
-                       float* running_mean, float* running_var, cudaStream_t stream);
-// a = [relu](y * scale + shift [+ residual])
-int bn_apply_launch(const void* y, const void* residual, void* a, int groups, int rows, int c, const float* scale,
-                    const float* shift, int relu, cudaStream_t stream);
-// backward of a = [relu](bn(y) [+ residual]):  g = da * (a > 0 if relu);  red[g][0][c] = sum g, red[g][1][c] =
-// sum g * xhat (double, zeroed by caller)
-int bn_bwd_reduce_launch(const void* da, const void* a, const void* y, int groups, int rows, int c, const float* mean,
-                         const float* invstd, int relu, double* red, cudaStream_t stream);
+// finalize + apply in one launch: mean / biased var from `sums` -> a = [relu](y * scale + shift [+ residual]);
+// block (0,0) stores save[4][groups][c] = (scale, shift, mean, invstd) for the backward pass, updates running_mean /
+// running_var (momentum, unbiased variance, once per group in group order) and zeroes `zero_me` (optional: the sums
+// buffer the NEXT BatchNorm will accumulate into -- never the one being read)
+int bn_apply_launch(const void* y, const void* residual, void* a, int groups, int rows, int c, const double* sums,
+                    const float* gamma, const float* beta, float eps, float momentum, float* save, float* running_mean,
+                    float* running_var, double* zero_me, int relu, cudaStream_t stream);
+// backward of a = [relu](bn(y) [+ residual]):  g = da * mask;  red[g][0][c] = sum g, red[g][1][c] = sum g * xhat
+// (double, must be zero on entry).  mask_mode 0: none, 1: a > 0 (stored activation), 2: y * scale + shift > 0
+int bn_bwd_reduce_launch(const void* da, const void* a, const void* y, int groups, int rows, int c, const float* save,
+                         int mask_mode, double* red, cudaStream_t stream);
 // dy = gamma * invstd * (g - sum_g / M - xhat * sum_gx / M)  (bf16);  if g_out != nullptr also writes g (the
-// gradient flowing into the residual branch);  accumulates dgamma += sum_gx, dbeta += sum_g into the flat grads
+// gradient flowing into the residual branch);  accumulates dgamma += sum_gx, dbeta += sum_g into the flat grads;
+// zeroes `zero_me` (optional, as above)
 int bn_bwd_apply_launch(const void* da, const void* a, const void* y, void* dy, void* g_out, int groups, int rows,
-                        int c, const float* gamma, const float* mean, const float* invstd, const double* red,
-                        int relu, float* dgamma, float* dbeta, cudaStream_t stream);
+                        int c, const float* gamma, const float* save, const double* red, int mask_mode, float* dgamma,
+                        float* dbeta, double* zero_me, cudaStream_t stream);
 // max-pool 3x3 s2 p1 forward with arg-max (first maximum in window scan order) and its backward
 int maxpool_fwd_idx_launch(const void* x, void* y, uint8_t* idx, int b, int h, int w, int c, cudaStream_t stream);
 int maxpool_bwd_launch(const void* dy, const uint8_t* idx, void* dx, int b, int h, int w, int c, cudaStream_t stream);

@@ -32,7 +32,9 @@ __device__ __forceinline__ uint4 pack8(const Vec8& f) {
 }
 
 // Geometry of the "slab" kernels: a block owns rows [slab * slab_rows, +slab_rows) of one group; thread t owns
-// channel vector (t % lanes_c) [+ k * lanes_c] and starts at row t / lanes_c, stepping rows_par rows.
+// channel vector t % lanes_c and rows (t / lanes_c) + k * rows_par of the slab.  Slabs are kept small (16 row steps
+// per thread, 32-64 KB per tensor) so that even the small late layers give hundreds of blocks, and every thread keeps
+// 2-4 independent 16-byte loads per tensor in flight.
 struct Slab {
   int c8, lanes_c, rows_par, slab_rows, slabs;
 };
@@ -41,7 +43,7 @@ static Slab slab_geom(int rows, int c) {
   s.c8 = c / 8;
   s.lanes_c = s.c8 < 256 ? s.c8 : 256;
   s.rows_par = 256 / s.lanes_c;
-  s.slab_rows = s.rows_par * 64;
+  s.slab_rows = s.rows_par * 16;
   s.slabs = (rows + s.slab_rows - 1) / s.slab_rows;
   return s;
 }
@@ -49,7 +51,7 @@ static Slab slab_geom(int rows, int c) {
 // block-level reduction of NV per-thread 8-vectors over the rows_par threads that share a channel vector, followed by
 // one double atomicAdd per channel: out[(g * NV + i) * C + c]
 template <int NV>
-__device__ __forceinline__ void slab_reduce_store(float (&acc)[NV][8], int lanes_c, int rows_par, int cv, int g, int c,
+__device__ __forceinline__ void slab_reduce_store(float (&acc)[NV][8], int lanes_c, int rows_par, int g, int c,
                                                   double* out) {
   __shared__ float red[256][NV * 8 + 1];
   const int t = threadIdx.x;
@@ -58,7 +60,6 @@ __device__ __forceinline__ void slab_reduce_store(float (&acc)[NV][8], int lanes
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[t][i * 8 + j] = acc[i][j];
   __syncthreads();
-  // thread (cv, j) pairs: lanes_c * 8 channels, NV values each
   for (int idx = t; idx < lanes_c * 8 * NV; idx += 256) {
     const int i = idx / (lanes_c * 8);
     const int rem = idx - i * lanes_c * 8;
@@ -67,8 +68,25 @@ __device__ __forceinline__ void slab_reduce_store(float (&acc)[NV][8], int lanes
     for (int r = 0; r < rows_par; ++r) s += red[r * lanes_c + lc][i * 8 + j];
     atomicAdd(out + (static_cast<size_t>(g) * NV + i) * c + lc * 8 + j, static_cast<double>(s));
   }
-  (void)cv;
-  __syncthreads();
+}
+
+// batch statistics -> per-channel BN coefficients of one (group, channel)
+struct BnCoef {
+  float mean, invstd, scale, shift;
+  double var;
+};
+__device__ __forceinline__ BnCoef bn_coef(const double* sums, int g, int c, int ch, double m, float gamma, float beta,
+                                          float eps) {
+  BnCoef k;
+  const double mean = sums[(static_cast<size_t>(g) * 2 + 0) * c + ch] / m;
+  double var = sums[(static_cast<size_t>(g) * 2 + 1) * c + ch] / m - mean * mean;
+  if (var < 0.0) var = 0.0;
+  k.var = var;
+  k.mean = static_cast<float>(mean);
+  k.invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  k.scale = gamma * k.invstd;
+  k.shift = beta - k.mean * k.scale;
+  return k;
 }
 
 }  // namespace
@@ -83,18 +101,25 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const uint4* __restrict__
   const int lc = t % s.lanes_c, roff = t / s.lanes_c;
   const int r0 = blockIdx.x * s.slab_rows;
   const int r1 = min(r0 + s.slab_rows, rows);
-  for (int cv = lc; cv < s.c8; cv += s.lanes_c) {   // one pass for every C <= 2048
-    float acc[2][8];
+  float acc[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
-    const uint4* base = y + (static_cast<size_t>(g) * rows) * s.c8 + cv;
-    for (int r = r0 + roff; r < r1; r += s.rows_par) {
-      const Vec8 f = unpack8(__ldg(base + static_cast<size_t>(r) * s.c8));
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  const uint4* base = y + (static_cast<size_t>(g) * rows) * s.c8 + lc;
+  for (int r = r0 + roff; r < r1; r += 4 * s.rows_par) {
+    uint4 v[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { acc[0][j] += f.v[j]; acc[1][j] += f.v[j] * f.v[j]; }
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + u * s.rows_par;
+      v[u] = rr < r1 ? __ldg(base + static_cast<size_t>(rr) * s.c8) : make_uint4(0, 0, 0, 0);
     }
-    slab_reduce_store<2>(acc, s.lanes_c, s.rows_par, cv, g, c, sums + (cv - lc) * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const Vec8 f = unpack8(v[u]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[0][j] += f.v[j]; acc[1][j] = fmaf(f.v[j], f.v[j], acc[1][j]); }
+    }
   }
+  slab_reduce_store<2>(acc, s.lanes_c, s.rows_par, g, c, sums);
 }
 
 int bn_stats_launch(const void* y, int groups, int rows, int c, double* sums, cudaStream_t stream) {
@@ -105,161 +130,191 @@ int bn_stats_launch(const void* y, int groups, int rows, int c, double* sums, cu
   return IO_OK;
 }
 
-__global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restrict__ sums, int groups, int rows, int c,
-                                                          const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, float eps, float momentum,
-                                                          float* __restrict__ scale, float* __restrict__ shift,
-                                                          float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                                          float* __restrict__ running_mean,
-                                                          float* __restrict__ running_var) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  float rm = running_mean[ch], rv = running_var[ch];
-  const double m = static_cast<double>(rows);
-  for (int g = 0; g < groups; ++g) {
-    const double mean = sums[(static_cast<size_t>(g) * 2 + 0) * c + ch] / m;
-    double var = sums[(static_cast<size_t>(g) * 2 + 1) * c + ch] / m - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float sc = gamma[ch] * invstd;
-    scale[g * c + ch] = sc;
-    shift[g * c + ch] = beta[ch] - static_cast<float>(mean) * sc;
-    mean_out[g * c + ch] = static_cast<float>(mean);
-    invstd_out[g * c + ch] = invstd;
-    // nn.BatchNorm2d: running = (1 - momentum) * running + momentum * batch (unbiased variance), one update per pass
-    const double unbiased = rows > 1 ? var * m / (m - 1.0) : var;
-    rm = (1.0f - momentum) * rm + momentum * static_cast<float>(mean);
-    rv = (1.0f - momentum) * rv + momentum * static_cast<float>(unbiased);
-  }
-  running_mean[ch] = rm;
-  running_var[ch] = rv;
-}
-
-int bn_finalize_launch(const double* sums, int groups, int rows, int c, const float* gamma, const float* beta,
-                       float eps, float momentum, float* scale, float* shift, float* mean, float* invstd,
-                       float* running_mean, float* running_var, cudaStream_t stream) {
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, groups, rows, c, gamma, beta, eps, momentum, scale,
-                                                          shift, mean, invstd, running_mean, running_var);
-  IO_CUDA(cudaGetLastError());
-  return IO_OK;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// BatchNorm apply (+ residual) (+ ReLU)
+// BatchNorm finalize + apply (+ residual) (+ ReLU), one launch: every block derives the coefficients of its 8-channel
+// vectors from the batch sums; block (0, 0) also stores them for the backward pass ([4][groups][c]: scale, shift,
+// mean, invstd), updates running_mean / running_var (momentum, unbiased variance; one update per group, in group
+// order, as the reference's two forward passes do) and clears `zero_me` (the sums buffer of the NEXT BatchNorm).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res,
-                                                       uint4* __restrict__ a, int rows, Slab s,
-                                                       const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, int c, int relu) {
+                                                       uint4* __restrict__ a, int groups, int rows, int c, Slab s,
+                                                       const double* __restrict__ sums,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, float momentum, float* __restrict__ save,
+                                                       float* __restrict__ running_mean,
+                                                       float* __restrict__ running_var, double* __restrict__ zero_me,
+                                                       int relu) {
   const int g = blockIdx.y;
   const int t = threadIdx.x;
+  const double m = static_cast<double>(rows);
+  if (blockIdx.x == 0 && g == 0) {
+    const size_t gc = static_cast<size_t>(groups) * c;
+    for (int ch = t; ch < c; ch += 256) {
+      float rm = running_mean[ch], rv = running_var[ch];
+      const float ga = gamma[ch], be = beta[ch];
+      for (int q = 0; q < groups; ++q) {
+        const BnCoef k = bn_coef(sums, q, c, ch, m, ga, be, eps);
+        save[0 * gc + q * c + ch] = k.scale;
+        save[1 * gc + q * c + ch] = k.shift;
+        save[2 * gc + q * c + ch] = k.mean;
+        save[3 * gc + q * c + ch] = k.invstd;
+        const double unbiased = rows > 1 ? k.var * m / (m - 1.0) : k.var;
+        rm = (1.0f - momentum) * rm + momentum * k.mean;
+        rv = (1.0f - momentum) * rv + momentum * static_cast<float>(unbiased);
+      }
+      running_mean[ch] = rm;
+      running_var[ch] = rv;
+    }
+    if (zero_me != nullptr)
+      for (int i = t; i < groups * 2 * c; i += 256) zero_me[i] = 0.0;
+  }
   const int lc = t % s.lanes_c, roff = t / s.lanes_c;
   const int r0 = blockIdx.x * s.slab_rows;
   const int r1 = min(r0 + s.slab_rows, rows);
-  for (int cv = lc; cv < s.c8; cv += s.lanes_c) {
-    float sc[8], sh[8];
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = __ldg(scale + g * c + cv * 8 + j);
-      sh[j] = __ldg(shift + g * c + cv * 8 + j);
+  for (int j = 0; j < 8; ++j) {
+    const int ch = lc * 8 + j;
+    const BnCoef k = bn_coef(sums, g, c, ch, m, __ldg(gamma + ch), __ldg(beta + ch), eps);
+    sc[j] = k.scale;
+    sh[j] = k.shift;
+  }
+  const size_t base = (static_cast<size_t>(g) * rows) * s.c8 + lc;
+  for (int r = r0 + roff; r < r1; r += 4 * s.rows_par) {
+    uint4 v[4], w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + u * s.rows_par;
+      if (rr < r1) {
+        const size_t o = base + static_cast<size_t>(rr) * s.c8;
+        v[u] = __ldg(y + o);
+        if (res != nullptr) w[u] = __ldg(res + o);
+      }
     }
-    const size_t base = (static_cast<size_t>(g) * rows) * s.c8 + cv;
-    for (int r = r0 + roff; r < r1; r += s.rows_par) {
-      const size_t o = base + static_cast<size_t>(r) * s.c8;
-      Vec8 f = unpack8(__ldg(y + o));
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f.v[j] = f.v[j] * sc[j] + sh[j];
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + u * s.rows_par;
+      if (rr >= r1) continue;
+      Vec8 f = unpack8(v[u]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
       if (res != nullptr) {
-        const Vec8 rr = unpack8(__ldg(res + o));
+        const Vec8 rv = unpack8(w[u]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f.v[j] += rr.v[j];
+        for (int j = 0; j < 8; ++j) f.v[j] += rv.v[j];
       }
       if (relu) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) f.v[j] = fmaxf(f.v[j], 0.f);
       }
-      a[o] = pack8(f);
+      a[base + static_cast<size_t>(rr) * s.c8] = pack8(f);
     }
   }
 }
 
-int bn_apply_launch(const void* y, const void* residual, void* a, int groups, int rows, int c, const float* scale,
-                    const float* shift, int relu, cudaStream_t stream) {
+int bn_apply_launch(const void* y, const void* residual, void* a, int groups, int rows, int c, const double* sums,
+                    const float* gamma, const float* beta, float eps, float momentum, float* save, float* running_mean,
+                    float* running_var, double* zero_me, int relu, cudaStream_t stream) {
   IO_REQUIRE(c % 8 == 0 && c <= 2048 && rows > 0, "bn_apply: bad shape");
   const Slab s = slab_geom(rows, c);
-  bn_apply_kernel<<<dim3(s.slabs, groups), 256, 0, stream>>>(reinterpret_cast<const uint4*>(y),
-                                                             reinterpret_cast<const uint4*>(residual),
-                                                             reinterpret_cast<uint4*>(a), rows, s, scale, shift, c,
-                                                             relu);
+  bn_apply_kernel<<<dim3(s.slabs, groups), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(residual), reinterpret_cast<uint4*>(a), groups,
+      rows, c, s, sums, gamma, beta, eps, momentum, save, running_mean, running_var, zero_me, relu);
   IO_CUDA(cudaGetLastError());
   return IO_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// BatchNorm backward (through the optional ReLU):  g = da * (a > 0)
+// BatchNorm backward (through the optional ReLU):  g = da * mask
+//   mask_mode 0: no ReLU;  1: mask = (a > 0) read from the stored activation (residual blocks);
+//             2: mask = (y * scale + shift > 0) recomputed from the raw convolution output with the forward pass's
+//                own fp32 expression (no residual) -- saves reading `a`
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a,
-                                                            const uint4* __restrict__ y, int rows, int c, Slab s,
-                                                            const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd, int relu,
+                                                            const uint4* __restrict__ y, int groups, int rows, int c,
+                                                            Slab s, const float* __restrict__ save, int mask_mode,
                                                             double* __restrict__ red) {
   const int g = blockIdx.y;
   const int t = threadIdx.x;
   const int lc = t % s.lanes_c, roff = t / s.lanes_c;
   const int r0 = blockIdx.x * s.slab_rows;
   const int r1 = min(r0 + s.slab_rows, rows);
-  for (int cv = lc; cv < s.c8; cv += s.lanes_c) {
-    float mu[8], is[8];
+  const size_t gc = static_cast<size_t>(groups) * c;
+  float sc[8], sh[8], mu[8], is[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mu[j] = __ldg(mean + g * c + cv * 8 + j);
-      is[j] = __ldg(invstd + g * c + cv * 8 + j);
+  for (int j = 0; j < 8; ++j) {
+    const int ch = g * c + lc * 8 + j;
+    sc[j] = __ldg(save + ch);
+    sh[j] = __ldg(save + gc + ch);
+    mu[j] = __ldg(save + 2 * gc + ch);
+    is[j] = __ldg(save + 3 * gc + ch);
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  const size_t base = (static_cast<size_t>(g) * rows) * s.c8 + lc;
+  for (int r = r0 + roff; r < r1; r += 2 * s.rows_par) {
+    uint4 vd[2], vy[2], va[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rr = r + u * s.rows_par;
+      if (rr < r1) {
+        const size_t o = base + static_cast<size_t>(rr) * s.c8;
+        vd[u] = __ldg(da + o);
+        vy[u] = __ldg(y + o);
+        if (mask_mode == 1) va[u] = __ldg(a + o);
+      } else {
+        vd[u] = make_uint4(0, 0, 0, 0);
+        vy[u] = make_uint4(0, 0, 0, 0);
+        va[u] = make_uint4(0, 0, 0, 0);
+      }
     }
-    float acc[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
-    const size_t base = (static_cast<size_t>(g) * rows) * s.c8 + cv;
-    for (int r = r0 + roff; r < r1; r += s.rows_par) {
-      const size_t o = base + static_cast<size_t>(r) * s.c8;
-      Vec8 gd = unpack8(__ldg(da + o));
-      if (relu) {
-        const Vec8 av = unpack8(__ldg(a + o));
+    for (int u = 0; u < 2; ++u) {
+      Vec8 gd = unpack8(vd[u]);
+      const Vec8 yv = unpack8(vy[u]);
+      if (mask_mode == 1) {
+        const Vec8 av = unpack8(va[u]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gd.v[j] = av.v[j] > 0.f ? gd.v[j] : 0.f;
+      } else if (mask_mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gd.v[j] = fmaf(yv.v[j], sc[j], sh[j]) > 0.f ? gd.v[j] : 0.f;
       }
-      const Vec8 yv = unpack8(__ldg(y + o));
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         acc[0][j] += gd.v[j];
-        acc[1][j] += gd.v[j] * ((yv.v[j] - mu[j]) * is[j]);
+        acc[1][j] = fmaf(gd.v[j], (yv.v[j] - mu[j]) * is[j], acc[1][j]);
       }
     }
-    slab_reduce_store<2>(acc, s.lanes_c, s.rows_par, cv, g, c, red + (cv - lc) * 8);
   }
+  slab_reduce_store<2>(acc, s.lanes_c, s.rows_par, g, c, red);
 }
 
-int bn_bwd_reduce_launch(const void* da, const void* a, const void* y, int groups, int rows, int c, const float* mean,
-                         const float* invstd, int relu, double* red, cudaStream_t stream) {
+int bn_bwd_reduce_launch(const void* da, const void* a, const void* y, int groups, int rows, int c, const float* save,
+                         int mask_mode, double* red, cudaStream_t stream) {
   IO_REQUIRE(c % 8 == 0 && c <= 2048 && rows > 0, "bn_bwd_reduce: bad shape");
   const Slab s = slab_geom(rows, c);
   bn_bwd_reduce_kernel<<<dim3(s.slabs, groups), 256, 0, stream>>>(
-      reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(y), rows, c,
-      s, mean, invstd, relu, red);
+      reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(y), groups,
+      rows, c, s, save, mask_mode, red);
   IO_CUDA(cudaGetLastError());
   return IO_OK;
 }
 
+// dy = gamma * invstd * (g - sum_g / M - xhat * sum_gx / M); optionally also writes g; block (0, 0) accumulates
+// dgamma / dbeta (summed over the groups: both forward passes share the parameters) and clears `zero_me`
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a,
                                                            const uint4* __restrict__ y, uint4* __restrict__ dy,
                                                            uint4* __restrict__ g_out, int groups, int rows, int c,
                                                            Slab s, const float* __restrict__ gamma,
-                                                           const float* __restrict__ mean,
-                                                           const float* __restrict__ invstd,
-                                                           const double* __restrict__ red, int relu,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                           const float* __restrict__ save,
+                                                           const double* __restrict__ red, int mask_mode,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           double* __restrict__ zero_me) {
   const int g = blockIdx.y;
   const int t = threadIdx.x;
-  if (blockIdx.x == 0 && g == 0) {   // parameter gradients: summed over the groups (both forward passes share gamma)
+  if (blockIdx.x == 0 && g == 0) {
     for (int ch = t; ch < c; ch += 256) {
       double sg = 0.0, sgx = 0.0;
       for (int q = 0; q < groups; ++q) {
@@ -269,33 +324,55 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
       dbeta[ch] += static_cast<float>(sg);
       dgamma[ch] += static_cast<float>(sgx);
     }
+    if (zero_me != nullptr)
+      for (int i = t; i < groups * 2 * c; i += 256) zero_me[i] = 0.0;
   }
   const int lc = t % s.lanes_c, roff = t / s.lanes_c;
   const int r0 = blockIdx.x * s.slab_rows;
   const int r1 = min(r0 + s.slab_rows, rows);
   const float inv_m = 1.0f / static_cast<float>(rows);
-  for (int cv = lc; cv < s.c8; cv += s.lanes_c) {
-    float mu[8], is[8], k1[8], k2[8], k3[8];
+  const size_t gc = static_cast<size_t>(groups) * c;
+  float sc[8], sh[8], mu[8], is[8], k1[8], k2[8], k3[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = cv * 8 + j;
-      mu[j] = __ldg(mean + g * c + ch);
-      is[j] = __ldg(invstd + g * c + ch);
-      k1[j] = __ldg(gamma + ch) * is[j];
-      k2[j] = static_cast<float>(red[(static_cast<size_t>(g) * 2 + 0) * c + ch]) * inv_m;
-      k3[j] = static_cast<float>(red[(static_cast<size_t>(g) * 2 + 1) * c + ch]) * inv_m;
+  for (int j = 0; j < 8; ++j) {
+    const int ch = lc * 8 + j;
+    sc[j] = __ldg(save + g * c + ch);
+    sh[j] = __ldg(save + gc + g * c + ch);
+    mu[j] = __ldg(save + 2 * gc + g * c + ch);
+    is[j] = __ldg(save + 3 * gc + g * c + ch);
+    k1[j] = __ldg(gamma + ch) * is[j];
+    k2[j] = static_cast<float>(red[(static_cast<size_t>(g) * 2 + 0) * c + ch]) * inv_m;
+    k3[j] = static_cast<float>(red[(static_cast<size_t>(g) * 2 + 1) * c + ch]) * inv_m;
+  }
+  const size_t base = (static_cast<size_t>(g) * rows) * s.c8 + lc;
+  for (int r = r0 + roff; r < r1; r += 2 * s.rows_par) {
+    uint4 vd[2], vy[2], va[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rr = r + u * s.rows_par;
+      if (rr < r1) {
+        const size_t o = base + static_cast<size_t>(rr) * s.c8;
+        vd[u] = __ldg(da + o);
+        vy[u] = __ldg(y + o);
+        if (mask_mode == 1) va[u] = __ldg(a + o);
+      }
     }
-    const size_t base = (static_cast<size_t>(g) * rows) * s.c8 + cv;
-    for (int r = r0 + roff; r < r1; r += s.rows_par) {
-      const size_t o = base + static_cast<size_t>(r) * s.c8;
-      Vec8 gd = unpack8(__ldg(da + o));
-      if (relu) {
-        const Vec8 av = unpack8(__ldg(a + o));
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rr = r + u * s.rows_par;
+      if (rr >= r1) continue;
+      const size_t o = base + static_cast<size_t>(rr) * s.c8;
+      Vec8 gd = unpack8(vd[u]);
+      const Vec8 yv = unpack8(vy[u]);
+      if (mask_mode == 1) {
+        const Vec8 av = unpack8(va[u]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gd.v[j] = av.v[j] > 0.f ? gd.v[j] : 0.f;
+      } else if (mask_mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gd.v[j] = fmaf(yv.v[j], sc[j], sh[j]) > 0.f ? gd.v[j] : 0.f;
       }
       if (g_out != nullptr) g_out[o] = pack8(gd);
-      const Vec8 yv = unpack8(__ldg(y + o));
       Vec8 out;
 #pragma unroll
       for (int j = 0; j < 8; ++j) out.v[j] = k1[j] * (gd.v[j] - k2[j] - (yv.v[j] - mu[j]) * is[j] * k3[j]);
@@ -305,14 +382,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
 }
 
 int bn_bwd_apply_launch(const void* da, const void* a, const void* y, void* dy, void* g_out, int groups, int rows,
-                        int c, const float* gamma, const float* mean, const float* invstd, const double* red, int relu,
-                        float* dgamma, float* dbeta, cudaStream_t stream) {
+                        int c, const float* gamma, const float* save, const double* red, int mask_mode, float* dgamma,
+                        float* dbeta, double* zero_me, cudaStream_t stream) {
   IO_REQUIRE(c % 8 == 0 && c <= 2048 && rows > 0, "bn_bwd_apply: bad shape");
   const Slab s = slab_geom(rows, c);
   bn_bwd_apply_kernel<<<dim3(s.slabs, groups), 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(y),
-      reinterpret_cast<uint4*>(dy), reinterpret_cast<uint4*>(g_out), groups, rows, c, s, gamma, mean, invstd, red, relu,
-      dgamma, dbeta);
+      reinterpret_cast<uint4*>(dy), reinterpret_cast<uint4*>(g_out), groups, rows, c, s, gamma, save, red, mask_mode,
+      dgamma, dbeta, zero_me);
   IO_CUDA(cudaGetLastError());
   return IO_OK;
 }

@@ -12,11 +12,14 @@
 // strided / padded input window of a tap is the same TMA view the forward convolution uses (OOB zero fill = the
 // convolution's zero padding), only with kp-pixel boxes.
 //
-// Work item = (K slice, filter tap, M tile, N tile), K slice slowest so that CTAs running at the same time read the
-// same pixels (the 9 taps and the M / N tiles of a K slice re-read them from L2, not HBM).  Partial sums of the K
-// slices are combined with vector fp32 reductions (red.global.add.v4.f32) into the flat gradient buffer.
+// Work item = (K slice, tap group, M tile, N tile), K slice slowest so that CTAs running at the same time read the
+// same pixels (the taps and the M / N tiles of a K slice re-read them from L2, not HBM).  A tap group is as many
+// filter taps as fit one accumulator tile (N = taps x cin <= 256: 3 taps for cin = 64, 2 for cin = 128, 4 + 3 filter
+// rows for the stem), so the dy slab is loaded once per group.  The K range is cut into just enough slices to fill
+// the SMs once: every item ends by adding its fp32 tile into the flat gradient buffer with vector reductions
+// (red.global.add.v4.f32), and that L2-atomic traffic (items x tile) is the cost to minimise.
 // Persistent CTAs, warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2..5 = epilogue; smem ring of
-// {2 A slabs, bn/64 B slabs} of 8 KB; two TMEM accumulators.
+// {2 A slabs, up to 4 B slabs} of 8 KB; two TMEM accumulators.
 #include "train.cuh"
 
 namespace io {
@@ -53,8 +56,8 @@ __device__ __forceinline__ KCoord kblock_coord(const WgradParams& p, int kb) {
 __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_slabs = p.bn / 64;
-  const int stage_bytes = A_BYTES + b_slabs * SLAB;
+  const int slabs_per_tap = p.bn / 64;
+  const int stage_bytes = A_BYTES + p.max_b_slabs * SLAB;
   const int n_stages = p.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
   uint64_t* empty = full + 8;
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = 2 * p.bn;
+  const uint32_t tmem_cols = p.tmem_cols;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.map_dy);
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int per_slice = p.taps * p.m_tiles * p.n_tiles;
+  const int per_slice = p.ngroups * p.m_tiles * p.n_tiles;
   const int items = p.ksplit * per_slice;
 
   if (warp == 0) {
@@ -95,17 +98,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = static_cast<uint32_t>(p.a_slabs + b_slabs) * p.kp * 128;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int ks = item / per_slice;
         int rem = item - ks * per_slice;
-        const int tap = rem / (p.m_tiles * p.n_tiles);
-        rem -= tap * p.m_tiles * p.n_tiles;
+        const int grp = rem / (p.m_tiles * p.n_tiles);
+        rem -= grp * p.m_tiles * p.n_tiles;
         const int m_tile = rem / p.n_tiles, n_tile = rem - m_tile * p.n_tiles;
         const int k0 = static_cast<int>(static_cast<int64_t>(ks) * p.kblocks / p.ksplit);
         const int k1 = static_cast<int>(static_cast<int64_t>(ks + 1) * p.kblocks / p.ksplit);
-        const int r = tap / p.taps_w, s = tap - r * p.taps_w;
-        const int dr = r - p.pad, ds = s - p.pad;
+        const int tap0 = p.g_tap0[grp], ntaps = p.g_ntaps[grp];
+        const uint32_t tx = static_cast<uint32_t>(p.a_slabs + ntaps * slabs_per_tap) * p.kp * 128;
         for (int kb = k0; kb < k1; ++kb) {
           const KCoord c = kblock_coord(p, kb);
           mbar_wait(&empty[stage], phase ^ 1);
@@ -116,9 +118,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
             if (p.a_split_rows) tma_load_2d(dA + j * SLAB, &p.map_dy, &full[stage], 0, c.row0 + j * p.a_split_rows);
             else tma_load_2d(dA + j * SLAB, &p.map_dy, &full[stage], m_tile * 128 + j * 64, c.row0);
           }
-          for (int j = 0; j < b_slabs; ++j) {
+          for (int jj = 0; jj < ntaps * slabs_per_tap; ++jj) {
+            const int tj = jj / slabs_per_tap, j = jj - tj * slabs_per_tap;
+            const int tap = tap0 + tj;
+            const int r = tap / p.taps_w, s = tap - r * p.taps_w;
+            const int dr = r - p.pad, ds = s - p.pad;
             const int ch = n_tile * p.bn + j * 64;
-            uint8_t* dst = dB + j * SLAB;
+            uint8_t* dst = dB + jj * SLAB;
             if (p.mode == CONV_GEMM) {
               tma_load_2d(dst, &p.map_x, &full[stage], ch, c.row0);
             } else if (p.mode == CONV_S1) {
@@ -138,20 +144,21 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.bn) | UMMA_A_MN | UMMA_B_MN;
       const int ksteps = p.kp / 16;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const int ks = item / per_slice;
+        const int grp = (item - ks * per_slice) / (p.m_tiles * p.n_tiles);
+        const uint32_t idesc = umma_idesc_bf16(128, p.g_ntaps[grp] * p.bn) | UMMA_A_MN | UMMA_B_MN;
         const int k0 = static_cast<int>(static_cast<int64_t>(ks) * p.kblocks / p.ksplit);
         const int k1 = static_cast<int>(static_cast<int64_t>(ks + 1) * p.kblocks / p.ksplit);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * p.bn;
+        const uint32_t d_tmem = tmem_base + acc * p.acc_cols;
         for (int kb = k0; kb < k1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -173,18 +180,21 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const int ks = item / per_slice;
       int rem = item - ks * per_slice;
-      const int tap = rem / (p.m_tiles * p.n_tiles);
-      rem -= tap * p.m_tiles * p.n_tiles;
+      const int grp = rem / (p.m_tiles * p.n_tiles);
+      rem -= grp * p.m_tiles * p.n_tiles;
       const int m_tile = rem / p.n_tiles, n_tile = rem - m_tile * p.n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m_tile * 128 + q * 32 + lane;
-      float* dst = p.dw + static_cast<size_t>(row) * p.ldw + tap * p.cin + n_tile * p.bn;
+      // accumulator column j * bn + c belongs to tap tap0 + j, input channel n_tile * bn + c: with one N tile per
+      // tap (bn == cin) the group's columns are contiguous in dW[row][tap * cin + channel]
+      float* dst = p.dw + static_cast<size_t>(row) * p.ldw + p.g_tap0[grp] * p.cin + n_tile * p.bn;
+      const int ncols = p.g_ntaps[grp] * p.bn;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      for (int c = 0; c < p.bn; c += 32) {
+      for (int c = 0; c < ncols; c += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.bn + c, v);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.acc_cols + c, v);
         tmem_ld_wait();
         if (row < p.cout) {
 #pragma unroll
@@ -212,7 +222,7 @@ int wgrad_launch(const WgradParams& p, cudaStream_t stream) {
     IO_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_MAX_SMEM));
     attr_set = true;
   }
-  const int items = p.ksplit * p.taps * p.m_tiles * p.n_tiles;
+  const int items = p.ksplit * p.ngroups * p.m_tiles * p.n_tiles;
   if (items <= 0 || p.kblocks <= 0) return IO_OK;
   const int grid = items < num_sms() ? items : num_sms();
   wgrad_kernel<<<grid, 192, p.smem_bytes, stream>>>(p);
@@ -252,13 +262,34 @@ static int plan_kblocks(WgradParams* p, int b, int h_out, int w_out) {
 }
 
 static void plan_split(WgradParams* p) {
-  const int base = p->taps * p->m_tiles * p->n_tiles;
-  int ks = (2 * num_sms() + base - 1) / base;
-  const int max_ks = p->kblocks / 4 > 0 ? p->kblocks / 4 : 1;
+  // tap groups: as many taps per accumulator tile as fit N <= 256 (only when one N tile covers all input channels)
+  int per = 1;
+  if (p->n_tiles == 1 && p->bn <= 128) {
+    per = 256 / p->bn;
+    if (per > p->taps) per = p->taps;
+    const int ng = (p->taps + per - 1) / per;
+    per = (p->taps + ng - 1) / ng;          // balanced: 9 taps -> 3+3+3 (cin 64) / 2+2+2+2+1 (cin 128), 7 -> 4+3
+  }
+  p->ngroups = 0;
+  for (int t0 = 0; t0 < p->taps; t0 += per) {
+    p->g_tap0[p->ngroups] = t0;
+    p->g_ntaps[p->ngroups] = (p->taps - t0 < per) ? p->taps - t0 : per;
+    ++p->ngroups;
+  }
+  p->max_b_slabs = per * (p->bn / 64);
+  p->acc_cols = per * p->bn;                 // <= 256
+  int cols = 2 * p->acc_cols;
+  p->tmem_cols = cols <= 128 ? 128 : (cols <= 256 ? 256 : 512);
+  // K split: ONE wave of work items.  Every item ends with a flush of its fp32 tile into dW through L2 atomics
+  // (measured ~2 TB/s aggregate), so the partial-sum volume (items x tile) is what to minimise; the K range of a
+  // (group, M tile, N tile) is cut just far enough to occupy all SMs once.
+  const int base = p->ngroups * p->m_tiles * p->n_tiles;
+  int ks = num_sms() / base;
+  const int max_ks = p->kblocks / 2 > 0 ? p->kblocks / 2 : 1;
   if (ks > max_ks) ks = max_ks;
   if (ks < 1) ks = 1;
   p->ksplit = ks;
-  const int stage_bytes = A_BYTES + (p->bn / 64) * SLAB;
+  const int stage_bytes = A_BYTES + p->max_b_slabs * SLAB;
   int st = (WG_MAX_SMEM - 1024 - WG_BAR_BYTES) / stage_bytes;
   p->stages = st > 8 ? 8 : st;
   p->smem_bytes = p->stages * stage_bytes + WG_BAR_BYTES + 1024;
