@@ -159,6 +159,172 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def cpu_train_pairs_per_s(n_pairs, d, threads=None):
+    """The training oracle (= the reference's step(): two train-mode fp32 forwards, loss, backward, SGD) timed on
+    the host cores for one small batch."""
+    import torch
+    from instaorder_b200 import synth
+    from oracle import train_oracle as T
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = synth.random_state_dict(0, 5, NUM_CLASSES)
+    batch = T.make_batch(7, n_pairs, d, ALGO)
+    t0 = time.perf_counter()
+    T.train_step(sd, batch, ALGO, lr=1e-4, weight_decay=1e-4, overlap_weight=0.1, distinct_weight=0.9)
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, n_pairs, dt, torch.get_num_threads()
+
+
+def run_train(args):
+    """BASELINE config C4: InstaOrderNet^od training step on synthetic pairs, per-GPU batch --train-batch, SGD
+    (lr 1e-4, momentum 0.9, wd 1e-4: experiments/InstaOrder/InstaOrderNet_od/config.yaml), NCCL all-reduce of the
+    flat gradient buffer for N > 1.  Not the headline metric: run explicitly with --workload train."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    B = args.train_batch
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = [cpu_train_pairs_per_s(2, D) for _ in range(args.warmup + args.steps)][args.warmup:]
+        pairs, secs = sum(v[1] for v in vals), sum(v[2] for v in vals)
+        value = pairs / secs
+        print(json.dumps(dict(impl="reference", metric="training pairs/s (InstaOrderNet^od step, 256^2)", value=value,
+                              unit="pairs/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                              ms_per_step=1000.0 * secs / len(vals), higher_is_better=True, scaling="weak",
+                              vs_baseline=None, dtype="f32", data="synthetic",
+                              config=dict(workload="C4: InstaOrderNet^od step() on 2 synthetic pairs per step, host "
+                                                   "cores (bounded sample)"),
+                              cpu_baseline=dict(value=value, unit="pairs/s", cores=vals[0][3], kind="port",
+                                                sample="2 pairs/step x %d steps, fp32 torch-CPU autograd" % len(vals)),
+                              e2e=dict(value=value, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+    import torch
+    import torch.distributed as dist
+    from instaorder_b200 import _lib, models, synth, training
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    params = dict(algo=ALGO, backbone_arch="resnet50_cls", backbone_param=dict(in_channels=5, num_classes=NUM_CLASSES),
+                  optim="SGD", lr=1e-4, weight_decay=1e-4, use_rgb=True, overlap_weight=0.1, distinct_weight=0.9,
+                  device=dev)
+    model = models.InstaOrderNet_od(params, dist_model=world > 1)
+    model.load_state_dict(synth.random_state_dict(0, 5, NUM_CLASSES))
+    model.switch_to("train")
+    g = torch.Generator().manual_seed(100 + rank)
+    n_batches = 4
+    host = []
+    for _ in range(n_batches):     # pinned host batches in the DataLoader's collated types
+        host.append(dict(rgb=torch.randn((B, 3, D, D), generator=g).pin_memory(),
+                         modal1=(torch.rand((B, 1, D, D), generator=g) > 0.7).float().pin_memory(),
+                         modal2=(torch.rand((B, 1, D, D), generator=g) > 0.7).float().pin_memory(),
+                         depth_order=torch.randint(0, 3, (B,), generator=g).pin_memory(),
+                         count=torch.randint(2, 4, (B,), generator=g).pin_memory(),
+                         is_overlap=(torch.rand((B,), generator=g) < 0.3).long().pin_memory(),
+                         occ_order=(torch.rand((B, 2), generator=g) < 0.2).float().pin_memory()))
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(batch):
+        model.set_input(**batch)
+        return model.step()
+
+    for i in range(args.warmup):
+        step(resident[i % n_batches])
+    sync_all()
+    eng = model._trainer
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.gpu_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(resident[i % n_batches])
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.gpu_launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps * B / (ms / 1000.0)
+    # end to end: pinned host batch -> H2D -> step -> loss read back, every step
+    for i in range(2):
+        float(step(host[i % n_batches])[1]["loss"])
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        float(step(host[i % n_batches])[1]["loss"])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = world * args.steps * B / dt
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    # per-kernel events of one step
+    _lib.check(eng.lib.io_train_profile(eng.handle, 1))
+    step(resident[0])
+    torch.cuda.synchronize()
+    mx = 4096
+    pms = np.zeros(mx, np.float32); kind = np.zeros(mx, np.int32); fl = np.zeros(mx, np.float64)
+    by = np.zeros(mx, np.float64)
+    n = _lib.check(eng.lib.io_train_profile_read(eng.handle, _lib.ptr(pms), _lib.ptr(kind), _lib.ptr(fl), _lib.ptr(by),
+                                                 None, mx))
+    _lib.check(eng.lib.io_train_profile(eng.handle, 0))
+    peaks = measured_peaks()
+    tc = kind[:n] <= 2
+    ew = kind[:n] == 3
+    tc_ms, tc_fl = float(pms[:n][tc].sum()), float(fl[:n][tc].sum())
+    ew_ms, ew_by = float(pms[:n][ew].sum()), float(by[:n][ew].sum())
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, npairs, cdt, threads = cpu_train_pairs_per_s(2, D)
+            cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
+                       sample="one step() on 2 pairs (%.1f s): training oracle, fp32 torch-CPU autograd" % cdt)
+        achieved = tc_fl / (tc_ms / 1000.0) / 1e12 if tc_ms > 0 else 0.0
+        print(json.dumps(dict(
+            metric="training pairs/s (InstaOrderNet^od step: fwd + bwd + all-reduce + SGD, 256^2, bf16)",
+            value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+            data="synthetic",
+            config=dict(workload="C4: InstaOrderNet^od training step, %d synthetic pairs per GPU per step at %d^2, SGD "
+                                 "lr 1e-4 momentum 0.9 wd 1e-4, random-init weights" % (B, D),
+                        pairs_per_step=B * world, parallelism="data parallel over %d GPU(s), one NCCL all-reduce of the "
+                        "flat fp32 gradient buffer (94 MB) per step" % world,
+                        l2="each step streams > 10 GB of saved activations and gradients, i.e. >> 126 MB L2"),
+            e2e=dict(value=e2e_value, unit="pairs/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4),
+            gpu_launches=launches, clocks=clocks,
+            roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
+                          frac=achieved / peaks["bf16"], traffic=None,
+                          kernel="conv_tc / conv_tn (forward + data gradient) + wgrad_kernel",
+                          tensor_share_of_step=tc_ms / float(pms[:n].sum()), peak_source=peaks["source"],
+                          elementwise=dict(bound="hbm", achieved=ew_by / (ew_ms / 1000.0) / 1e9 if ew_ms else 0.0,
+                                           peak=peaks["hbm"], unit="GB/s",
+                                           frac=ew_by / (ew_ms / 1000.0) / 1e9 / peaks["hbm"] if ew_ms else 0.0,
+                                           share_of_step=ew_ms / float(pms[:n].sum())),
+                          step_frac=value / world * 3 * FLOP_PER_PAIR / 1e12 / peaks["bf16"]),
+            cpu_baseline=cpu)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,7 +336,13 @@ def main():
     ap.add_argument("--mode", default="patch256", choices=["patch256", "resize384"],
                     help="patch256 = the BASELINE.json metric (default); resize384 = the shipped InstaOrderNet^od "
                          "config (whole image -> 384^2), reported as a second row in DESIGN.md")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer = the BASELINE.json headline (default); train = BASELINE config C4, one "
+                         "InstaOrderNet^od training step (fwd + bwd + all-reduce + SGD) per step")
+    ap.add_argument("--train-batch", type=int, default=32, help="pairs per GPU per training step (reference: 32)")
     args = ap.parse_args()
+    if args.workload == "train":
+        return run_train(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 

@@ -32,6 +32,8 @@ struct WgradParams {
   int wseg, bh, bi, bpr, bpi;   // K-block geometry: box {wseg, bh, bi} pixels, blocks per row / per image
   int stages, smem_bytes;
   int mn_lbo, mn_sbo;
+  uint32_t debug_idesc_xor;   // bring-up timing experiments only
+  int debug_skip_flush;
   double flops;
 };
 int wgrad_plan(WgradParams* p, const ConvDesc& d, const void* x, const void* dy, float* dw);

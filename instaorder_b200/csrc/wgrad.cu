@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const int ks = item / per_slice;
         const int grp = (item - ks * per_slice) / (p.m_tiles * p.n_tiles);
-        const uint32_t idesc = umma_idesc_bf16(128, p.g_ntaps[grp] * p.bn) | UMMA_A_MN | UMMA_B_MN;
+        const uint32_t idesc = (umma_idesc_bf16(128, p.g_ntaps[grp] * p.bn) | UMMA_A_MN | UMMA_B_MN) ^ p.debug_idesc_xor;
         const int k0 = static_cast<int>(static_cast<int64_t>(ks) * p.kblocks / p.ksplit);
         const int k1 = static_cast<int>(static_cast<int64_t>(ks + 1) * p.kblocks / p.ksplit);
         const int acc = it & 1;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.acc_cols + c, v);
         tmem_ld_wait();
-        if (row < p.cout) {
+        if (row < p.cout && !p.debug_skip_flush) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c + 4 * j),
@@ -295,6 +295,10 @@ static void plan_split(WgradParams* p) {
   p->smem_bytes = p->stages * stage_bytes + WG_BAR_BYTES + 1024;
   p->mn_lbo = mn_lbo();
   p->mn_sbo = mn_sbo();
+  // timing experiments only (results become garbage): INSTAORDER_WGRAD_DEBUG_MAJOR = 1 -> A read as K-major, 2 -> B
+  static const int dbg = []() { const char* e = getenv("INSTAORDER_WGRAD_DEBUG_MAJOR"); return e ? atoi(e) : 0; }();
+  p->debug_idesc_xor = ((dbg & 1) ? UMMA_A_MN : 0u) | ((dbg & 2) ? UMMA_B_MN : 0u);
+  p->debug_skip_flush = (dbg & 4) ? 1 : 0;
 }
 
 int wgrad_plan(WgradParams* p, const ConvDesc& d, const void* x, const void* dy, float* dw) {

@@ -16,6 +16,24 @@ import torch
 from . import _lib
 
 
+def all_reduce_sum_(flat):
+    """utils.average_gradients (utils/distributed_utils.py:27-31) on the flat buffer: the reference all-reduces every
+    ``param.grad`` with SUM (the loss is already divided by world_size, models/supervised_order.py:78); here it is
+    ONE collective over all 23.5 M gradients.  No-op without an initialised process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat)
+    return flat
+
+
+def broadcast_(flat, src=0):
+    """DistModule.broadcast_params (utils/distributed_utils.py:17-24) on a flat buffer."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(flat, src)
+    return flat
+
+
 class FlatOptim(object):
     """Stands in for ``torch.optim.SGD`` / ``Adam`` of the reference wrapper: ``param_groups[0]['lr']`` is what
     ``utils.StepLRScheduler`` writes (utils/scheduler.py:77-80), ``state_dict()`` / ``load_state_dict()`` keep the
@@ -265,14 +283,12 @@ class TrainEngine(object):
     def all_reduce_grads(self):
         """utils.average_gradients (utils/distributed_utils.py:27-31): SUM all-reduce (the loss is pre-divided by
         world_size) -- one NCCL call on the flat buffer instead of one per parameter."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grads)
+        all_reduce_sum_(self.grads)
 
     def broadcast_params(self):
         """DistModule.broadcast_params (utils/distributed_utils.py:17-24): rank 0's parameters to everyone."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.broadcast(self.params, 0)
-            dist.broadcast(self.stats, 0)
+            broadcast_(self.params, 0)
+            broadcast_(self.stats, 0)
             _lib.check(self.lib.io_train_sync_weights(self.handle, _lib.stream_ptr()))
