@@ -30,6 +30,7 @@ struct WgradParams {
   int a_split_rows;     // stem: slab j = channels [0,64) of rows + j * a_split_rows (direction j); 0 = plain
   int kblocks, ksplit, kp;
   int wseg, bh, bi, bpr, bpi;   // K-block geometry: box {wseg, bh, bi} pixels, blocks per row / per image
+  int w_out, h_out;             // output size of the convolution (K blocks walk it row-major)
   int stages, smem_bytes;
   int mn_lbo, mn_sbo;
   uint32_t debug_idesc_xor;   // bring-up timing experiments only

@@ -105,15 +105,15 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const uint4* __restrict__
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
   const uint4* base = y + (static_cast<size_t>(g) * rows) * s.c8 + lc;
-  for (int r = r0 + roff; r < r1; r += 4 * s.rows_par) {
-    uint4 v[4];
+  for (int r = r0 + roff; r < r1; r += 8 * s.rows_par) {
+    uint4 v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int rr = r + u * s.rows_par;
       v[u] = rr < r1 ? __ldg(base + static_cast<size_t>(rr) * s.c8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const Vec8 f = unpack8(v[u]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { acc[0][j] += f.v[j]; acc[1][j] = fmaf(f.v[j], f.v[j], acc[1][j]); }
@@ -253,10 +253,10 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
   const size_t base = (static_cast<size_t>(g) * rows) * s.c8 + lc;
-  for (int r = r0 + roff; r < r1; r += 2 * s.rows_par) {
-    uint4 vd[2], vy[2], va[2];
+  for (int r = r0 + roff; r < r1; r += 4 * s.rows_par) {
+    uint4 vd[4], vy[4], va[4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int rr = r + u * s.rows_par;
       if (rr < r1) {
         const size_t o = base + static_cast<size_t>(rr) * s.c8;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 4; ++u) {
       Vec8 gd = unpack8(vd[u]);
       const Vec8 yv = unpack8(vy[u]);
       if (mask_mode == 1) {

@@ -94,51 +94,85 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const int items = p.ksplit * per_slice;
 
   if (warp == 0) {
-    // ======================= TMA producer =======================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int ks = item / per_slice;
-        int rem = item - ks * per_slice;
-        const int grp = rem / (p.m_tiles * p.n_tiles);
-        rem -= grp * p.m_tiles * p.n_tiles;
-        const int m_tile = rem / p.n_tiles, n_tile = rem - m_tile * p.n_tiles;
-        const int k0 = static_cast<int>(static_cast<int64_t>(ks) * p.kblocks / p.ksplit);
-        const int k1 = static_cast<int>(static_cast<int64_t>(ks + 1) * p.kblocks / p.ksplit);
-        const int tap0 = p.g_tap0[grp], ntaps = p.g_ntaps[grp];
-        const uint32_t tx = static_cast<uint32_t>(p.a_slabs + ntaps * slabs_per_tap) * p.kp * 128;
-        for (int kb = k0; kb < k1; ++kb) {
-          const KCoord c = kblock_coord(p, kb);
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], tx);
-          uint8_t* dA = smem + stage * stage_bytes;
-          uint8_t* dB = dA + A_BYTES;
-          for (int j = 0; j < p.a_slabs; ++j) {
-            if (p.a_split_rows) tma_load_2d(dA + j * SLAB, &p.map_dy, &full[stage], 0, c.row0 + j * p.a_split_rows);
-            else tma_load_2d(dA + j * SLAB, &p.map_dy, &full[stage], m_tile * 128 + j * 64, c.row0);
+    // ======================= TMA producer (whole warp) =======================
+    // One lane per slab: lane j < a_slabs loads dy slab j, the next ntaps * slabs_per_tap lanes one x slab each.  All
+    // per-slab address arithmetic is done once per work item, and the K-block coordinates advance incrementally, so
+    // a K block costs one barrier wait + one TMA issue per lane (a single thread computing six box addresses per
+    // block was measured to be the kernel's bottleneck: ~3000 cycles per block).
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int ks = item / per_slice;
+      int rem = item - ks * per_slice;
+      const int grp = rem / (p.m_tiles * p.n_tiles);
+      rem -= grp * p.m_tiles * p.n_tiles;
+      const int m_tile = rem / p.n_tiles, n_tile = rem - m_tile * p.n_tiles;
+      const int k0 = static_cast<int>(static_cast<int64_t>(ks) * p.kblocks / p.ksplit);
+      const int k1 = static_cast<int>(static_cast<int64_t>(ks + 1) * p.kblocks / p.ksplit);
+      const int tap0 = p.g_tap0[grp], ntaps = p.g_ntaps[grp];
+      const int n_loads = p.a_slabs + ntaps * slabs_per_tap;
+      const uint32_t tx = static_cast<uint32_t>(n_loads) * p.kp * 128;
+      // this lane's slab
+      const bool is_a = lane < p.a_slabs;
+      int c0 = 0, row_off = 0, dw_ = 0, dh_ = 0, par = 0, tap = 0;
+      uint32_t dst_off = 0;
+      if (is_a) {
+        dst_off = lane * SLAB;
+        if (p.a_split_rows) row_off = lane * p.a_split_rows;
+        else c0 = m_tile * 128 + lane * 64;
+      } else if (lane < n_loads) {
+        const int jj = lane - p.a_slabs;
+        const int tj = jj / slabs_per_tap, j = jj - tj * slabs_per_tap;
+        tap = tap0 + tj;
+        const int r = tap / p.taps_w, sx = tap - r * p.taps_w;
+        const int dr = r - p.pad, ds = sx - p.pad;
+        c0 = n_tile * p.bn + j * 64;
+        dst_off = A_BYTES + jj * SLAB;
+        if (p.mode == CONV_S2) {
+          const int ph = dr & 1, pw = ds & 1;
+          c0 += pw * p.cin;
+          dw_ = (ds - pw) / 2;
+          dh_ = (dr - ph) / 2;
+          par = ph;
+        } else {
+          dw_ = ds;
+          dh_ = dr;
+        }
+      }
+      KCoord c = kblock_coord(p, k0);
+      for (int kb = k0; kb < k1; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) mbar_expect_tx(&full[stage], tx);
+        __syncwarp();
+        if (lane < n_loads) {
+          uint8_t* dst = smem + stage * stage_bytes + dst_off;
+          if (is_a) {
+            tma_load_2d(dst, &p.map_dy, &full[stage], c0, c.row0 + row_off);
+          } else if (p.mode == CONV_GEMM) {
+            tma_load_2d(dst, &p.map_x, &full[stage], c0, c.row0);
+          } else if (p.mode == CONV_S1) {
+            tma_load_4d(dst, &p.map_x, &full[stage], c0, c.w0 + dw_, c.h0 + dh_, c.n0);
+          } else if (p.mode == CONV_S2) {
+            tma_load_5d(dst, &p.map_x, &full[stage], c0, c.w0 + dw_, par, c.h0 + dh_, c.n0);
+          } else {  // CONV_STEM: filter row `tap` of the overlapping-window view (8 taps x 8 channels per pixel)
+            tma_load_4d(dst, &p.map_x, &full[stage], 0, c.w0, 2 * c.h0 + tap, c.n0);
           }
-          for (int jj = 0; jj < ntaps * slabs_per_tap; ++jj) {
-            const int tj = jj / slabs_per_tap, j = jj - tj * slabs_per_tap;
-            const int tap = tap0 + tj;
-            const int r = tap / p.taps_w, s = tap - r * p.taps_w;
-            const int dr = r - p.pad, ds = s - p.pad;
-            const int ch = n_tile * p.bn + j * 64;
-            uint8_t* dst = dB + jj * SLAB;
-            if (p.mode == CONV_GEMM) {
-              tma_load_2d(dst, &p.map_x, &full[stage], ch, c.row0);
-            } else if (p.mode == CONV_S1) {
-              tma_load_4d(dst, &p.map_x, &full[stage], ch, c.w0 + ds, c.h0 + dr, c.n0);
-            } else if (p.mode == CONV_S2) {
-              const int ph = dr & 1, pw = ds & 1;
-              tma_load_5d(dst, &p.map_x, &full[stage], pw * p.cin + ch, c.w0 + (ds - pw) / 2, ph,
-                          c.h0 + (dr - ph) / 2, c.n0);
-            } else {  // CONV_STEM: filter row `tap` of the overlapping-window view (8 taps x 8 channels per pixel)
-              tma_load_4d(dst, &p.map_x, &full[stage], 0, c.w0, 2 * c.h0 + tap, c.n0);
+        }
+        // next K block (uniform across the warp)
+        c.row0 += p.kp;
+        if (p.mode != CONV_GEMM) {
+          if (p.bi > 1) {
+            c.n0 += p.bi;
+          } else {
+            c.w0 += p.wseg;
+            if (c.w0 >= p.w_out) {
+              c.w0 = 0;
+              c.h0 += p.bh;
+              if (c.h0 >= p.h_out) { c.h0 = 0; ++c.n0; }
             }
           }
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -309,6 +343,8 @@ int wgrad_plan(WgradParams* p, const ConvDesc& d, const void* x, const void* dy,
   *p = WgradParams{};
   const int h_out = d.h / d.stride, w_out = d.w / d.stride;
   p->dw = dw;
+  p->w_out = w_out;
+  p->h_out = h_out;
   p->cout = d.cout;
   p->cin = d.cin;
   p->taps = d.kernel * d.kernel;
@@ -368,6 +404,8 @@ int stem_wgrad_plan(WgradParams* p, int pairs, int d, const void* x, const void*
   const int64_t pitch = io_pair_tensor_row_pitch(d);
   const int hp = d + 6;
   p->dw = dw_scratch;
+  p->w_out = w_out;
+  p->h_out = h_out;
   p->mode = CONV_STEM;
   p->cout = 128;
   p->cin = 64;
