@@ -29,6 +29,26 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#ifdef __CUDACC__
+// Launch with programmatic stream serialization (PDL): the grid may be scheduled while its predecessor on the stream
+// drains; the kernel must execute pdl_sync() before its first global-memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 int num_sms();
 // byte distances of the MN-major operand descriptors (defaults 8192 / 1024; INSTAORDER_MN_LBO / _SBO override them
 // for bring-up experiments)
@@ -44,6 +64,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // device-side PTX
 // ---------------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+// PDL: let the next grid on the stream start its prologue, then wait until everything this grid depends on has
+// completed and is visible
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

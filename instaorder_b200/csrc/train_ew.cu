@@ -96,6 +96,7 @@ __device__ __forceinline__ BnCoef bn_coef(const double* sums, int g, int c, int 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_stats_kernel(const uint4* __restrict__ y, int rows, int c, Slab s,
                                                        double* __restrict__ sums) {
+  pdl_sync();
   const int g = blockIdx.y;
   const int t = threadIdx.x;
   const int lc = t % s.lanes_c, roff = t / s.lanes_c;
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const uint4* __restrict__
 int bn_stats_launch(const void* y, int groups, int rows, int c, double* sums, cudaStream_t stream) {
   IO_REQUIRE(c % 8 == 0 && c <= 2048 && rows > 0 && groups > 0, "bn_stats: bad shape (rows %d c %d)", rows, c);
   const Slab s = slab_geom(rows, c);
-  bn_stats_kernel<<<dim3(s.slabs, groups), 256, 0, stream>>>(reinterpret_cast<const uint4*>(y), rows, c, s, sums);
-  IO_CUDA(cudaGetLastError());
+  IO_CUDA(launch_pdl(bn_stats_kernel, dim3(s.slabs, groups), dim3(256), 0, stream, reinterpret_cast<const uint4*>(y),
+                     rows, c, s, sums));
   return IO_OK;
 }
 
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                                                        float* __restrict__ running_mean,
                                                        float* __restrict__ running_var, double* __restrict__ zero_me,
                                                        int relu) {
+  pdl_sync();
   const int g = blockIdx.y;
   const int t = threadIdx.x;
   const double m = static_cast<double>(rows);
@@ -217,10 +219,10 @@ int bn_apply_launch(const void* y, const void* residual, void* a, int groups, in
                     float* running_var, double* zero_me, int relu, cudaStream_t stream) {
   IO_REQUIRE(c % 8 == 0 && c <= 2048 && rows > 0, "bn_apply: bad shape");
   const Slab s = slab_geom(rows, c);
-  bn_apply_kernel<<<dim3(s.slabs, groups), 256, 0, stream>>>(
-      reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(residual), reinterpret_cast<uint4*>(a), groups,
-      rows, c, s, sums, gamma, beta, eps, momentum, save, running_mean, running_var, zero_me, relu);
-  IO_CUDA(cudaGetLastError());
+  IO_CUDA(launch_pdl(bn_apply_kernel, dim3(s.slabs, groups), dim3(256), 0, stream,
+                     reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(residual),
+                     reinterpret_cast<uint4*>(a), groups, rows, c, s, sums, gamma, beta, eps, momentum, save,
+                     running_mean, running_var, zero_me, relu));
   return IO_OK;
 }
 
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
                                                             const uint4* __restrict__ y, int groups, int rows, int c,
                                                             Slab s, const float* __restrict__ save, int mask_mode,
                                                             double* __restrict__ red) {
+  pdl_sync();
   const int g = blockIdx.y;
   const int t = threadIdx.x;
   const int lc = t % s.lanes_c, roff = t / s.lanes_c;
@@ -295,10 +298,9 @@ int bn_bwd_reduce_launch(const void* da, const void* a, const void* y, int group
                          int mask_mode, double* red, cudaStream_t stream) {
   IO_REQUIRE(c % 8 == 0 && c <= 2048 && rows > 0, "bn_bwd_reduce: bad shape");
   const Slab s = slab_geom(rows, c);
-  bn_bwd_reduce_kernel<<<dim3(s.slabs, groups), 256, 0, stream>>>(
-      reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(y), groups,
-      rows, c, s, save, mask_mode, red);
-  IO_CUDA(cudaGetLastError());
+  IO_CUDA(launch_pdl(bn_bwd_reduce_kernel, dim3(s.slabs, groups), dim3(256), 0, stream,
+                     reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(a),
+                     reinterpret_cast<const uint4*>(y), groups, rows, c, s, save, mask_mode, red));
   return IO_OK;
 }
 
@@ -312,6 +314,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
                                                            const double* __restrict__ red, int mask_mode,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            double* __restrict__ zero_me) {
+  pdl_sync();
   const int g = blockIdx.y;
   const int t = threadIdx.x;
   if (blockIdx.x == 0 && g == 0) {
@@ -386,11 +389,10 @@ int bn_bwd_apply_launch(const void* da, const void* a, const void* y, void* dy, 
                         float* dbeta, double* zero_me, cudaStream_t stream) {
   IO_REQUIRE(c % 8 == 0 && c <= 2048 && rows > 0, "bn_bwd_apply: bad shape");
   const Slab s = slab_geom(rows, c);
-  bn_bwd_apply_kernel<<<dim3(s.slabs, groups), 256, 0, stream>>>(
-      reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(y),
-      reinterpret_cast<uint4*>(dy), reinterpret_cast<uint4*>(g_out), groups, rows, c, s, gamma, save, red, mask_mode,
-      dgamma, dbeta, zero_me);
-  IO_CUDA(cudaGetLastError());
+  IO_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(s.slabs, groups), dim3(256), 0, stream,
+                     reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(a),
+                     reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(dy), reinterpret_cast<uint4*>(g_out),
+                     groups, rows, c, s, gamma, save, red, mask_mode, dgamma, dbeta, zero_me));
   return IO_OK;
 }
 
@@ -399,6 +401,7 @@ int bn_bwd_apply_launch(const void* da, const void* a, const void* y, void* dy, 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool_idx_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
                                                           uint2* __restrict__ idx, int b, int h, int w, int c8) {
+  pdl_sync();
   const int ho = h / 2, wo = w / 2;
   const size_t total = static_cast<size_t>(b) * ho * wo * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -438,14 +441,14 @@ int maxpool_fwd_idx_launch(const void* x, void* y, uint8_t* idx, int b, int h, i
   const size_t total = static_cast<size_t>(b) * (h / 2) * (w / 2) * (c / 8);
   if (total == 0) return IO_OK;
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  maxpool_idx_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y),
-                                               reinterpret_cast<uint2*>(idx), b, h, w, c / 8);
-  IO_CUDA(cudaGetLastError());
+  IO_CUDA(launch_pdl(maxpool_idx_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const uint4*>(x),
+                     reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(idx), b, h, w, c / 8));
   return IO_OK;
 }
 
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
                                                           uint4* __restrict__ dx, int b, int h, int w, int c8) {
+  pdl_sync();
   const int ho = h / 2, wo = w / 2;
   const size_t total = static_cast<size_t>(b) * h * w * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -490,9 +493,8 @@ int maxpool_bwd_launch(const void* dy, const uint8_t* idx, void* dx, int b, int 
   const size_t total = static_cast<size_t>(b) * h * w * (c / 8);
   if (total == 0) return IO_OK;
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  maxpool_bwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(idx),
-                                               reinterpret_cast<uint4*>(dx), b, h, w, c / 8);
-  IO_CUDA(cudaGetLastError());
+  IO_CUDA(launch_pdl(maxpool_bwd_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const uint4*>(dy),
+                     reinterpret_cast<const uint2*>(idx), reinterpret_cast<uint4*>(dx), b, h, w, c / 8));
   return IO_OK;
 }
 
@@ -501,6 +503,7 @@ int maxpool_bwd_launch(const void* dy, const uint8_t* idx, void* dx, int b, int 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) upsample2_zero_kernel(const uint4* __restrict__ dy, uint4* __restrict__ z, int b,
                                                              int ho, int wo, int c8) {
+  pdl_sync();
   const int h = 2 * ho, w = 2 * wo;
   const size_t total = static_cast<size_t>(b) * h * w * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -521,14 +524,14 @@ int upsample2_zero_launch(const void* dy, void* z, int b, int ho, int wo, int c,
   const size_t total = static_cast<size_t>(b) * ho * wo * 4 * (c / 8);
   if (total == 0) return IO_OK;
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  upsample2_zero_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(z), b,
-                                                  ho, wo, c / 8);
-  IO_CUDA(cudaGetLastError());
+  IO_CUDA(launch_pdl(upsample2_zero_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const uint4*>(dy),
+                     reinterpret_cast<uint4*>(z), b, ho, wo, c / 8));
   return IO_OK;
 }
 
 __global__ void __launch_bounds__(256) scatter_add2_kernel(const uint4* __restrict__ d, uint4* __restrict__ dx, int b,
                                                            int ho, int wo, int c8) {
+  pdl_sync();
   const size_t total = static_cast<size_t>(b) * ho * wo * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -551,9 +554,8 @@ int scatter_add2_launch(const void* d, void* dx, int b, int ho, int wo, int c, c
   const size_t total = static_cast<size_t>(b) * ho * wo * (c / 8);
   if (total == 0) return IO_OK;
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  scatter_add2_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(d), reinterpret_cast<uint4*>(dx), b, ho,
-                                                wo, c / 8);
-  IO_CUDA(cudaGetLastError());
+  IO_CUDA(launch_pdl(scatter_add2_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const uint4*>(d),
+                     reinterpret_cast<uint4*>(dx), b, ho, wo, c / 8));
   return IO_OK;
 }
 

@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
+  // PDL: the prologue above overlaps the previous kernel's tail; no global access before this point
+  pdl_sync();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -259,8 +261,7 @@ int wgrad_launch(const WgradParams& p, cudaStream_t stream) {
   const int items = p.ksplit * p.ngroups * p.m_tiles * p.n_tiles;
   if (items <= 0 || p.kblocks <= 0) return IO_OK;
   const int grid = items < num_sms() ? items : num_sms();
-  wgrad_kernel<<<grid, 192, p.smem_bytes, stream>>>(p);
-  IO_CUDA(cudaGetLastError());
+  IO_CUDA(launch_pdl(wgrad_kernel, dim3(grid), dim3(192), static_cast<size_t>(p.smem_bytes), stream, p));
   return IO_OK;
 }
 
