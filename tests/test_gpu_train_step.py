@@ -239,3 +239,32 @@ def test_model_api_train_eval_resume(golden_dir):
             if s1[k].dtype == torch.float32:
                 d = float((s1[k] - s2[k]).abs().max())
                 assert d <= 1e-3 * (float(s1[k].abs().max()) + 1e-3), "resume: %s differs by %.4g" % (k, d)
+
+
+def test_trainer_loop(tmp_path):
+    """instaorder_b200.trainer.Trainer (reference trainer.py:143-266): iteration loop with the LR schedule, loss
+    recording, checkpoint cadence and on-line validation, on the synthetic dataset."""
+    import types
+    from instaorder_b200 import trainer as TR
+    args = types.SimpleNamespace(
+        seed=0, validate=False, load_pretrain=None, load_model=None,
+        model=dict(G.case_params(G.CASES["od_sgd"]), device=DEV, total_iter=6, lr_steps=[4], lr_mults=[0.1], lr=1e-3,
+                   warmup_lr=[], warmup_steps=[]),
+        data=dict(dataset="synthetic", base_dir=str(tmp_path), patch_or_image="patch", batch_size=4, batch_size_val=4,
+                  workers=0),
+        trainer=dict(initial_val=False, val_freq=3, val_iter=2, print_freq=1, save_freq=3, loss_record=["loss"],
+                     exp_name="unit"))
+    tr = TR.Trainer(args, train_dataset=TR.SyntheticPairDataset("InstaOrderNet_od", 64, 64, seed=1),
+                    val_dataset=TR.SyntheticPairDataset("InstaOrderNet_od", 64, 16, seed=2))
+    tr.model.load_state_dict(synth.random_state_dict(20, 5, [2, 3]))
+    tr.run()
+    assert tr.curr_step == 6
+    train_pts = [h for h in tr.history if "loss" in h[1]]
+    val_pts = [h for h in tr.history if "val_loss" in h[1]]
+    assert len(train_pts) == 6 and len(val_pts) == 2
+    assert all(np.isfinite(h[1]["loss"]) for h in train_pts) and all(np.isfinite(h[1]["val_loss"]) for h in val_pts)
+    assert abs(tr.model.optim.param_groups[0]["lr"] - 1e-4) < 1e-12          # milestone at iteration 4: lr x 0.1
+    ck = os.path.join(tr.folder2save, "checkpoints")
+    assert sorted(os.listdir(ck)) == ["ckpt_iter_3.pth.tar", "ckpt_iter_6.pth.tar"]
+    st = torch.load(os.path.join(ck, "ckpt_iter_6.pth.tar"), map_location="cpu", weights_only=False)
+    assert st["step"] == 6 and int(st["state_dict"]["module.bn1.num_batches_tracked"]) == 1 + 2 * 6
