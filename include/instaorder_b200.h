@@ -80,7 +80,9 @@ typedef struct io_pair_desc {
   int64_t mask_b_off; /* start of instance j's H x W u8 modal mask                       */
   int32_t h, w;       /* image size                                                      */
   int32_t x, y, s;    /* crop window (io_pair_crop_boxes); ignored in resize mode        */
-  int32_t rgb_slot;   /* resize mode: index of the image's pre-resized rgb plane         */
+  int32_t rgb_slot;   /* resize mode: index of the image's pre-resized rgb plane;
+                         patch mode: flags, bit 0 = horizontal flip of the resized crop
+                         (training augmentation, datasets/depth_occ_order_dataset.py:166-181) */
 } io_pair_desc;
 
 /* Geometry of the gather output ("pair tensor"): [P, D + 6, row_pitch, 8] bf16, NHWC with 3 zero pixels of border

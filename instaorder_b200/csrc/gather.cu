@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_patch_kernel(const uint
   const uint8_t* __restrict__ ma = masks + ds.mask_a_off;
   const uint8_t* __restrict__ mb = masks + ds.mask_b_off;
   const int H = ds.h, W = ds.w, X = ds.x, Y = ds.y;
+  const bool flip = (ds.rgb_slot & 1) != 0;   // training augmentation: horizontal flip AFTER the resize
   __nv_bfloat16* out_pair = out + static_cast<size_t>(blockIdx.y) * (d + 6) * pitch * 8;
   const int row0 = blockIdx.x * GATHER_ROWS;
   const int row1 = min(d, row0 + GATHER_ROWS);
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_patch_kernel(const uint
       by[k] = __fmul_rn(static_cast<float>(ty.coef[k]), kscale);
     }
     for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
-      const AxisTab tx = tab[dx];
+      const AxisTab tx = tab[flip ? d - 1 - dx : dx];
       // ---- modal masks: nearest
       const int mx = X + tx.near;
       float va = 0.0f, vb = 0.0f;

@@ -132,11 +132,29 @@ class _OrderModel(object):
             self._trainer = t
         return t
 
+    def set_input_pairs(self, pair_tensor, input_size, *labels):
+        """Batched alternative to ``set_input`` for the GPU data pipeline (instaorder_b200.train_data): the pair
+        tensor of the batch as written by ``io_pair_gather_patch`` (both masks + normalised rgb, bf16) plus the same
+        label tensors ``set_input`` takes.  The fp32 ``rgb / modal1 / modal2`` tensors of the reference never exist."""
+        self._pair_tensor = (pair_tensor, int(input_size))
+        dummy = torch.empty((self._n_from_labels(labels), 0, int(input_size), int(input_size)))
+        self.set_input(dummy, dummy, dummy, *labels)
+
+    @staticmethod
+    def _n_from_labels(labels):
+        return int(labels[0].shape[0])
+
     def _step(self, occ_off, class_off, class_k, occ_target, class_target, is_overlap):
         if self.phase != "train":
             raise RuntimeError("step() needs switch_to('train')")
         t = self._train_engine(int(self.rgb.shape[0]), int(self.rgb.shape[-1]))
-        t.pack_inputs(self.rgb, self.modal1, self.modal2)
+        pt = getattr(self, "_pair_tensor", None)
+        if pt is not None:
+            self._pair_tensor = None
+            if pt[0].data_ptr() != t.pair_tensor.data_ptr():
+                t.pair_tensor[:pt[0].numel()].copy_(pt[0].view(torch.uint8).reshape(-1))
+        else:
+            t.pack_inputs(self.rgb, self.modal1, self.modal2)
         losses = t.forward_backward(occ_off, class_off, class_k, occ_target, class_target, is_overlap,
                                     float(self.params.get("overlap_weight", 1.0)),
                                     float(self.params.get("distinct_weight", 1.0)), self.world_size)
