@@ -273,11 +273,12 @@ IO_API int io_stem_wgrad(const void* pair_tensor_dev, int pairs, int d, const vo
                          void* stream);
 /* train-mode BatchNorm over [groups][rows][c] (+ residual) (+ ReLU) and its backward; save_dev = 4 x [groups][c] fp32
  * (scale, shift, mean, invstd), scratch_dev = [groups][2][c] doubles.  Backward mask_mode: 0 = no ReLU, 1 = ReLU mask
- * from the stored activation a_dev (needed when a residual was added), 2 = mask recomputed from y_dev (a_dev unused). */
+ * from the stored activation a_dev (needed when a residual was added), 2 = mask recomputed from y_dev (a_dev unused),
+ * 3 = a_dev points to the bit mask written by io_bn_train_forward's mask_out_dev (one byte per 8 channels; optional). */
 IO_API int io_bn_train_forward(const void* y_dev, const void* residual_dev, void* a_dev, int groups, int rows, int c,
                                const float* gamma_dev, const float* beta_dev, float eps, float momentum,
                                float* running_mean_dev, float* running_var_dev, float* save_dev, double* scratch_dev,
-                               int relu, void* stream);
+                               int relu, uint8_t* mask_out_dev, void* stream);
 IO_API int io_bn_train_backward(const void* da_dev, const void* a_dev, const void* y_dev, void* dy_dev, void* g_out_dev,
                                 int groups, int rows, int c, const float* gamma_dev, const float* save_dev,
                                 double* scratch_dev, int mask_mode, float* dgamma_dev, float* dbeta_dev, void* stream);

@@ -83,7 +83,7 @@ _SIGS.update({
     "io_conv_wgrad": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "io_conv_dgrad": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "io_stem_wgrad": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
-    "io_bn_train_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    "io_bn_train_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "io_bn_train_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "io_maxpool_train": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 })

@@ -255,7 +255,7 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
   }
   net->d = input_size;
   net->max_pairs = max_pairs;
-  int chunk_a = 128, chunk_b = 256;
+  int chunk_a = 256, chunk_b = 256;
   if (const char* e = getenv("INSTAORDER_CHUNK_A")) chunk_a = atoi(e) > 0 ? atoi(e) : chunk_a;
   if (const char* e = getenv("INSTAORDER_CHUNK_B")) chunk_b = atoi(e) > 0 ? atoi(e) : chunk_b;
   if (const char* e = getenv("INSTAORDER_FUSE")) net->fuse = atoi(e) != 0;

@@ -48,6 +48,7 @@ struct Unit {        // one convolution + BatchNorm
   __nv_bfloat16* y = nullptr;    // raw convolution output [imgs, h_out, w_out, cout]
   __nv_bfloat16* a = nullptr;    // activation after BN (+ residual) (+ ReLU)
   float* save = nullptr;         // [4][2][cout]: scale, shift, mean, invstd of the last forward (per direction)
+  uint8_t* mask = nullptr;       // residual units: ReLU bit mask of `a` (1 byte per 8 channels), read by the backward
 };
 
 struct TOp {
@@ -220,7 +221,8 @@ static void add_bn_fwd(io_train* t, Unit& u, const __nv_bfloat16* residual, int 
   });
   push(t->fwd, 3, 0, act * (residual ? 3.0 : 2.0), tag, [t, up, residual, rows, c, relu, mine, next](cudaStream_t s) {
     return bn_apply_launch(up->y, residual, up->a, 2, rows, c, mine, t->params + up->g_off, t->params + up->b_off,
-                           1e-5f, 0.1f, up->save, t->stats + up->rm_off, t->stats + up->rv_off, next, relu, s);
+                           1e-5f, 0.1f, up->save, t->stats + up->rm_off, t->stats + up->rv_off, next, relu,
+                           (residual && relu) ? up->mask : nullptr, s);
   });
 }
 
@@ -230,17 +232,18 @@ static void add_bn_bwd(io_train* t, Unit& u, const __nv_bfloat16* da, __nv_bfloa
                        int mask_mode, int tag) {
   const int rows = t->pairs * u.h_out * u.w_out, c = u.cout;
   const double act = 2.0 * 2 * rows * c;
-  const double reads = mask_mode == 1 ? 3.0 : 2.0;
+  const double reads = mask_mode == 1 ? 3.0 : (mask_mode == 3 ? 2.0625 : 2.0);
   Unit* up = &u;
+  const void* mask_src = mask_mode == 3 ? static_cast<const void*>(u.mask) : static_cast<const void*>(u.a);
   double* mine = t->red[t->red_sel];
   double* next = t->red[t->red_sel ^ 1];
   t->red_sel ^= 1;
-  push(t->bwd, 3, 0, act * reads, tag, [up, da, rows, c, mask_mode, mine](cudaStream_t s) {
-    return bn_bwd_reduce_launch(da, up->a, up->y, 2, rows, c, up->save, mask_mode, mine, s);
+  push(t->bwd, 3, 0, act * reads, tag, [up, da, rows, c, mask_mode, mine, mask_src](cudaStream_t s) {
+    return bn_bwd_reduce_launch(da, mask_src, up->y, 2, rows, c, up->save, mask_mode, mine, s);
   });
   push(t->bwd, 3, 0, act * (reads + 1.0 + (g_out ? 1.0 : 0.0)), tag,
-       [t, up, da, dy, g_out, rows, c, mask_mode, mine, next](cudaStream_t s) {
-         return bn_bwd_apply_launch(da, up->a, up->y, dy, g_out, 2, rows, c, t->params + up->g_off, up->save, mine,
+       [t, up, da, dy, g_out, rows, c, mask_mode, mine, next, mask_src](cudaStream_t s) {
+         return bn_bwd_apply_launch(da, mask_src, up->y, dy, g_out, 2, rows, c, t->params + up->g_off, up->save, mine,
                                     mask_mode, t->grads + up->g_off, t->grads + up->b_off, next, s);
        });
 }
@@ -286,6 +289,8 @@ static int build_graph(io_train* t) {
     if (int rc = dev_alloc(t, &u.y, out * I)) return rc;
     if (int rc = dev_alloc(t, &u.a, out * I)) return rc;
     if (int rc = dev_alloc(t, &u.save, static_cast<size_t>(8) * u.cout)) return rc;
+    if (u.conv.find(".conv3") != std::string::npos)
+      if (int rc = dev_alloc(t, &u.mask, out * I / 8)) return rc;
   }
   for (int i = 0; i < 5; ++i)
     if (int rc = dev_alloc(t, &t->gbuf[i], max_act * I)) return rc;
@@ -386,7 +391,7 @@ static int build_graph(io_train* t) {
     const Blk& k = blks[bi];
     Unit &u1 = t->units[k.c1], &u2 = t->units[k.c2], &u3 = t->units[k.c3];
     // out = relu(bn3(conv3(a2)) + identity):  GA = d out  ->  GY = d y3, GG = masked gradient (identity branch)
-    add_bn_bwd(t, u3, GA, GY, GG, 1, k.tag + 3);   // mask from the stored block output
+    add_bn_bwd(t, u3, GA, GY, GG, 3, k.tag + 3);   // ReLU bit mask of the block output
     if (int rc = add_wgrad(t, u3, u2.a, GY, k.tag + 3)) return rc;
     if (int rc = add_dgrad(t, u3, u3.h_out, u3.w_out, GY, nullptr, GT, k.tag + 3)) return rc;   // GT = d a2
     add_bn_bwd(t, u2, GT, GY, nullptr, 2, k.tag + 2);                                          // GY = d y2
@@ -634,7 +639,7 @@ extern "C" int io_train_profile_read(io_train_t* t, float* ms, int32_t* kind, do
 extern "C" int io_bn_train_forward(const void* y_dev, const void* residual_dev, void* a_dev, int groups, int rows, int c,
                                    const float* gamma_dev, const float* beta_dev, float eps, float momentum,
                                    float* running_mean_dev, float* running_var_dev, float* save_dev,
-                                   double* scratch_dev, int relu, void* stream_) {
+                                   double* scratch_dev, int relu, uint8_t* mask_out_dev, void* stream_) {
   // save_dev: 4 x [groups][c] fp32 (scale, shift, mean, invstd); scratch_dev: [groups][2][c] doubles
   IO_REQUIRE(y_dev && a_dev && gamma_dev && beta_dev && running_mean_dev && running_var_dev && save_dev && scratch_dev,
              "io_bn_train_forward: null pointer");
@@ -643,7 +648,7 @@ extern "C" int io_bn_train_forward(const void* y_dev, const void* residual_dev, 
   IO_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(double) * 2 * gc, s));
   if (int rc = bn_stats_launch(y_dev, groups, rows, c, scratch_dev, s)) return rc;
   return bn_apply_launch(y_dev, residual_dev, a_dev, groups, rows, c, scratch_dev, gamma_dev, beta_dev, eps, momentum,
-                         save_dev, running_mean_dev, running_var_dev, nullptr, relu, s);
+                         save_dev, running_mean_dev, running_var_dev, nullptr, relu, mask_out_dev, s);
 }
 
 extern "C" int io_bn_train_backward(const void* da_dev, const void* a_dev, const void* y_dev, void* dy_dev,
@@ -652,8 +657,8 @@ extern "C" int io_bn_train_backward(const void* da_dev, const void* a_dev, const
                                     float* dbeta_dev, void* stream_) {
   IO_REQUIRE(da_dev && y_dev && dy_dev && gamma_dev && save_dev && scratch_dev && dgamma_dev && dbeta_dev,
              "io_bn_train_backward: null pointer");
-  IO_REQUIRE(mask_mode >= 0 && mask_mode <= 2 && (mask_mode != 1 || a_dev),
-             "io_bn_train_backward: mask_mode %d (1 needs the activation)", mask_mode);
+  IO_REQUIRE(mask_mode >= 0 && mask_mode <= 3 && ((mask_mode != 1 && mask_mode != 3) || a_dev),
+             "io_bn_train_backward: mask_mode %d (1 needs the activation, 3 the bit mask)", mask_mode);
   cudaStream_t s = as_stream(stream_);
   const size_t gc = static_cast<size_t>(groups) * c;
   IO_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(double) * 2 * gc, s));

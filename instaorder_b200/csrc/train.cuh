@@ -54,9 +54,10 @@ int bn_stats_launch(const void* y, int groups, int rows, int c, double* sums, cu
 // buffer the NEXT BatchNorm will accumulate into -- never the one being read)
 int bn_apply_launch(const void* y, const void* residual, void* a, int groups, int rows, int c, const double* sums,
                     const float* gamma, const float* beta, float eps, float momentum, float* save, float* running_mean,
-                    float* running_var, double* zero_me, int relu, cudaStream_t stream);
+                    float* running_var, double* zero_me, int relu, uint8_t* mask_out, cudaStream_t stream);
 // backward of a = [relu](bn(y) [+ residual]):  g = da * mask;  red[g][0][c] = sum g, red[g][1][c] = sum g * xhat
-// (double, must be zero on entry).  mask_mode 0: none, 1: a > 0 (stored activation), 2: y * scale + shift > 0
+// (double, must be zero on entry).  mask_mode 0: none, 1: a > 0 (stored activation), 2: y * scale + shift > 0,
+// 3: bit mask written by bn_apply_launch's mask_out (passed through `a`: one byte per 8 channels)
 int bn_bwd_reduce_launch(const void* da, const void* a, const void* y, int groups, int rows, int c, const float* save,
                          int mask_mode, double* red, cudaStream_t stream);
 // dy = gamma * invstd * (g - sum_g / M - xhat * sum_gx / M)  (bf16);  if g_out != nullptr also writes g (the

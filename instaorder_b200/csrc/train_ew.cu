@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                                                        float eps, float momentum, float* __restrict__ save,
                                                        float* __restrict__ running_mean,
                                                        float* __restrict__ running_var, double* __restrict__ zero_me,
-                                                       int relu) {
+                                                       int relu, uint8_t* __restrict__ mask_out) {
   pdl_sync();
   const int g = blockIdx.y;
   const int t = threadIdx.x;
@@ -209,20 +209,28 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) f.v[j] = fmaxf(f.v[j], 0.f);
       }
-      a[base + static_cast<size_t>(rr) * s.c8] = pack8(f);
+      const uint4 packed = pack8(f);
+      a[base + static_cast<size_t>(rr) * s.c8] = packed;
+      if (mask_out != nullptr) {   // ReLU mask of the STORED (bf16) activation, 1 bit per element
+        const Vec8 st = unpack8(packed);
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m |= (st.v[j] > 0.f ? 1u : 0u) << j;
+        mask_out[base + static_cast<size_t>(rr) * s.c8] = static_cast<uint8_t>(m);
+      }
     }
   }
 }
 
 int bn_apply_launch(const void* y, const void* residual, void* a, int groups, int rows, int c, const double* sums,
                     const float* gamma, const float* beta, float eps, float momentum, float* save, float* running_mean,
-                    float* running_var, double* zero_me, int relu, cudaStream_t stream) {
+                    float* running_var, double* zero_me, int relu, uint8_t* mask_out, cudaStream_t stream) {
   IO_REQUIRE(c % 8 == 0 && c <= 2048 && rows > 0, "bn_apply: bad shape");
   const Slab s = slab_geom(rows, c);
   IO_CUDA(launch_pdl(bn_apply_kernel, dim3(s.slabs, groups), dim3(256), 0, stream,
                      reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(residual),
                      reinterpret_cast<uint4*>(a), groups, rows, c, s, sums, gamma, beta, eps, momentum, save,
-                     running_mean, running_var, zero_me, relu));
+                     running_mean, running_var, zero_me, relu, mask_out));
   return IO_OK;
 }
 
@@ -230,7 +238,8 @@ int bn_apply_launch(const void* y, const void* residual, void* a, int groups, in
 // BatchNorm backward (through the optional ReLU):  g = da * mask
 //   mask_mode 0: no ReLU;  1: mask = (a > 0) read from the stored activation (residual blocks);
 //             2: mask = (y * scale + shift > 0) recomputed from the raw convolution output with the forward pass's
-//                own fp32 expression (no residual) -- saves reading `a`
+//                own fp32 expression (no residual) -- saves reading `a`;
+//             3: bit mask written by bn_apply (`a` then points to one byte per 8 channels) -- 1/16 of the bytes
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a,
                                                             const uint4* __restrict__ y, int groups, int rows, int c,
@@ -266,6 +275,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
         vd[u] = __ldg(da + o);
         vy[u] = __ldg(y + o);
         if (mask_mode == 1) va[u] = __ldg(a + o);
+        else if (mask_mode == 3) va[u].x = __ldg(reinterpret_cast<const uint8_t*>(a) + o);
       } else {
         vd[u] = make_uint4(0, 0, 0, 0);
         vy[u] = make_uint4(0, 0, 0, 0);
@@ -283,6 +293,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
       } else if (mask_mode == 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) gd.v[j] = fmaf(yv.v[j], sc[j], sh[j]) > 0.f ? gd.v[j] : 0.f;
+      } else if (mask_mode == 3) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gd.v[j] = ((va[u].x >> j) & 1u) ? gd.v[j] : 0.f;
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -358,6 +371,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
         vd[u] = __ldg(da + o);
         vy[u] = __ldg(y + o);
         if (mask_mode == 1) va[u] = __ldg(a + o);
+        else if (mask_mode == 3) va[u].x = __ldg(reinterpret_cast<const uint8_t*>(a) + o);
       }
     }
 #pragma unroll
@@ -374,6 +388,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
       } else if (mask_mode == 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) gd.v[j] = fmaf(yv.v[j], sc[j], sh[j]) > 0.f ? gd.v[j] : 0.f;
+      } else if (mask_mode == 3) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gd.v[j] = ((va[u].x >> j) & 1u) ? gd.v[j] : 0.f;
       }
       if (g_out != nullptr) g_out[o] = pack8(gd);
       Vec8 out;

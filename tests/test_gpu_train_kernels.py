@@ -154,21 +154,31 @@ def test_bn_train_forward_backward(case):
     rm0, rv0 = rm.clone(), rv.clone()
     a = torch.full((groups, rows, c), float("nan"), device=DEV, dtype=torch.bfloat16)
     save = torch.zeros(4 * groups * c, device=DEV)
+    bits = torch.zeros(groups * rows * c // 8, device=DEV, dtype=torch.uint8)
     scratch = torch.zeros(groups * 2 * c, device=DEV, dtype=torch.float64)
     _lib.check(L.io_bn_train_forward(y.data_ptr(), res.data_ptr() if use_res else None, a.data_ptr(), groups, rows, c,
                                      gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(),
-                                     save.data_ptr(), scratch.data_ptr(), int(relu), _lib.stream_ptr()))
+                                     save.data_ptr(), scratch.data_ptr(), int(relu),
+                                     bits.data_ptr() if (relu and use_res) else None, _lib.stream_ptr()))
     # ReLU mask: read from the stored activation when a residual was added, recomputed from y otherwise
-    mask_mode = 0 if not relu else (1 if use_res else 2)
+    mask_mode = 0 if not relu else (3 if use_res else 2)
     da = torch.randn((groups, rows, c), generator=g, device=DEV).to(torch.bfloat16).contiguous()
     dy = torch.full((groups, rows, c), float("nan"), device=DEV, dtype=torch.bfloat16)
     gout = torch.full((groups, rows, c), float("nan"), device=DEV, dtype=torch.bfloat16)
     dgamma = torch.zeros(c, device=DEV)
     dbeta = torch.zeros(c, device=DEV)
-    _lib.check(L.io_bn_train_backward(da.data_ptr(), a.data_ptr() if mask_mode == 1 else None, y.data_ptr(),
+    _lib.check(L.io_bn_train_backward(da.data_ptr(), bits.data_ptr() if mask_mode == 3 else None, y.data_ptr(),
                                       dy.data_ptr(), gout.data_ptr(),
                                       groups, rows, c, gamma.data_ptr(), save.data_ptr(), scratch.data_ptr(),
                                       mask_mode, dgamma.data_ptr(), dbeta.data_ptr(), _lib.stream_ptr()))
+    if mask_mode == 3:   # the mask read from the stored activation (mode 1) must give the same result as the bit mask
+        dy1 = torch.empty_like(dy)
+        dg1, db1 = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+        _lib.check(L.io_bn_train_backward(da.data_ptr(), a.data_ptr(), y.data_ptr(), dy1.data_ptr(), None, groups, rows,
+                                          c, gamma.data_ptr(), save.data_ptr(), scratch.data_ptr(), 1, dg1.data_ptr(),
+                                          db1.data_ptr(), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(dy1, dy)
     torch.cuda.synchronize()
     # reference: one F.batch_norm call per group (the reference's two forward passes), shared gamma / beta
     yf = y.float().requires_grad_(True)
