@@ -56,6 +56,11 @@ struct TOp {
   int kind;        // 0 conv fwd, 1 dgrad, 2 wgrad, 3 element-wise / reduction, 4 other
   double flops, bytes;
   int tag;
+  // side-stream scheduling of the weight gradients (they feed nothing but the gradient buffer): a `side` op reads the
+  // dy buffer `reads`; a main-stream op that overwrites a buffer (`writes`) first waits for its last side reader
+  int side = 0;
+  const void* reads = nullptr;
+  const void* writes = nullptr;
 };
 
 }  // namespace io
@@ -88,6 +93,11 @@ struct io_train {
   float* logits = nullptr;              // [imgs][k]
   float* dlogits = nullptr;
   __nv_bfloat16* gbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // GA, GG, GY, GT, GD, GZ
+  __nv_bfloat16* dy_ring[3] = {nullptr, nullptr, nullptr};   // dy buffers (gbuf[2] + 2 more) used in rotation, so a
+  int dy_cursor = 0;                                         // weight gradient may lag two units behind the main chain
+  cudaStream_t side_stream = nullptr;
+  std::vector<cudaEvent_t> side_ev;     // fork / done event per side op
+  bool use_side = true;
   std::vector<void*> allocs;
   std::vector<io::TOp> fwd, bwd;
   bool built = false;
@@ -186,7 +196,10 @@ static int dev_alloc(io_train* t, T** p, size_t count) {
 // ---- op builders ------------------------------------------------------------------------------------------------
 static void push(std::vector<TOp>& v, int kind, double flops, double bytes, int tag,
                  std::function<int(cudaStream_t)> f) {
-  v.push_back(TOp{std::move(f), kind, flops, bytes, tag});
+  TOp op;
+  op.run = std::move(f);
+  op.kind = kind; op.flops = flops; op.bytes = bytes; op.tag = tag;
+  v.push_back(std::move(op));
 }
 
 // forward convolution of unit u over `x` -> u.y (raw, no bias / ReLU)
@@ -246,6 +259,7 @@ static void add_bn_bwd(io_train* t, Unit& u, const __nv_bfloat16* da, __nv_bfloa
          return bn_bwd_apply_launch(da, mask_src, up->y, dy, g_out, 2, rows, c, t->params + up->g_off, up->save, mine,
                                     mask_mode, t->grads + up->g_off, t->grads + up->b_off, next, s);
        });
+  t->bwd.back().writes = dy;
 }
 
 static int add_wgrad(io_train* t, const Unit& u, const __nv_bfloat16* x, const __nv_bfloat16* dy, int tag) {
@@ -261,6 +275,8 @@ static int add_wgrad(io_train* t, const Unit& u, const __nv_bfloat16* x, const _
     q.dw = t->grads + off;
     return wgrad_launch(q, s);
   });
+  t->bwd.back().side = 1;
+  t->bwd.back().reads = dy;
   return IO_OK;
 }
 
@@ -310,8 +326,12 @@ static int build_graph(io_train* t) {
   if (int rc = dev_alloc(t, &t->pooled, static_cast<size_t>(I) * 2048)) return rc;
   if (int rc = dev_alloc(t, &t->logits, static_cast<size_t>(I) * t->k_total)) return rc;
   if (int rc = dev_alloc(t, &t->dlogits, static_cast<size_t>(I) * t->k_total)) return rc;
+  t->dy_ring[0] = t->gbuf[2];
+  for (int i = 1; i < 3; ++i)
+    if (int rc = dev_alloc(t, &t->dy_ring[i], max_act * I)) return rc;
   __nv_bfloat16 *GA = t->gbuf[0], *GG = t->gbuf[1], *GY = t->gbuf[2], *GT = t->gbuf[3], *GD = t->gbuf[4],
                 *GZ = t->gbuf[5];
+  auto next_dy = [t]() { return t->dy_ring[t->dy_cursor++ % 3]; };
 
   // ---- forward ----
   Unit& stem = t->units[0];
@@ -391,9 +411,11 @@ static int build_graph(io_train* t) {
     const Blk& k = blks[bi];
     Unit &u1 = t->units[k.c1], &u2 = t->units[k.c2], &u3 = t->units[k.c3];
     // out = relu(bn3(conv3(a2)) + identity):  GA = d out  ->  GY = d y3, GG = masked gradient (identity branch)
+    GY = next_dy();
     add_bn_bwd(t, u3, GA, GY, GG, 3, k.tag + 3);   // ReLU bit mask of the block output
     if (int rc = add_wgrad(t, u3, u2.a, GY, k.tag + 3)) return rc;
     if (int rc = add_dgrad(t, u3, u3.h_out, u3.w_out, GY, nullptr, GT, k.tag + 3)) return rc;   // GT = d a2
+    GY = next_dy();
     add_bn_bwd(t, u2, GT, GY, nullptr, 2, k.tag + 2);                                          // GY = d y2
     if (int rc = add_wgrad(t, u2, u1.a, GY, k.tag + 2)) return rc;
     if (u2.stride == 1) {
@@ -405,6 +427,7 @@ static int build_graph(io_train* t) {
       });
       if (int rc = add_dgrad(t, u2, u2.h_in, u2.w_in, GZ, nullptr, GT, k.tag + 2)) return rc;
     }
+    GY = next_dy();
     add_bn_bwd(t, u1, GT, GY, nullptr, 2, k.tag + 1);                                          // GY = d y1
     if (int rc = add_wgrad(t, u1, k.x, GY, k.tag + 1)) return rc;
     if (k.ds < 0) {
@@ -429,6 +452,7 @@ static int build_graph(io_train* t) {
   push(t->bwd, 3, 0, 2.0 * I * (d / 2) * (d / 2) * 64 * 2.0, 2, [t, GA, GT](cudaStream_t s) {
     return maxpool_bwd_launch(GA, t->pool_idx, GT, t->imgs, t->d / 2, t->d / 2, 64, s);
   });
+  GY = next_dy();
   add_bn_bwd(t, stem, GT, GY, nullptr, 2, 1);
   {
     const double flops = 2.0 * I * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
@@ -442,11 +466,28 @@ static int build_graph(io_train* t) {
       return stem_unpack_grad_launch(t->stem_scratch, t->grads + off, s);
     });
   }
+  IO_CUDA(cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking));
+  if (const char* e = getenv("INSTAORDER_TRAIN_SIDE_STREAM")) t->use_side = atoi(e) != 0;
   t->built = true;
   return IO_OK;
 }
 
 static int run_ops(io_train* t, std::vector<TOp>& ops, cudaStream_t stream) {
+  // weight gradients go to a side stream (they only feed the gradient buffer) so that their tensor work overlaps the
+  // HBM-bound BatchNorm passes of the main chain; per-op profiling keeps everything on one stream
+  const bool side_on = t->use_side && !t->profile && t->side_stream != nullptr;
+  std::vector<std::pair<const void*, cudaEvent_t>> pending;   // dy buffer -> "its side reader is done" event
+  size_t ev_i = 0;
+  auto next_event = [&](cudaEvent_t* out) -> int {
+    if (ev_i >= t->side_ev.size()) {
+      cudaEvent_t e;
+      IO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      t->side_ev.push_back(e);
+    }
+    *out = t->side_ev[ev_i++];
+    return IO_OK;
+  };
+  bool forked = false;
   for (TOp& op : ops) {
     size_t idx = 0;
     if (t->profile) {
@@ -458,7 +499,30 @@ static int run_ops(io_train* t, std::vector<TOp>& ops, cudaStream_t stream) {
       }
       IO_CUDA(cudaEventRecord(t->ev[idx], stream));
     }
-    if (int rc = op.run(stream)) return rc;
+    if (side_on && op.writes != nullptr) {
+      for (size_t k = 0; k < pending.size(); ++k)
+        if (pending[k].first == op.writes) {
+          IO_CUDA(cudaStreamWaitEvent(stream, pending[k].second, 0));
+          pending.erase(pending.begin() + k);
+          break;
+        }
+    }
+    if (side_on && op.side) {
+      cudaEvent_t fork, done;
+      if (int rc = next_event(&fork)) return rc;
+      if (int rc = next_event(&done)) return rc;
+      IO_CUDA(cudaEventRecord(fork, stream));
+      IO_CUDA(cudaStreamWaitEvent(t->side_stream, fork, 0));
+      if (int rc = op.run(t->side_stream)) return rc;
+      IO_CUDA(cudaEventRecord(done, t->side_stream));
+      bool replaced = false;
+      for (auto& pr : pending)
+        if (pr.first == op.reads) { pr.second = done; replaced = true; }
+      if (!replaced) pending.emplace_back(op.reads, done);
+      forked = true;
+    } else {
+      if (int rc = op.run(stream)) return rc;
+    }
     if (t->profile) {
       IO_CUDA(cudaEventRecord(t->ev[idx + 1], stream));
       t->prof_kind.push_back(op.kind);
@@ -467,6 +531,12 @@ static int run_ops(io_train* t, std::vector<TOp>& ops, cudaStream_t stream) {
       t->prof_bytes.push_back(op.bytes);
     }
     ++t->last_launches;
+  }
+  if (forked) {   // join: everything the side stream did is ordered before whatever follows on the caller's stream
+    cudaEvent_t join;
+    if (int rc = next_event(&join)) return rc;
+    IO_CUDA(cudaEventRecord(join, t->side_stream));
+    IO_CUDA(cudaStreamWaitEvent(stream, join, 0));
   }
   return IO_OK;
 }
@@ -503,6 +573,8 @@ extern "C" int io_train_destroy(io_train_t* t) {
   if (!t) return IO_OK;
   for (void* p : t->allocs) cudaFree(p);
   for (cudaEvent_t e : t->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : t->side_ev) cudaEventDestroy(e);
+  if (t->side_stream) cudaStreamDestroy(t->side_stream);
   delete t;
   return IO_OK;
 }
