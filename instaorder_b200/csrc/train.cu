@@ -95,6 +95,9 @@ struct io_train {
   __nv_bfloat16* gbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // GA, GG, GY, GT, GD, GZ
   __nv_bfloat16* dy_ring[3] = {nullptr, nullptr, nullptr};   // dy buffers (gbuf[2] + 2 more) used in rotation, so a
   int dy_cursor = 0;                                         // weight gradient may lag two units behind the main chain
+  unsigned int* barriers = nullptr;     // [256] grid-barrier counters of the fused BatchNorm kernels (zeroed per step)
+  int barrier_cursor = 0;
+  bool fused_bn = true;
   cudaStream_t side_stream = nullptr;
   std::vector<cudaEvent_t> side_ev;     // fork / done event per side op
   bool use_side = true;
@@ -229,6 +232,15 @@ static void add_bn_fwd(io_train* t, Unit& u, const __nv_bfloat16* residual, int 
   double* mine = t->red[t->red_sel];
   double* next = t->red[t->red_sel ^ 1];
   t->red_sel ^= 1;
+  if (t->fused_bn) {   // statistics + apply in one cooperative launch (grid barrier in between)
+    unsigned int* bar = t->barriers + (t->barrier_cursor++ % 256);
+    push(t->fwd, 3, 0, act * (residual ? 4.0 : 3.0), tag, [t, up, residual, rows, c, relu, mine, next, bar](cudaStream_t s) {
+      return bn_fwd_fused_launch(up->y, residual, up->a, 2, rows, c, mine, t->params + up->g_off,
+                                 t->params + up->b_off, 1e-5f, 0.1f, up->save, t->stats + up->rm_off,
+                                 t->stats + up->rv_off, next, relu, (residual && relu) ? up->mask : nullptr, bar, s);
+    });
+    return;
+  }
   push(t->fwd, 3, 0, act, tag, [up, rows, c, mine](cudaStream_t s) {
     return bn_stats_launch(up->y, 2, rows, c, mine, s);
   });
@@ -251,6 +263,16 @@ static void add_bn_bwd(io_train* t, Unit& u, const __nv_bfloat16* da, __nv_bfloa
   double* mine = t->red[t->red_sel];
   double* next = t->red[t->red_sel ^ 1];
   t->red_sel ^= 1;
+  if (t->fused_bn) {
+    unsigned int* bar = t->barriers + (t->barrier_cursor++ % 256);
+    push(t->bwd, 3, 0, act * (2.0 * reads + 1.0 + (g_out ? 1.0 : 0.0)), tag,
+         [t, up, da, dy, g_out, rows, c, mask_mode, mine, next, mask_src, bar](cudaStream_t s) {
+           return bn_bwd_fused_launch(da, mask_src, up->y, dy, g_out, 2, rows, c, t->params + up->g_off, up->save,
+                                      mine, mask_mode, t->grads + up->g_off, t->grads + up->b_off, next, bar, s);
+         });
+    t->bwd.back().writes = dy;
+    return;
+  }
   push(t->bwd, 3, 0, act * reads, tag, [up, da, rows, c, mask_mode, mine, mask_src](cudaStream_t s) {
     return bn_bwd_reduce_launch(da, mask_src, up->y, 2, rows, c, up->save, mask_mode, mine, s);
   });
@@ -316,6 +338,8 @@ static int build_graph(io_train* t) {
   if (int rc = dev_alloc(t, &t->stem_scratch, 128 * 448)) return rc;
   if (int rc = dev_alloc(t, &t->zero_bias, 2048)) return rc;
   IO_CUDA(cudaMemset(t->zero_bias, 0, 2048 * sizeof(float)));
+  if (int rc = dev_alloc(t, &t->barriers, 256)) return rc;
+  if (const char* e = getenv("INSTAORDER_TRAIN_FUSED_BN")) t->fused_bn = atoi(e) != 0;
   for (int i = 0; i < 2; ++i) {
     if (int rc = dev_alloc(t, &t->red[i], 2 * 2 * 2048)) return rc;
     IO_CUDA(cudaMemset(t->red[i], 0, sizeof(double) * 2 * 2 * 2048));
@@ -638,6 +662,7 @@ extern "C" int io_train_forward_backward(io_train_t* t, const void* pair_tensor_
   t->out_losses = out_losses_dev;
   t->last_launches = 0;
   t->prof_kind.clear(); t->prof_tag.clear(); t->prof_flops.clear(); t->prof_bytes.clear();
+  IO_CUDA(cudaMemsetAsync(t->barriers, 0, sizeof(unsigned int) * 256, stream));
   if (int rc = run_ops(t, t->fwd, stream)) return rc;
   if (run_backward) {
     IO_CUDA(cudaMemsetAsync(t->grads, 0, sizeof(float) * t->n_params, stream));

@@ -66,6 +66,14 @@ int bn_bwd_reduce_launch(const void* da, const void* a, const void* y, int group
 int bn_bwd_apply_launch(const void* da, const void* a, const void* y, void* dy, void* g_out, int groups, int rows,
                         int c, const float* gamma, const float* save, const double* red, int mask_mode, float* dgamma,
                         float* dbeta, double* zero_me, cudaStream_t stream);
+// one-launch variants (cooperative grid, grid-wide barrier between the two passes); `barrier` = one zeroed counter
+int bn_fwd_fused_launch(const void* y, const void* residual, void* a, int groups, int rows, int c, double* sums,
+                        const float* gamma, const float* beta, float eps, float momentum, float* save,
+                        float* running_mean, float* running_var, double* zero_me, int relu, uint8_t* mask_out,
+                        unsigned int* barrier, cudaStream_t stream);
+int bn_bwd_fused_launch(const void* da, const void* a, const void* y, void* dy, void* g_out, int groups, int rows,
+                        int c, const float* gamma, const float* save, double* red, int mask_mode, float* dgamma,
+                        float* dbeta, double* zero_me, unsigned int* barrier, cudaStream_t stream);
 // max-pool 3x3 s2 p1 forward with arg-max (first maximum in window scan order) and its backward
 int maxpool_fwd_idx_launch(const void* x, void* y, uint8_t* idx, int b, int h, int w, int c, cudaStream_t stream);
 int maxpool_bwd_launch(const void* dy, const uint8_t* idx, void* dx, int b, int h, int w, int c, cudaStream_t stream);

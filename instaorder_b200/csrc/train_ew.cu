@@ -78,8 +78,8 @@ struct BnCoef {
 __device__ __forceinline__ BnCoef bn_coef(const double* sums, int g, int c, int ch, double m, float gamma, float beta,
                                           float eps) {
   BnCoef k;
-  const double mean = sums[(static_cast<size_t>(g) * 2 + 0) * c + ch] / m;
-  double var = sums[(static_cast<size_t>(g) * 2 + 1) * c + ch] / m - mean * mean;
+  const double mean = __ldcg(sums + (static_cast<size_t>(g) * 2 + 0) * c + ch) / m;
+  double var = __ldcg(sums + (static_cast<size_t>(g) * 2 + 1) * c + ch) / m - mean * mean;
   if (var < 0.0) var = 0.0;
   k.var = var;
   k.mean = static_cast<float>(mean);
@@ -410,6 +410,328 @@ int bn_bwd_apply_launch(const void* da, const void* a, const void* y, void* dy, 
                      reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(a),
                      reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(dy), reinterpret_cast<uint4*>(g_out),
                      groups, rows, c, s, gamma, save, red, mask_mode, dgamma, dbeta, zero_me));
+  return IO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two-phase cooperative BatchNorm kernels: statistics + apply (forward) and reduce + apply (backward) in ONE launch
+// each, separated by a grid-wide barrier.  A persistent grid (all blocks co-resident: cooperative launch) walks the
+// slabs twice; the per-thread partial sums live in registers across all of a block's slabs, so there is ONE
+// shared-memory reduction + atomic flush per block instead of one per slab, and for every tensor that fits the
+// 126 MB L2 the second pass never touches HBM.  Halves the number of element-wise launches of a training step.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int n_blocks) {
+  __threadfence();      // every thread's atomics / stores of phase 1 are visible before its block signals
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < n_blocks) __nanosleep(40);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) bn_fwd_fused_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res,
+                                                           uint4* __restrict__ a, int groups, int rows, int c, Slab s,
+                                                           double* __restrict__ sums, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, float momentum,
+                                                           float* __restrict__ save, float* __restrict__ running_mean,
+                                                           float* __restrict__ running_var,
+                                                           double* __restrict__ zero_me, int relu,
+                                                           uint8_t* __restrict__ mask_out,
+                                                           unsigned int* __restrict__ barrier) {
+  const int g = blockIdx.y;
+  const int t = threadIdx.x;
+  const int lc = t % s.lanes_c, roff = t / s.lanes_c;
+  const size_t base = (static_cast<size_t>(g) * rows) * s.c8 + lc;
+  // ---- phase 1: statistics
+  {
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+    for (int slab = blockIdx.x; slab < s.slabs; slab += gridDim.x) {
+      const int r0 = slab * s.slab_rows;
+      const int r1 = min(r0 + s.slab_rows, rows);
+      for (int r = r0 + roff; r < r1; r += 8 * s.rows_par) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rr = r + u * s.rows_par;
+          v[u] = rr < r1 ? __ldg(y + base + static_cast<size_t>(rr) * s.c8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const Vec8 f = unpack8(v[u]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[0][j] += f.v[j]; acc[1][j] = fmaf(f.v[j], f.v[j], acc[1][j]); }
+        }
+      }
+    }
+    slab_reduce_store<2>(acc, s.lanes_c, s.rows_par, g, c, sums);
+  }
+  grid_barrier(barrier, gridDim.x * gridDim.y);
+  // ---- phase 2: coefficients, bookkeeping (block (0,0)), apply
+  const double m = static_cast<double>(rows);
+  if (blockIdx.x == 0 && g == 0) {
+    const size_t gc = static_cast<size_t>(groups) * c;
+    for (int ch = t; ch < c; ch += 256) {
+      float rm = running_mean[ch], rv = running_var[ch];
+      const float ga = gamma[ch], be = beta[ch];
+      for (int q = 0; q < groups; ++q) {
+        const BnCoef k = bn_coef(sums, q, c, ch, m, ga, be, eps);
+        save[0 * gc + q * c + ch] = k.scale;
+        save[1 * gc + q * c + ch] = k.shift;
+        save[2 * gc + q * c + ch] = k.mean;
+        save[3 * gc + q * c + ch] = k.invstd;
+        const double unbiased = rows > 1 ? k.var * m / (m - 1.0) : k.var;
+        rm = (1.0f - momentum) * rm + momentum * k.mean;
+        rv = (1.0f - momentum) * rv + momentum * static_cast<float>(unbiased);
+      }
+      running_mean[ch] = rm;
+      running_var[ch] = rv;
+    }
+    if (zero_me != nullptr)
+      for (int i = t; i < groups * 2 * c; i += 256) zero_me[i] = 0.0;
+  }
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = lc * 8 + j;
+    const BnCoef k = bn_coef(sums, g, c, ch, m, __ldg(gamma + ch), __ldg(beta + ch), eps);
+    sc[j] = k.scale;
+    sh[j] = k.shift;
+  }
+  for (int slab = blockIdx.x; slab < s.slabs; slab += gridDim.x) {
+    const int r0 = slab * s.slab_rows;
+    const int r1 = min(r0 + s.slab_rows, rows);
+    for (int r = r0 + roff; r < r1; r += 4 * s.rows_par) {
+      uint4 v[4], w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r + u * s.rows_par;
+        if (rr < r1) {
+          const size_t o = base + static_cast<size_t>(rr) * s.c8;
+          v[u] = __ldcg(y + o);
+          if (res != nullptr) w[u] = __ldg(res + o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r + u * s.rows_par;
+        if (rr >= r1) continue;
+        Vec8 f = unpack8(v[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f.v[j] = fmaf(f.v[j], sc[j], sh[j]);
+        if (res != nullptr) {
+          const Vec8 rv = unpack8(w[u]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f.v[j] += rv.v[j];
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f.v[j] = fmaxf(f.v[j], 0.f);
+        }
+        const uint4 packed = pack8(f);
+        a[base + static_cast<size_t>(rr) * s.c8] = packed;
+        if (mask_out != nullptr) {
+          const Vec8 st = unpack8(packed);
+          uint32_t mk = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mk |= (st.v[j] > 0.f ? 1u : 0u) << j;
+          mask_out[base + static_cast<size_t>(rr) * s.c8] = static_cast<uint8_t>(mk);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a,
+                                                           const uint4* __restrict__ y, uint4* __restrict__ dy,
+                                                           uint4* __restrict__ g_out, int groups, int rows, int c,
+                                                           Slab s, const float* __restrict__ gamma,
+                                                           const float* __restrict__ save, double* __restrict__ red,
+                                                           int mask_mode, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, double* __restrict__ zero_me,
+                                                           unsigned int* __restrict__ barrier) {
+  const int g = blockIdx.y;
+  const int t = threadIdx.x;
+  const int lc = t % s.lanes_c, roff = t / s.lanes_c;
+  const size_t gc = static_cast<size_t>(groups) * c;
+  const size_t base = (static_cast<size_t>(g) * rows) * s.c8 + lc;
+  float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = g * c + lc * 8 + j;
+    sc[j] = __ldg(save + ch);
+    sh[j] = __ldg(save + gc + ch);
+    mu[j] = __ldg(save + 2 * gc + ch);
+    is[j] = __ldg(save + 3 * gc + ch);
+  }
+  // ---- phase 1: sum g, sum g * xhat
+  {
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+    for (int slab = blockIdx.x; slab < s.slabs; slab += gridDim.x) {
+      const int r0 = slab * s.slab_rows;
+      const int r1 = min(r0 + s.slab_rows, rows);
+      for (int r = r0 + roff; r < r1; r += 4 * s.rows_par) {
+        uint4 vd[4], vy[4], va[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = r + u * s.rows_par;
+          if (rr < r1) {
+            const size_t o = base + static_cast<size_t>(rr) * s.c8;
+            vd[u] = __ldg(da + o);
+            vy[u] = __ldg(y + o);
+            if (mask_mode == 1) va[u] = __ldg(a + o);
+            else if (mask_mode == 3) va[u].x = __ldg(reinterpret_cast<const uint8_t*>(a) + o);
+          } else {
+            vd[u] = make_uint4(0, 0, 0, 0);
+            vy[u] = make_uint4(0, 0, 0, 0);
+            va[u] = make_uint4(0, 0, 0, 0);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          Vec8 gd = unpack8(vd[u]);
+          const Vec8 yv = unpack8(vy[u]);
+          if (mask_mode == 1) {
+            const Vec8 av = unpack8(va[u]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gd.v[j] = av.v[j] > 0.f ? gd.v[j] : 0.f;
+          } else if (mask_mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gd.v[j] = fmaf(yv.v[j], sc[j], sh[j]) > 0.f ? gd.v[j] : 0.f;
+          } else if (mask_mode == 3) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gd.v[j] = ((va[u].x >> j) & 1u) ? gd.v[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[0][j] += gd.v[j];
+            acc[1][j] = fmaf(gd.v[j], (yv.v[j] - mu[j]) * is[j], acc[1][j]);
+          }
+        }
+      }
+    }
+    slab_reduce_store<2>(acc, s.lanes_c, s.rows_par, g, c, red);
+  }
+  grid_barrier(barrier, gridDim.x * gridDim.y);
+  // ---- phase 2
+  if (blockIdx.x == 0 && g == 0) {
+    for (int ch = t; ch < c; ch += 256) {
+      double sg = 0.0, sgx = 0.0;
+      for (int q = 0; q < groups; ++q) {
+        sg += __ldcg(red + (static_cast<size_t>(q) * 2 + 0) * c + ch);
+        sgx += __ldcg(red + (static_cast<size_t>(q) * 2 + 1) * c + ch);
+      }
+      dbeta[ch] += static_cast<float>(sg);
+      dgamma[ch] += static_cast<float>(sgx);
+    }
+    if (zero_me != nullptr)
+      for (int i = t; i < groups * 2 * c; i += 256) zero_me[i] = 0.0;
+  }
+  const float inv_m = 1.0f / static_cast<float>(rows);
+  float k1[8], k2[8], k3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = lc * 8 + j;
+    k1[j] = __ldg(gamma + ch) * is[j];
+    k2[j] = static_cast<float>(__ldcg(red + (static_cast<size_t>(g) * 2 + 0) * c + ch)) * inv_m;
+    k3[j] = static_cast<float>(__ldcg(red + (static_cast<size_t>(g) * 2 + 1) * c + ch)) * inv_m;
+  }
+  for (int slab = blockIdx.x; slab < s.slabs; slab += gridDim.x) {
+    const int r0 = slab * s.slab_rows;
+    const int r1 = min(r0 + s.slab_rows, rows);
+    for (int r = r0 + roff; r < r1; r += 2 * s.rows_par) {
+      uint4 vd[2], vy[2], va[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int rr = r + u * s.rows_par;
+        if (rr < r1) {
+          const size_t o = base + static_cast<size_t>(rr) * s.c8;
+          vd[u] = __ldg(da + o);
+          vy[u] = __ldg(y + o);
+          if (mask_mode == 1) va[u] = __ldg(a + o);
+          else if (mask_mode == 3) va[u].x = __ldg(reinterpret_cast<const uint8_t*>(a) + o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int rr = r + u * s.rows_par;
+        if (rr >= r1) continue;
+        const size_t o = base + static_cast<size_t>(rr) * s.c8;
+        Vec8 gd = unpack8(vd[u]);
+        const Vec8 yv = unpack8(vy[u]);
+        if (mask_mode == 1) {
+          const Vec8 av = unpack8(va[u]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gd.v[j] = av.v[j] > 0.f ? gd.v[j] : 0.f;
+        } else if (mask_mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gd.v[j] = fmaf(yv.v[j], sc[j], sh[j]) > 0.f ? gd.v[j] : 0.f;
+        } else if (mask_mode == 3) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gd.v[j] = ((va[u].x >> j) & 1u) ? gd.v[j] : 0.f;
+        }
+        if (g_out != nullptr) g_out[o] = pack8(gd);
+        Vec8 out;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out.v[j] = k1[j] * (gd.v[j] - k2[j] - (yv.v[j] - mu[j]) * is[j] * k3[j]);
+        dy[o] = pack8(out);
+      }
+    }
+  }
+}
+
+// co-resident capacity of a cooperative 256-thread kernel
+template <typename K>
+static int coop_capacity(K kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * num_sms();
+}
+
+int bn_fwd_fused_launch(const void* y, const void* residual, void* a, int groups, int rows, int c, double* sums,
+                        const float* gamma, const float* beta, float eps, float momentum, float* save,
+                        float* running_mean, float* running_var, double* zero_me, int relu, uint8_t* mask_out,
+                        unsigned int* barrier, cudaStream_t stream) {
+  IO_REQUIRE(c % 8 == 0 && c <= 2048 && rows > 0 && groups > 0, "bn_fwd_fused: bad shape");
+  Slab s = slab_geom(rows, c);
+  static const int cap = coop_capacity(bn_fwd_fused_kernel);
+  int gx = cap / groups;
+  if (gx > s.slabs) gx = s.slabs;
+  if (gx < 1) gx = 1;
+  const uint4* yp = reinterpret_cast<const uint4*>(y);
+  const uint4* rp = reinterpret_cast<const uint4*>(residual);
+  uint4* ap = reinterpret_cast<uint4*>(a);
+  void* args[] = {&yp, &rp, &ap, &groups, &rows, &c, &s, &sums, &gamma, &beta, &eps, &momentum, &save, &running_mean,
+                  &running_var, &zero_me, &relu, &mask_out, &barrier};
+  IO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bn_fwd_fused_kernel), dim3(gx, groups), dim3(256), args,
+                                      0, stream));
+  return IO_OK;
+}
+
+int bn_bwd_fused_launch(const void* da, const void* a, const void* y, void* dy, void* g_out, int groups, int rows,
+                        int c, const float* gamma, const float* save, double* red, int mask_mode, float* dgamma,
+                        float* dbeta, double* zero_me, unsigned int* barrier, cudaStream_t stream) {
+  IO_REQUIRE(c % 8 == 0 && c <= 2048 && rows > 0 && groups > 0, "bn_bwd_fused: bad shape");
+  Slab s = slab_geom(rows, c);
+  static const int cap = coop_capacity(bn_bwd_fused_kernel);
+  int gx = cap / groups;
+  if (gx > s.slabs) gx = s.slabs;
+  if (gx < 1) gx = 1;
+  const uint4* dap = reinterpret_cast<const uint4*>(da);
+  const uint4* ap = reinterpret_cast<const uint4*>(a);
+  const uint4* yp = reinterpret_cast<const uint4*>(y);
+  uint4* dyp = reinterpret_cast<uint4*>(dy);
+  uint4* gp = reinterpret_cast<uint4*>(g_out);
+  void* args[] = {&dap, &ap, &yp, &dyp, &gp, &groups, &rows, &c, &s, &gamma, &save, &red, &mask_mode, &dgamma, &dbeta,
+                  &zero_me, &barrier};
+  IO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bn_bwd_fused_kernel), dim3(gx, groups), dim3(256), args,
+                                      0, stream));
   return IO_OK;
 }
 
