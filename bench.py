@@ -24,6 +24,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION (the image default): keep stdout to the ONE JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 FLOP_PER_PAIR = 21.764e9          # 2 x 10.882 GFLOP (conv + FC, 2*MAC) @256^2
 PAIRS_PER_STEP = 256
