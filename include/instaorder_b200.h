@@ -111,6 +111,13 @@ IO_API int io_image_resize_rgb(const uint8_t* image_dev, int h, int w, int d, co
 IO_API int io_image_square_linear_rgb(const uint8_t* image_dev, int h, int w, int d, const float* mean_host,
                                       const float* std_host, float* lut_scratch_dev, float* rgb_plane_dev,
                                       void* stream);
+/* Training `resize` mode rgb (datasets/depth_occ_order_dataset.py:83-86): cv2.resize(image_u8, (d, d), INTER_LINEAR)
+ * (8-bit generic path, bit-exact) + Normalize -> fp32 plane [d][d][3]; pairs are assembled by io_pair_gather_resize
+ * with desc.s = 0.  In both resize-type modes bit 30 of desc.rgb_slot requests the horizontal flip of the training
+ * augmentation (:91-94, :122-129). */
+IO_API int io_image_resize_linear_rgb(const uint8_t* image_dev, int h, int w, int d, const float* mean_host,
+                                      const float* std_host, float* lut_scratch_dev, float* rgb_plane_dev,
+                                      void* stream);
 IO_API int io_pair_gather_resize(const float* rgb_planes_dev, const uint8_t* masks_dev, const io_pair_desc* descs_dev,
                           int p, int d, void* out_dev, void* stream);
 

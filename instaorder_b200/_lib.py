@@ -43,6 +43,7 @@ _SIGS = {
     "io_pair_gather_patch": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "io_image_resize_rgb": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "io_image_square_linear_rgb": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "io_image_resize_linear_rgb": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "io_pair_gather_resize": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "io_normalize_lut": (_i, [_vp, _vp, _vp]),
     "io_net_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),

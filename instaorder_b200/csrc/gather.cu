@@ -294,17 +294,20 @@ struct LutF {
   float v[3][256];
 };
 
+// square = 1: image mode (source = the centred zero-padded max(H, W) square); square = 0: plain H x W -> d x d resize
+// (training `resize` mode, datasets/depth_occ_order_dataset.py:83-86)
 __global__ void __launch_bounds__(GATHER_THREADS) square_linear_rgb_kernel(const uint8_t* __restrict__ img, int H, int W,
                                                                            int d, const float* __restrict__ lut,
-                                                                           float* __restrict__ plane) {
+                                                                           float* __restrict__ plane, int square) {
   const int S = max(H, W);
-  const int left = (S - W) / 2, top = (S - H) / 2;
+  const int SH = square ? S : H, SW = square ? S : W;
+  const int left = square ? (S - W) / 2 : 0, top = square ? (S - H) / 2 : 0;
   const int dy = blockIdx.x;
-  const LinTab ty = linear_entry(dy, S, d, false);
-  const int r0 = min(max(ty.idx, 0), S - 1) - top, r1 = min(max(ty.idx + 1, 0), S - 1) - top;
+  const LinTab ty = linear_entry(dy, SH, d, false);
+  const int r0 = min(max(ty.idx, 0), SH - 1) - top, r1 = min(max(ty.idx + 1, 0), SH - 1) - top;
   const bool ok0 = r0 >= 0 && r0 < H, ok1 = r1 >= 0 && r1 < H;
   for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
-    const LinTab tx = linear_entry(dx, S, d, true);
+    const LinTab tx = linear_entry(dx, SW, d, true);
     const int c0 = tx.idx - left, c1 = tx.idx + 1 - left;
     const bool okc0 = c0 >= 0 && c0 < W, okc1 = !tx.single && c1 >= 0 && c1 < W;
     float* o = plane + (static_cast<size_t>(dy) * d + dx) * 3;
@@ -335,7 +338,8 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_resize_kernel(const flo
   const io_pair_desc ds = descs[blockIdx.y];
   const uint8_t* __restrict__ ma = masks + ds.mask_a_off;
   const uint8_t* __restrict__ mb = masks + ds.mask_b_off;
-  const float* __restrict__ plane = planes + static_cast<size_t>(ds.rgb_slot) * d * d * 3;
+  const float* __restrict__ plane = planes + static_cast<size_t>(ds.rgb_slot & 0x3FFFFFFF) * d * d * 3;
+  const bool flip = (ds.rgb_slot & 0x40000000) != 0;   // training augmentation: mirror the resized pair horizontally
   const int H = ds.h, W = ds.w;
   __nv_bfloat16* out_pair = out + static_cast<size_t>(blockIdx.y) * (d + 6) * pitch * 8;
   const int row0 = blockIdx.x * GATHER_ROWS;
@@ -350,14 +354,15 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_resize_kernel(const flo
   for (int dy = row0; dy < row1; ++dy) {
     const int my = min(static_cast<int>(floor(__dmul_rn(static_cast<double>(dy), sy))), SH - 1) - top;
     for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
-      const int mx = min(static_cast<int>(floor(__dmul_rn(static_cast<double>(dx), sx))), SW - 1) - left;
+      const int sxp = flip ? d - 1 - dx : dx;           // output column dx shows the un-flipped column sxp
+      const int mx = min(static_cast<int>(floor(__dmul_rn(static_cast<double>(sxp), sx))), SW - 1) - left;
       float va = 0.f, vb = 0.f;
       if (my >= 0 && my < H && mx >= 0 && mx < W) {
         const size_t o = static_cast<size_t>(my) * W + mx;
         va = static_cast<float>(ma[o]);
         vb = static_cast<float>(mb[o]);
       }
-      const float* px = plane + (static_cast<size_t>(dy) * d + dx) * 3;
+      const float* px = plane + (static_cast<size_t>(dy) * d + sxp) * 3;
       const uint32_t rg = pack_bf16(px[0], px[1]);
       const uint32_t b = pack_bf16(px[2], 0.0f);
       store_pixel(out_pair + (static_cast<size_t>(dy + 3) * pitch + dx + 3) * 8, va, vb,
@@ -617,7 +622,21 @@ extern "C" int io_image_square_linear_rgb(const uint8_t* image, int h, int w, in
   fill_lut_f32(mean, stdv, lutf);
   IO_CUDA(cudaMemcpyAsync(lut_dev_scratch, lutf, sizeof(lutf), cudaMemcpyHostToDevice, as_stream(stream)));
   IO_CUDA(cudaStreamSynchronize(as_stream(stream)));   // lutf lives on this stack frame
-  square_linear_rgb_kernel<<<d, GATHER_THREADS, 0, as_stream(stream)>>>(image, h, w, d, lut_dev_scratch, plane);
+  square_linear_rgb_kernel<<<d, GATHER_THREADS, 0, as_stream(stream)>>>(image, h, w, d, lut_dev_scratch, plane, 1);
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
+extern "C" int io_image_resize_linear_rgb(const uint8_t* image, int h, int w, int d, const float* mean, const float* stdv,
+                                          float* lut_dev_scratch, float* plane, void* stream) {
+  IO_REQUIRE(image && mean && stdv && lut_dev_scratch && plane && h > 0 && w > 0,
+             "io_image_resize_linear_rgb: bad arguments");
+  if (int rc = check_d(d)) return rc;
+  float lutf[768];
+  fill_lut_f32(mean, stdv, lutf);
+  IO_CUDA(cudaMemcpyAsync(lut_dev_scratch, lutf, sizeof(lutf), cudaMemcpyHostToDevice, as_stream(stream)));
+  IO_CUDA(cudaStreamSynchronize(as_stream(stream)));   // lutf lives on this stack frame
+  square_linear_rgb_kernel<<<d, GATHER_THREADS, 0, as_stream(stream)>>>(image, h, w, d, lut_dev_scratch, plane, 0);
   IO_CUDA(cudaGetLastError());
   return IO_OK;
 }

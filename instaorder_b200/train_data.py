@@ -35,7 +35,8 @@ def _crop_box(boxes, idx1, idx2, base_aug, phase, randshift, rng):
     return int(cx - size / 2.), int(cy - size / 2.), int(size)
 
 
-def sample_pair(algo, boxes, gt, base_aug, pair=None, phase="train", extend_bidirec=False, rng=np.random):
+def sample_pair(algo, boxes, gt, base_aug, pair=None, phase="train", extend_bidirec=False, rng=np.random,
+                mode="patch"):
     """One training sample's random draws + labels, in the reference's order.  ``gt``: dict with the image's
     ``occ`` / ``depth`` / ``overlap`` / ``count`` matrices (reader.get_gt_ordering).  ``pair``: (idx1, idx2) for the
     depth datasets (they enumerate annotated pairs); None for the occlusion datasets, which draw it (70 % occluding
@@ -57,7 +58,10 @@ def sample_pair(algo, boxes, gt, base_aug, pair=None, phase="train", extend_bidi
             label = 2
     else:
         idx1, idx2 = int(pair[0]), int(pair[1])
-    x, y, s = _crop_box(boxes, idx1, idx2, base_aug, phase, True, rng)
+    if mode == "patch":
+        x, y, s = _crop_box(boxes, idx1, idx2, base_aug, phase, True, rng)
+    else:                        # `resize` / `image` modes use the whole image: no crop jitter is drawn (:81-140)
+        x, y, s = 0, 0, 0
     flip = bool(base_aug["flip"] and rng.rand() > 0.5)
     swapped = not (rng.rand() < 0.5)
     if algo in ("InstaOrderNet_od", "InstaOrderNet_d"):
@@ -89,10 +93,13 @@ class TrainBatchBuilder(object):
     [H,W,3] u8, ``masks`` [N,H,W] u8 (instaorder_b200.engine.Scene); images and masks are uploaded once per scene and
     cached, so a batch costs one small descriptor upload + one kernel."""
 
-    def __init__(self, algo, input_size, batch_pairs, device="cuda:0"):
+    def __init__(self, algo, input_size, batch_pairs, device="cuda:0", mode="patch", max_scenes=64):
         self.lib = _lib.lib()
         if not torch.cuda.is_available():
             raise RuntimeError("TrainBatchBuilder needs a CUDA device (there is no CPU fallback)")
+        if mode not in ("patch", "resize", "image"):
+            raise ValueError("patch_or_image %r" % (mode,))
+        self.mode = mode
         self.algo, self.D, self.B = algo, int(input_size), int(batch_pairs)
         self.device = torch.device(device)
         self.pair_tensor = torch.zeros(int(self.lib.io_pair_tensor_bytes(self.B, self.D)), dtype=torch.uint8,
@@ -101,13 +108,29 @@ class TrainBatchBuilder(object):
         self.std = np.asarray(DATA_STD, dtype=np.float32)
         self._cache = {}
         self.gpu_launches = 0
+        # whole-image modes: one pre-resized fp32 rgb plane per resident scene, addressed by slot
+        self._planes = torch.empty((int(max_scenes), self.D, self.D, 3), dtype=torch.float32, device=self.device) \
+            if mode != "patch" else None
+        self._lut = torch.empty(768, dtype=torch.float32, device=self.device)
 
     def _resident(self, scene):
         key = id(scene)
         if key not in self._cache:
             img = torch.from_numpy(scene.image).to(self.device)
             msk = torch.from_numpy(scene.masks).to(self.device)
-            self._cache[key] = (scene, img, msk)
+            slot = None
+            if self.mode != "patch":     # the whole-image rgb is the same for every pair of the scene: resize it once
+                slot = len(self._cache)
+                if slot >= self._planes.shape[0]:
+                    raise RuntimeError("TrainBatchBuilder: more than max_scenes = %d resident scenes" %
+                                       self._planes.shape[0])
+                h, w = scene.image.shape[:2]
+                fn = self.lib.io_image_resize_linear_rgb if self.mode == "resize" else \
+                    self.lib.io_image_square_linear_rgb
+                _lib.check(fn(img.data_ptr(), h, w, self.D, _lib.ptr(self.mean), _lib.ptr(self.std),
+                              self._lut.data_ptr(), self._planes[slot].data_ptr(), _lib.stream_ptr()))
+                self.gpu_launches += 1
+            self._cache[key] = (scene, img, msk, slot)
         return self._cache[key][1:]
 
     def build(self, scenes, specs):
@@ -118,17 +141,29 @@ class TrainBatchBuilder(object):
         img_base = min(t[0].data_ptr() for t in res)
         msk_base = min(t[1].data_ptr() for t in res)
         desc = np.zeros(self.B, dtype=_lib.PAIR_DESC_DTYPE)
-        for k, (sc, sp, (img, msk)) in enumerate(zip(scenes, specs, res)):
-            if sp.s <= 0:
-                raise _lib.IoError(_lib.IO_ERR_DEGENERATE, "degenerate training pair (crop side %d)" % sp.s)
-            n, h, w = sc.masks.shape
-            a, b = (sp.idx2, sp.idx1) if sp.swapped else (sp.idx1, sp.idx2)
-            desc[k] = (img.data_ptr() - img_base, msk.data_ptr() - msk_base + a * h * w,
-                       msk.data_ptr() - msk_base + b * h * w, h, w, sp.x, sp.y, sp.s, 1 if sp.flip else 0)
-        d_desc = torch.from_numpy(desc.view(np.uint8)).to(self.device)
-        _lib.check(self.lib.io_pair_gather_patch(img_base, msk_base, d_desc.data_ptr(), self.B, self.D,
-                                                 _lib.ptr(self.mean), _lib.ptr(self.std), self.pair_tensor.data_ptr(),
-                                                 _lib.stream_ptr()))
+        if self.mode == "patch":
+            for k, (sc, sp, (img, msk, _)) in enumerate(zip(scenes, specs, res)):
+                if sp.s <= 0:
+                    raise _lib.IoError(_lib.IO_ERR_DEGENERATE, "degenerate training pair (crop side %d)" % sp.s)
+                n, h, w = sc.masks.shape
+                a, b = (sp.idx2, sp.idx1) if sp.swapped else (sp.idx1, sp.idx2)
+                desc[k] = (img.data_ptr() - img_base, msk.data_ptr() - msk_base + a * h * w,
+                           msk.data_ptr() - msk_base + b * h * w, h, w, sp.x, sp.y, sp.s, 1 if sp.flip else 0)
+            d_desc = torch.from_numpy(desc.view(np.uint8)).to(self.device)
+            _lib.check(self.lib.io_pair_gather_patch(img_base, msk_base, d_desc.data_ptr(), self.B, self.D,
+                                                     _lib.ptr(self.mean), _lib.ptr(self.std),
+                                                     self.pair_tensor.data_ptr(), _lib.stream_ptr()))
+        else:
+            for k, (sc, sp, (img, msk, slot)) in enumerate(zip(scenes, specs, res)):
+                n, h, w = sc.masks.shape
+                a, b = (sp.idx2, sp.idx1) if sp.swapped else (sp.idx1, sp.idx2)
+                sq = max(h, w) if self.mode == "image" else 0
+                desc[k] = (0, msk.data_ptr() - msk_base + a * h * w, msk.data_ptr() - msk_base + b * h * w, h, w,
+                           (sq - w) // 2 if sq else 0, (sq - h) // 2 if sq else 0, sq,
+                           slot | (0x40000000 if sp.flip else 0))
+            d_desc = torch.from_numpy(desc.view(np.uint8)).to(self.device)
+            _lib.check(self.lib.io_pair_gather_resize(self._planes.data_ptr(), msk_base, d_desc.data_ptr(), self.B,
+                                                      self.D, self.pair_tensor.data_ptr(), _lib.stream_ptr()))
         self.gpu_launches += 1
         labels = np.asarray([sp.labels for sp in specs], dtype=np.float64)
         return self.pair_tensor, labels

@@ -67,7 +67,7 @@ def load_reference_datasets():
     return r_datasets
 
 
-def make_dataset(r_datasets, cls_name, algo, scene):
+def make_dataset(r_datasets, cls_name, algo, scene, mode="patch"):
     import torchvision.transforms as transforms
     from PIL import Image
     cls = getattr(r_datasets, cls_name)
@@ -80,10 +80,11 @@ def make_dataset(r_datasets, cls_name, algo, scene):
     ds.img_transform = transforms.Compose([transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
     ds.sz = SZ
     ds.phase = "train"
-    ds.config = dict(base_aug=BASE_AUG, load_rgb=True, patch_or_image="patch", train_image_root="", use_category=False,
+    ds.config = dict(base_aug=BASE_AUG, load_rgb=True, patch_or_image=mode, train_image_root="", use_category=False,
                      extend_bidirec=False, dataset="InstaOrder")
     ds.memcached = False
-    ds.get_pair_patch_or_image = ds._get_pair
+    ds.get_pair_patch_or_image = {"patch": ds._get_pair, "resize": ds._get_pair_resize,
+                                  "image": ds._get_pair_image}[mode]
     ds._load_image = lambda fn: Image.fromarray(scene[0])
     return ds
 
@@ -103,6 +104,15 @@ def main():
             x = np.concatenate([s[1].numpy(), s[2].numpy(), s[0].numpy()], 0).astype(np.float32)   # (m1, m2, rgb)
             out["%s_%d_x" % (name, k)] = x
             out["%s_%d_labels" % (name, k)] = np.concatenate(
+                [np.asarray(v, dtype=np.float64).reshape(-1) for v in s[3:]])
+    # the shipped ^od / ^d training configs use patch_or_image = "resize"; "image" is the third branch
+    for mode in ("resize", "image"):
+        ds = make_dataset(r_datasets, "SupDepthOccOrderDataset", "InstaOrderNet_od", scene, mode)
+        for k in range(N_SAMPLES):
+            np.random.seed(2000 + k)
+            s = ds[k]
+            out["od_%s_%d_x" % (mode, k)] = np.concatenate([s[1].numpy(), s[2].numpy(), s[0].numpy()], 0).astype(np.float32)
+            out["od_%s_%d_labels" % (mode, k)] = np.concatenate(
                 [np.asarray(v, dtype=np.float64).reshape(-1) for v in s[3:]])
     path = os.path.join(GOLDEN, "traindata.npz")
     np.savez_compressed(path, **out)

@@ -36,6 +36,36 @@ def get_pair(image, modal, bboxes, idx1, idx2, sz, base_aug, phase="train", rand
     return np.ascontiguousarray(m1), np.ascontiguousarray(m2), O.transform_rgb(np.ascontiguousarray(rgb)), new_bbox, flip
 
 
+def get_pair_resize(image, modal, idx1, idx2, sz, base_aug, rng=np.random):
+    """_get_pair_resize (depth_occ_order_dataset.py:81-99): whole image -> sz x sz, INTER_LINEAR on u8; masks nearest."""
+    rgb = O.resize_linear_u8(image, sz, sz)
+    m1 = O.resize_nearest(modal[idx1], sz, sz)
+    m2 = O.resize_nearest(modal[idx2], sz, sz)
+    flip = bool(base_aug["flip"] and rng.rand() > 0.5)
+    if flip:
+        m1, m2, rgb = m1[:, ::-1], m2[:, ::-1], rgb[:, ::-1, :]
+    return np.ascontiguousarray(m1), np.ascontiguousarray(m2), O.transform_rgb(np.ascontiguousarray(rgb)), None, flip
+
+
+def get_pair_image(image, modal, idx1, idx2, sz, base_aug, rng=np.random):
+    """_get_pair_image (depth_occ_order_dataset.py:101-140): centred zero-padded square -> sz x sz."""
+    m1 = O.resize_nearest(O.pad_square(modal[idx1]), sz, sz)
+    m2 = O.resize_nearest(O.pad_square(modal[idx2]), sz, sz)
+    flip = bool(base_aug["flip"] and rng.rand() > 0.5)
+    rgb = O.resize_linear_u8(O.pad_square(image), sz, sz)
+    if flip:
+        m1, m2, rgb = m1[:, ::-1], m2[:, ::-1], rgb[:, ::-1, :]
+    return np.ascontiguousarray(m1), np.ascontiguousarray(m2), O.transform_rgb(np.ascontiguousarray(rgb)), None, flip
+
+
+def get_pair_any(mode, image, modal, bboxes, idx1, idx2, sz, base_aug, rng=np.random):
+    if mode == "patch":
+        return get_pair(image, modal, bboxes, idx1, idx2, sz, base_aug, rng=rng)
+    if mode == "resize":
+        return get_pair_resize(image, modal, idx1, idx2, sz, base_aug, rng=rng)
+    return get_pair_image(image, modal, idx1, idx2, sz, base_aug, rng=rng)
+
+
 def depth_label(gt_depth, idx1, idx2):
     """depth_occ_order_dataset.py:229-235: A<B -> 0, A=B -> 2, no annotation -> -1."""
     if gt_depth[idx1, idx2] == -1:
@@ -47,9 +77,10 @@ def depth_label(gt_depth, idx1, idx2):
     raise ValueError("inconsistent depth annotation for (%d, %d)" % (idx1, idx2))
 
 
-def getitem_od(image, modal, bboxes, idx1, idx2, gt_depth, gt_overlap, gt_count, gt_occ, sz, base_aug, rng=np.random):
+def getitem_od(image, modal, bboxes, idx1, idx2, gt_depth, gt_overlap, gt_count, gt_occ, sz, base_aug, rng=np.random,
+               mode="patch"):
     """SupDepthOccOrderDataset.__getitem__ (depth_occ_order_dataset.py:207-252)."""
-    m1, m2, rgb, nb, flip = get_pair(image, modal, bboxes, idx1, idx2, sz, base_aug, rng=rng)
+    m1, m2, rgb, nb, flip = get_pair_any(mode, image, modal, bboxes, idx1, idx2, sz, base_aug, rng=rng)
     lab = depth_label(gt_depth, idx1, idx2)
     count, ovl = gt_count[idx1, idx2], gt_overlap[idx1, idx2]
     a_over_b, b_over_a = gt_occ[idx1, idx2], gt_occ[idx2, idx1]

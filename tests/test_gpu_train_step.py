@@ -310,3 +310,30 @@ def test_train_batch_builder_matches_reference_getitem(name, algo, golden_dir):
         m.set_input_pairs(pt, GG.SZ, lab[:, 0].long(), lab[:, 1].long(), lab[:, 2].long(), lab[:, 3:5].float())
         log, out = m.step()
         assert np.isfinite(float(out["loss"]))
+
+
+@pytest.mark.parametrize("mode", ["resize", "image"])
+def test_train_batch_builder_whole_image_modes(mode, golden_dir):
+    """G13, `resize` (shipped ^od training config) and `image` modes on the GPU: per-scene u8 INTER_LINEAR plane (once) +
+    one gather launch per batch (nearest masks, flip, A/B swap); masks bit-exact, rgb equal to bf16(reference)."""
+    from instaorder_b200 import engine, train_data as TD
+    from oracle import gen_golden_traindata as GG
+    z = np.load(os.path.join(golden_dir, "traindata.npz"))
+    image, masks, boxes, occ, depth, overlap, count, geo = GG.make_scene()
+    gt = dict(occ=occ, depth=depth, overlap=overlap, count=count)
+    scene = engine.Scene(image, masks, boxes)
+    B = GG.N_SAMPLES
+    specs = []
+    for k in range(B):
+        np.random.seed(2000 + k)
+        s = geo[k % len(geo)]
+        specs.append(TD.sample_pair("InstaOrderNet_od", boxes, gt, GG.BASE_AUG,
+                                    pair=tuple(map(int, s.split("<" if "<" in s else "="))), mode=mode))
+    bld = TD.TrainBatchBuilder("InstaOrderNet_od", GG.SZ, B, DEV, mode=mode)
+    pt, labels = bld.build([scene] * B, specs)
+    torch.cuda.synchronize()
+    got, _ = U.unpack_pair_tensor(pt, B, GG.SZ)
+    for k in range(B):
+        want = U.f32_to_bf16_rn(z["od_%s_%d_x" % (mode, k)])
+        assert np.array_equal(got[k], want), "%s sample %d differs (%d elements)" % (mode, k, int((got[k] != want).sum()))
+        assert np.array_equal(labels[k], z["od_%s_%d_labels" % (mode, k)])

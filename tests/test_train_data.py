@@ -63,3 +63,24 @@ def test_host_sampler_matches_oracle(name, algo):
         assert np.array_equal(np.asarray(spec.labels, dtype=np.float64), labels)
         if pair is None:
             assert (spec.idx1, spec.idx2) == r["idx"]
+
+
+@pytest.mark.parametrize("mode", ["resize", "image"])
+def test_oracle_getitem_whole_image_modes(mode, golden_dir):
+    """`resize` (the shipped ^od / ^d training config) and `image` modes: u8 INTER_LINEAR + nearest + flip + swap."""
+    z = np.load(os.path.join(golden_dir, "traindata.npz"))
+    image, masks, boxes, occ, depth, overlap, count, geo = GG.make_scene()
+    gt = dict(occ=occ, depth=depth, overlap=overlap, count=count)
+    for k in range(GG.N_SAMPLES):
+        s = geo[k % len(geo)]
+        i1, i2 = map(int, s.split("<" if "<" in s else "="))
+        np.random.seed(2000 + k)
+        r = TO.getitem_od(image, masks, boxes, i1, i2, depth, overlap, count, occ, GG.SZ, GG.BASE_AUG, mode=mode)
+        x = np.concatenate([r["modal1"][None].astype(np.float32), r["modal2"][None].astype(np.float32), r["rgb"]], 0)
+        assert np.array_equal(x, z["od_%s_%d_x" % (mode, k)]), (mode, k)
+        labels = np.asarray([r["depth"], r["count"], r["overlap"]] + list(r["occ"]), dtype=np.float64)
+        assert np.array_equal(labels, z["od_%s_%d_labels" % (mode, k)])
+        np.random.seed(2000 + k)
+        spec = TD.sample_pair("InstaOrderNet_od", boxes, gt, GG.BASE_AUG, pair=(i1, i2), mode=mode)
+        assert spec.flip == r["flip"] and spec.swapped == r["swapped"]
+        assert np.array_equal(np.asarray(spec.labels, dtype=np.float64), labels)
