@@ -73,6 +73,11 @@ IO_API int io_pair_bordering(const uint8_t* masks_dev, int n, int h, int w, cons
 IO_API int io_infer_gt_order(const uint8_t* modal_dev, const uint8_t* amodal_dev, int n, int h, int w,
                              const int32_t* pairs_dev, int p, int64_t* mat_dev, void* stream);
 
+/* Per-instance statistics behind the heuristic baselines infer_occ_order_area / _yaxis and infer_depth_order_area /
+ * _yaxis (inference.py:272-346): out_dev[i] = (sum of mask values, #pixels == 1, sum of the row index over pixels == 1)
+ * as exact int64; the N x N comparison (with io_pair_bordering for the occlusion variants) is host logic. */
+IO_API int io_mask_stats(const uint8_t* masks_dev, int n, int h, int w, int64_t* out_dev, void* stream);
+
 /* One record per pair for the fused gather.  Offsets are in bytes from the base pointers passed to the call. */
 typedef struct io_pair_desc {
   int64_t image_off;  /* start of the pair's H x W x 3 u8 image                         */

@@ -38,6 +38,7 @@ _SIGS = {
     "io_pair_crop_boxes": (_i, [_vp, _vp, _i, _vp]),
     "io_pair_bordering": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "io_infer_gt_order": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "io_mask_stats": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "io_pair_tensor_row_pitch": (_i64, [_i]),
     "io_pair_tensor_bytes": (_i64, [_i, _i]),
     "io_pair_gather_patch": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),

@@ -560,6 +560,42 @@ extern "C" int io_pair_bordering(const uint8_t* masks, int n, int h, int w, cons
   return IO_OK;
 }
 
+// ---- per-instance mask statistics for the heuristic baselines (reference inference.py:272-346) -----------------
+// out[i] = (sum of mask values, number of pixels == 1, sum of the row index over pixels == 1), exact integers
+__global__ void __launch_bounds__(256) mask_stats_kernel(const uint8_t* __restrict__ masks, int h, int w,
+                                                         unsigned long long* __restrict__ out) {
+  const int inst = blockIdx.y;
+  const uint8_t* m = masks + static_cast<size_t>(inst) * h * w;
+  unsigned long long sv = 0, cnt = 0, sy = 0;
+  const size_t total = static_cast<size_t>(h) * w;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const unsigned v = m[i];
+    sv += v;
+    if (v == 1u) { cnt += 1; sy += static_cast<unsigned long long>(i / w); }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + inst * 3 + 0, sv);
+    atomicAdd(out + inst * 3 + 1, cnt);
+    atomicAdd(out + inst * 3 + 2, sy);
+  }
+}
+
+extern "C" int io_mask_stats(const uint8_t* masks, int n, int h, int w, int64_t* out, void* stream) {
+  IO_REQUIRE(masks && out && n > 0 && h > 0 && w > 0, "io_mask_stats: bad arguments");
+  IO_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t) * 3 * n, as_stream(stream)));
+  const int gx = static_cast<int>(std::min<size_t>((static_cast<size_t>(h) * w + 256 * 8 - 1) / (256 * 8), 64));
+  mask_stats_kernel<<<dim3(gx, n), 256, 0, as_stream(stream)>>>(masks, h, w,
+                                                                reinterpret_cast<unsigned long long*>(out));
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
 extern "C" int io_infer_gt_order(const uint8_t* modal, const uint8_t* amodal, int n, int h, int w, const int32_t* pairs,
                                  int p, int64_t* mat, void* stream) {
   IO_REQUIRE(modal && amodal && pairs && mat && n > 0 && h > 0 && w > 0 && p >= 0, "io_infer_gt_order: bad arguments");

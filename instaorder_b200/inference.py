@@ -68,6 +68,70 @@ def infer_gt_order(inmodal, amodal):
     return mat.cpu().numpy()
 
 
+def _mask_stats_and_bordering(inmodal, need_bordering):
+    """(stats int64 [N, 3] = (sum, #ones, sum of y over ones), bordering bool [P] for the row-major i < j pairs)."""
+    import torch
+    from . import _lib
+    inmodal = np.ascontiguousarray(inmodal, dtype=np.uint8)
+    n, h, w = inmodal.shape
+    dev = torch.device("cuda", torch.cuda.current_device())
+    m = torch.from_numpy(inmodal).to(dev)
+    st = torch.empty((n, 3), dtype=torch.int64, device=dev)
+    _lib.check(_lib.lib().io_mask_stats(m.data_ptr(), n, h, w, st.data_ptr(), _lib.stream_ptr()))
+    pairs = _engine.enumerate_pairs(n)
+    flags = None
+    if need_bordering and pairs.shape[0]:
+        pr = torch.from_numpy(pairs).to(dev)
+        fl = torch.zeros(pairs.shape[0], dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().io_pair_bordering(m.data_ptr(), n, h, w, pr.data_ptr(), pairs.shape[0], fl.data_ptr(),
+                                                _lib.stream_ptr()))
+        flags = fl.cpu().numpy().astype(bool)
+    return st.cpu().numpy(), pairs, flags
+
+
+def _heuristic(inmodal, key, first_wins, use_bordering):
+    """Shared body of the four baselines: for every pair (optionally only bordering ones) the instance with the
+    SMALLER key is ``a``; ``first_wins`` selects order[a, b] = 1, otherwise order[b, a] = 1.  Ties go to (j, i) exactly
+    as the reference's ``(i, j) if key_i < key_j else (j, i)``."""
+    st, pairs, flags = _mask_stats_and_bordering(inmodal, use_bordering)
+    n = st.shape[0]
+    order = np.zeros((n, n), dtype=np.int64)
+    if key == "area":
+        k = st[:, 0].astype(np.float64)
+    else:   # mean row index of the pixels == 1 (np.where(mask == 1)[0].mean()): exact int sums -> one fp64 division
+        with np.errstate(invalid="ignore", divide="ignore"):
+            k = st[:, 2].astype(np.float64) / st[:, 1].astype(np.float64)
+    for p, (i, j) in enumerate(pairs):
+        if flags is not None and not flags[p]:
+            continue
+        a, b = (i, j) if k[i] < k[j] else (j, i)
+        if first_wins:
+            order[a, b] = 1
+        else:
+            order[b, a] = 1
+    return order
+
+
+def infer_occ_order_area(inmodal, occluder="smaller"):
+    """reference inference.py:272-289: among bordering pairs the smaller (or larger) mask occludes."""
+    return _heuristic(inmodal, "area", occluder == "smaller", True)
+
+
+def infer_occ_order_yaxis(inmodal, occluder="lower"):
+    """reference inference.py:292-307 (``lower`` = smaller mean y, as the reference names it)."""
+    return _heuristic(inmodal, "y", occluder == "lower", True)
+
+
+def infer_depth_order_area(inmodal, closer="smaller"):
+    """reference inference.py:310-328: every pair, the smaller (or larger) mask is closer."""
+    return _heuristic(inmodal, "area", closer == "smaller", False)
+
+
+def infer_depth_order_yaxis(inmodal, closer="lower"):
+    """reference inference.py:331-346: ``higher`` = smaller mean y; closer == 'lower' writes order[lower, higher]."""
+    return _heuristic(inmodal, "y", closer != "lower", False)
+
+
 def eval_order_recall_precision_f1(order_matrix, gt_order_matrix, zd):
     """reference inference.py:794-802 -> (recall, precision, f1) x100, python floats."""
     if not np.any(np.asarray(gt_order_matrix) != -1):

@@ -55,3 +55,19 @@ def test_infer_gt_order_matches_reference(golden_dir):
         modal, amodal = gen_golden.kins_scene(int(z["seed%d" % t]))
         got = inference.infer_gt_order(modal, amodal)
         assert got.dtype == np.int64 and np.array_equal(got, z["gt%d" % t])
+
+
+def test_heuristic_baselines_match_reference(golden_dir):
+    """infer_occ_order_area / _yaxis and infer_depth_order_area / _yaxis (reference inference.py:272-346) through the
+    io_mask_stats + io_pair_bordering kernels: matrices identical to the unmodified reference's (integer work)."""
+    import os
+    import numpy as np
+    from instaorder_b200 import inference as infer
+    from oracle import gen_golden_heuristics as GH
+    z = np.load(os.path.join(golden_dir, "heuristics.npz"))
+    for k in range(len(GH.SCENES)):
+        masks = GH.scene_masks(k)
+        for fn, kw, opts in GH.VARIANTS:
+            for o in opts:
+                got = getattr(infer, fn)(masks, **{kw: o})
+                assert np.array_equal(got, z["s%d_%s_%s" % (k, fn, o)]), (k, fn, o)
