@@ -186,6 +186,14 @@ IO_API int io_order_decide(const float* logits_dev, int p, int k_total, int head
 IO_API int io_conv_bn_act(const void* x_dev, int b, int h, int w, int cin, const void* w_dev, const float* bias_dev,
                    const void* residual_dev, int cout, int kernel, int stride, int relu, void* y_dev, void* stream);
 
+/* First bottleneck of a ResNet layer (resnet_cls.py:107-116 with the downsample branch :112-113): y = ReLU(conv3(t2) +
+ * downsample(x)) as ONE GEMM over the concatenated K = [cmid channels of t2 | cin channels of x]; x_dev [b][h][w][cin],
+ * t2_dev [b*(h/stride)*(w/stride)][cmid], wcat_dev [cout][cmid + cin] (conv3 columns first, BN folded), bias_dev =
+ * sum of the two folded-BN shifts; stride 1 or 2.  The identity tensor never exists in HBM.  Exported for the parity
+ * test; io_net_forward_pairs uses it for layerN.0 (INSTAORDER_FUSE_DS=0 falls back to two launches). */
+IO_API int io_conv_dual(const void* x_dev, int b, int h, int w, int cin, int stride, const void* t2_dev, int cmid,
+                 const void* wcat_dev, const float* bias_dev, int cout, int relu, void* y_dev, void* stream);
+
 /* conv3 (1x1, cmid -> 4*cmid, + residual + ReLU -> y) of one bottleneck fused with conv1 (1x1, 4*cmid -> n2, + ReLU
  * -> y2) of the next one (resnet_cls.py:107-116 then :99-101): the block output is written once and consumed from
  * shared memory by the second GEMM.  x_dev: [rows][cmid], w3_dev: [4*cmid][cmid], w1n_dev: [n2][4*cmid], all bf16;

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     prefetch_tmap(&p.map_b);
     prefetch_tmap(&p.map_out);
     if (p.residual != nullptr) prefetch_tmap(&p.map_res);
+    if (p.k1 > 0) prefetch_tmap(&p.map_a2);
     for (int i = 0; i < 16; ++i) mbar_init(&rbar[i], 1);
     for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full[i], 1);
@@ -164,7 +165,9 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           mbar_expect_tx(&full[stage], p.a_bytes + (b_res ? 0 : C::B_STAGE_BYTES));
           void* dA = sA + stage * A_STAGE_BYTES;
           void* dB = sB + stage * C::B_STAGE_BYTES;
-          if (p.mode == CONV_GEMM) {
+          if (ki < p.k1) {   // dual-source K: leading blocks from the flat second matrix
+            tma_load_2d(dA, &p.map_a2, &full[stage], ki * BK, t.base_row);
+          } else if (p.mode == CONV_GEMM) {
             tma_load_2d(dA, &p.map_a, &full[stage], kb * BK, t.base_row);
           } else if (p.mode == CONV_S1) {
             const int r = tap / 3, s = tap - r * 3;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           } else if (!b_res) {
             tma_load_2d(dB, &p.map_b, &full[stage], ki * BK, n_tile * BN);
           }
-          if (++kb == p.kpt) { kb = 0; ++tap; }
+          if (ki >= p.k1 && ++kb == p.kpt) { kb = 0; ++tap; }
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -567,6 +570,28 @@ int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, con
   return make_out_maps(p, p->m_total);
 }
 
+int conv_plan_dual(ConvParams* p, int* bn_tile, const ConvDesc& ds, const void* x, const void* t2, int cmid,
+                   const void* wcat, const float* bias, void* y, int relu) {
+  IO_REQUIRE(ds.kernel == 1 && cmid % 64 == 0 && cmid > 0, "dual conv: 1x1 downsample and cmid %% 64 == 0 expected");
+  // geometry, activation map of x, output map: those of the downsample convolution alone
+  int rc = conv_plan(p, bn_tile, ds, x, wcat, bias, nullptr, y, relu);
+  if (rc) return rc;
+  const int bn = *bn_tile;
+  const int ktot = cmid + ds.cin;
+  p->k1 = cmid / 64;
+  p->k_iters = ktot / 64;
+  const uint64_t wdims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(ds.cout)};
+  const uint64_t wstr[1] = {static_cast<uint64_t>(ktot) * 2};
+  const uint32_t wbox[2] = {64, static_cast<uint32_t>(bn)};
+  if ((rc = make_tmap_bf16(&p->map_b, wcat, 2, wdims, wstr, wbox, true))) return rc;
+  const uint64_t dims[2] = {static_cast<uint64_t>(cmid), static_cast<uint64_t>(p->m_total)};
+  const uint64_t str[1] = {static_cast<uint64_t>(cmid) * 2};
+  const uint32_t box[2] = {64, static_cast<uint32_t>(p->rows_per_tile)};
+  if ((rc = make_tmap_bf16(&p->map_a2, t2, 2, dims, str, box, true))) return rc;
+  plan_smem(p, bn);
+  return IO_OK;
+}
+
 int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, const void* wgt, const float* bias,
               void* y) {
   IO_REQUIRE(d % 2 == 0 && d >= 32, "stem: input size %d", d);
@@ -661,6 +686,18 @@ extern "C" int io_conv_bn_act(const void* x_dev, int b, int h, int w, int cin, c
     return io::conv_tn_launch(tp, io::as_stream(stream));
   }
   int rc = io::conv_plan(&p, &bn, d, x_dev, w_dev, bias_dev, residual_dev, y_dev, relu);
+  if (rc) return rc;
+  return io::conv_tc_launch(p, bn, io::as_stream(stream));
+}
+
+// conv3 + downsample of a layer's first bottleneck as one GEMM over concatenated K (conv_plan_dual), for the parity test
+extern "C" int io_conv_dual(const void* x_dev, int b, int h, int w, int cin, int stride, const void* t2_dev, int cmid,
+                            const void* wcat_dev, const float* bias_dev, int cout, int relu, void* y_dev, void* stream) {
+  IO_REQUIRE(x_dev && t2_dev && wcat_dev && bias_dev && y_dev, "io_conv_dual: null pointer");
+  io::ConvParams p;
+  int bn = 0;
+  int rc = io::conv_plan_dual(&p, &bn, io::ConvDesc{b, h, w, cin, cout, 1, stride}, x_dev, t2_dev, cmid, wcat_dev,
+                              bias_dev, y_dev, relu);
   if (rc) return rc;
   return io::conv_tc_launch(p, bn, io::as_stream(stream));
 }

@@ -56,6 +56,10 @@ struct ConvParams {
   int mn_lbo, mn_sbo; // b_mn: descriptor byte offsets (8192 / 1024)
   int b_tap_cols;     // b_mn: columns per filter tap in the weight matrix (= Cin_f)
   int img_mul;        // CONV_STEM: output image of pair n, direction 0 is img_mul * n (2 = interleaved, 1 = [dir][pair])
+  // dual-source K (conv_plan_dual): the first k1 K blocks of every tile come from a second, flat [m_total, 64*k1]
+  // matrix (map_a2, box 64 x rows_per_tile at the tile's first output row); the remaining blocks from map_a as usual
+  CUtensorMap map_a2;
+  int k1;
 };
 
 // conv3 (+ residual + ReLU) of one bottleneck fused with conv1 (+ ReLU) of the next one (conv_fused.cu)
@@ -95,6 +99,12 @@ int conv_tc_launch(const ConvParams& p, int bn_tile, cudaStream_t stream);
 // Fills tile geometry + tensor maps for a conv over NHWC bf16 input [b, h, w, cin] (or the pair tensor for the stem).
 int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, const void* wgt, const float* bias,
               const void* residual, void* y, int relu);
+// First block of a ResNet layer: out = ReLU(conv3(t2) + bn3 + downsample(x) + bn_ds) as ONE GEMM over the concatenated
+// K = [t2 channels | x channels] (reference resnet_cls.py:107-116 with :112-113).  `ds` describes the 1x1 downsample
+// convolution over x (stride 1 or 2); t2 is the flat [b*ho*wo, cmid] conv2 output; wcat = [cout][cmid + ds.cin] bf16
+// (conv3 columns first), bias = the two folded-BN shifts added.  The identity tensor is never written to HBM.
+int conv_plan_dual(ConvParams* p, int* bn_tile, const ConvDesc& ds, const void* x, const void* t2, int cmid,
+                   const void* wcat, const float* bias, void* y, int relu);
 // Stem plan: x is the padded pair tensor [pairs, d+6, pitch, 8]; y is [2*pairs, d/2, d/2, 64] (image 2p + dir).
 int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, const void* wgt, const float* bias, void* y);
 // Data gradient of a stride-1 convolution (1x1 or 3x3 pad 1) as a convolution over dy [b, h, w, cout_f] with the

@@ -21,6 +21,10 @@ struct ConvW {
   int cin, cout, k, stride;
   __nv_bfloat16* w = nullptr;  // [cout][k*k*cin]
   float* bias = nullptr;       // [cout]
+  // downsample convs only: [cout][cmid + cin] = (conv3 | downsample) weights side by side and the two biases added,
+  // for the single-GEMM block output of conv_plan_dual
+  __nv_bfloat16* wcat = nullptr;
+  float* bias_cat = nullptr;
 };
 
 struct Op {
@@ -62,6 +66,7 @@ struct io_net {
   // phase A (stem .. layer2) works on sub-chunks of chunk_a pairs so that its large activations stay in L2;
   // phase B (layer3, layer4, tail) runs over chunk_b pairs at once so that its small GEMMs fill all SMs.
   int chunk_a = 0, chunk_b = 0;
+  bool fuse_ds = true;  // first block of a layer: conv3 + downsample as one GEMM over concatenated K (INSTAORDER_FUSE_DS=0 disables)
   bool fuse = false;  // conv3 -> next conv1 back-to-back GEMM fusion (INSTAORDER_FUSE=1 enables; parity-tested, not yet faster)
   __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase A: X, Y, T1, T2, DS
   __nv_bfloat16* bufb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase B: X, Y, T1, T2, DS
@@ -158,6 +163,20 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       o2.tag = (li + 1) * 100 + blk * 10 + 2;
       plan->ops.push_back(o2);
       const __nv_bfloat16* identity = src;
+      if (ds && net->fuse_ds) {
+        // block output = ReLU(conv3(T2) + downsample(src)) as one GEMM, K = [T2 channels | src channels]; the
+        // identity tensor is neither written nor re-read
+        Op o3; o3.kind = Op::CONV;
+        if (int rc = conv_plan_dual(&o3.p, &o3.bn_tile, ConvDesc{b, h, w, ds->cin, ds->cout, 1, ds->stride}, src, T2,
+                                    c3.cin, ds->wcat, ds->bias_cat, dst, 1)) return rc;
+        o3.flops = 2.0 * b * ho * wo * (static_cast<double>(c3.cin) + ds->cin) * c3.cout;
+        o3.bytes = 2.0 * b * ho * wo * (c3.cin + ds->cin + c3.cout) + 2.0 * (c3.cin + ds->cin) * c3.cout;
+        o3.tag = (li + 1) * 100 + blk * 10 + 6;
+        plan->ops.push_back(o3);
+        src = dst;
+        h = ho; w = wo;
+        continue;
+      }
       if (ds) {
         Op od; od.kind = Op::CONV;
         if (int rc = conv_plan(&od.p, &od.bn_tile, ConvDesc{b, h, w, ds->cin, ds->cout, 1, ds->stride}, src, ds->w,
@@ -259,6 +278,7 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
   if (const char* e = getenv("INSTAORDER_CHUNK_A")) chunk_a = atoi(e) > 0 ? atoi(e) : chunk_a;
   if (const char* e = getenv("INSTAORDER_CHUNK_B")) chunk_b = atoi(e) > 0 ? atoi(e) : chunk_b;
   if (const char* e = getenv("INSTAORDER_FUSE")) net->fuse = atoi(e) != 0;
+  if (const char* e = getenv("INSTAORDER_FUSE_DS")) net->fuse_ds = atoi(e) != 0;
   net->chunk_b = std::min(chunk_b, max_pairs);
   net->chunk_a = std::min(chunk_a, net->chunk_b);
   build_conv_list(net.get());
@@ -267,6 +287,10 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
     ConvW& c = net->convs[i];
     IO_CUDA(cudaMalloc(&c.w, static_cast<size_t>(c.cout) * c.k * c.k * c.cin * 2));
     IO_CUDA(cudaMalloc(&c.bias, static_cast<size_t>(c.cout) * 4));
+    if (c.name.find("downsample") != std::string::npos) {
+      IO_CUDA(cudaMalloc(&c.wcat, static_cast<size_t>(c.cout) * (c.cout / 4 + c.cin) * 2));
+      IO_CUDA(cudaMalloc(&c.bias_cat, static_cast<size_t>(c.cout) * 4));
+    }
   }
   IO_CUDA(cudaMalloc(&net->stem_w, 128 * 448 * 2));
   IO_CUDA(cudaMalloc(&net->stem_bias, 128 * 4));
@@ -289,6 +313,8 @@ extern "C" int io_net_destroy(io_net_t* net) {
   for (auto& c : net->convs) {
     cudaFree(c.w);
     cudaFree(c.bias);
+    cudaFree(c.wcat);
+    cudaFree(c.bias_cat);
   }
   cudaFree(net->stem_w);
   cudaFree(net->stem_bias);
@@ -322,6 +348,8 @@ extern "C" int io_net_load_state(io_net_t* net, const char* const* names, const 
     return IO_OK;
   };
   const double eps = 1e-5;  // nn.BatchNorm2d default
+  std::vector<uint16_t> ds_w;   // folded downsample weights / bias, waiting for the conv3 that follows in the list
+  std::vector<float> ds_bias;
   for (size_t ci = 0; ci < net->convs.size(); ++ci) {
     ConvW& c = net->convs[ci];
     const float *w, *g, *bt, *mu, *var;
@@ -367,6 +395,23 @@ extern "C" int io_net_load_state(io_net_t* net, const char* const* names, const 
           }
       IO_CUDA(cudaMemcpy(c.w, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
       IO_CUDA(cudaMemcpy(c.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+      if (c.wcat != nullptr) {
+        ds_w = pk;
+        ds_bias = bias;
+      } else if (ci >= 1 && net->convs[ci - 1].wcat != nullptr) {
+        // conv3 right after a downsample conv: rows = [conv3 weights (cin = cmid) | downsample weights]
+        ConvW& dsc = net->convs[ci - 1];
+        const size_t kc = static_cast<size_t>(c.cin) + dsc.cin;
+        std::vector<uint16_t> cat(static_cast<size_t>(c.cout) * kc);
+        std::vector<float> bsum(c.cout);
+        for (int co = 0; co < c.cout; ++co) {
+          memcpy(&cat[co * kc], &pk[static_cast<size_t>(co) * c.cin], static_cast<size_t>(c.cin) * 2);
+          memcpy(&cat[co * kc + c.cin], &ds_w[static_cast<size_t>(co) * dsc.cin], static_cast<size_t>(dsc.cin) * 2);
+          bsum[co] = bias[co] + ds_bias[co];
+        }
+        IO_CUDA(cudaMemcpy(dsc.wcat, cat.data(), cat.size() * 2, cudaMemcpyHostToDevice));
+        IO_CUDA(cudaMemcpy(dsc.bias_cat, bsum.data(), bsum.size() * 4, cudaMemcpyHostToDevice));
+      }
     }
   }
   const char* heads1[1] = {"fc"};

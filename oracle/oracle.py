@@ -326,10 +326,12 @@ def resnet50_forward(sd, x, prefix="module.", eps=1e-5, bn_override=None, return
         return out
 
 
-def resnet50_forward_bf16(sd, x, prefix="module.", eps=1e-5):
+def resnet50_forward_bf16(sd, x, prefix="module.", eps=1e-5, round_identity=False):
     """The same network evaluated with *ideal* bf16 storage: BN folded into bf16 weights (fp32 bias), every stored
     activation rounded to bf16, fp32 accumulation -- the arithmetic contract of the CUDA path.  Used to
-    separate kernel bugs (CUDA vs this, tight tolerance) from bf16-vs-fp32 sensitivity (this vs resnet50_forward)."""
+    separate kernel bugs (CUDA vs this, tight tolerance) from bf16-vs-fp32 sensitivity (this vs resnet50_forward).
+    The downsample branch of layerN.0 is accumulated in fp32 together with conv3 (the CUDA path computes both in one
+    GEMM and never stores the identity); ``round_identity=True`` emulates the two-launch fallback instead."""
     import torch
     import torch.nn.functional as F
 
@@ -364,7 +366,9 @@ def resnet50_forward_bf16(sd, x, prefix="module.", eps=1e-5):
                 o = F.conv2d(o, w) + b
                 if blk == 0:
                     w, b = fold(p + ".downsample.0", p + ".downsample.1")
-                    idt = r(F.conv2d(t, w, stride=stride) + b)
+                    idt = F.conv2d(t, w, stride=stride) + b
+                    if round_identity:
+                        idt = r(idt)
                 t = r(F.relu(o + idt))
         feat = torch.flatten(F.adaptive_avg_pool2d(t, 1), 1)
         out = {}

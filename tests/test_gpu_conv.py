@@ -94,3 +94,37 @@ def test_conv_fused_pair(case):
         err = (got - want).abs()
         tol = 1.5e-2 + 1e-2 * want.abs()
         assert not (err > tol).any(), "%s: max err %.4g, %d bad" % (name, float(err.max()), int((err > tol).sum()))
+
+
+# (B, H, W, Cin, cmid, stride): layerN.0 of ResNet-50 at 256^2 (+ ragged batches) and the 384^2 geometries
+DUAL_CASES = [(2, 64, 64, 64, 64, 1), (3, 64, 64, 256, 128, 2), (3, 32, 32, 512, 256, 2), (5, 16, 16, 1024, 512, 2),
+              (1, 64, 64, 64, 64, 1), (2, 96, 96, 64, 64, 1), (2, 96, 96, 256, 128, 2), (2, 48, 48, 512, 256, 2),
+              (3, 24, 24, 1024, 512, 2)]
+
+
+@pytest.mark.parametrize("case", DUAL_CASES, ids=lambda c: "B%d_%dx%d_%d+%d_s%d" % c)
+def test_conv_dual(case):
+    """Block output of a layer's first bottleneck, ReLU(conv3(t2) + downsample(x)), as one GEMM over concatenated K
+    (io_conv_dual) vs the two torch fp32 convolutions added."""
+    B, H, W, Cin, cmid, stride = case
+    cout = 4 * cmid
+    Ho, Wo = H // stride, W // stride
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + H + Cin + cmid)
+    dev = "cuda"
+    x = torch.randn((B, H, W, Cin), generator=g, device=dev).to(torch.bfloat16).contiguous()
+    t2 = torch.randn((B, Ho, Wo, cmid), generator=g, device=dev).to(torch.bfloat16).contiguous()
+    w3 = (torch.randn((cout, cmid), generator=g, device=dev) / cmid ** 0.5).to(torch.bfloat16)
+    wd = (torch.randn((cout, Cin), generator=g, device=dev) / Cin ** 0.5).to(torch.bfloat16)
+    bias = torch.randn((cout,), generator=g, device=dev)
+    wcat = torch.cat([w3, wd], dim=1).contiguous()
+    y = torch.full((B, Ho, Wo, cout), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().io_conv_dual(x.data_ptr(), B, H, W, Cin, stride, t2.data_ptr(), cmid, wcat.data_ptr(),
+                                       bias.data_ptr(), cout, 1, y.data_ptr(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    xs = x[:, ::stride, ::stride, :].float()
+    ref = torch.relu(t2.float() @ w3.float().t() + xs @ wd.float().t() + bias)
+    got = y.float()
+    assert torch.isfinite(got).all(), "unwritten / non-finite outputs: %d" % int((~torch.isfinite(got)).sum())
+    err = (got - ref).abs()
+    tol = 1e-2 + 1e-2 * ref.abs()
+    assert not (err > tol).any(), "max err %.4g, %d bad" % (float(err.max()), int((err > tol).sum()))
