@@ -1,12 +1,20 @@
 // Back-to-back GEMM: a bottleneck's conv3 (1x1, K1 = C -> N1 = 4C, + folded BN + residual + ReLU) fused with the
-// NEXT bottleneck's conv1 (1x1, K2 = 4C -> N2 = C', + folded BN + ReLU)  (reference resnet_cls.py:107-116 followed
-// by :99-101 of the next block).  The block output tile is written to HBM once (it is the next block's identity)
-// and, while it still sits in shared memory in the 128B-swizzled K-major layout, it is the A operand of the second
-// GEMM -- the next block never re-reads it from HBM and one launch per block disappears.
+// NEXT bottleneck's conv1 (1x1, K2 = 4C -> N2, + folded BN + ReLU)  (reference resnet_cls.py:107-116 followed by
+// :99-101 of the next block).  The block output is written to HBM once (it is the next block's identity) and, while
+// it still sits in shared memory in the 128B-swizzled K-major layout, it is the A operand of the second GEMM -- the
+// next block never re-reads it from HBM and one launch per block disappears.
 //
-// One persistent CTA per SM, same warp roles as conv_tc_kernel.  A CTA owns whole M tiles (128 pixels) and walks
-// all N1/256 column tiles of the first GEMM itself, accumulating the second GEMM (D2, N2 <= 256 TMEM columns)
-// across them.  TMEM: columns [0,256) first-GEMM accumulator (single buffer), [256, 256+N2) D2.
+// One persistent CTA per SM, 12 warps: two TMA producers, two one-thread MMA issuers (one per GEMM: a single thread
+// issuing both was instruction-latency bound -- ncu source page, profiles/), 8 epilogue warps (two per TMEM lane
+// quadrant, one 64-column group each).  Work is cut into UNITS of (128 rows) x (128 columns of the first GEMM):
+//   G1(u): D1[u & 1] = x[rows, C] * w3[128 columns of unit u]^T          (TMEM, double buffered, N = 128)
+//   E(u) : D1 + bias + residual -> ReLU -> bf16 into tile buffer u % 3 (in place over the TMA-loaded residual),
+//          TMA store to HBM, per-group "ready" barrier
+//   G2(u): D2[tile & 1] += tile buffer u % 3 [128 x 128] * w1n[:, columns of unit u]^T  (accumulates over an M tile)
+// G1 runs ahead of the epilogue by one unit, G2 follows it group by group; residual tiles are prefetched two units
+// ahead into the buffer that G2(u-1) has just released (per-group commit barriers), so no HBM latency sits on the
+// critical path; the second epilogue (D2 -> next block's T1) runs one unit late, behind E of the next M tile's
+// first unit.  TMEM: [0,256) two D1 buffers, [256,512) two D2 buffers of N2 <= 128 columns.
 #include "conv_tc.cuh"
 
 namespace io {
@@ -14,62 +22,85 @@ namespace io {
 namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int BN = 256;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB (also holds one [N2 x 64] block of the second weights)
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int STAGES = 3;
-constexpr int REGION_BYTES = 32 * 128;       // 32 rows x 64 columns bf16
-constexpr int EPI_BYTES = 16 * REGION_BYTES; // 4 column groups x 4 warps: the [128 x 256] bf16 tile = 64 KB
-constexpr int BIAS_BYTES = 4096 + 1024;      // bias1 (<= 1024 floats) + bias2 (<= 256 floats)
-constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+constexpr int UN = 128;                      // first-GEMM columns per unit = two 64-column groups
+constexpr int A_BYTES = BM * BK * 2;         // 16 KB
+constexpr int B1_BYTES = UN * BK * 2;        // 16 KB
+constexpr int STAGE1_BYTES = A_BYTES + B1_BYTES;   // ring 1: one K block of x rows + of w3 rows
+constexpr int MAX_ST1 = 3;
+constexpr int MAX_ST2 = 4;                   // ring 2: [N2 x 64] blocks of the next conv1's weights (8 / 16 KB)
+constexpr int NB = 3;                        // block-output tile buffers
+constexpr int REGION_BYTES = 32 * 128;       // 32 rows x 64 columns bf16 (one epilogue warp)
+constexpr int GROUP_BYTES = 4 * REGION_BYTES;  // 128 rows x 64 columns = one K block of the second GEMM's A operand
+constexpr int TILE_BYTES = 2 * GROUP_BYTES;
+constexpr int BIAS_BYTES = 2048 + 512;       // bias1 (<= 512 floats) + bias2 (<= 128 floats)
+constexpr int BAR_BYTES = 512;
+constexpr int FIXED_BYTES = NB * TILE_BYTES + BIAS_BYTES + BAR_BYTES;
+constexpr int MAX_SMEM = 232448;             // 227 KB
 constexpr int TMEM_COLS = 512;
+constexpr int THREADS = 384;
 }  // namespace
 
-__global__ void __launch_bounds__(192, 1) conv_fused_kernel(const __grid_constant__ FusedParams fp) {
+__global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_constant__ FusedParams fp) {
   const ConvParams& p = fp.c;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* sEpi = smem + STAGES * STAGE_BYTES;            // region (g, q) at (g * 4 + q) * REGION_BYTES
-  float* sBias1 = reinterpret_cast<float*>(sEpi + EPI_BYTES);
-  float* sBias2 = sBias1 + 1024;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + EPI_BYTES + BIAS_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;   // first-GEMM accumulator complete
-  uint64_t* tempty = tfull + 1;       // ... drained by the epilogue (4 arrivals)
-  uint64_t* sready = tempty + 1;      // block-output tile complete in shared memory (4 arrivals)
-  uint64_t* sdone = sready + 1;       // second GEMM has finished reading the tile
-  uint64_t* d2full = sdone + 1;       // D2 complete for this M tile
-  uint64_t* d2empty = d2full + 1;     // ... drained (4 arrivals)
-  uint64_t* rbar = d2empty + 1;       // residual tile landed, one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 4);
+  // 128B-swizzled operands need 1024-byte aligned bases: the kernel has no static shared memory, so the dynamic
+  // segment starts aligned (checked below; a mis-aligned base traps instead of computing garbage)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int k1 = p.k_iters;             // K blocks of the first GEMM
+  const int n2 = fp.n2;
+  const int st1 = fp.st1, st2 = fp.st2;
+  const int slot2_bytes = n2 * 128;
+  uint8_t* sS1 = smem;                                  // ring 1: st1 stages of 32 KB
+  uint8_t* sS2 = sS1 + st1 * STAGE1_BYTES;              // ring 2: st2 slots of n2 * 128 B
+  uint8_t* sT = sS2 + st2 * slot2_bytes;                // tile buffers: [NB][2 groups][4 quadrants][32 x 128 B]
+  float* sBias1 = reinterpret_cast<float*>(sT + NB * TILE_BYTES);
+  float* sBias2 = sBias1 + 512;
+  uint64_t* full1 = reinterpret_cast<uint64_t*>(sT + NB * TILE_BYTES + BIAS_BYTES);
+  uint64_t* empty1 = full1 + MAX_ST1;
+  uint64_t* full2 = empty1 + MAX_ST1;
+  uint64_t* empty2 = full2 + MAX_ST2;
+  uint64_t* tfull = empty2 + MAX_ST2;   // D1[acc] complete
+  uint64_t* tempty = tfull + 2;         // ... drained by the 8 epilogue warps
+  uint64_t* gready = tempty + 2;        // [NB][2]: group complete in shared memory (4 quadrant warps)
+  uint64_t* gfree = gready + NB * 2;    // [NB][2]: the second GEMM has finished reading the group
+  uint64_t* rbar = gfree + NB * 2;      // [8 warps][NB]: residual region landed
+  uint64_t* d2full = rbar + 8 * NB;     // [2]
+  uint64_t* d2empty = d2full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nt = p.n_tiles;           // column tiles of the first GEMM (N1 / 256)
-  const int n2 = fp.n2;
+  const int nu = p.n_total / UN;        // units per M tile
+  const int my_tiles = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+  const int tile_stride_rows = static_cast<int>(gridDim.x) * BM;
+  const int first_row = static_cast<int>(blockIdx.x) * BM;
 
   if (warp == 0 && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     prefetch_tmap(&p.map_a);
     prefetch_tmap(&p.map_b);
     prefetch_tmap(&p.map_out);
     prefetch_tmap(&p.map_res);
     prefetch_tmap(&fp.map_b2);
-    prefetch_tmap(&fp.map_out2);
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+    for (int i = 0; i < MAX_ST1; ++i) {
+      mbar_init(&full1[i], 1);
+      mbar_init(&empty1[i], 1);
     }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, 4);
-    mbar_init(sready, 4);
-    mbar_init(sdone, 1);
-    mbar_init(d2full, 1);
-    mbar_init(d2empty, 4);
-    for (int i = 0; i < 4; ++i) mbar_init(&rbar[i], 1);
+    for (int i = 0; i < MAX_ST2; ++i) {
+      mbar_init(&full2[i], 1);
+      mbar_init(&empty2[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+      mbar_init(&d2full[i], 1);
+      mbar_init(&d2empty[i], 8);
+    }
+    for (int i = 0; i < NB * 2; ++i) {
+      mbar_init(&gready[i], 4);
+      mbar_init(&gfree[i], 1);
+    }
+    for (int i = 0; i < 8 * NB; ++i) mbar_init(&rbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -84,175 +115,127 @@ __global__ void __launch_bounds__(192, 1) conv_fused_kernel(const __grid_constan
   tc_fence_after();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d2 = tmem_base + BN;
+  const uint32_t tmem_d2 = tmem_base + 2 * UN;
 
   if (warp == 0) {
-    // ======================= TMA producer =======================
+    // ======================= TMA producer 1: x rows + w3 rows =======================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int m_tile = blockIdx.x; m_tile < p.m_tiles; m_tile += gridDim.x) {
-        const int row0 = m_tile * BM;
-        for (int j = 0; j < nt; ++j) {
-          for (int ki = 0; ki < p.k_iters; ++ki) {       // first GEMM: A = conv2 output, B = conv3 weights
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-            tma_load_2d(sA + stage * A_STAGE_BYTES, &p.map_a, &full[stage], ki * BK, row0);
-            tma_load_2d(sB + stage * B_STAGE_BYTES, &p.map_b, &full[stage], ki * BK, j * BN);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-          for (int kb = 0; kb < BN / BK; ++kb) {         // second GEMM: B = next conv1 weights, K block j*4+kb
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], n2 * 128);
-            tma_load_2d(sB + stage * B_STAGE_BYTES, &fp.map_b2, &full[stage], j * BN + kb * BK, 0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int t = 0; t < my_tiles; ++t) {
+        const int row0 = first_row + t * tile_stride_rows;
+        for (int j = 0; j < nu; ++j) {
+          for (int ki = 0; ki < k1; ++ki) {
+            mbar_wait(&empty1[stage], phase ^ 1);
+            mbar_expect_tx(&full1[stage], STAGE1_BYTES);
+            tma_load_2d(sS1 + stage * STAGE1_BYTES, &p.map_a, &full1[stage], ki * BK, row0);
+            tma_load_2d(sS1 + stage * STAGE1_BYTES + A_BYTES, &p.map_b, &full1[stage], ki * BK, j * UN);
+            if (++stage == st1) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
+    // ======================= MMA issuer 1: D1[acc] = x * w3^T =======================
     if (lane == 0) {
-      constexpr uint32_t idesc1 = umma_idesc_bf16(BM, BN);
-      const uint32_t idesc2 = umma_idesc_bf16(BM, n2);
+      constexpr uint32_t idesc1 = umma_idesc_bf16(BM, UN);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t u = 0;    // (M tile, column tile) counter
-      uint32_t mt = 0;   // M tile counter
-      for (int m_tile = blockIdx.x; m_tile < p.m_tiles; m_tile += gridDim.x, ++mt) {
-        for (int j = 0; j < nt; ++j, ++u) {
-          mbar_wait(tempty, (u & 1) ^ 1);                // epilogue has drained the accumulator of (u - 1)
+      const int U = my_tiles * nu;
+      for (int i = 0; i < U; ++i) {
+        const int acc = i & 1;
+        mbar_wait(&tempty[acc], ((i >> 1) & 1) ^ 1);     // the epilogue has drained this D1 buffer
+        tc_fence_after();
+        const uint32_t d1 = tmem_base + acc * UN;
+        for (int ki = 0; ki < k1; ++ki) {
+          mbar_wait(&full1[stage], phase);
           tc_fence_after();
-          for (int ki = 0; ki < p.k_iters; ++ki) {
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-            const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(smem_u32(sS1 + stage * STAGE1_BYTES));
+          const uint64_t b_desc = umma_desc_sw128(smem_u32(sS1 + stage * STAGE1_BYTES + A_BYTES));
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc1,
-                        (ki > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&empty[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-          umma_commit(tfull);
-          // second GEMM on the finished block-output tile (bf16, in the staging regions)
-          mbar_wait(sready, u & 1);
-          tc_fence_after();
-          if (j == 0) {
-            mbar_wait(d2empty, (mt & 1) ^ 1);            // previous M tile's D2 has been drained
-            tc_fence_after();
-          }
-          for (int kb = 0; kb < BN / BK; ++kb) {
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(sEpi + kb * 4 * REGION_BYTES);
-            const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem_d2, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc2,
-                        (j > 0 || kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&empty[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-          umma_commit(sdone);
+          for (int k = 0; k < BK / 16; ++k)   // + 32 bytes per K step = + 2 in the descriptor's address field
+            umma_bf16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (ki > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty1[stage]);
+          if (++stage == st1) { stage = 0; phase ^= 1; }
         }
-        umma_commit(d2full);
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp == 2) {
+    // ======================= TMA producer 2: next conv1 weights =======================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int j = 0; j < nu; ++j) {
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&empty2[slot], phase ^ 1);
+            mbar_expect_tx(&full2[slot], slot2_bytes);
+            tma_load_2d(sS2 + slot * slot2_bytes, &fp.map_b2, &full2[slot], j * UN + g * BK, 0);
+            if (++slot == st2) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ======================= MMA issuer 2: D2[t & 1] += tile * w1n^T =======================
+    if (lane == 0) {
+      const uint32_t idesc2 = umma_idesc_bf16(BM, n2);
+      int slot = 0;
+      uint32_t phase = 0;
+      int b = 0;            // tile buffer of the unit, u % NB
+      uint32_t nuse = 0;    // u / NB
+      for (int t = 0; t < my_tiles; ++t) {
+        const int dbuf = t & 1;
+        mbar_wait(&d2empty[dbuf], ((t >> 1) & 1) ^ 1);   // D2 buffer drained (tile t - 2)
+        tc_fence_after();
+        const uint32_t d2 = tmem_d2 + dbuf * UN;
+        for (int j = 0; j < nu; ++j) {
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&gready[b * 2 + g], nuse & 1);
+            mbar_wait(&full2[slot], phase);
+            tc_fence_after();
+            const uint64_t a_desc = umma_desc_sw128(smem_u32(sT + b * TILE_BYTES + g * GROUP_BYTES));
+            const uint64_t b_desc = umma_desc_sw128(smem_u32(sS2 + slot * slot2_bytes));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d2, a_desc + 2 * k, b_desc + 2 * k, idesc2, (j > 0 || g > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty2[slot]);
+            umma_commit(&gfree[b * 2 + g]);
+            if (++slot == st2) { slot = 0; phase ^= 1; }
+          }
+          if (++b == NB) { b = 0; ++nuse; }
+        }
+        umma_commit(&d2full[dbuf]);
       }
     }
   } else {
-    // ======================= epilogue (warps 2..5) =======================
-    const int q = warp & 3;
-    uint64_t* my_rbar = &rbar[q];
-    uint32_t u = 0, mt = 0, rphase = 0;
-    for (int m_tile = blockIdx.x; m_tile < p.m_tiles; m_tile += gridDim.x, ++mt) {
-      const int row0 = m_tile * BM + q * 32;
-      const bool active = row0 < p.m_total;               // slab has at least one real row (TMA clips the rest)
-      for (int j = 0; j < nt; ++j, ++u) {
-        if (lane == 0) {
-          tma_store_wait_read<0>();                       // our earlier stores no longer read the regions
-          if (j > 0) mbar_wait(sdone, (u - 1) & 1);       // ... nor does the previous second GEMM
-          if (active) {
-            mbar_expect_tx(my_rbar, 4 * REGION_BYTES);
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              tma_load_2d(sEpi + (g * 4 + q) * REGION_BYTES, &p.map_res, my_rbar, j * BN + g * 64, row0);
-          }
-        }
-        __syncwarp();
-        mbar_wait(tfull, u & 1);
-        tc_fence_after();
-        if (active) {
-          mbar_wait(my_rbar, rphase);
-          rphase ^= 1;
-        }
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t v[2][32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 64;
-          tmem_ld32(taddr, v[0]);
-          tmem_ld32(taddr + 32, v[1]);
-          tmem_ld_wait();
-          uint8_t* region = sEpi + (g * 4 + q) * REGION_BYTES;
-          uint8_t* rowp = region + lane * 128;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const float4* bias4 = reinterpret_cast<const float4*>(sBias1 + j * BN + g * 64 + half * 32);
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = bias4[i];
-              f[4 * i + 0] = __uint_as_float(v[half][4 * i + 0]) + b.x;
-              f[4 * i + 1] = __uint_as_float(v[half][4 * i + 1]) + b.y;
-              f[4 * i + 2] = __uint_as_float(v[half][4 * i + 2]) + b.z;
-              f[4 * i + 3] = __uint_as_float(v[half][4 * i + 3]) + b.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4* cp = reinterpret_cast<uint4*>(rowp + (((half * 4 + i) ^ (lane & 7)) << 4));
-              if (active) {
-                const uint4 rr = *cp;
-                f[8 * i + 0] += bf16_lo(rr.x); f[8 * i + 1] += bf16_hi(rr.x);
-                f[8 * i + 2] += bf16_lo(rr.y); f[8 * i + 3] += bf16_hi(rr.y);
-                f[8 * i + 4] += bf16_lo(rr.z); f[8 * i + 5] += bf16_hi(rr.z);
-                f[8 * i + 6] += bf16_lo(rr.w); f[8 * i + 7] += bf16_hi(rr.w);
-              }
-              uint4 o;
-              o.x = pack_bf16(fmaxf(f[8 * i + 0], 0.f), fmaxf(f[8 * i + 1], 0.f));
-              o.y = pack_bf16(fmaxf(f[8 * i + 2], 0.f), fmaxf(f[8 * i + 3], 0.f));
-              o.z = pack_bf16(fmaxf(f[8 * i + 4], 0.f), fmaxf(f[8 * i + 5], 0.f));
-              o.w = pack_bf16(fmaxf(f[8 * i + 6], 0.f), fmaxf(f[8 * i + 7], 0.f));
-              *cp = o;   // inactive slabs still write finite values: the second GEMM reads all 128 rows
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (active) tma_store_2d(&p.map_out, region, j * BN + g * 64, row0);
-            tma_store_commit();
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(tempty);   // accumulator drained
-          mbar_arrive(sready);   // tile complete in shared memory (writes fenced to the async proxy above)
-        }
+    // ======================= epilogue (warps 4..11) =======================
+    const int e = warp - 4;
+    const int q = warp & 3;               // TMEM lane quadrant: tile rows 32q .. 32q+31
+    const int g = e >> 2;                 // 64-column group of the unit owned by this warp
+    uint64_t* my_rbar = &rbar[e * NB];
+    uint8_t* my_region0 = sT + g * GROUP_BYTES + q * REGION_BYTES;   // + b * TILE_BYTES
+    const int U = my_tiles * nu;
+    auto issue_residual = [&](int t, int j, int b) {    // lane 0: residual region of unit (t, j) -> tile buffer b
+      const int row0 = first_row + t * tile_stride_rows + q * 32;
+      if (row0 < p.m_total) {
+        mbar_expect_tx(&my_rbar[b], REGION_BYTES);
+        tma_load_2d(my_region0 + b * TILE_BYTES, &p.map_res, &my_rbar[b], j * UN + g * 64, row0);
       }
-      // ---- second epilogue: D2 = conv1_next(out tile) + bias2, ReLU -> T1 of the next block
-      mbar_wait(d2full, mt & 1);
+    };
+    auto d2_epilogue = [&](int t) {       // D2 = conv1_next(block output) + bias2, ReLU -> T1 of the next block
+      const int dbuf = t & 1;
+      mbar_wait(&d2full[dbuf], (t >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) tma_store_wait_read<0>();
-      __syncwarp();
-#pragma unroll 1
-      for (int g = 0; g < n2 / 64; ++g) {
+      const int row = first_row + t * tile_stride_rows + q * 32 + lane;
+      if (g < n2 / 64) {                  // n2 = 64: the g = 1 warps have no columns
         uint32_t v[2][32];
-        const uint32_t taddr = tmem_d2 + (static_cast<uint32_t>(q * 32) << 16) + g * 64;
+        const uint32_t taddr = tmem_d2 + dbuf * UN + (static_cast<uint32_t>(q * 32) << 16) + g * 64;
         tmem_ld32(taddr, v[0]);
         tmem_ld32(taddr + 32, v[1]);
         tmem_ld_wait();
-        uint8_t* region = sEpi + (g * 4 + q) * REGION_BYTES;
-        uint8_t* rowp = region + lane * 128;
+        uint4* dst = reinterpret_cast<uint4*>(fp.out2 + static_cast<size_t>(row) * n2 + g * 64);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const float4* bias4 = reinterpret_cast<const float4*>(sBias2 + g * 64 + half * 32);
@@ -268,20 +251,102 @@ __global__ void __launch_bounds__(192, 1) conv_fused_kernel(const __grid_constan
                             fmaxf(__uint_as_float(v[half][8 * i + 5]) + b1.y, 0.f));
             o.w = pack_bf16(fmaxf(__uint_as_float(v[half][8 * i + 6]) + b1.z, 0.f),
                             fmaxf(__uint_as_float(v[half][8 * i + 7]) + b1.w, 0.f));
-            *reinterpret_cast<uint4*>(rowp + (((half * 4 + i) ^ (lane & 7)) << 4)) = o;
+            if (row < p.m_total) dst[half * 4 + i] = o;
           }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          if (active) tma_store_2d(&fp.map_out2, region, g * 64, row0);
-          tma_store_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(d2empty);
+      if (lane == 0) mbar_arrive(&d2empty[dbuf]);
+    };
+
+    // unit i = (t, j), tile buffer b = i % NB (use number nuse = i / NB); the residual prefetch runs two units ahead
+    if (lane == 0) {
+      if (U > 0) issue_residual(0, 0, 0);
+      if (U > 1) issue_residual(0, 1, 1);     // nu >= 2
     }
+    __syncwarp();
+    int t = 0, j = 0, b = 0;
+    uint32_t nuse = 0;
+    int pt = 0, pj = 2, pb = 2;               // unit i + 2
+    if (pj >= nu) { pj -= nu; pt = 1; }
+    int fb = NB - 1;                          // tile buffer and use number of unit i - 1 (= those of unit i + 2)
+    uint32_t fuse_n = 0;
+    for (int i = 0; i < U; ++i) {
+      const int acc = i & 1;
+      const int row0 = first_row + t * tile_stride_rows + q * 32;
+      const bool active = row0 < p.m_total;               // region has at least one real row (TMA clips the rest)
+      mbar_wait(&tfull[acc], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[2][32];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * UN + g * 64;
+      tmem_ld32(taddr, v[0]);
+      tmem_ld32(taddr + 32, v[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);           // D1 buffer read: issuer 1 may refill it
+      if (active) mbar_wait(&my_rbar[b], nuse & 1);
+      uint8_t* region = my_region0 + b * TILE_BYTES;
+      uint8_t* rowp = region + lane * 128;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const float4* bias4 = reinterpret_cast<const float4*>(sBias1 + j * UN + g * 64 + half * 32);
+        float f[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 bb = bias4[k];
+          f[4 * k + 0] = __uint_as_float(v[half][4 * k + 0]) + bb.x;
+          f[4 * k + 1] = __uint_as_float(v[half][4 * k + 1]) + bb.y;
+          f[4 * k + 2] = __uint_as_float(v[half][4 * k + 2]) + bb.z;
+          f[4 * k + 3] = __uint_as_float(v[half][4 * k + 3]) + bb.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4* cp = reinterpret_cast<uint4*>(rowp + (((half * 4 + k) ^ (lane & 7)) << 4));
+          if (active) {
+            const uint4 rr = *cp;
+            f[8 * k + 0] += bf16_lo(rr.x); f[8 * k + 1] += bf16_hi(rr.x);
+            f[8 * k + 2] += bf16_lo(rr.y); f[8 * k + 3] += bf16_hi(rr.y);
+            f[8 * k + 4] += bf16_lo(rr.z); f[8 * k + 5] += bf16_hi(rr.z);
+            f[8 * k + 6] += bf16_lo(rr.w); f[8 * k + 7] += bf16_hi(rr.w);
+          }
+          uint4 o;
+          o.x = pack_bf16(fmaxf(f[8 * k + 0], 0.f), fmaxf(f[8 * k + 1], 0.f));
+          o.y = pack_bf16(fmaxf(f[8 * k + 2], 0.f), fmaxf(f[8 * k + 3], 0.f));
+          o.z = pack_bf16(fmaxf(f[8 * k + 4], 0.f), fmaxf(f[8 * k + 5], 0.f));
+          o.w = pack_bf16(fmaxf(f[8 * k + 6], 0.f), fmaxf(f[8 * k + 7], 0.f));
+          *cp = o;   // inactive regions still get finite values: the second GEMM reads all 128 rows
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (active) tma_store_2d(&p.map_out, region, j * UN + g * 64, row0);
+        tma_store_commit();
+        mbar_arrive(&gready[b * 2 + g]);
+        if (i + 2 < U) {
+          // the residual of unit i + 2 goes into the buffer unit i - 1 used: wait until G2(i - 1) has consumed this
+          // group and until this warp's own store of it has finished reading shared memory
+          if (i >= 1) {
+            mbar_wait(&gfree[fb * 2 + g], fuse_n & 1);
+            tma_store_wait_read<1>();
+          }
+          issue_residual(pt, pj, pb);
+        }
+      }
+      __syncwarp();
+      const bool first_of_tile = (j == 0);
+      const int t_now = t;
+      // advance the unit counters
+      if (i >= 1) { if (++fb == NB) { fb = 0; ++fuse_n; } } else { fb = 0; fuse_n = 0; }
+      if (++j == nu) { j = 0; ++t; }
+      if (++b == NB) { b = 0; ++nuse; }
+      if (++pj == nu) { pj = 0; ++pt; }
+      if (++pb == NB) pb = 0;
+      if (first_of_tile && t_now > 0) d2_epilogue(t_now - 1);
+    }
+    if (my_tiles > 0) d2_epilogue(my_tiles - 1);
     if (lane == 0) tma_store_wait_all();
   }
 
@@ -293,15 +358,15 @@ __global__ void __launch_bounds__(192, 1) conv_fused_kernel(const __grid_constan
 int conv_fused_launch(const FusedParams& fp, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    IO_CUDA(cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IO_CUDA(cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     attr_set = true;
   }
   if (fp.c.m_tiles <= 0) return IO_OK;
   const int grid = fp.c.m_tiles < num_sms() ? fp.c.m_tiles : num_sms();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(192);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = fp.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -317,8 +382,8 @@ int conv_fused_launch(const FusedParams& fp, cudaStream_t stream) {
 int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, const void* w3, const float* bias3,
                     const void* residual, void* y, const void* w1n, const float* bias1n, void* y2) {
   const int n1 = 4 * cmid;
-  IO_REQUIRE(cmid % 64 == 0 && n1 % 256 == 0 && n1 <= 1024, "fused conv: C = %d not supported", cmid);
-  IO_REQUIRE(n2 % 64 == 0 && n2 >= 64 && n2 <= 256, "fused conv: N2 = %d not supported", n2);
+  IO_REQUIRE(cmid == 64 || cmid == 128, "fused conv: C = %d not supported (64 or 128: layer1 / layer2)", cmid);
+  IO_REQUIRE(n2 % 64 == 0 && n2 >= 64 && n2 <= 128, "fused conv: N2 = %d not supported (64 or 128)", n2);
   IO_REQUIRE(residual != nullptr, "fused conv: the block output needs its identity");
   *fp = FusedParams{};
   ConvParams* p = &fp->c;
@@ -332,9 +397,9 @@ int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, 
   p->kpt = p->k_iters;
   p->taps_w = 1;
   p->cin = cmid;
-  p->a_bytes = A_STAGE_BYTES;
+  p->a_bytes = A_BYTES;
   p->m_tiles = (rows + BM - 1) / BM;
-  p->n_tiles = n1 / BN;
+  p->n_tiles = n1 / UN;
   p->rows_per_tile = BM;
   p->tpg = 1; p->bi = 1; p->bh = 1; p->tpr = 1;
   p->ldc = n1;
@@ -352,7 +417,7 @@ int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, 
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(cmid), static_cast<uint64_t>(n1)};
     const uint64_t str[1] = {static_cast<uint64_t>(cmid) * 2};
-    const uint32_t box[2] = {64, BN};
+    const uint32_t box[2] = {64, UN};
     if ((rc = make_tmap_bf16(&p->map_b, w3, 2, dims, str, box, true))) return rc;
   }
   {
@@ -368,12 +433,12 @@ int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, 
     const uint32_t box[2] = {64, static_cast<uint32_t>(n2)};
     if ((rc = make_tmap_bf16(&fp->map_b2, w1n, 2, dims, str, box, true))) return rc;
   }
-  {
-    const uint64_t dims[2] = {static_cast<uint64_t>(n2), static_cast<uint64_t>(rows)};
-    const uint64_t str[1] = {static_cast<uint64_t>(n2) * 2};
-    const uint32_t box[2] = {64, 32};
-    if ((rc = make_tmap_bf16(&fp->map_out2, y2, 2, dims, str, box, true))) return rc;
-  }
+  fp->out2 = reinterpret_cast<__nv_bfloat16*>(y2);
+  // shared memory: ring 1 (x + w3 K blocks, 32 KB stages) and ring 2 ([n2 x 64] blocks of the next conv1's weights)
+  fp->st1 = 3;
+  fp->st2 = (n2 == 64) ? 4 : 2;
+  fp->smem_bytes = fp->st1 * STAGE1_BYTES + fp->st2 * n2 * 128 + FIXED_BYTES;
+  IO_REQUIRE(fp->smem_bytes <= MAX_SMEM, "fused conv: shared-memory plan %d B", fp->smem_bytes);
   return IO_OK;
 }
 

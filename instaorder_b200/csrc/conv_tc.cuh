@@ -64,11 +64,13 @@ struct ConvParams {
 
 // conv3 (+ residual + ReLU) of one bottleneck fused with conv1 (+ ReLU) of the next one (conv_fused.cu)
 struct FusedParams {
-  ConvParams c;          // the conv3 GEMM: CONV_GEMM mode, N tile 256, residual required
+  ConvParams c;          // the conv3 GEMM: CONV_GEMM mode, 128-column units (map_b box 64 x 128), residual required
   CUtensorMap map_b2;    // next conv1 weights [n2][n_total] bf16, box 64 x n2
-  CUtensorMap map_out2;  // next block's T1 [rows][n2] bf16, box 64 x 32
+  __nv_bfloat16* out2;   // next block's T1 [rows][n2] bf16
   const float* bias2;
   int n2;
+  int st1, st2;          // ring depths: (x + w3) stages of 32 KB, next-conv1 weight slots of n2 * 128 B
+  int smem_bytes;
 };
 int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, const void* w3, const float* bias3,
                     const void* residual, void* y, const void* w1n, const float* bias1n, void* y2);

@@ -67,7 +67,8 @@ struct io_net {
   // phase B (layer3, layer4, tail) runs over chunk_b pairs at once so that its small GEMMs fill all SMs.
   int chunk_a = 0, chunk_b = 0;
   bool fuse_ds = true;  // first block of a layer: conv3 + downsample as one GEMM over concatenated K (INSTAORDER_FUSE_DS=0 disables)
-  bool fuse = false;  // conv3 -> next conv1 back-to-back GEMM fusion (INSTAORDER_FUSE=1 enables; parity-tested, not yet faster)
+  bool fuse = true;   // conv3 -> next conv1 back-to-back GEMM fusion in layer1 / layer2 (INSTAORDER_FUSE=0 disables)
+  int fuse_layers = 0x3;  // bit li: fuse inside layer li+1 (INSTAORDER_FUSE_LAYERS)
   __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase A: X, Y, T1, T2, DS
   __nv_bfloat16* bufb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase B: X, Y, T1, T2, DS
   __nv_bfloat16* big = nullptr;                                            // layer2 output of a whole B chunk
@@ -187,9 +188,13 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
         plan->ops.push_back(od);
         identity = DS;
       }
-      const bool fuse_next = net->fuse && (blk + 1 < blocks_[li]) && c3.cout <= 1024;
+      // the next bottleneck's conv1 (same layer, or the first block of the next layer inside this plan: its conv1 is
+      // a stride-1 1x1 over this block's output) can be computed from the block-output tile while it is on chip
+      const bool has_next = (blk + 1 < blocks_[li]) || (li + 1 < l1);
+      const bool fuse_next = net->fuse && ((net->fuse_layers >> li) & 1) && has_next && c3.cin <= 128 &&
+                             net->convs[ci].cout <= 128;
       if (fuse_next) {
-        const ConvW& n1 = net->convs[ci];   // next block's conv1 (no downsample in blocks >= 1)
+        const ConvW& n1 = net->convs[ci];   // next block's conv1
         Op of; of.kind = Op::FUSED;
         if (int rc = conv_fused_plan(&of.fp, b * ho * wo, c3.cin, n1.cout, T2, c3.w, c3.bias, identity, dst, n1.w,
                                      n1.bias, T1)) return rc;
@@ -279,6 +284,7 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
   if (const char* e = getenv("INSTAORDER_CHUNK_B")) chunk_b = atoi(e) > 0 ? atoi(e) : chunk_b;
   if (const char* e = getenv("INSTAORDER_FUSE")) net->fuse = atoi(e) != 0;
   if (const char* e = getenv("INSTAORDER_FUSE_DS")) net->fuse_ds = atoi(e) != 0;
+  if (const char* e = getenv("INSTAORDER_FUSE_LAYERS")) net->fuse_layers = atoi(e);
   net->chunk_b = std::min(chunk_b, max_pairs);
   net->chunk_a = std::min(chunk_a, net->chunk_b);
   build_conv_list(net.get());

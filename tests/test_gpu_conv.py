@@ -64,8 +64,8 @@ def test_conv_bn_act(case):
 
 
 # (rows, cmid, n2): layer1 / layer2 / layer3 bottleneck pairs + a ragged row count (row guard by TMA clipping)
-FUSED_CASES = [(2 * 64 * 64, 64, 64), (3 * 32 * 32, 128, 128), (5 * 16 * 16, 256, 256), (1000, 64, 64),
-               (148 * 128 * 2 + 77, 128, 128)]
+FUSED_CASES = [(2 * 64 * 64, 64, 64), (3 * 32 * 32, 128, 128), (5 * 16 * 16, 128, 64), (1000, 64, 64),
+               (148 * 128 * 2 + 77, 128, 128), (148 * 128 * 3 + 5, 64, 128), (148 * 128 * 4 + 300, 128, 64), (100, 64, 64)]
 
 
 @pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: "rows%d_c%d_n%d" % c)
