@@ -202,6 +202,13 @@ IO_API int io_conv_fused_pair(const void* x_dev, int rows, int cmid, const void*
                               const void* residual_dev, void* y_dev, const void* w1n_dev, const float* bias1n_dev,
                               int n2, void* y2_dev, void* stream);
 
+/* The same fusion for the FIRST bottleneck of a layer: y = ReLU([t2 | x(stride)] * wcat^T + bias) (io_conv_dual) and
+ * y2 = ReLU(y * w1n^T + bias1n), the next block's conv1, computed from the block-output tile while it is in shared
+ * memory.  cmid in {64, 128}; n2 in {64, 128, 256}; stride 2 needs M tiles of exactly 128 output pixels. */
+IO_API int io_conv_fused_dual(const void* x_dev, int b, int h, int w, int cin, int stride, const void* t2_dev, int cmid,
+                       const void* wcat_dev, const float* bias_dev, void* y_dev, const void* w1n_dev,
+                       const float* bias1n_dev, int n2, void* y2_dev, void* stream);
+
 /* Validation losses (forward only) -- models/supervised_order.py:60-81 (^od), :397-411 (^d), :465-479 (OrderNet),
  * :518-533 (^o), including the swapped-direction labels of set_input and the reference's softmax-then-CrossEntropy
  * / sigmoid-then-BCELoss quirks.  logits_dev[n][2][k_total]; occ_off >= 0 selects a 2-logit sigmoid head with

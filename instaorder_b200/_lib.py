@@ -57,6 +57,7 @@ _SIGS = {
     "io_order_decide": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "io_conv_bn_act": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "io_conv_dual": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "io_conv_fused_dual": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "io_conv_fused_pair": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "io_pair_pack_nchw": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "io_loss_forward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, C.c_float, C.c_float, _i, _vp, _vp]),

@@ -32,9 +32,14 @@ constexpr int NB = 3;                        // block-output tile buffers
 constexpr int REGION_BYTES = 32 * 128;       // 32 rows x 64 columns bf16 (one epilogue warp)
 constexpr int GROUP_BYTES = 4 * REGION_BYTES;  // 128 rows x 64 columns = one K block of the second GEMM's A operand
 constexpr int TILE_BYTES = 2 * GROUP_BYTES;
-constexpr int BIAS_BYTES = 2048 + 512;       // bias1 (<= 512 floats) + bias2 (<= 128 floats)
 constexpr int BAR_BYTES = 512;
-constexpr int FIXED_BYTES = NB * TILE_BYTES + BIAS_BYTES + BAR_BYTES;
+// bias2 (n2 floats, 512 B granules) always sits in shared memory, bias1 only when n1 <= 512 (2 KB); the 1024-column
+// layers read it through L1 instead -- the shared memory is needed for the rings
+__host__ __device__ constexpr int bias2_bytes(int n2) { return n2 <= 128 ? 512 : 1024; }
+__host__ __device__ constexpr int bias1_bytes(int n1) { return n1 <= 512 ? 2048 : 0; }
+__host__ __device__ constexpr int fixed_bytes(int n1, int n2) {
+  return NB * TILE_BYTES + bias2_bytes(n2) + bias1_bytes(n1) + BAR_BYTES;
+}
 constexpr int MAX_SMEM = 232448;             // 227 KB
 constexpr int TMEM_COLS = 512;
 constexpr int THREADS = 384;
@@ -52,9 +57,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
   uint8_t* sS1 = smem;                                  // ring 1: st1 stages of 32 KB
   uint8_t* sS2 = sS1 + st1 * STAGE1_BYTES;              // ring 2: st2 slots of n2 * 128 B
   uint8_t* sT = sS2 + st2 * slot2_bytes;                // tile buffers: [NB][2 groups][4 quadrants][32 x 128 B]
-  float* sBias1 = reinterpret_cast<float*>(sT + NB * TILE_BYTES);
-  float* sBias2 = sBias1 + 512;
-  uint64_t* full1 = reinterpret_cast<uint64_t*>(sT + NB * TILE_BYTES + BIAS_BYTES);
+  float* sBias2 = reinterpret_cast<float*>(sT + NB * TILE_BYTES);
+  float* sBias1 = reinterpret_cast<float*>(sT + NB * TILE_BYTES + bias2_bytes(n2));
+  const bool bias1_smem = bias1_bytes(p.n_total) != 0;
+  const float* bias1p = bias1_smem ? sBias1 : p.bias;
+  uint64_t* full1 = reinterpret_cast<uint64_t*>(sT + NB * TILE_BYTES + bias2_bytes(n2) + bias1_bytes(p.n_total));
   uint64_t* empty1 = full1 + MAX_ST1;
   uint64_t* full2 = empty1 + MAX_ST1;
   uint64_t* empty2 = full2 + MAX_ST2;
@@ -80,7 +87,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
     prefetch_tmap(&p.map_a);
     prefetch_tmap(&p.map_b);
     prefetch_tmap(&p.map_out);
-    prefetch_tmap(&p.map_res);
+    if (p.residual != nullptr) prefetch_tmap(&p.map_res);
+    if (fp.k1a < p.k_iters) prefetch_tmap(&p.map_a2);
     prefetch_tmap(&fp.map_b2);
     for (int i = 0; i < MAX_ST1; ++i) {
       mbar_init(&full1[i], 1);
@@ -107,7 +115,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) sBias1[i] = p.bias[i];
+  if (bias1_smem)
+    for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) sBias1[i] = p.bias[i];
   for (int i = threadIdx.x; i < n2; i += blockDim.x) sBias2[i] = fp.bias2[i];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tc_fence_before();
@@ -116,6 +125,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d2 = tmem_base + 2 * UN;
+  const bool two_d2 = n2 <= 128;        // D2 double buffered when it fits ([256, 512) holds 2 x 128 or 1 x 256 columns)
+  const bool has_res = p.residual != nullptr;
 
   if (warp == 0) {
     // ======================= TMA producer 1: x rows + w3 rows =======================
@@ -124,11 +135,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
       uint32_t phase = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const int row0 = first_row + t * tile_stride_rows;
+        // second A source (block 0 of a layer: the downsample branch reads the block input, possibly at stride 2)
+        const int m_tile = static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x);
+        const int grp = m_tile / fp.a2_tpg;
+        const int a2_img = grp * fp.a2_bi, a2_h0 = (m_tile - grp * fp.a2_tpg) * fp.a2_bh;
         for (int j = 0; j < nu; ++j) {
           for (int ki = 0; ki < k1; ++ki) {
             mbar_wait(&empty1[stage], phase ^ 1);
             mbar_expect_tx(&full1[stage], STAGE1_BYTES);
-            tma_load_2d(sS1 + stage * STAGE1_BYTES, &p.map_a, &full1[stage], ki * BK, row0);
+            if (ki < fp.k1a) tma_load_2d(sS1 + stage * STAGE1_BYTES, &p.map_a, &full1[stage], ki * BK, row0);
+            else if (fp.a2_mode == CONV_GEMM)
+              tma_load_2d(sS1 + stage * STAGE1_BYTES, &p.map_a2, &full1[stage], (ki - fp.k1a) * BK, row0);
+            else
+              tma_load_5d(sS1 + stage * STAGE1_BYTES, &p.map_a2, &full1[stage], (ki - fp.k1a) * BK, 0, 0, a2_h0, a2_img);
             tma_load_2d(sS1 + stage * STAGE1_BYTES + A_BYTES, &p.map_b, &full1[stage], ki * BK, j * UN);
             if (++stage == st1) { stage = 0; phase ^= 1; }
           }
@@ -186,8 +205,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
       int b = 0;            // tile buffer of the unit, u % NB
       uint32_t nuse = 0;    // u / NB
       for (int t = 0; t < my_tiles; ++t) {
-        const int dbuf = t & 1;
-        mbar_wait(&d2empty[dbuf], ((t >> 1) & 1) ^ 1);   // D2 buffer drained (tile t - 2)
+        const int dbuf = two_d2 ? (t & 1) : 0;
+        const uint32_t duse = static_cast<uint32_t>(two_d2 ? (t >> 1) : t);
+        mbar_wait(&d2empty[dbuf], (duse & 1) ^ 1);       // D2 buffer drained (its previous tile)
         tc_fence_after();
         const uint32_t d2 = tmem_d2 + dbuf * UN;
         for (int j = 0; j < nu; ++j) {
@@ -225,20 +245,22 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
       }
     };
     auto d2_epilogue = [&](int t) {       // D2 = conv1_next(block output) + bias2, ReLU -> T1 of the next block
-      const int dbuf = t & 1;
-      mbar_wait(&d2full[dbuf], (t >> 1) & 1);
+      const int dbuf = two_d2 ? (t & 1) : 0;
+      const uint32_t duse = static_cast<uint32_t>(two_d2 ? (t >> 1) : t);
+      mbar_wait(&d2full[dbuf], duse & 1);
       tc_fence_after();
       const int row = first_row + t * tile_stride_rows + q * 32 + lane;
-      if (g < n2 / 64) {                  // n2 = 64: the g = 1 warps have no columns
+#pragma unroll 1
+      for (int gg = g; gg < n2 / 64; gg += 2) {   // n2 = 64: the g = 1 warps have no columns; n2 = 256: two groups each
         uint32_t v[2][32];
-        const uint32_t taddr = tmem_d2 + dbuf * UN + (static_cast<uint32_t>(q * 32) << 16) + g * 64;
+        const uint32_t taddr = tmem_d2 + dbuf * UN + (static_cast<uint32_t>(q * 32) << 16) + gg * 64;
         tmem_ld32(taddr, v[0]);
         tmem_ld32(taddr + 32, v[1]);
         tmem_ld_wait();
-        uint4* dst = reinterpret_cast<uint4*>(fp.out2 + static_cast<size_t>(row) * n2 + g * 64);
+        uint4* dst = reinterpret_cast<uint4*>(fp.out2 + static_cast<size_t>(row) * n2 + gg * 64);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          const float4* bias4 = reinterpret_cast<const float4*>(sBias2 + g * 64 + half * 32);
+          const float4* bias4 = reinterpret_cast<const float4*>(sBias2 + gg * 64 + half * 32);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 b0 = bias4[2 * i], b1 = bias4[2 * i + 1];
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
     };
 
     // unit i = (t, j), tile buffer b = i % NB (use number nuse = i / NB); the residual prefetch runs two units ahead
-    if (lane == 0) {
+    if (lane == 0 && has_res) {
       if (U > 0) issue_residual(0, 0, 0);
       if (U > 1) issue_residual(0, 1, 1);     // nu >= 2
     }
@@ -286,12 +308,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);           // D1 buffer read: issuer 1 may refill it
-      if (active) mbar_wait(&my_rbar[b], nuse & 1);
+      const bool add_res = active && has_res;
+      if (add_res) mbar_wait(&my_rbar[b], nuse & 1);
       uint8_t* region = my_region0 + b * TILE_BYTES;
       uint8_t* rowp = region + lane * 128;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const float4* bias4 = reinterpret_cast<const float4*>(sBias1 + j * UN + g * 64 + half * 32);
+        const float4* bias4 = reinterpret_cast<const float4*>(bias1p + j * UN + g * 64 + half * 32);
         float f[32];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -304,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           uint4* cp = reinterpret_cast<uint4*>(rowp + (((half * 4 + k) ^ (lane & 7)) << 4));
-          if (active) {
+          if (add_res) {
             const uint4 rr = *cp;
             f[8 * k + 0] += bf16_lo(rr.x); f[8 * k + 1] += bf16_hi(rr.x);
             f[8 * k + 2] += bf16_lo(rr.y); f[8 * k + 3] += bf16_hi(rr.y);
@@ -332,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
             mbar_wait(&gfree[fb * 2 + g], fuse_n & 1);
             tma_store_wait_read<1>();
           }
-          issue_residual(pt, pj, pb);
+          if (has_res) issue_residual(pt, pj, pb);
         }
       }
       __syncwarp();
@@ -377,23 +400,74 @@ int conv_fused_launch(const FusedParams& fp, cudaStream_t stream) {
   return IO_OK;
 }
 
-// conv3 of one bottleneck (x: [rows, cmid] = conv2 output; w3: [4*cmid][cmid]; residual + ReLU -> y: [rows, 4*cmid])
-// fused with conv1 of the next (w1n: [n2][4*cmid]; ReLU -> y2: [rows, n2]).
-int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, const void* w3, const float* bias3,
-                    const void* residual, void* y, const void* w1n, const float* bias1n, void* y2) {
-  const int n1 = 4 * cmid;
-  IO_REQUIRE(cmid == 64 || cmid == 128, "fused conv: C = %d not supported (64 or 128: layer1 / layer2)", cmid);
-  IO_REQUIRE(n2 % 64 == 0 && n2 >= 64 && n2 <= 128, "fused conv: N2 = %d not supported (64 or 128)", n2);
-  IO_REQUIRE(residual != nullptr, "fused conv: the block output needs its identity");
+// Ring depths: prefer 3 stages for the (x + w3) ring, then as many next-conv1 weight slots as fit (2..4).
+static bool fused_smem_plan(int n1, int n2, int* st1, int* st2, int* bytes) {
+  const int budget = MAX_SMEM - fixed_bytes(n1, n2);
+  const int slot2 = n2 * 128;
+  int s1 = (3 * STAGE1_BYTES + 2 * slot2 <= budget) ? 3 : 2;
+  int s2 = (budget - s1 * STAGE1_BYTES) / slot2;
+  if (s2 > MAX_ST2) s2 = MAX_ST2;
+  if (s2 < 2) return false;
+  *st1 = s1; *st2 = s2;
+  *bytes = s1 * STAGE1_BYTES + s2 * slot2 + fixed_bytes(n1, n2);
+  return true;
+}
+
+bool conv_fused_supported(int cmid, int n1, int n2, const ConvDesc* ds) {
+  if (cmid % 64 != 0 || cmid < 64 || n1 % UN != 0 || n1 < 2 * UN || n1 > 1024) return false;
+  if (n2 != 64 && n2 != 128 && n2 != 256) return false;
+  int a, b, c;
+  if (!fused_smem_plan(n1, n2, &a, &b, &c)) return false;
+  if (ds != nullptr) {
+    // block 0 of a layer: K = [t2 | x].  The first GEMM runs N = 128 MMAs (half rate), which only pays while the
+    // block is HBM-bound (layer1 / layer2); the strided source needs M tiles of exactly 128 output pixels
+    if (cmid > 128 || ds->kernel != 1 || ds->cin % 64 != 0) return false;
+    if (ds->stride == 2) {
+      const int ho = ds->h / 2, wo = ds->w / 2;
+      if (ds->h % 2 || ds->w % 2 || wo > BM) return false;
+      const int hw = ho * wo;
+      if (hw <= BM ? (BM % hw != 0) : (BM % wo != 0 || hw % BM != 0)) return false;
+    } else if (ds->stride != 1) {
+      return false;
+    }
+  }
+  return true;
+}
+
+// conv3 of one bottleneck (t2: [rows, cmid] = conv2 output; wb1: [n1][K1] with K1 = cmid (+ ds->cin: the downsample
+// weights side by side, block 0 of a layer, x = the block input, no residual); + residual, ReLU -> y: [rows, n1]) fused
+// with conv1 of the next block (w1n: [n2][n1]; ReLU -> y2: [rows, n2]).
+int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n1, int n2, const void* t2, const void* wb1,
+                    const float* bias1, const void* residual, void* y, const void* w1n, const float* bias2, void* y2,
+                    const ConvDesc* ds, const void* x) {
+  IO_REQUIRE(conv_fused_supported(cmid, n1, n2, ds), "fused conv: C = %d, N1 = %d, N2 = %d not supported", cmid, n1, n2);
+  IO_REQUIRE((residual != nullptr) != (ds != nullptr), "fused conv: exactly one of identity / downsample source expected");
   *fp = FusedParams{};
   ConvParams* p = &fp->c;
-  p->bias = bias3;
+  const int ktot = cmid + (ds ? ds->cin : 0);
+  int rc;
+  fp->a2_mode = CONV_GEMM;
+  fp->a2_tpg = 1; fp->a2_bi = 1; fp->a2_bh = 1;
+  CUtensorMap map_a2{};
+  if (ds != nullptr) {
+    ConvParams tmp;
+    int bn = 0;
+    if ((rc = conv_plan(&tmp, &bn, *ds, x, wb1, bias1, nullptr, y, 1))) return rc;
+    IO_REQUIRE(tmp.rows_per_tile == BM && tmp.m_total == rows, "fused conv: downsample source tiling (%d rows per tile)",
+               tmp.rows_per_tile);
+    map_a2 = tmp.map_a;
+    fp->a2_mode = tmp.mode;
+    fp->a2_tpg = tmp.tpg; fp->a2_bi = tmp.bi; fp->a2_bh = tmp.bh;
+  }
+  p->map_a2 = map_a2;
+  p->bias = bias1;
   p->residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p->out = reinterpret_cast<__nv_bfloat16*>(y);
   p->mode = CONV_GEMM;
   p->m_total = rows;
   p->n_total = n1;
-  p->k_iters = cmid / 64;
+  p->k_iters = ktot / 64;
+  fp->k1a = cmid / 64;
   p->kpt = p->k_iters;
   p->taps_w = 1;
   p->cin = cmid;
@@ -405,27 +479,26 @@ int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, 
   p->ldc = n1;
   p->n_split = n1;
   p->relu = 1;
-  fp->bias2 = bias1n;
+  fp->bias2 = bias2;
   fp->n2 = n2;
-  int rc;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(cmid), static_cast<uint64_t>(rows)};
     const uint64_t str[1] = {static_cast<uint64_t>(cmid) * 2};
     const uint32_t box[2] = {64, BM};
-    if ((rc = make_tmap_bf16(&p->map_a, x, 2, dims, str, box, true))) return rc;
+    if ((rc = make_tmap_bf16(&p->map_a, t2, 2, dims, str, box, true))) return rc;
   }
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(cmid), static_cast<uint64_t>(n1)};
-    const uint64_t str[1] = {static_cast<uint64_t>(cmid) * 2};
+    const uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(n1)};
+    const uint64_t str[1] = {static_cast<uint64_t>(ktot) * 2};
     const uint32_t box[2] = {64, UN};
-    if ((rc = make_tmap_bf16(&p->map_b, w3, 2, dims, str, box, true))) return rc;
+    if ((rc = make_tmap_bf16(&p->map_b, wb1, 2, dims, str, box, true))) return rc;
   }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(n1), static_cast<uint64_t>(rows)};
     const uint64_t str[1] = {static_cast<uint64_t>(n1) * 2};
     const uint32_t box[2] = {64, 32};
     if ((rc = make_tmap_bf16(&p->map_out, y, 2, dims, str, box, true))) return rc;
-    if ((rc = make_tmap_bf16(&p->map_res, residual, 2, dims, str, box, true))) return rc;
+    if (residual != nullptr && (rc = make_tmap_bf16(&p->map_res, residual, 2, dims, str, box, true))) return rc;
   }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(n1), static_cast<uint64_t>(n2)};
@@ -434,25 +507,36 @@ int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, 
     if ((rc = make_tmap_bf16(&fp->map_b2, w1n, 2, dims, str, box, true))) return rc;
   }
   fp->out2 = reinterpret_cast<__nv_bfloat16*>(y2);
-  // shared memory: ring 1 (x + w3 K blocks, 32 KB stages) and ring 2 ([n2 x 64] blocks of the next conv1's weights)
-  fp->st1 = 3;
-  fp->st2 = (n2 == 64) ? 4 : 2;
-  fp->smem_bytes = fp->st1 * STAGE1_BYTES + fp->st2 * n2 * 128 + FIXED_BYTES;
-  IO_REQUIRE(fp->smem_bytes <= MAX_SMEM, "fused conv: shared-memory plan %d B", fp->smem_bytes);
+  IO_REQUIRE(fused_smem_plan(n1, n2, &fp->st1, &fp->st2, &fp->smem_bytes), "fused conv: no shared-memory plan");
   return IO_OK;
 }
 
 }  // namespace io
 
-// exported for the parity test of the fused pair of convolutions
+// exported for the parity tests of the fused pair of convolutions
 extern "C" int io_conv_fused_pair(const void* x_dev, int rows, int cmid, const void* w3_dev, const float* bias3_dev,
                                   const void* residual_dev, void* y_dev, const void* w1n_dev, const float* bias1n_dev,
                                   int n2, void* y2_dev, void* stream) {
   IO_REQUIRE(x_dev && w3_dev && bias3_dev && residual_dev && y_dev && w1n_dev && bias1n_dev && y2_dev,
              "io_conv_fused_pair: null pointer");
   io::FusedParams fp;
-  int rc = io::conv_fused_plan(&fp, rows, cmid, n2, x_dev, w3_dev, bias3_dev, residual_dev, y_dev, w1n_dev, bias1n_dev,
-                               y2_dev);
+  int rc = io::conv_fused_plan(&fp, rows, cmid, 4 * cmid, n2, x_dev, w3_dev, bias3_dev, residual_dev, y_dev, w1n_dev,
+                               bias1n_dev, y2_dev, nullptr, nullptr);
+  if (rc) return rc;
+  return io::conv_fused_launch(fp, io::as_stream(stream));
+}
+
+extern "C" int io_conv_fused_dual(const void* x_dev, int b, int h, int w, int cin, int stride, const void* t2_dev,
+                                  int cmid, const void* wcat_dev, const float* bias_dev, void* y_dev,
+                                  const void* w1n_dev, const float* bias1n_dev, int n2, void* y2_dev, void* stream) {
+  IO_REQUIRE(x_dev && t2_dev && wcat_dev && bias_dev && y_dev && w1n_dev && bias1n_dev && y2_dev,
+             "io_conv_fused_dual: null pointer");
+  IO_REQUIRE(stride == 1 || stride == 2, "io_conv_fused_dual: stride %d", stride);
+  io::FusedParams fp;
+  const io::ConvDesc ds{b, h, w, cin, 4 * cmid, 1, stride};
+  const int rows = b * (h / stride) * (w / stride);
+  int rc = io::conv_fused_plan(&fp, rows, cmid, 4 * cmid, n2, t2_dev, wcat_dev, bias_dev, nullptr, y_dev, w1n_dev,
+                               bias1n_dev, y2_dev, &ds, x_dev);
   if (rc) return rc;
   return io::conv_fused_launch(fp, io::as_stream(stream));
 }

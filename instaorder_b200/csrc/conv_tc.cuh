@@ -71,9 +71,15 @@ struct FusedParams {
   int n2;
   int st1, st2;          // ring depths: (x + w3) stages of 32 KB, next-conv1 weight slots of n2 * 128 B
   int smem_bytes;
+  // block 0 of a layer: K blocks [0, k1a) of the first GEMM come from c.map_a (conv2 output), the rest from c.map_a2,
+  // the block input seen through the downsample convolution's activation view (flat, or the stride-2 parity view)
+  int k1a;
+  int a2_mode, a2_tpg, a2_bi, a2_bh;
 };
-int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n2, const void* x, const void* w3, const float* bias3,
-                    const void* residual, void* y, const void* w1n, const float* bias1n, void* y2);
+bool conv_fused_supported(int cmid, int n1, int n2, const ConvDesc* ds);
+int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n1, int n2, const void* t2, const void* wb1,
+                    const float* bias1, const void* residual, void* y, const void* w1n, const float* bias2, void* y2,
+                    const ConvDesc* ds, const void* x);
 int conv_fused_launch(const FusedParams& fp, cudaStream_t stream);
 
 // Transposed kernel (conv_tn.cu): 128 output channels on the MMA's M side, 256 pixels on its N side

@@ -68,7 +68,7 @@ struct io_net {
   int chunk_a = 0, chunk_b = 0;
   bool fuse_ds = true;  // first block of a layer: conv3 + downsample as one GEMM over concatenated K (INSTAORDER_FUSE_DS=0 disables)
   bool fuse = true;   // conv3 -> next conv1 back-to-back GEMM fusion in layer1 / layer2 (INSTAORDER_FUSE=0 disables)
-  int fuse_layers = 0x3;  // bit li: fuse inside layer li+1 (INSTAORDER_FUSE_LAYERS)
+  int fuse_layers = 0x7;  // bit li: fuse inside layer li+1 (INSTAORDER_FUSE_LAYERS)
   __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase A: X, Y, T1, T2, DS
   __nv_bfloat16* bufb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase B: X, Y, T1, T2, DS
   __nv_bfloat16* big = nullptr;                                            // layer2 output of a whole B chunk
@@ -164,16 +164,34 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       o2.tag = (li + 1) * 100 + blk * 10 + 2;
       plan->ops.push_back(o2);
       const __nv_bfloat16* identity = src;
+      // the next bottleneck's conv1 (same layer, or the first block of the next layer inside this plan: its conv1 is
+      // a stride-1 1x1 over this block's output) can be computed from the block-output tile while it is on chip
+      const bool has_next = (blk + 1 < blocks_[li]) || (li + 1 < l1);
+      const bool want_fuse = net->fuse && ((net->fuse_layers >> li) & 1) && has_next;
       if (ds && net->fuse_ds) {
         // block output = ReLU(conv3(T2) + downsample(src)) as one GEMM, K = [T2 channels | src channels]; the
         // identity tensor is neither written nor re-read
-        Op o3; o3.kind = Op::CONV;
-        if (int rc = conv_plan_dual(&o3.p, &o3.bn_tile, ConvDesc{b, h, w, ds->cin, ds->cout, 1, ds->stride}, src, T2,
-                                    c3.cin, ds->wcat, ds->bias_cat, dst, 1)) return rc;
-        o3.flops = 2.0 * b * ho * wo * (static_cast<double>(c3.cin) + ds->cin) * c3.cout;
-        o3.bytes = 2.0 * b * ho * wo * (c3.cin + ds->cin + c3.cout) + 2.0 * (c3.cin + ds->cin) * c3.cout;
-        o3.tag = (li + 1) * 100 + blk * 10 + 6;
-        plan->ops.push_back(o3);
+        const ConvDesc dsd{b, h, w, ds->cin, ds->cout, 1, ds->stride};
+        if (want_fuse && conv_fused_supported(c3.cin, c3.cout, net->convs[ci].cout, &dsd)) {
+          const ConvW& n1 = net->convs[ci];
+          Op of; of.kind = Op::FUSED;
+          if (int rc = conv_fused_plan(&of.fp, b * ho * wo, c3.cin, c3.cout, n1.cout, T2, ds->wcat, ds->bias_cat,
+                                       nullptr, dst, n1.w, n1.bias, T1, &dsd, src)) return rc;
+          of.flops = 2.0 * b * ho * wo * ((static_cast<double>(c3.cin) + ds->cin) * c3.cout +
+                                          static_cast<double>(n1.cin) * n1.cout);
+          of.bytes = 2.0 * b * ho * wo * (c3.cin + ds->cin + c3.cout + n1.cout) + 2.0 * (c3.cin + ds->cin) * c3.cout +
+                     2.0 * n1.cin * n1.cout;
+          of.tag = (li + 1) * 100 + blk * 10 + 7;
+          plan->ops.push_back(of);
+          t1_ready = true;
+        } else {
+          Op o3; o3.kind = Op::CONV;
+          if (int rc = conv_plan_dual(&o3.p, &o3.bn_tile, dsd, src, T2, c3.cin, ds->wcat, ds->bias_cat, dst, 1)) return rc;
+          o3.flops = 2.0 * b * ho * wo * (static_cast<double>(c3.cin) + ds->cin) * c3.cout;
+          o3.bytes = 2.0 * b * ho * wo * (c3.cin + ds->cin + c3.cout) + 2.0 * (c3.cin + ds->cin) * c3.cout;
+          o3.tag = (li + 1) * 100 + blk * 10 + 6;
+          plan->ops.push_back(o3);
+        }
         src = dst;
         h = ho; w = wo;
         continue;
@@ -188,16 +206,12 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
         plan->ops.push_back(od);
         identity = DS;
       }
-      // the next bottleneck's conv1 (same layer, or the first block of the next layer inside this plan: its conv1 is
-      // a stride-1 1x1 over this block's output) can be computed from the block-output tile while it is on chip
-      const bool has_next = (blk + 1 < blocks_[li]) || (li + 1 < l1);
-      const bool fuse_next = net->fuse && ((net->fuse_layers >> li) & 1) && has_next && c3.cin <= 128 &&
-                             net->convs[ci].cout <= 128;
+      const bool fuse_next = want_fuse && conv_fused_supported(c3.cin, c3.cout, net->convs[ci].cout, nullptr);
       if (fuse_next) {
         const ConvW& n1 = net->convs[ci];   // next block's conv1
         Op of; of.kind = Op::FUSED;
-        if (int rc = conv_fused_plan(&of.fp, b * ho * wo, c3.cin, n1.cout, T2, c3.w, c3.bias, identity, dst, n1.w,
-                                     n1.bias, T1)) return rc;
+        if (int rc = conv_fused_plan(&of.fp, b * ho * wo, c3.cin, c3.cout, n1.cout, T2, c3.w, c3.bias, identity, dst,
+                                     n1.w, n1.bias, T1, nullptr, nullptr)) return rc;
         of.flops = 2.0 * b * ho * wo * (static_cast<double>(c3.cin) * c3.cout + static_cast<double>(n1.cin) * n1.cout);
         of.bytes = 2.0 * b * ho * wo * (c3.cin + 2 * c3.cout + n1.cout) + 2.0 * c3.cin * c3.cout + 2.0 * n1.cin * n1.cout;
         of.tag = (li + 1) * 100 + blk * 10 + 5;

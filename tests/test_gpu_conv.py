@@ -65,7 +65,8 @@ def test_conv_bn_act(case):
 
 # (rows, cmid, n2): layer1 / layer2 / layer3 bottleneck pairs + a ragged row count (row guard by TMA clipping)
 FUSED_CASES = [(2 * 64 * 64, 64, 64), (3 * 32 * 32, 128, 128), (5 * 16 * 16, 128, 64), (1000, 64, 64),
-               (148 * 128 * 2 + 77, 128, 128), (148 * 128 * 3 + 5, 64, 128), (148 * 128 * 4 + 300, 128, 64), (100, 64, 64)]
+               (148 * 128 * 2 + 77, 128, 128), (148 * 128 * 3 + 5, 64, 128), (148 * 128 * 4 + 300, 128, 64), (100, 64, 64),
+               (5 * 16 * 16, 256, 256), (148 * 128 * 2 + 200, 256, 256), (40 * 24 * 24, 256, 128)]
 
 
 @pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: "rows%d_c%d_n%d" % c)
@@ -128,3 +129,41 @@ def test_conv_dual(case):
     err = (got - ref).abs()
     tol = 1e-2 + 1e-2 * ref.abs()
     assert not (err > tol).any(), "max err %.4g, %d bad" % (float(err.max()), int((err > tol).sum()))
+
+
+# (B, H, W, Cin, cmid, stride, n2): layer1.0 -> layer1.1.conv1, layer2.0 -> layer2.1.conv1 (+ ragged / multi-tile cases)
+FUSED_DUAL_CASES = [(2, 64, 64, 64, 64, 1, 64), (3, 64, 64, 256, 128, 2, 128), (37, 64, 64, 64, 64, 1, 64),
+                    (150, 32, 32, 256, 128, 2, 128), (5, 16, 16, 256, 128, 2, 64)]
+
+
+@pytest.mark.parametrize("case", FUSED_DUAL_CASES, ids=lambda c: "B%d_%dx%d_%d+%d_s%d_n%d" % c)
+def test_conv_fused_dual(case):
+    """First bottleneck of a layer (conv3 + downsample as one GEMM) fused with the next block's conv1."""
+    B, H, W, Cin, cmid, stride, n2 = case
+    cout = 4 * cmid
+    Ho, Wo = H // stride, W // stride
+    rows = B * Ho * Wo
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + H + Cin + cmid + n2)
+    dev = "cuda"
+    x = torch.randn((B, H, W, Cin), generator=g, device=dev).to(torch.bfloat16).contiguous()
+    t2 = torch.randn((rows, cmid), generator=g, device=dev).to(torch.bfloat16).contiguous()
+    w3 = (torch.randn((cout, cmid), generator=g, device=dev) / cmid ** 0.5).to(torch.bfloat16)
+    wd = (torch.randn((cout, Cin), generator=g, device=dev) / Cin ** 0.5).to(torch.bfloat16)
+    bias = torch.randn((cout,), generator=g, device=dev)
+    wcat = torch.cat([w3, wd], dim=1).contiguous()
+    w1 = (torch.randn((n2, cout), generator=g, device=dev) / cout ** 0.5).to(torch.bfloat16)
+    b1 = torch.randn((n2,), generator=g, device=dev)
+    y = torch.full((rows, cout), float("nan"), device=dev, dtype=torch.bfloat16)
+    y2 = torch.full((rows, n2), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().io_conv_fused_dual(x.data_ptr(), B, H, W, Cin, stride, t2.data_ptr(), cmid, wcat.data_ptr(),
+                                             bias.data_ptr(), y.data_ptr(), w1.data_ptr(), b1.data_ptr(), n2,
+                                             y2.data_ptr(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    xs = x[:, ::stride, ::stride, :].reshape(rows, Cin).float()
+    ref = torch.relu(t2.float() @ w3.float().t() + xs @ wd.float().t() + bias)
+    ref2 = torch.relu(ref.to(torch.bfloat16).float() @ w1.float().t() + b1)
+    for got, want, name in ((y.float(), ref, "y"), (y2.float(), ref2, "y2")):
+        assert torch.isfinite(got).all(), "%s: %d unwritten outputs" % (name, int((~torch.isfinite(got)).sum()))
+        err = (got - want).abs()
+        tol = 1.5e-2 + 1e-2 * want.abs()
+        assert not (err > tol).any(), "%s: max err %.4g, %d bad" % (name, float(err.max()), int((err > tol).sum()))
