@@ -14,7 +14,7 @@
 
 namespace io {
 
-constexpr int GATHER_ROWS = 8;      // output rows per CTA
+constexpr int GATHER_ROWS = 8;      // output rows per CTA (32-row bands: 10 % fewer instructions, same time -- fewer CTAs)
 constexpr int GATHER_THREADS = 128;
 constexpr int MAX_D = 512;
 
@@ -111,12 +111,22 @@ __device__ __forceinline__ void zero_borders(__nv_bfloat16* out_pair, int d, int
       *reinterpret_cast<uint4*>(out_pair + (static_cast<size_t>(hp - 3) * pitch + i) * 8) = z;
 }
 
+// Separable form of the same arithmetic (OpenCV's generic resize is separable too): the integer horizontal pass is
+// done ONCE per source row of the band -- its three channel sums per output column go into a ring of 8 rows in shared
+// memory -- and the fp32 vertical pass combines four ring rows per output row.  A CTA owns (pair, 8 output rows) and
+// walks them top to bottom, so every source row is resampled once per band instead of once per output row and tap
+// (ncu: the direct form issued 353 warp instructions per pixel and was issue / L1 bound at 1.1 TB/s).
+// Per-column tap offsets / validity / weights depend only on the column and are hoisted into registers (NPX columns
+// per thread).  Dynamic shared memory: AxisTab[d] + int32 ring[8][3][d].
+template <int NPX>
 __global__ void __launch_bounds__(GATHER_THREADS) gather_patch_kernel(const uint8_t* __restrict__ images,
                                                                       const uint8_t* __restrict__ masks,
                                                                       const io_pair_desc* __restrict__ descs, int d,
                                                                       int pitch, NormLut lut,
                                                                       __nv_bfloat16* __restrict__ out) {
-  __shared__ AxisTab tab[MAX_D];
+  extern __shared__ __align__(16) uint8_t gsm[];
+  AxisTab* tab = reinterpret_cast<AxisTab*>(gsm);
+  int* ring = reinterpret_cast<int*>(gsm + static_cast<size_t>(d) * sizeof(AxisTab));   // [8][3][d]
   __shared__ uint16_t slut[3][256];
   const io_pair_desc ds = descs[blockIdx.y];
   const int S = ds.s;
@@ -135,68 +145,103 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_patch_kernel(const uint
   zero_borders(out_pair, d, pitch, blockIdx.x, gridDim.x, row0, row1);
   const float kscale = 1.0f / (2048.0f * 2048.0f);
 
-  for (int dy = row0; dy < row1; ++dy) {
-    const AxisTab ty = tab[dy];
-    const int my = Y + ty.near;
-    const bool my_ok = my >= 0 && my < H;
-    int iy[4];
-    bool oky[4];
-    float by[4];
+  // ---- per-column state (registers): byte offsets of the four taps inside an image row (-1 = outside the image:
+  // crop_padding's zero), their 11-bit weights, and the nearest-neighbour mask column
+  int off[NPX][4];
+  int cf[NPX][4];
+  int mcol[NPX];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int yy = min(max(ty.first + k, 0), S - 1);
-      iy[k] = Y + yy;
-      oky[k] = iy[k] >= 0 && iy[k] < H;
-      by[k] = __fmul_rn(static_cast<float>(ty.coef[k]), kscale);
-    }
-    for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
+  for (int m = 0; m < NPX; ++m) {
+    const int dx = threadIdx.x + m * GATHER_THREADS;
+    if (dx < d) {
       const AxisTab tx = tab[flip ? d - 1 - dx : dx];
-      // ---- modal masks: nearest
       const int mx = X + tx.near;
-      float va = 0.0f, vb = 0.0f;
-      if (my_ok && mx >= 0 && mx < W) {
-        const size_t o = static_cast<size_t>(my) * W + mx;
-        va = static_cast<float>(ma[o]);
-        vb = static_cast<float>(mb[o]);
-      }
-      // ---- rgb: bicubic, horizontal (int) then vertical (fp32)
-      int ix[4];
-      bool okx[4];
+      mcol[m] = (mx >= 0 && mx < W) ? mx : -1;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int xx = min(max(tx.first + j, 0), S - 1);
-        ix[j] = X + xx;
-        okx[j] = ix[j] >= 0 && ix[j] < W;
+        const int ix = X + xx;
+        off[m][j] = (ix >= 0 && ix < W) ? ix * 3 : -1;
+        cf[m][j] = tx.coef[j];
       }
-      int hsum[4][3];
+    } else {
+      mcol[m] = -1;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        hsum[k][0] = hsum[k][1] = hsum[k][2] = 0;
-        if (oky[k]) {
-          const uint8_t* rowp = img + static_cast<size_t>(iy[k]) * W * 3;
+      for (int j = 0; j < 4; ++j) { off[m][j] = -1; cf[m][j] = 0; }
+    }
+  }
+
+  int hi = -1;   // crop rows < hi have been resampled into the ring (or skipped for good)
+  for (int dy = row0; dy < row1; ++dy) {
+    const AxisTab ty = tab[dy];
+    int cr[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (okx[j]) {
-              const uint8_t* px = rowp + ix[j] * 3;
-              const int cj = tx.coef[j];
-              hsum[k][0] += static_cast<int>(px[0]) * cj;
-              hsum[k][1] += static_cast<int>(px[1]) * cj;
-              hsum[k][2] += static_cast<int>(px[2]) * cj;
+    for (int k = 0; k < 4; ++k) cr[k] = min(max(ty.first + k, 0), S - 1);   // crop rows of the four taps (non-decreasing)
+    const int start = max(hi, cr[0]);
+    if (start <= cr[3]) {              // uniform over the CTA
+      __syncthreads();                 // the previous row's vertical pass has finished reading the ring
+      for (int c = start; c <= cr[3]; ++c) {
+        const int iy = Y + c;
+        const bool oky = iy >= 0 && iy < H;
+        const uint8_t* rowp = img + static_cast<size_t>(oky ? iy : 0) * W * 3;
+        int* rr = ring + (c & 7) * 3 * d;
+#pragma unroll
+        for (int m = 0; m < NPX; ++m) {
+          const int dx = threadIdx.x + m * GATHER_THREADS;
+          if (dx < d) {
+            int h0 = 0, h1 = 0, h2 = 0;
+            if (oky) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (off[m][j] >= 0) {
+                  const uint8_t* px = rowp + off[m][j];
+                  h0 += static_cast<int>(px[0]) * cf[m][j];
+                  h1 += static_cast<int>(px[1]) * cf[m][j];
+                  h2 += static_cast<int>(px[2]) * cf[m][j];
+                }
+              }
             }
+            rr[dx] = h0;
+            rr[d + dx] = h1;
+            rr[2 * d + dx] = h2;
           }
         }
       }
-      uint16_t rgb[3];
+      hi = cr[3] + 1;
+      __syncthreads();
+    }
+    // ---- vertical pass (fp32, taps 3,2,1,0, no fma) + modal masks (nearest) + normalisation LUT
+    const int my = Y + ty.near;
+    const bool my_ok = my >= 0 && my < H;
+    float by[4];
+    const int* rk[4];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = __fmul_rn(static_cast<float>(hsum[3][c]), by[3]);
-        v = __fadd_rn(__fmul_rn(static_cast<float>(hsum[2][c]), by[2]), v);
-        v = __fadd_rn(__fmul_rn(static_cast<float>(hsum[1][c]), by[1]), v);
-        v = __fadd_rn(__fmul_rn(static_cast<float>(hsum[0][c]), by[0]), v);
-        const int u = min(max(__float2int_rn(v), 0), 255);
-        rgb[c] = slut[c][u];
+    for (int k = 0; k < 4; ++k) {
+      by[k] = __fmul_rn(static_cast<float>(ty.coef[k]), kscale);
+      rk[k] = ring + (cr[k] & 7) * 3 * d;
+    }
+#pragma unroll
+    for (int m = 0; m < NPX; ++m) {
+      const int dx = threadIdx.x + m * GATHER_THREADS;
+      if (dx < d) {
+        float va = 0.0f, vb = 0.0f;
+        if (my_ok && mcol[m] >= 0) {
+          const size_t o = static_cast<size_t>(my) * W + mcol[m];
+          va = static_cast<float>(ma[o]);
+          vb = static_cast<float>(mb[o]);
+        }
+        uint16_t rgb[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v = __fmul_rn(static_cast<float>(rk[3][c * d + dx]), by[3]);
+          v = __fadd_rn(__fmul_rn(static_cast<float>(rk[2][c * d + dx]), by[2]), v);
+          v = __fadd_rn(__fmul_rn(static_cast<float>(rk[1][c * d + dx]), by[1]), v);
+          v = __fadd_rn(__fmul_rn(static_cast<float>(rk[0][c * d + dx]), by[0]), v);
+          const int u = min(max(__float2int_rn(v), 0), 255);
+          rgb[c] = slut[c][u];
+        }
+        store_pixel(out_pair + (static_cast<size_t>(dy + 3) * pitch + dx + 3) * 8, va, vb, rgb[0], rgb[1], rgb[2]);
       }
-      store_pixel(out_pair + (static_cast<size_t>(dy + 3) * pitch + dx + 3) * 8, va, vb, rgb[0], rgb[1], rgb[2]);
     }
   }
 }
@@ -615,9 +660,20 @@ extern "C" int io_pair_gather_patch(const uint8_t* images, const uint8_t* masks,
   NormLut lut;
   for (int i = 0; i < 768; ++i) (&lut.v[0][0])[i] = f32_to_bf16_rn(lutf[i]);
   dim3 grid((d + GATHER_ROWS - 1) / GATHER_ROWS, p);
-  gather_patch_kernel<<<grid, GATHER_THREADS, 0, as_stream(stream)>>>(images, masks, descs, d,
-                                                                      static_cast<int>(io_pair_tensor_row_pitch(d)),
-                                                                      lut, reinterpret_cast<__nv_bfloat16*>(out));
+  const size_t smem = static_cast<size_t>(d) * (sizeof(AxisTab) + 8 * 3 * sizeof(int));
+  const int pitch = static_cast<int>(io_pair_tensor_row_pitch(d));
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (d <= 2 * GATHER_THREADS) {
+    gather_patch_kernel<2><<<grid, GATHER_THREADS, smem, as_stream(stream)>>>(images, masks, descs, d, pitch, lut, o);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      IO_CUDA(cudaFuncSetAttribute(gather_patch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   MAX_D * (sizeof(AxisTab) + 8 * 3 * sizeof(int))));
+      attr_set = true;
+    }
+    gather_patch_kernel<4><<<grid, GATHER_THREADS, smem, as_stream(stream)>>>(images, masks, descs, d, pitch, lut, o);
+  }
   IO_CUDA(cudaGetLastError());
   return IO_OK;
 }

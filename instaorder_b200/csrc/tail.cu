@@ -6,51 +6,52 @@ namespace io {
 
 // ---- nn.MaxPool2d(3, 2, 1) on NHWC bf16 (models/backbone/resnet_cls.py:144,207) -------------------------------
 // one thread = 8 channels of one output pixel; padding never wins because the input is post-ReLU (>= 0) and the
-// window always contains at least one real pixel.
-__global__ void __launch_bounds__(256) maxpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int b, int h,
-                                                      int w, int c8) {
+// window always contains at least one real pixel.  One CTA per output row (image, oy): the three input row pointers
+// are block-uniform and (ox, channel group) come from the thread index by shifts -- the first version decoded a flat
+// index with three 64-bit divisions per output and was issue-bound at 60 % of the HBM roofline.
+__global__ void __launch_bounds__(256) maxpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int h, int w,
+                                                      int c8_shift) {
   const int ho = h / 2, wo = w / 2;
-  const size_t total = static_cast<size_t>(b) * ho * wo * c8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % c8);
-    size_t t = i / c8;
-    const int ox = static_cast<int>(t % wo);
-    t /= wo;
-    const int oy = static_cast<int>(t % ho);
-    const int n = static_cast<int>(t / ho);
+  const int n = blockIdx.x / ho, oy = blockIdx.x - n * ho;
+  const int c8 = 1 << c8_shift;
+  const uint4* __restrict__ xin = x + static_cast<size_t>(n) * h * w * c8;
+  const int iy0 = 2 * oy - 1;
+  const bool top_ok = iy0 >= 0;               // rows 2oy and 2oy + 1 always exist (h even)
+  const uint4* __restrict__ r0 = xin + static_cast<size_t>(top_ok ? iy0 : 2 * oy) * w * c8;   // duplicate = harmless for max
+  const uint4* __restrict__ r1 = xin + static_cast<size_t>(2 * oy) * w * c8;
+  const uint4* __restrict__ r2 = xin + static_cast<size_t>(2 * oy + 1) * w * c8;
+  uint4* __restrict__ yout = y + static_cast<size_t>(blockIdx.x) * wo * c8;
+  for (int i = threadIdx.x; i < wo * c8; i += blockDim.x) {
+    const int ox = i >> c8_shift, cg = i & (c8 - 1);
+    const int xl = (ox > 0) ? 2 * ox - 1 : 0;  // left tap clamped to column 0 (duplicate of the centre tap)
+    const int o0 = xl * c8 + cg, o1 = (2 * ox) * c8 + cg, o2 = (2 * ox + 1) * c8 + cg;
+    uint4 v[9];
+    v[0] = __ldg(r0 + o0); v[1] = __ldg(r0 + o1); v[2] = __ldg(r0 + o2);
+    v[3] = __ldg(r1 + o0); v[4] = __ldg(r1 + o1); v[5] = __ldg(r1 + o2);
+    v[6] = __ldg(r2 + o0); v[7] = __ldg(r2 + o1); v[8] = __ldg(r2 + o2);
     __nv_bfloat162 m[4];
-    bool first = true;
+    const __nv_bfloat162* p0 = reinterpret_cast<const __nv_bfloat162*>(&v[0]);
+    m[0] = p0[0]; m[1] = p0[1]; m[2] = p0[2]; m[3] = p0[3];
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int iy = 2 * oy + dy;
-      if (iy < 0 || iy >= h) continue;
-#pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int ix = 2 * ox + dx;
-        if (ix < 0 || ix >= w) continue;
-        const uint4 v = __ldg(x + ((static_cast<size_t>(n) * h + iy) * w + ix) * c8 + cg);
-        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
-        if (first) {
-          m[0] = pv[0]; m[1] = pv[1]; m[2] = pv[2]; m[3] = pv[3];
-          first = false;
-        } else {
-          m[0] = __hmax2(m[0], pv[0]); m[1] = __hmax2(m[1], pv[1]);
-          m[2] = __hmax2(m[2], pv[2]); m[3] = __hmax2(m[3], pv[3]);
-        }
-      }
+    for (int k = 1; k < 9; ++k) {
+      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v[k]);
+      m[0] = __hmax2(m[0], pv[0]); m[1] = __hmax2(m[1], pv[1]);
+      m[2] = __hmax2(m[2], pv[2]); m[3] = __hmax2(m[3], pv[3]);
     }
-    y[i] = *reinterpret_cast<uint4*>(m);
+    yout[i] = *reinterpret_cast<uint4*>(m);
   }
 }
 
 int maxpool_launch(const void* x, void* y, int b, int h, int w, int c, cudaStream_t stream) {
   IO_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool: bad shape");
-  const size_t total = static_cast<size_t>(b) * (h / 2) * (w / 2) * (c / 8);
-  if (total == 0) return IO_OK;
-  const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
-  maxpool_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), b, h, w,
-                                           c / 8);
+  const int c8 = c / 8;
+  int shift = 0;
+  while ((1 << shift) < c8) ++shift;
+  IO_REQUIRE((1 << shift) == c8, "maxpool: channel count %d (8 x a power of two expected)", c);
+  const long long blocks = static_cast<long long>(b) * (h / 2);
+  if (blocks == 0) return IO_OK;
+  maxpool_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                     reinterpret_cast<uint4*>(y), h, w, shift);
   IO_CUDA(cudaGetLastError());
   return IO_OK;
 }
