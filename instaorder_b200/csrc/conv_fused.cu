@@ -33,12 +33,12 @@ constexpr int REGION_BYTES = 32 * 128;       // 32 rows x 64 columns bf16 (one e
 constexpr int GROUP_BYTES = 4 * REGION_BYTES;  // 128 rows x 64 columns = one K block of the second GEMM's A operand
 constexpr int TILE_BYTES = 2 * GROUP_BYTES;
 constexpr int BAR_BYTES = 512;
-// bias2 (n2 floats, 512 B granules) always sits in shared memory, bias1 only when n1 <= 512 (2 KB); the 1024-column
-// layers read it through L1 instead -- the shared memory is needed for the rings
+// bias2 (n2 floats, 512 B granules) always sits in shared memory, bias1 only when n1 <= 512 and n2 <= 128 (2 KB);
+// the other shapes read it through L1 instead -- their shared memory is needed for the rings
 __host__ __device__ constexpr int bias2_bytes(int n2) { return n2 <= 128 ? 512 : 1024; }
-__host__ __device__ constexpr int bias1_bytes(int n1) { return n1 <= 512 ? 2048 : 0; }
+__host__ __device__ constexpr int bias1_bytes(int n1, int n2) { return (n1 <= 512 && n2 <= 128) ? 2048 : 0; }
 __host__ __device__ constexpr int fixed_bytes(int n1, int n2) {
-  return NB * TILE_BYTES + bias2_bytes(n2) + bias1_bytes(n1) + BAR_BYTES;
+  return NB * TILE_BYTES + bias2_bytes(n2) + bias1_bytes(n1, n2) + BAR_BYTES;
 }
 constexpr int MAX_SMEM = 232448;             // 227 KB
 constexpr int TMEM_COLS = 512;
@@ -59,9 +59,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
   uint8_t* sT = sS2 + st2 * slot2_bytes;                // tile buffers: [NB][2 groups][4 quadrants][32 x 128 B]
   float* sBias2 = reinterpret_cast<float*>(sT + NB * TILE_BYTES);
   float* sBias1 = reinterpret_cast<float*>(sT + NB * TILE_BYTES + bias2_bytes(n2));
-  const bool bias1_smem = bias1_bytes(p.n_total) != 0;
+  const bool bias1_smem = bias1_bytes(p.n_total, n2) != 0;
   const float* bias1p = bias1_smem ? sBias1 : p.bias;
-  uint64_t* full1 = reinterpret_cast<uint64_t*>(sT + NB * TILE_BYTES + bias2_bytes(n2) + bias1_bytes(p.n_total));
+  uint64_t* full1 = reinterpret_cast<uint64_t*>(sT + NB * TILE_BYTES + bias2_bytes(n2) + bias1_bytes(p.n_total, n2));
   uint64_t* empty1 = full1 + MAX_ST1;
   uint64_t* full2 = empty1 + MAX_ST1;
   uint64_t* empty2 = full2 + MAX_ST2;

@@ -69,6 +69,7 @@ struct io_net {
   bool fuse_ds = true;  // first block of a layer: conv3 + downsample as one GEMM over concatenated K (INSTAORDER_FUSE_DS=0 disables)
   bool fuse = true;   // conv3 -> next conv1 back-to-back GEMM fusion in layer1 / layer2 (INSTAORDER_FUSE=0 disables)
   int fuse_layers = 0x7;  // bit li: fuse inside layer li+1 (INSTAORDER_FUSE_LAYERS)
+  bool cross_fuse = false;  // layer2's last conv3 also produces layer3.0's conv1 output (phase A writes phase B's T1)
   __nv_bfloat16* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // phase A: X, Y, T1, T2, DS
   __nv_bfloat16* bufb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase B: X, Y, T1, T2, DS
   __nv_bfloat16* big = nullptr;                                            // layer2 output of a whole B chunk
@@ -126,12 +127,14 @@ static void build_conv_list(io_net* net) {
 static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_io, int* w_io,
                         const __nv_bfloat16* src, __nv_bfloat16* P0, __nv_bfloat16* P1, __nv_bfloat16* T1,
                         __nv_bfloat16* T2, __nv_bfloat16* DS, __nv_bfloat16* final_dst,
-                        const __nv_bfloat16** out_ptr) {
+                        const __nv_bfloat16** out_ptr, __nv_bfloat16* next_t1 = nullptr, bool t1_in = false) {
   const int blocks_[4] = {3, 4, 6, 3};
   size_t ci = 1;
   for (int li = 0; li < l0; ++li) ci += 3 * blocks_[li] + 1;
   int h = *h_io, w = *w_io;
-  bool t1_ready = false;   // the previous block's fused conv3 already produced this block's conv1 output
+  // next_t1: where the conv1 output of the block FOLLOWING this plan's last one goes (phase A -> phase B fusion);
+  // t1_in: this plan's first conv1 output has already been produced that way
+  bool t1_ready = t1_in;   // the previous block's fused conv3 already produced this block's conv1 output
   for (int li = l0; li < l1; ++li) {
     for (int blk = 0; blk < blocks_[li]; ++blk) {
       const ConvW& c1 = net->convs[ci++];
@@ -166,7 +169,8 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       const __nv_bfloat16* identity = src;
       // the next bottleneck's conv1 (same layer, or the first block of the next layer inside this plan: its conv1 is
       // a stride-1 1x1 over this block's output) can be computed from the block-output tile while it is on chip
-      const bool has_next = (blk + 1 < blocks_[li]) || (li + 1 < l1);
+      const bool has_next = (blk + 1 < blocks_[li]) || (li + 1 < l1) || (next_t1 != nullptr);
+      __nv_bfloat16* t1_dst = ((blk + 1 < blocks_[li]) || (li + 1 < l1)) ? T1 : next_t1;
       const bool want_fuse = net->fuse && ((net->fuse_layers >> li) & 1) && has_next;
       if (ds && net->fuse_ds) {
         // block output = ReLU(conv3(T2) + downsample(src)) as one GEMM, K = [T2 channels | src channels]; the
@@ -176,7 +180,7 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
           const ConvW& n1 = net->convs[ci];
           Op of; of.kind = Op::FUSED;
           if (int rc = conv_fused_plan(&of.fp, b * ho * wo, c3.cin, c3.cout, n1.cout, T2, ds->wcat, ds->bias_cat,
-                                       nullptr, dst, n1.w, n1.bias, T1, &dsd, src)) return rc;
+                                       nullptr, dst, n1.w, n1.bias, t1_dst, &dsd, src)) return rc;
           of.flops = 2.0 * b * ho * wo * ((static_cast<double>(c3.cin) + ds->cin) * c3.cout +
                                           static_cast<double>(n1.cin) * n1.cout);
           of.bytes = 2.0 * b * ho * wo * (c3.cin + ds->cin + c3.cout + n1.cout) + 2.0 * (c3.cin + ds->cin) * c3.cout +
@@ -211,7 +215,7 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
         const ConvW& n1 = net->convs[ci];   // next block's conv1
         Op of; of.kind = Op::FUSED;
         if (int rc = conv_fused_plan(&of.fp, b * ho * wo, c3.cin, c3.cout, n1.cout, T2, c3.w, c3.bias, identity, dst,
-                                     n1.w, n1.bias, T1, nullptr, nullptr)) return rc;
+                                     n1.w, n1.bias, t1_dst, nullptr, nullptr)) return rc;
         of.flops = 2.0 * b * ho * wo * (static_cast<double>(c3.cin) * c3.cout + static_cast<double>(n1.cin) * n1.cout);
         of.bytes = 2.0 * b * ho * wo * (c3.cin + 2 * c3.cout + n1.cout) + 2.0 * c3.cin * c3.cout + 2.0 * n1.cin * n1.cout;
         of.tag = (li + 1) * 100 + blk * 10 + 5;
@@ -236,7 +240,7 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
 }
 
 // phase A: stem + max-pool + layer1 + layer2 for `pa` pairs; layer2's output goes to `dst` ([2*pa, D/8, D/8, 512])
-static int build_plan_a(io_net* net, int pa, __nv_bfloat16* dst, Plan* plan) {
+static int build_plan_a(io_net* net, int pa, __nv_bfloat16* dst, __nv_bfloat16* next_t1, Plan* plan) {
   const int b = 2 * pa, d = net->d;
   plan->ops.clear();
   __nv_bfloat16 *X = net->buf[0], *Y = net->buf[1];
@@ -255,7 +259,7 @@ static int build_plan_a(io_net* net, int pa, __nv_bfloat16* dst, Plan* plan) {
   plan->ops.push_back(pool);
   int h = d / 4, w = d / 4;
   const __nv_bfloat16* out = nullptr;
-  return build_blocks(net, plan, 0, 2, b, &h, &w, Y, X, Y, net->buf[2], net->buf[3], net->buf[4], dst, &out);
+  return build_blocks(net, plan, 0, 2, b, &h, &w, Y, X, Y, net->buf[2], net->buf[3], net->buf[4], dst, &out, next_t1);
 }
 
 // phase B: layer3 + layer4 for `pb` pairs reading the big layer2-output buffer
@@ -266,7 +270,7 @@ static int build_plan_b(io_net* net, int pb, Plan* plan) {
   const __nv_bfloat16* out = nullptr;
   // the first block reads `big` (kept intact) and writes bufb[0]; afterwards bufb[0] / bufb[1] ping-pong
   int rc = build_blocks(net, plan, 2, 4, b, &h, &w, net->big, net->bufb[0], net->bufb[1], net->bufb[2], net->bufb[3],
-                        net->bufb[4], nullptr, &out);
+                        net->bufb[4], nullptr, &out, nullptr, net->cross_fuse);
   plan->feat = out;
   plan->hw_final = h * w;
   return rc;
@@ -299,6 +303,8 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
   if (const char* e = getenv("INSTAORDER_FUSE")) net->fuse = atoi(e) != 0;
   if (const char* e = getenv("INSTAORDER_FUSE_DS")) net->fuse_ds = atoi(e) != 0;
   if (const char* e = getenv("INSTAORDER_FUSE_LAYERS")) net->fuse_layers = atoi(e);
+  net->cross_fuse = net->fuse && (net->fuse_layers & 2) && conv_fused_supported(128, 512, 256, nullptr);
+  if (const char* e = getenv("INSTAORDER_FUSE_CROSS")) net->cross_fuse = net->cross_fuse && atoi(e) != 0;
   net->chunk_b = std::min(chunk_b, max_pairs);
   net->chunk_a = std::min(chunk_a, net->chunk_b);
   build_conv_list(net.get());
@@ -527,7 +533,8 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
       auto it = net->plans_a.find(key);
       if (it == net->plans_a.end()) {
         std::unique_ptr<Plan> plan(new Plan());
-        if (int rc = build_plan_a(net, pa, net->big + static_cast<size_t>(a0) * l2_elems_per_pair, plan.get())) return rc;
+        __nv_bfloat16* next_t1 = net->cross_fuse ? net->bufb[2] + static_cast<size_t>(a0) * (l2_elems_per_pair / 2) : nullptr;
+        if (int rc = build_plan_a(net, pa, net->big + static_cast<size_t>(a0) * l2_elems_per_pair, next_t1, plan.get())) return rc;
         it = net->plans_a.emplace(key, std::move(plan)).first;
       }
       const uint8_t* pair_ptr = reinterpret_cast<const uint8_t*>(pair_tensor) + static_cast<int64_t>(b0 + a0) * pair_bytes;
