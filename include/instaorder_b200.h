@@ -180,6 +180,18 @@ IO_API int io_order_decide(const float* logits_dev, int p, int k_total, int head
                     const int32_t* pair_ij_dev, const int64_t* mat_off_dev, const int32_t* mat_n_dev,
                     int64_t* mat_dev, float* margin_dev, void* stream);
 
+/* ---- annotation -> modal masks (replaces pycocotools' frPyObjects / merge / decode as called by
+ * reference datasets/reader.py:20-66 read_KINS / read_LVIS / read_COCOA) ------------------------------------------
+ * Host: run lengths (column-major, starting with zeros) of one RLE part.  io_rle_from_string decodes the compressed
+ * ASCII `counts` of an RLE dict; io_rle_from_polygon rasterises one polygon [x0, y0, x1, y1, ...] (k points) of an
+ * h x w image.  counts[max_counts]; *n_out = number of runs. */
+IO_API int io_rle_from_string(const char* s, int64_t len, uint32_t* counts, int max_counts, int* n_out);
+IO_API int io_rle_from_polygon(const double* xy, int k, int h, int w, uint32_t* counts, int max_counts, int* n_out);
+/* Device: out_dev[n_inst][h][w] uint8 {0,1}, instance i = the union of its parts comp in [inst_off[i], inst_off[i+1]);
+ * part c owns the inclusive prefix sums cum_dev[comp_off[c] .. comp_off[c+1]) of its run lengths. */
+IO_API int io_masks_from_rle(const uint32_t* cum_dev, const int32_t* comp_off_dev, const int32_t* inst_off_dev, int n_inst,
+                      int h, int w, uint8_t* out_dev, void* stream);
+
 /* Single convolution + folded BN (+ residual) (+ ReLU) on NHWC bf16, the building block of io_net_forward_pairs,
  * exported for the per-layer parity tests.  w_dev: [Cout][kh*kw*Cin] bf16 (tap-major, channel-minor);
  * kernel 1 or 3, stride 1 or 2, padding = kernel / 2; Cin, Cout multiples of 64. */

@@ -47,15 +47,22 @@ def heads_for(algo, num_classes):
 class Scene:
     """One image with its instances: the input contract of ``infer_order_sup_*`` (image [H,W,3] u8, inmodal
     [N,H,W] u8, bboxes [N,4] xywh)."""
-    __slots__ = ("image", "masks", "boxes", "n", "h", "w")
+    __slots__ = ("image", "masks", "masks_dev", "boxes", "n", "h", "w")
 
     def __init__(self, image, masks, boxes):
         self.image = np.ascontiguousarray(image, dtype=np.uint8)
-        self.masks = np.ascontiguousarray(masks, dtype=np.uint8)
+        if isinstance(masks, torch.Tensor) and masks.is_cuda:
+            # masks already in HBM (instaorder_b200.masks.rasterize): staged device-to-device, never through the host
+            if masks.dtype != torch.uint8 or masks.dim() != 3:
+                raise ValueError("device masks must be uint8 [N, H, W]")
+            self.masks, self.masks_dev = None, masks.contiguous()
+            self.n, self.h, self.w = (int(v) for v in masks.shape)
+        else:
+            self.masks, self.masks_dev = np.ascontiguousarray(masks, dtype=np.uint8), None
+            self.n, self.h, self.w = self.masks.shape
         self.boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 4))
-        self.n, self.h, self.w = self.masks.shape
         if self.image.shape != (self.h, self.w, 3):
-            raise ValueError("image %r does not match masks %r" % (self.image.shape, self.masks.shape))
+            raise ValueError("image %r does not match masks %r" % (self.image.shape, (self.n, self.h, self.w)))
         if self.boxes.shape[0] != self.n:
             raise ValueError("%d boxes for %d masks" % (self.boxes.shape[0], self.n))
 
@@ -185,13 +192,17 @@ class OrderEngine:
         himg, hmask = s.h_img.numpy(), s.h_mask.numpy()
         slot_idx = 0
         self.resize_jobs = []
+        dev_masks = []
         for (sc, pairs, crops, mat_off, _) in items:
             p = pairs.shape[0]
             ib, mb = sc.h * sc.w * 3, sc.n * sc.h * sc.w
             if img_off + ib > himg.size or mask_off + mb > hmask.size:
                 raise ValueError("staging buffers too small for this batch (image %d B, masks %d B)" % (ib, mb))
             himg[img_off:img_off + ib] = sc.image.reshape(-1)
-            hmask[mask_off:mask_off + mb] = sc.masks.reshape(-1)
+            if sc.masks_dev is None:
+                hmask[mask_off:mask_off + mb] = sc.masks.reshape(-1)
+            else:
+                dev_masks.append((mask_off, mb, sc.masks_dev))
             d = desc[P:P + p]
             d["image_off"] = img_off
             d["mask_a_off"] = mask_off + pairs[:, 0].astype(np.int64) * (sc.h * sc.w)
@@ -219,13 +230,18 @@ class OrderEngine:
             if s.event is not None:
                 self.copy_stream.wait_event(s.event)   # kernels of the batch that last used these device buffers
             s.d_img[:img_off].copy_(s.h_img[:img_off], non_blocking=True)
-            s.d_mask[:mask_off].copy_(s.h_mask[:mask_off], non_blocking=True)
+            if len(dev_masks) < len(items):
+                s.d_mask[:mask_off].copy_(s.h_mask[:mask_off], non_blocking=True)
+            if dev_masks:
+                self.copy_stream.wait_stream(compute)     # the kernels that produced the device masks
+                for (o, nb, t) in dev_masks:
+                    s.d_mask[o:o + nb].copy_(t.reshape(-1), non_blocking=True)
             s.d_desc[:P * 48].copy_(s.h_desc[:P * 48], non_blocking=True)
             s.d_meta.copy_(s.h_meta, non_blocking=True)
             s.copied = torch.cuda.Event()
             s.copied.record(self.copy_stream)
         compute.wait_event(s.copied)
-        self.h2d_bytes += img_off + mask_off + P * 48 + s.h_meta.numel() * 8
+        self.h2d_bytes += img_off + mask_off - sum(nb for (_, nb, _) in dev_masks) + P * 48 + s.h_meta.numel() * 8
         return s, P
 
     def gather(self, s, P, mode="patch"):
@@ -413,7 +429,7 @@ class OrderEngine:
 
     def bordering(self, sc, pairs):
         """``bordering`` (reference inference.py:691-696) for every candidate pair of one scene -> bool[p]."""
-        m = torch.from_numpy(sc.masks).to(self.device)
+        m = sc.masks_dev if sc.masks_dev is not None else torch.from_numpy(sc.masks).to(self.device)
         pr = torch.from_numpy(np.ascontiguousarray(pairs, dtype=np.int32)).to(self.device)
         flags = torch.empty(pairs.shape[0], dtype=torch.uint8, device=self.device)
         _lib.check(self.lib.io_pair_bordering(m.data_ptr(), sc.n, sc.h, sc.w, pr.data_ptr(), pairs.shape[0],
