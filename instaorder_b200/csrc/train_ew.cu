@@ -745,8 +745,9 @@ __global__ void __launch_bounds__(256) maxpool_idx_kernel(const uint4* __restric
   const size_t total = static_cast<size_t>(b) * ho * wo * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % c8);
-    size_t t = i / c8;
+    const uint32_t i32 = static_cast<uint32_t>(i);   // total < 2^32 (checked at launch): 32-bit divisions, not 64-bit
+    const int cg = static_cast<int>(i32 % static_cast<uint32_t>(c8));
+    uint32_t t = i32 / static_cast<uint32_t>(c8);
     const int ox = static_cast<int>(t % wo);
     t /= wo;
     const int oy = static_cast<int>(t % ho);
@@ -779,6 +780,7 @@ int maxpool_fwd_idx_launch(const void* x, void* y, uint8_t* idx, int b, int h, i
   IO_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool: bad shape");
   const size_t total = static_cast<size_t>(b) * (h / 2) * (w / 2) * (c / 8);
   if (total == 0) return IO_OK;
+  IO_REQUIRE(total < (1ull << 32), "element-wise kernel: %zu work items (32-bit index decoding)", total);
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   IO_CUDA(launch_pdl(maxpool_idx_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const uint4*>(x),
                      reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(idx), b, h, w, c / 8));
@@ -792,8 +794,9 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint4* __restric
   const size_t total = static_cast<size_t>(b) * h * w * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % c8);
-    size_t t = i / c8;
+    const uint32_t i32 = static_cast<uint32_t>(i);   // total < 2^32 (checked at launch): 32-bit divisions, not 64-bit
+    const int cg = static_cast<int>(i32 % static_cast<uint32_t>(c8));
+    uint32_t t = i32 / static_cast<uint32_t>(c8);
     const int ix = static_cast<int>(t % w);
     t /= w;
     const int iy = static_cast<int>(t % h);
@@ -831,6 +834,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint4* __restric
 int maxpool_bwd_launch(const void* dy, const uint8_t* idx, void* dx, int b, int h, int w, int c, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(b) * h * w * (c / 8);
   if (total == 0) return IO_OK;
+  IO_REQUIRE(total < (1ull << 32), "element-wise kernel: %zu work items (32-bit index decoding)", total);
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   IO_CUDA(launch_pdl(maxpool_bwd_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const uint4*>(dy),
                      reinterpret_cast<const uint2*>(idx), reinterpret_cast<uint4*>(dx), b, h, w, c / 8));
@@ -847,8 +851,9 @@ __global__ void __launch_bounds__(256) upsample2_zero_kernel(const uint4* __rest
   const size_t total = static_cast<size_t>(b) * h * w * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % c8);
-    size_t t = i / c8;
+    const uint32_t i32 = static_cast<uint32_t>(i);   // total < 2^32 (checked at launch): 32-bit divisions, not 64-bit
+    const int cg = static_cast<int>(i32 % static_cast<uint32_t>(c8));
+    uint32_t t = i32 / static_cast<uint32_t>(c8);
     const int ix = static_cast<int>(t % w);
     t /= w;
     const int iy = static_cast<int>(t % h);
@@ -862,6 +867,7 @@ __global__ void __launch_bounds__(256) upsample2_zero_kernel(const uint4* __rest
 int upsample2_zero_launch(const void* dy, void* z, int b, int ho, int wo, int c, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(b) * ho * wo * 4 * (c / 8);
   if (total == 0) return IO_OK;
+  IO_REQUIRE(total < (1ull << 32), "element-wise kernel: %zu work items (32-bit index decoding)", total);
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   IO_CUDA(launch_pdl(upsample2_zero_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const uint4*>(dy),
                      reinterpret_cast<uint4*>(z), b, ho, wo, c / 8));
@@ -874,8 +880,9 @@ __global__ void __launch_bounds__(256) scatter_add2_kernel(const uint4* __restri
   const size_t total = static_cast<size_t>(b) * ho * wo * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % c8);
-    size_t t = i / c8;
+    const uint32_t i32 = static_cast<uint32_t>(i);   // total < 2^32 (checked at launch): 32-bit divisions, not 64-bit
+    const int cg = static_cast<int>(i32 % static_cast<uint32_t>(c8));
+    uint32_t t = i32 / static_cast<uint32_t>(c8);
     const int ox = static_cast<int>(t % wo);
     t /= wo;
     const int oy = static_cast<int>(t % ho);
@@ -892,6 +899,7 @@ __global__ void __launch_bounds__(256) scatter_add2_kernel(const uint4* __restri
 int scatter_add2_launch(const void* d, void* dx, int b, int ho, int wo, int c, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(b) * ho * wo * (c / 8);
   if (total == 0) return IO_OK;
+  IO_REQUIRE(total < (1ull << 32), "element-wise kernel: %zu work items (32-bit index decoding)", total);
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   IO_CUDA(launch_pdl(scatter_add2_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const uint4*>(d),
                      reinterpret_cast<uint4*>(dx), b, ho, wo, c / 8));
