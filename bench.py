@@ -24,9 +24,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION (the image default): keep stdout to the ONE JSON line
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL prints its version banner on STDOUT (file descriptor 1, from C) at communicator creation whenever NCCL_DEBUG is
+# VERSION or above: keep stdout to the ONE JSON line by pointing fd 1 at stderr for the whole run and writing the result
+# line to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 FLOP_PER_PAIR = 21.764e9          # 2 x 10.882 GFLOP (conv + FC, 2*MAC) @256^2
 PAIRS_PER_STEP = 256
@@ -119,18 +127,27 @@ def cpu_port_pairs_per_s(n_pairs, threads=None):
     torch.set_num_threads(threads)
     rng = np.random.RandomState(1234)
     sd = synth.random_state_dict(0, 5, NUM_CLASSES)
-    image, masks, boxes = next(synth.coco_scene_stream(99, 1, N=10))
+    # whole 10-instance images (45 pairs each) until n_pairs is reached; the last image is cut by dropping instances
+    # (k instances -> k(k-1)/2 pairs)
+    n_img = max(1, (n_pairs + 44) // 45)
+    scenes = list(synth.coco_scene_stream(99, n_img, N=10))
+    image, masks, boxes = scenes[0]
     bexp = O.expand_bbox(boxes, 3.0)
-    # restrict to n_pairs pairs by dropping instances: k instances -> k(k-1)/2 pairs
-    k = 2
-    while k * (k - 1) // 2 < n_pairs and k < 10:
-        k += 1
-    m, b = masks[:k], bexp[:k]
-    O.infer_order(sd, image, m[:2], b[:2], "all", ALGO, "patch", D)          # warm-up (1 pair)
-    t0 = time.perf_counter()
-    r = O.infer_order(sd, image, m, b, "all", ALGO, "patch", D, chunk=8)
-    dt = time.perf_counter() - t0
-    return len(r["pairs"]) / dt, len(r["pairs"]), dt, torch.get_num_threads()
+    O.infer_order(sd, image, masks[:2], bexp[:2], "all", ALGO, "patch", D)          # warm-up (1 pair)
+    done, dt = 0, 0.0
+    for (image, masks, boxes) in scenes:
+        left = n_pairs - done
+        if left <= 0:
+            break
+        k = 2
+        while k * (k - 1) // 2 < left and k < 10:
+            k += 1
+        bexp = O.expand_bbox(boxes, 3.0)
+        t0 = time.perf_counter()
+        r = O.infer_order(sd, image, masks[:k], bexp[:k], "all", ALGO, "patch", D, chunk=8)
+        dt += time.perf_counter() - t0
+        done += len(r["pairs"])
+    return done / dt, done, dt, torch.get_num_threads()
 
 
 def run_reference_arm(args):
@@ -159,7 +176,7 @@ def run_reference_arm(args):
                 cpu_baseline=dict(value=value, unit="pairs/s", cores=threads, kind="port",
                                   sample="%d pairs/step x %d steps, batched fp32 torch-CPU forward" % (sample_pairs, steps)),
                 e2e=dict(value=value, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_train_pairs_per_s(n_pairs, d, threads=None):
@@ -196,7 +213,7 @@ def run_train(args):
         vals = [cpu_train_pairs_per_s(2, D) for _ in range(args.warmup + args.steps)][args.warmup:]
         pairs, secs = sum(v[1] for v in vals), sum(v[2] for v in vals)
         value = pairs / secs
-        print(json.dumps(dict(impl="reference", metric="training pairs/s (InstaOrderNet^od step, 256^2)", value=value,
+        emit((dict(impl="reference", metric="training pairs/s (InstaOrderNet^od step, 256^2)", value=value,
                               unit="pairs/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                               ms_per_step=1000.0 * secs / len(vals), higher_is_better=True, scaling="weak",
                               vs_baseline=None, dtype="f32", data="synthetic",
@@ -302,7 +319,7 @@ def run_train(args):
             cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
                        sample="one step() on 2 pairs (%.1f s): training oracle, fp32 torch-CPU autograd" % cdt)
         achieved = tc_fl / (tc_ms / 1000.0) / 1e12 if tc_ms > 0 else 0.0
-        print(json.dumps(dict(
+        emit((dict(
             metric="training pairs/s (InstaOrderNet^od step: fwd + bwd + all-reduce + SGD, 256^2, bf16)",
             value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
@@ -335,7 +352,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=28)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=225)
     ap.add_argument("--mode", default="patch256", choices=["patch256", "resize384"],
                     help="patch256 = the BASELINE.json metric (default); resize384 = the shipped InstaOrderNet^od "
                          "config (whole image -> 384^2), reported as a second row in DESIGN.md")
@@ -462,7 +479,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, n, cdt, threads = cpu_port_pairs_per_s(args.cpu_sample_pairs)
             cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
-                       sample="%d pairs of one C2 image (%.1f s): oracle port of inference.py patch path + fp32 "
+                       sample="%d pairs of C2 images (%.1f s): oracle port of inference.py patch path + fp32 "
                               "torch-CPU ResNet-50, batched 16 forwards" % (n, cdt))
         line = dict(
             metric="instance pairs/s (InstaOrderNet^od, %s, bf16)" % ("256^2" if gmode == "patch" else "resize 384^2"),
@@ -485,7 +502,7 @@ def main():
                           step_frac=value / world * FLOP_PER_PAIR / 1e12 / peaks["bf16"]),
             cpu_baseline=cpu,
         )
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
