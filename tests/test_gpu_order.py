@@ -123,3 +123,43 @@ def test_nbor_pairs_and_multi_image_batching(golden_dir):
     # empty / single-instance images are legal and give empty / 1x1 zero matrices
     e = eng.infer_scenes([engine.Scene(scenes[0].image, scenes[0].masks[:1], scenes[0].boxes[:1])], c["algo"])[0]
     assert e["occ"].shape == (1, 1) and e["occ"][0, 0] == 0
+
+
+def test_fused_and_unfused_schedules_agree():
+    """The fused launches (dual-source layer-first blocks, conv3 -> next conv1 back-to-back GEMMs, the phase A -> B
+    hand-over) against the one-launch-per-convolution schedule (INSTAORDER_FUSE=0, INSTAORDER_FUSE_DS=0) on the same
+    pairs: same arithmetic up to the bf16 rounding of the identity tensor, which only the unfused schedule stores."""
+    from instaorder_b200 import synth
+    rng = np.random.RandomState(5)
+    image, masks, boxes = synth.make_scene(rng, 240, 320, 6, wh_range=((30, 140), (30, 120)))
+    bexp = engine.expand_bbox(boxes, 3.0)
+    sd = calib.load_calibrated(gen_golden.calib_path("c2_od"), gen_golden.CASES["c2_od"]["wseed"], 5, [2, 3])
+    out = {}
+    for name, env in (("fused", {}), ("plain", {"INSTAORDER_FUSE": "0", "INSTAORDER_FUSE_DS": "0"})):
+        old = {k: os.environ.get(k) for k in ("INSTAORDER_FUSE", "INSTAORDER_FUSE_DS")}
+        os.environ.update(env)
+        try:
+            eng = engine.OrderEngine([2, 3], 256, max_pairs=16)     # the switches are read by io_net_create
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        eng.load_state_dict(sd)
+        out[name] = eng.infer_scenes([engine.Scene(image, masks, bexp)], "InstaOrderNet_od", "all", "patch",
+                                     return_details=True)[0]
+        out[name + "_launches"] = eng.gpu_launches
+    assert out["fused_launches"] < out["plain_launches"] - 10
+    # two bf16 realisations of the same network (the identity of the four layer-first blocks is rounded to bf16 only
+    # in the unfused schedule): each sits within BF16_EMU_TOL of the ideal emulation, so they sit within twice that
+    err = np.abs(out["fused"]["logits"] - out["plain"]["logits"]).max()
+    print("fused vs unfused: max |logit difference| = %.5f, launches %d vs %d" % (err, out["fused_launches"],
+                                                                                  out["plain_launches"]))
+    assert err < 2 * BF16_EMU_TOL, "fused vs unfused logits differ by %.4f" % err
+    for what in ("occ", "depth"):
+        ok = np.minimum(out["fused"]["margin_" + what], out["plain"]["margin_" + what]) > 1e-3
+        ij = out["fused"]["pairs"][ok]
+        for (i, j) in ij:
+            assert out["fused"][what][i, j] == out["plain"][what][i, j]
+            assert out["fused"][what][j, i] == out["plain"][what][j, i]
