@@ -303,23 +303,18 @@ class OrderEngine:
         if mode not in ("patch", "resize", "image"):
             raise NotImplementedError("patch_or_image=%r (supported: 'patch', 'resize', 'image'; 'orig' needs "
                                       "non-square network inputs)" % (mode,))
-        # 1. pairs + crop windows per scene (host, float64 -- bit-exact with the reference's geometry)
-        work = []
+        if pairs not in ("all", "nbor"):
+            raise ValueError("pairs must be 'all' or 'nbor'")
         mat_offs = []
-        tot = 0
-        for si, sc in enumerate(scenes):
-            pr = enumerate_pairs(sc.n)
-            if pairs == "nbor" and pr.shape[0]:
-                pr = pr[self.bordering(sc, pr)]
-            elif pairs not in ("all", "nbor"):
-                raise ValueError("pairs must be 'all' or 'nbor'")
-            crops = pair_crop_boxes(sc.boxes, pr) if (mode == "patch" and pr.shape[0]) else None
-            work.append((sc, pr, crops))
+        tot = total_pairs = 0
+        for sc in scenes:
             mat_offs.append(tot)
             tot += sc.n * sc.n
+            total_pairs += sc.n * (sc.n - 1) // 2
         mats = {w: torch.zeros(max(tot, 1), dtype=torch.int64, device=self.device) for (_, _, w) in heads}
-        details = [dict(pairs=w[1], logits=[], margins=[]) for w in work] if return_details else None
-        # 2. batches of <= max_pairs pairs
+        details = [dict(pairs=None, logits=[], margins=[]) for _ in scenes] if return_details else None
+        # batches of <= max_pairs pairs; pairs + crop windows (host, float64 -- bit-exact with the reference's
+        # geometry) are computed scene by scene while earlier batches already run on the GPU
         batch, count = [], 0
 
         def flush():
@@ -344,9 +339,14 @@ class OrderEngine:
 
         # the first batch of a long call is kept short: the GPU starts while the host is still packing the second one
         # (staging = a host memcpy into pinned memory, ~0.1 ms per MB, otherwise fully exposed at the start of the call)
-        total_pairs = sum(w[1].shape[0] for w in work)
         cap = self.first_batch_pairs if total_pairs > self.max_pairs else self.max_pairs
-        for si, (sc, pr, crops) in enumerate(work):
+        for si, sc in enumerate(scenes):
+            pr = enumerate_pairs(sc.n)
+            if pairs == "nbor" and pr.shape[0]:
+                pr = pr[self.bordering(sc, pr)]
+            crops = pair_crop_boxes(sc.boxes, pr) if (mode == "patch" and pr.shape[0]) else None
+            if return_details:
+                details[si]["pairs"] = pr
             o = 0
             while o < pr.shape[0]:
                 take = min(pr.shape[0] - o, cap - count)

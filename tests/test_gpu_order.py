@@ -163,3 +163,39 @@ def test_fused_and_unfused_schedules_agree():
         for (i, j) in ij:
             assert out["fused"][what][i, j] == out["plain"][what][i, j]
             assert out["fused"][what][j, i] == out["plain"][what][j, i]
+
+
+def test_full_size_permutation_property(golden_dir):
+    """BASELINE-size check without an oracle run (the fp32 CPU reference needs minutes for 256 pairs): at one full
+    256-pair batch (23 instances -> 253 pairs, plus a second image) relabelling the instances must permute the order
+    matrices -- pair (i, j) becomes (pi(i), pi(j)), possibly with A and B exchanged, which swaps the two directions of
+    the network (reference inference.py:144-161 averages them, so the decision is symmetric).  Exact off ties."""
+    case = "c2_od"
+    c = gen_golden.CASES[case]
+    from instaorder_b200 import synth
+    sd = calib.load_calibrated(gen_golden.calib_path(case), c["wseed"], 5, c["num_classes"])
+    eng = engine.OrderEngine([2, 3], 256, max_pairs=256)
+    eng.load_state_dict(sd)
+    rng = np.random.RandomState(77)
+    n = 23
+    img, masks, boxes = synth.make_scene(rng, 427, 640, n, wh_range=((40, 300), (40, 300)))
+    img2, masks2, boxes2 = synth.make_scene(rng, 375, 500, 4, wh_range=((40, 200), (40, 200)))
+    bexp = engine.expand_bbox(boxes, 3.0)
+    extra = engine.Scene(img2, masks2, engine.expand_bbox(boxes2, 3.0))
+    base = eng.infer_scenes([engine.Scene(img, masks, bexp), extra], c["algo"], "all", "patch", return_details=True)[0]
+    assert base["pairs"].shape[0] == 253
+    perm = rng.permutation(n)                      # new index k holds old instance perm[k]
+    r = eng.infer_scenes([extra, engine.Scene(img, masks[perm], bexp[perm])], c["algo"], "all", "patch",
+                         return_details=True)[1]
+    inv = np.argsort(perm)                         # old instance i sits at new index inv[i]
+    checked = 0
+    for what in ("occ", "depth"):
+        mg = np.zeros((n, n))
+        for (i, j), m in zip(base["pairs"], base["margin_" + what]):
+            mg[i, j] = mg[j, i] = m
+        for i in range(n):
+            for j in range(n):
+                if i != j and mg[i, j] > 1e-3:
+                    assert r[what][inv[i], inv[j]] == base[what][i, j], (what, i, j)
+                    checked += 1
+    assert checked >= 0.8 * 2 * n * (n - 1)
