@@ -159,3 +159,81 @@ def random_state_dict(seed, in_channels=5, num_classes=(2, 3), prefix="module.")
             v = (rng.standard_normal(shape) * 0.05).astype(np.float32)
         sd[prefix + key] = v
     return sd
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# InstaDepthNet^od (reference midas/midas_net.py:113-212): ResNeXt-101 32x8d encoder + two 2-channel ResNet-50 trunks.
+# Only the tensors the ORDER outputs depend on are generated (encoder layer1-3, do_net, oo_net, depth_fc, occ_fc); the
+# MiDaS decoder (scratch.*) and encoder layer4 feed the disparity output only.
+# ----------------------------------------------------------------------------------------------------------------
+RESNEXT_WIDTHS = (256, 512, 1024, 2048)     # resnext101_32x8d: conv2 width = planes * (8 / 64) * 32, out = planes * 4
+RESNEXT_OUTS = (256, 512, 1024, 2048)
+RESNEXT_BLOCKS = (3, 4, 23, 3)
+RESNEXT_GROUPS = 32
+
+
+def _sub_key(sub, key):
+    """Reference state_dict key of canonical ResNet key ``key`` ('conv1.weight', 'bn1.bias', 'layer2.0.conv1.weight',
+    ...) inside sub-module ``sub``: ``pretrained`` wraps conv1/bn1/relu/maxpool/layer1 into ``layer1 = nn.Sequential``
+    (midas/blocks.py:_make_resnet_backbone), ``do_net`` / ``oo_net`` do the same but also keep the original attributes
+    (midas_net.py:149-161), so conv1 / bn1 / layer1 exist under two names there."""
+    head, rest = key.split(".", 1)
+    if head == "conv1":
+        return ["%s.layer1.0.%s" % (sub, rest)] + (["%s.conv1.%s" % (sub, rest)] if sub != "pretrained" else [])
+    if head == "bn1":
+        return ["%s.layer1.1.%s" % (sub, rest)] + (["%s.bn1.%s" % (sub, rest)] if sub != "pretrained" else [])
+    if head == "layer1":
+        return ["%s.layer1.4.%s" % (sub, rest)]
+    return ["%s.%s" % (sub, key)]
+
+
+def bottleneck_layout(in_channels, widths, outs, blocks, groups, n_layers=4):
+    out = [("conv1.weight", (64, in_channels, 7, 7))]
+    for leaf in ("weight", "bias", "running_mean", "running_var"):
+        out.append(("bn1." + leaf, (64,)))
+    inpl = 64
+    for li in range(n_layers):
+        for b in range(blocks[li]):
+            p = "layer%d.%d" % (li + 1, b)
+            convs = [(".conv1", ".bn1", widths[li], inpl, 1, 1), (".conv2", ".bn2", widths[li], widths[li] // groups, 3, groups),
+                     (".conv3", ".bn3", outs[li], widths[li], 1, 1)]
+            if b == 0:
+                convs.append((".downsample.0", ".downsample.1", outs[li], inpl, 1, 1))
+            for (cn, bnn, co, ci, k, _) in convs:
+                out.append((p + cn + ".weight", (co, ci, k, k)))
+                for leaf in ("weight", "bias", "running_mean", "running_var"):
+                    out.append((p + bnn + "." + leaf, (co,)))
+            inpl = outs[li]
+    return out
+
+
+def instadepth_state_dict(seed, prefix="module."):
+    """Random weights for the order branch of InstaDepthNet^od, keyed like the reference model's ``state_dict``
+    (numpy fp32).  Same recipe as ``random_state_dict`` (kaiming fan_out convolutions, BN drawn to keep an O(1)
+    scale); the parity tests calibrate BN statistics and heads on top (oracle/instadepth_oracle.py)."""
+    rng = np.random.RandomState(seed)
+    sd = {}
+    subs = (("pretrained", 3, RESNEXT_WIDTHS, RESNEXT_OUTS, RESNEXT_BLOCKS, RESNEXT_GROUPS, 3),
+            ("do_net", 2, (64, 128, 256, 512), (256, 512, 1024, 2048), (3, 4, 6, 3), 1, 4),
+            ("oo_net", 2, (64, 128, 256, 512), (256, 512, 1024, 2048), (3, 4, 6, 3), 1, 4))
+    for (sub, cin, widths, outs, blocks, groups, n_layers) in subs:
+        for key, shape in bottleneck_layout(cin, widths, outs, blocks, groups, n_layers):
+            leaf = key.rsplit(".", 1)[1]
+            if len(shape) == 4:
+                fan_out = shape[0] * shape[2] * shape[3] // (groups if (shape[2] == 3 and groups > 1) else 1)
+                v = rng.standard_normal(shape).astype(np.float32) * np.float32(np.sqrt(2.0 / fan_out))
+            elif leaf == "running_mean":
+                v = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+            elif leaf == "running_var":
+                v = rng.uniform(0.8, 1.2, size=shape).astype(np.float32)
+            elif leaf == "weight":
+                v = rng.uniform(0.2, 0.4, size=shape).astype(np.float32) if ".bn3." in key \
+                    else rng.uniform(0.8, 1.2, size=shape).astype(np.float32)
+            else:
+                v = (rng.standard_normal(shape) * 0.05).astype(np.float32)
+            for k in _sub_key(sub, key):
+                sd[prefix + k] = v
+    for head, k in (("depth_fc", 3), ("occ_fc", 2)):
+        sd[prefix + head + ".weight"] = (rng.standard_normal((k, 2048)) * 0.05).astype(np.float32)
+        sd[prefix + head + ".bias"] = (rng.standard_normal(k) * 0.1).astype(np.float32)
+    return sd

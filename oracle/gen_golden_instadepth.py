@@ -1,0 +1,87 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/instadepth_{calib,order}.npz by running the UNMODIFIED
+reference (``midas/midas_net.py`` InstaDepthNet_od through ``inference.infer_order_sup_occ_depth`` with
+``method="InstaDepthNet_od"``, ``patch_or_image="resize"``, 384^2) on CPU in this container.
+
+    python -m oracle.gen_golden_instadepth
+
+torch.hub is patched to return torchvision's resnext101_32x8d (same architecture as the WSL hub model, no network);
+the synthetic calibrated weights (instaorder_b200.synth.instadepth_state_dict + oracle.instadepth_oracle.calibrate)
+are loaded into the reference module; tensors the order outputs do not depend on (encoder layer4, the MiDaS decoder,
+the trunks' unused fc) keep the reference's own initialisation."""
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from instaorder_b200 import synth  # noqa: E402
+from oracle import instadepth_oracle as IO, ref_shim  # noqa: E402
+
+SEED, SCENE_SEED, N_INST, D = 11, 4242, 4, 384
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def build_scene():
+    rng = np.random.RandomState(SCENE_SEED)
+    return synth.make_scene(rng, 375, 500, N_INST, wh_range=((60, 260), (60, 220)))
+
+
+def main():
+    import torch
+    import torchvision
+    torch.hub.load = lambda *a, **k: torchvision.models.resnext101_32x8d(weights=None)
+    ns = ref_shim.load()
+    midas_net = sys.modules["_instaorder_ref.midas.midas_net"]
+    sd = synth.instadepth_state_dict(SEED, prefix="")
+    changed = IO.calibrate(sd, prefix="")
+    np.savez_compressed(os.path.join(GOLDEN, "instadepth_calib.npz"), **{"module." + k: v for k, v in changed.items()})
+    torch.manual_seed(0)
+    net = midas_net.InstaDepthNet_od(path=None)
+    missing, unexpected = net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith(("scratch.", "pretrained.layer4", "do_net.fc", "oo_net.fc")) or "num_batches_tracked" in k
+               for k in missing), [k for k in missing][:5]
+    net.eval()
+    image, masks, boxes = build_scene()
+    logits = {}
+
+    class Rec(torch.nn.Module):          # records the raw logits of every forward the reference makes
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+            self.calls = []
+
+        def forward(self, img, a, b):
+            disp, d, o = self.m(img, a, b)
+            self.calls.append((d.numpy().copy(), o.numpy().copy()))
+            return disp, d, o
+
+    rec = Rec(net)
+    model = types.SimpleNamespace(model=rec)
+    occ, depth = ns.inference.infer_order_sup_occ_depth(model, image, masks, boxes, "all", "InstaDepthNet_od", "resize",
+                                                        D, "")
+    P = N_INST * (N_INST - 1) // 2
+    assert len(rec.calls) == 2 * P
+    dl = np.stack([c[0][0] for c in rec.calls]).reshape(P, 2, 3)
+    ol = np.stack([c[1][0] for c in rec.calls]).reshape(P, 2, 2)
+    np.savez_compressed(os.path.join(GOLDEN, "instadepth_order.npz"), occ=occ.astype(np.int64), depth=depth.astype(np.int64),
+                        depth_logits=dl.astype(np.float32), occ_logits=ol.astype(np.float32))
+    print("occ\n", occ, "\ndepth\n", depth, "\nlogit std", dl.std(), ol.std())
+    # the restatement against what the reference just computed
+    from oracle import oracle as O
+    rgb = O.resize_mode_rgb(image, D)[None]
+    mm = [O.resize_mode_mask(m, D)[None, None].astype(np.float32) for m in masks]
+    m1, m2 = [], []
+    for (i, j) in O.enumerate_pairs(N_INST):
+        m1 += [mm[i][0], mm[j][0]]
+        m2 += [mm[j][0], mm[i][0]]
+    sdm = {"module." + k: v for k, v in sd.items()}
+    out = IO.order_forward(sdm, rgb, np.stack(m1), np.stack(m2), np.zeros(2 * P, np.int64))
+    print("oracle vs reference: depth %.2e occ %.2e" % (np.abs(out["depth"].reshape(P, 2, 3) - dl).max(),
+                                                        np.abs(out["occ"].reshape(P, 2, 2) - ol).max()))
+
+
+if __name__ == "__main__":
+    main()
