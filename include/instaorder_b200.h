@@ -143,6 +143,21 @@ typedef struct io_net io_net_t;
 /* n_heads = 1 (`fc`, num_classes int) or 2 (`fc_occ`, `fc_depth`; num_classes list) -- resnet_cls.py:153-160.
  * input_size: 256 or 384 (any multiple of 32); max_pairs: largest P of a forward call (workspace is sized once). */
 IO_API int io_net_create(const int32_t* num_classes, int n_heads, int input_size, int max_pairs, io_net_t** out);
+/* Generalised handle for the bottleneck-ResNet family (InstaDepthNet^od, reference midas/midas_net.py:113-212): per layer the
+ * 3x3 width, the block output channels and the block count (ResNet-50: {64,128,256,512} / {256,..,2048} / {3,4,6,3};
+ * the ResNeXt-101 32x8d encoder: {256,512,1024,2048} / same / {3,4,23,3} with its grouped 3x3 weights passed to
+ * io_net_load_state as dense block-diagonal [cout, cin, 3, 3] tensors).  n_layers = 3 stops after layer3; keep_layers = 1
+ * keeps every layer's output (io_net_feature); n_heads = 0 makes a feature extractor (logits may be NULL in
+ * io_net_forward_pairs).  The stem is always the 5-channel pair-tensor stem: embed 3-channel (RGB -> channels 2..4) or
+ * 2-channel (masks -> channels 0..1) conv1 weights with zeros. */
+IO_API int io_net_create_arch(const int32_t* widths4, const int32_t* outs4, const int32_t* blocks4, int n_layers,
+                       int keep_layers, const int32_t* num_classes, int n_heads, int input_size, int max_pairs,
+                       io_net_t** out);
+/* Layer `layer` (0-based) output of a keep_layers handle: bf16 [2 * pairs, D >> (2 + layer), same, outs[layer]]. */
+IO_API int io_net_feature(io_net_t* net, int layer, void** ptr, int64_t* elems_per_image);
+/* Trunks of InstaDepthNet (midas_net.py:200-210): after layers 1, 2, 3 add f_l[idx_dev[image]] (image = 2 * pair +
+ * direction; idx_dev is read at run time, int32 [2 * max_pairs]).  All NULL switches the injection off. */
+IO_API int io_net_set_inject(io_net_t* net, const void* f1, const void* f2, const void* f3, const int32_t* idx_dev);
 IO_API int io_net_destroy(io_net_t* net);
 
 /* Loads a reference checkpoint's state_dict (models/single_stage_model.py:54-61, utils/common_utils.py:128-149):

@@ -48,6 +48,9 @@ _SIGS = {
     "io_pair_gather_resize": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "io_normalize_lut": (_i, [_vp, _vp, _vp]),
     "io_net_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "io_net_create_arch": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, C.POINTER(_vp)]),
+    "io_net_feature": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i64)]),
+    "io_net_set_inject": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "io_net_destroy": (_i, [_vp]),
     "io_net_load_state": (_i, [_vp, _vp, _vp, _i]),
     "io_net_forward_pairs": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -25,10 +25,11 @@ struct ConvW {
   // for the single-GEMM block output of conv_plan_dual
   __nv_bfloat16* wcat = nullptr;
   float* bias_cat = nullptr;
+  int cat_k = 0;               // K of wcat = conv3's input channels + this convolution's
 };
 
 struct Op {
-  enum Kind { STEM, POOL, CONV, TAIL, FUSED, CONV_TN, STEM_TN } kind;
+  enum Kind { STEM, POOL, CONV, TAIL, FUSED, CONV_TN, STEM_TN, ADD } kind;
   ConvParams p;
   FusedParams fp;
   TnParams tp;
@@ -36,7 +37,8 @@ struct Op {
   double flops = 0.0;  // algorithmic 2*MAC of this launch
   double bytes = 0.0;  // algorithmic HBM bytes of this launch (activations in + out + residual + weights)
   int tag = 0;         // layer*100 + block*10 + conv index (profiling label)
-  // POOL
+  // POOL / ADD (ADD: dst += src[idx[image]], b images of h*w*c elements)
+  const int32_t* idx = nullptr;
   const void* src = nullptr;
   void* dst = nullptr;
   int b = 0, h = 0, w = 0, c = 0;
@@ -51,6 +53,18 @@ struct Plan {
 }  // namespace io
 
 struct io_net {
+  // architecture: bottleneck ResNet family (reference resnet_cls.py Bottleneck / torchvision ResNeXt): per layer the
+  // 3x3 width, the block output channels and the block count; n_layers < 4 = feature extractor without layer4
+  int widths[4] = {64, 128, 256, 512};
+  int outs[4] = {256, 512, 1024, 2048};
+  int blocks[4] = {3, 4, 6, 3};
+  int n_layers = 4;
+  // feature extractor (InstaDepthNet encoder): the output of every layer is kept in its own buffer
+  bool keep_layers = false;
+  __nv_bfloat16* keep[4] = {nullptr, nullptr, nullptr, nullptr};
+  // feature injection (InstaDepthNet trunks, midas_net.py:201-203): x += enc_l[inject_idx[image]] after layer l
+  const __nv_bfloat16* inject[3] = {nullptr, nullptr, nullptr};
+  const int32_t* inject_idx = nullptr;
   int n_heads = 0;
   int num_classes[2] = {0, 0};
   int k_total = 0;
@@ -99,26 +113,64 @@ static void build_conv_list(io_net* net) {
   stem.name = "conv1"; stem.bn = "bn1"; stem.cin = 5; stem.cout = 64; stem.k = 7; stem.stride = 2;
   net->convs.push_back(stem);
   int inpl = 64;
-  const int planes_[4] = {64, 128, 256, 512};
-  const int blocks_[4] = {3, 4, 6, 3};
-  for (int li = 0; li < 4; ++li) {
-    for (int b = 0; b < blocks_[li]; ++b) {
+  for (int li = 0; li < net->n_layers; ++li) {
+    for (int b = 0; b < net->blocks[li]; ++b) {
       const std::string pre = "layer" + std::to_string(li + 1) + "." + std::to_string(b);
-      const int planes = planes_[li];
+      const int width = net->widths[li], outc = net->outs[li];
       const int stride = (b == 0 && li > 0) ? 2 : 1;
-      ConvW c1{pre + ".conv1", pre + ".bn1", inpl, planes, 1, 1};
-      ConvW c2{pre + ".conv2", pre + ".bn2", planes, planes, 3, stride};
-      ConvW c3{pre + ".conv3", pre + ".bn3", planes, planes * 4, 1, 1};
+      ConvW c1{pre + ".conv1", pre + ".bn1", inpl, width, 1, 1};
+      ConvW c2{pre + ".conv2", pre + ".bn2", width, width, 3, stride};
+      ConvW c3{pre + ".conv3", pre + ".bn3", width, outc, 1, 1};
       net->convs.push_back(c1);
       net->convs.push_back(c2);
       if (b == 0) {
-        ConvW ds{pre + ".downsample.0", pre + ".downsample.1", inpl, planes * 4, 1, stride};
+        ConvW ds{pre + ".downsample.0", pre + ".downsample.1", inpl, outc, 1, stride};
+        ds.cat_k = width + inpl;
         net->convs.push_back(ds);
       }
       net->convs.push_back(c3);
-      inpl = planes * 4;
+      inpl = outc;
     }
   }
+}
+
+// x[img] += enc[idx[img]] over [h*w*c] bf16 elements per image, 8 channels (16 B) per thread (midas_net.py:201-203)
+__global__ void __launch_bounds__(256) add_bcast_kernel(uint4* __restrict__ x, const uint4* __restrict__ enc,
+                                                        const int32_t* __restrict__ idx, int per_img8) {
+  const int img = blockIdx.y;
+  const uint4* __restrict__ e = enc + static_cast<size_t>(idx[img]) * per_img8;
+  uint4* __restrict__ xi = x + static_cast<size_t>(img) * per_img8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img8; i += gridDim.x * blockDim.x) {
+    const uint4 a = xi[i], b = __ldg(e + i);
+    uint4 o;
+    o.x = pack_bf16(bf16_lo(a.x) + bf16_lo(b.x), bf16_hi(a.x) + bf16_hi(b.x));
+    o.y = pack_bf16(bf16_lo(a.y) + bf16_lo(b.y), bf16_hi(a.y) + bf16_hi(b.y));
+    o.z = pack_bf16(bf16_lo(a.z) + bf16_lo(b.z), bf16_hi(a.z) + bf16_hi(b.z));
+    o.w = pack_bf16(bf16_lo(a.w) + bf16_lo(b.w), bf16_hi(a.w) + bf16_hi(b.w));
+    xi[i] = o;
+  }
+}
+
+// elements per image of layer li's output at the handle's input size
+static size_t per_img_out(const io_net* net, int li) {
+  const size_t side = static_cast<size_t>(net->d) >> (2 + li);
+  return side * side * net->outs[li];
+}
+
+// InstaDepthNet trunks: after the last block of layers 1..3 the encoder's feature of the pair's image is added in place
+static int maybe_inject(io_net* net, Plan* plan, int li, bool layer_end, int b, int h, int w, __nv_bfloat16* dst,
+                        int idx_off) {
+  if (!layer_end || li > 2 || net->inject_idx == nullptr || net->inject[li] == nullptr) return IO_OK;
+  Op a;
+  a.kind = Op::ADD;
+  a.src = net->inject[li];
+  a.dst = dst;
+  a.idx = net->inject_idx + idx_off;
+  a.b = b; a.h = h; a.w = w; a.c = net->outs[li];
+  a.bytes = 2.0 * b * h * w * net->outs[li] * 2.0;
+  a.tag = (li + 1) * 100 + 98;
+  plan->ops.push_back(a);
+  return IO_OK;
 }
 
 // Appends the bottlenecks of layers [l0, l1) for `b` images whose input [b, h, w, C] is `src`.  Block outputs
@@ -127,10 +179,12 @@ static void build_conv_list(io_net* net) {
 static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_io, int* w_io,
                         const __nv_bfloat16* src, __nv_bfloat16* P0, __nv_bfloat16* P1, __nv_bfloat16* T1,
                         __nv_bfloat16* T2, __nv_bfloat16* DS, __nv_bfloat16* final_dst,
-                        const __nv_bfloat16** out_ptr, __nv_bfloat16* next_t1 = nullptr, bool t1_in = false) {
-  const int blocks_[4] = {3, 4, 6, 3};
+                        const __nv_bfloat16** out_ptr, __nv_bfloat16* next_t1 = nullptr, bool t1_in = false,
+                        long long keep_off = -1, int idx_off = 0) {
+  const int* blocks_ = net->blocks;
   size_t ci = 1;
   for (int li = 0; li < l0; ++li) ci += 3 * blocks_[li] + 1;
+  const bool injecting = net->inject_idx != nullptr;
   int h = *h_io, w = *w_io;
   // next_t1: where the conv1 output of the block FOLLOWING this plan's last one goes (phase A -> phase B fusion);
   // t1_in: this plan's first conv1 output has already been produced that way
@@ -143,7 +197,9 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       const ConvW& c3 = net->convs[ci++];
       const int ho = h / c2.stride, wo = w / c2.stride;
       const bool last = (li == l1 - 1) && (blk == blocks_[li] - 1);
+      const bool layer_end = blk == blocks_[li] - 1;
       __nv_bfloat16* dst = (last && final_dst) ? final_dst : (src == P0 ? P1 : P0);
+      if (layer_end && !last && keep_off >= 0 && net->keep[li] != nullptr) dst = net->keep[li] + keep_off * per_img_out(net, li);
       if (!t1_ready) {
         Op o1; o1.kind = Op::CONV;
         if (int rc = conv_plan(&o1.p, &o1.bn_tile, ConvDesc{b, h, w, c1.cin, c1.cout, 1, 1}, src, c1.w, c1.bias,
@@ -169,7 +225,8 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       const __nv_bfloat16* identity = src;
       // the next bottleneck's conv1 (same layer, or the first block of the next layer inside this plan: its conv1 is
       // a stride-1 1x1 over this block's output) can be computed from the block-output tile while it is on chip
-      const bool has_next = (blk + 1 < blocks_[li]) || (li + 1 < l1) || (next_t1 != nullptr);
+      // (not across a layer boundary when encoder features are added in between)
+      const bool has_next = (blk + 1 < blocks_[li]) || ((li + 1 < l1 || next_t1 != nullptr) && !injecting);
       __nv_bfloat16* t1_dst = ((blk + 1 < blocks_[li]) || (li + 1 < l1)) ? T1 : next_t1;
       const bool want_fuse = net->fuse && ((net->fuse_layers >> li) & 1) && has_next;
       if (ds && net->fuse_ds) {
@@ -198,6 +255,7 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
         }
         src = dst;
         h = ho; w = wo;
+        if (int rc = maybe_inject(net, plan, li, layer_end, b, h, w, dst, idx_off)) return rc;
         continue;
       }
       if (ds) {
@@ -232,6 +290,7 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       }
       src = dst;  // the next block reads what was just written
       h = ho; w = wo;
+      if (int rc = maybe_inject(net, plan, li, layer_end, b, h, w, dst, idx_off)) return rc;
     }
   }
   *h_io = h; *w_io = w;
@@ -240,7 +299,7 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
 }
 
 // phase A: stem + max-pool + layer1 + layer2 for `pa` pairs; layer2's output goes to `dst` ([2*pa, D/8, D/8, 512])
-static int build_plan_a(io_net* net, int pa, __nv_bfloat16* dst, __nv_bfloat16* next_t1, Plan* plan) {
+static int build_plan_a(io_net* net, int pa, int a0, __nv_bfloat16* dst, __nv_bfloat16* next_t1, Plan* plan) {
   const int b = 2 * pa, d = net->d;
   plan->ops.clear();
   __nv_bfloat16 *X = net->buf[0], *Y = net->buf[1];
@@ -259,7 +318,8 @@ static int build_plan_a(io_net* net, int pa, __nv_bfloat16* dst, __nv_bfloat16* 
   plan->ops.push_back(pool);
   int h = d / 4, w = d / 4;
   const __nv_bfloat16* out = nullptr;
-  return build_blocks(net, plan, 0, 2, b, &h, &w, Y, X, Y, net->buf[2], net->buf[3], net->buf[4], dst, &out, next_t1);
+  return build_blocks(net, plan, 0, 2, b, &h, &w, Y, X, Y, net->buf[2], net->buf[3], net->buf[4], dst, &out, next_t1,
+                      false, net->keep_layers ? 2LL * a0 : -1, 2 * a0);
 }
 
 // phase B: layer3 + layer4 for `pb` pairs reading the big layer2-output buffer
@@ -269,8 +329,9 @@ static int build_plan_b(io_net* net, int pb, Plan* plan) {
   int h = d / 8, w = d / 8;
   const __nv_bfloat16* out = nullptr;
   // the first block reads `big` (kept intact) and writes bufb[0]; afterwards bufb[0] / bufb[1] ping-pong
-  int rc = build_blocks(net, plan, 2, 4, b, &h, &w, net->big, net->bufb[0], net->bufb[1], net->bufb[2], net->bufb[3],
-                        net->bufb[4], nullptr, &out, nullptr, net->cross_fuse);
+  int rc = build_blocks(net, plan, 2, net->n_layers, b, &h, &w, net->big, net->bufb[0], net->bufb[1], net->bufb[2],
+                        net->bufb[3], net->bufb[4], net->keep_layers ? net->keep[net->n_layers - 1] : nullptr, &out,
+                        nullptr, net->cross_fuse, -1, 0);
   plan->feat = out;
   plan->hw_final = h * w;
   return rc;
@@ -280,15 +341,28 @@ static int build_plan_b(io_net* net, int pb, Plan* plan) {
 
 using namespace io;
 
-extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_size, int max_pairs, io_net_t** out) {
-  IO_REQUIRE(num_classes && out, "io_net_create: null pointer");
-  IO_REQUIRE(n_heads == 1 || n_heads == 2, "io_net_create: n_heads must be 1 (fc) or 2 (fc_occ + fc_depth)");
+extern "C" int io_net_create_arch(const int32_t* widths, const int32_t* outs, const int32_t* blocks, int n_layers,
+                                  int keep_layers, const int32_t* num_classes, int n_heads, int input_size,
+                                  int max_pairs, io_net_t** out) {
+  IO_REQUIRE(widths && outs && blocks && out, "io_net_create_arch: null pointer");
+  IO_REQUIRE(n_layers == 3 || n_layers == 4, "io_net_create_arch: n_layers %d (3 or 4)", n_layers);
+  IO_REQUIRE(n_heads >= 0 && n_heads <= 2 && (n_heads == 0 || (num_classes && n_layers == 4)),
+             "io_net_create_arch: n_heads must be 0 (feature extractor), 1 (fc) or 2 (fc_occ + fc_depth)");
   IO_REQUIRE(input_size >= 64 && input_size <= 512 && input_size % 32 == 0,
              "io_net_create: input_size %d (multiple of 32 in [64, 512])", input_size);
   IO_REQUIRE(max_pairs >= 1, "io_net_create: max_pairs %d", max_pairs);
   int dev_count = 0;
   IO_CUDA(cudaGetDeviceCount(&dev_count));
   std::unique_ptr<io_net> net(new io_net());
+  for (int i = 0; i < 4; ++i) {
+    IO_REQUIRE(i >= n_layers || (widths[i] % 64 == 0 && outs[i] % 64 == 0 && widths[i] >= 64 && outs[i] >= 64 &&
+                                 outs[i] <= 2048 && blocks[i] >= 1),
+               "io_net_create_arch: layer %d: width %d, out %d, blocks %d", i + 1, widths[i], outs[i], blocks[i]);
+    net->widths[i] = widths[i]; net->outs[i] = outs[i]; net->blocks[i] = blocks[i];
+  }
+  IO_REQUIRE(n_heads == 0 || outs[3] == 2048, "io_net_create_arch: the head kernel expects 2048 features");
+  net->n_layers = n_layers;
+  net->keep_layers = keep_layers != 0;
   net->n_heads = n_heads;
   for (int i = 0; i < n_heads; ++i) {
     IO_REQUIRE(num_classes[i] >= 1 && num_classes[i] <= 4, "io_net_create: num_classes[%d] = %d", i, num_classes[i]);
@@ -303,7 +377,8 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
   if (const char* e = getenv("INSTAORDER_FUSE")) net->fuse = atoi(e) != 0;
   if (const char* e = getenv("INSTAORDER_FUSE_DS")) net->fuse_ds = atoi(e) != 0;
   if (const char* e = getenv("INSTAORDER_FUSE_LAYERS")) net->fuse_layers = atoi(e);
-  net->cross_fuse = net->fuse && (net->fuse_layers & 2) && conv_fused_supported(128, 512, 256, nullptr);
+  net->cross_fuse = net->fuse && (net->fuse_layers & 2) && !net->keep_layers &&
+                    conv_fused_supported(net->widths[1], net->outs[1], net->widths[2], nullptr);
   if (const char* e = getenv("INSTAORDER_FUSE_CROSS")) net->cross_fuse = net->cross_fuse && atoi(e) != 0;
   net->chunk_b = std::min(chunk_b, max_pairs);
   net->chunk_a = std::min(chunk_a, net->chunk_b);
@@ -313,24 +388,76 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
     ConvW& c = net->convs[i];
     IO_CUDA(cudaMalloc(&c.w, static_cast<size_t>(c.cout) * c.k * c.k * c.cin * 2));
     IO_CUDA(cudaMalloc(&c.bias, static_cast<size_t>(c.cout) * 4));
-    if (c.name.find("downsample") != std::string::npos) {
-      IO_CUDA(cudaMalloc(&c.wcat, static_cast<size_t>(c.cout) * (c.cout / 4 + c.cin) * 2));
+    if (c.cat_k > 0) {
+      IO_CUDA(cudaMalloc(&c.wcat, static_cast<size_t>(c.cout) * c.cat_k * 2));
       IO_CUDA(cudaMalloc(&c.bias_cat, static_cast<size_t>(c.cout) * 4));
     }
   }
   IO_CUDA(cudaMalloc(&net->stem_w, 128 * 448 * 2));
   IO_CUDA(cudaMalloc(&net->stem_bias, 128 * 4));
-  IO_CUDA(cudaMalloc(&net->fc_w, static_cast<size_t>(net->k_total) * 2048 * 4));
-  IO_CUDA(cudaMalloc(&net->fc_b, static_cast<size_t>(net->k_total) * 4));
-  // phase A activations: 5 buffers of [2*chunk_a, D/2, D/2, 64] elements (the stem output is the largest tensor per
-  // image); phase B: 5 buffers of [2*chunk_b, D/8, D/8, 256] (layer3.0 conv1 output) + `big` [2*chunk_b, D/8, D/8, 512]
+  if (n_heads > 0) {
+    IO_CUDA(cudaMalloc(&net->fc_w, static_cast<size_t>(net->k_total) * 2048 * 4));
+    IO_CUDA(cudaMalloc(&net->fc_b, static_cast<size_t>(net->k_total) * 4));
+  }
+  // activation buffers, sized by the largest tensor of each phase (elements per image):
+  //   phase A (stem .. layer2): stem output, layer1 tensors at D/4, layer2.0's conv1 output (still D/4), layer2 at D/8
+  //   phase B (layer3 ..):      layer3.0's conv1 output (still D/8), layer3 at D/16, layer4.0's conv1 at D/16, layer4
+  // ResNet-50: 16 D^2 and 4 D^2 elements per image (the stem / layer3.0 conv1 outputs)
   const size_t d = input_size;
-  const size_t ea = static_cast<size_t>(2 * net->chunk_a) * (d / 2) * (d / 2) * 64;
-  const size_t eb = static_cast<size_t>(2 * net->chunk_b) * (d / 8) * (d / 8) * 256;
+  const int* W = net->widths; const int* O = net->outs;
+  size_t ea_img = (d / 2) * (d / 2) * 64;
+  ea_img = std::max(ea_img, (d / 4) * (d / 4) * static_cast<size_t>(std::max(std::max(O[0], W[0]), W[1])));
+  ea_img = std::max(ea_img, (d / 8) * (d / 8) * static_cast<size_t>(std::max(O[1], W[1])));
+  size_t eb_img = (d / 8) * (d / 8) * static_cast<size_t>(W[2]);
+  eb_img = std::max(eb_img, (d / 16) * (d / 16) * static_cast<size_t>(std::max(O[2], W[2])));
+  if (n_layers == 4) {
+    eb_img = std::max(eb_img, (d / 16) * (d / 16) * static_cast<size_t>(W[3]));
+    eb_img = std::max(eb_img, (d / 32) * (d / 32) * static_cast<size_t>(std::max(O[3], W[3])));
+  }
+  const size_t ea = static_cast<size_t>(2 * net->chunk_a) * ea_img;
+  const size_t eb = static_cast<size_t>(2 * net->chunk_b) * eb_img;
   for (int i = 0; i < 5; ++i) IO_CUDA(cudaMalloc(&net->buf[i], ea * 2));
   for (int i = 0; i < 5; ++i) IO_CUDA(cudaMalloc(&net->bufb[i], eb * 2));
-  IO_CUDA(cudaMalloc(&net->big, eb * 2 * 2));
+  IO_CUDA(cudaMalloc(&net->big, static_cast<size_t>(2 * net->chunk_b) * per_img_out(net.get(), 1) * 2));
+  if (net->keep_layers) {
+    for (int li = 0; li < n_layers; ++li)
+      if (li != 1)   // layer2's output lives in `big`
+        IO_CUDA(cudaMalloc(&net->keep[li], static_cast<size_t>(2 * net->chunk_b) * per_img_out(net.get(), li) * 2));
+  }
   *out = net.release();
+  return IO_OK;
+}
+
+extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_size, int max_pairs, io_net_t** out) {
+  IO_REQUIRE(num_classes && out, "io_net_create: null pointer");
+  IO_REQUIRE(n_heads == 1 || n_heads == 2, "io_net_create: n_heads must be 1 (fc) or 2 (fc_occ + fc_depth)");
+  const int32_t widths[4] = {64, 128, 256, 512}, outs[4] = {256, 512, 1024, 2048}, blocks[4] = {3, 4, 6, 3};
+  return io_net_create_arch(widths, outs, blocks, 4, 0, num_classes, n_heads, input_size, max_pairs, out);
+}
+
+// Output of layer `layer` (0-based) of a keep_layers handle: [2 * pairs, D >> (2 + layer), same, outs[layer]] bf16, image
+// 2p = direction (A,B) of pair p (the RGB-only encoder's two directions are identical).
+extern "C" int io_net_feature(io_net_t* net, int layer, void** ptr, int64_t* elems_per_image) {
+  IO_REQUIRE(net && ptr && elems_per_image && net->keep_layers && layer >= 0 && layer < net->n_layers,
+             "io_net_feature: bad arguments");
+  *ptr = layer == 1 ? net->big : net->keep[layer];
+  *elems_per_image = static_cast<int64_t>(per_img_out(net, layer));
+  return IO_OK;
+}
+
+// x += f_l[idx[image]] after layers 1..3 (InstaDepthNet trunks, midas_net.py:201-203).  f_l: [n, h_l, w_l, outs[l]] bf16 with
+// the handle's own layer geometry; idx_dev: int32 [2 * max_pairs] (one entry per image = pair direction), read at run
+// time.  The pointers are baked into the cached launch plans: changing them drops the plans.
+extern "C" int io_net_set_inject(io_net_t* net, const void* f1, const void* f2, const void* f3, const int32_t* idx_dev) {
+  IO_REQUIRE(net && ((f1 && f2 && f3 && idx_dev) || (!f1 && !f2 && !f3 && !idx_dev)), "io_net_set_inject: bad arguments");
+  IO_REQUIRE(net->max_pairs <= net->chunk_b, "io_net_set_inject: max_pairs %d > chunk %d", net->max_pairs, net->chunk_b);
+  net->inject[0] = reinterpret_cast<const __nv_bfloat16*>(f1);
+  net->inject[1] = reinterpret_cast<const __nv_bfloat16*>(f2);
+  net->inject[2] = reinterpret_cast<const __nv_bfloat16*>(f3);
+  net->inject_idx = idx_dev;
+  if (idx_dev) net->cross_fuse = false;
+  net->plans_a.clear();
+  net->plans_b.clear();
   return IO_OK;
 }
 
@@ -348,6 +475,7 @@ extern "C" int io_net_destroy(io_net_t* net) {
   cudaFree(net->fc_b);
   for (int i = 0; i < 5; ++i) cudaFree(net->buf[i]);
   for (int i = 0; i < 5; ++i) cudaFree(net->bufb[i]);
+  for (int i = 0; i < 4; ++i) cudaFree(net->keep[i]);
   cudaFree(net->big);
   for (cudaEvent_t e : net->ev) cudaEventDestroy(e);
   delete net;
@@ -440,6 +568,10 @@ extern "C" int io_net_load_state(io_net_t* net, const char* const* names, const 
       }
     }
   }
+  if (net->n_heads == 0) {
+    net->loaded = true;
+    return IO_OK;
+  }
   const char* heads1[1] = {"fc"};
   const char* heads2[2] = {"fc_occ", "fc_depth"};
   const char* const* heads = net->n_heads == 1 ? heads1 : heads2;
@@ -459,7 +591,7 @@ extern "C" int io_net_load_state(io_net_t* net, const char* const* names, const 
 }
 
 extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int p, float* logits, void* stream_) {
-  IO_REQUIRE(net && pair_tensor && logits, "io_net_forward_pairs: null pointer");
+  IO_REQUIRE(net && pair_tensor && (logits || net->n_heads == 0), "io_net_forward_pairs: null pointer");
   if (!net->loaded) {
     set_error("io_net_forward_pairs: no weights loaded (call io_net_load_state first)");
     return IO_ERR_STATE;
@@ -490,7 +622,8 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
     return IO_OK;
   };
   const int64_t pair_bytes = io_pair_tensor_bytes(1, net->d);
-  const size_t l2_elems_per_pair = static_cast<size_t>(2) * (net->d / 8) * (net->d / 8) * 512;
+  const size_t l2_elems_per_pair = 2 * per_img_out(net, 1);
+  const size_t t1b_elems_per_pair = static_cast<size_t>(2) * (net->d / 8) * (net->d / 8) * net->widths[2];
   auto run_ops = [&](Plan& plan, const uint8_t* pair_ptr, int pa) -> int {
     for (Op& op : plan.ops) {
       int rc = mark(static_cast<int>(op.kind), op.flops, true);
@@ -512,6 +645,14 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
         case Op::CONV_TN:
           rc = conv_tn_launch(op.tp, stream);
           break;
+        case Op::ADD: {
+          const int per8 = op.h * op.w * op.c / 8;
+          dim3 grid(std::min((per8 + 255) / 256, 64), op.b);
+          add_bcast_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(op.dst),
+                                                     reinterpret_cast<const uint4*>(op.src), op.idx, per8);
+          rc = cudaGetLastError() == cudaSuccess ? IO_OK : IO_ERR_CUDA;
+          break;
+        }
         case Op::STEM_TN:
           rc = stem_tn_plan(&op.tp, pa, net->d, pair_ptr, net->stem_w, net->stem_bias, net->buf[0]);
           if (!rc) rc = conv_tn_launch(op.tp, stream);
@@ -533,8 +674,8 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
       auto it = net->plans_a.find(key);
       if (it == net->plans_a.end()) {
         std::unique_ptr<Plan> plan(new Plan());
-        __nv_bfloat16* next_t1 = net->cross_fuse ? net->bufb[2] + static_cast<size_t>(a0) * (l2_elems_per_pair / 2) : nullptr;
-        if (int rc = build_plan_a(net, pa, net->big + static_cast<size_t>(a0) * l2_elems_per_pair, next_t1, plan.get())) return rc;
+        __nv_bfloat16* next_t1 = net->cross_fuse ? net->bufb[2] + static_cast<size_t>(a0) * t1b_elems_per_pair : nullptr;
+        if (int rc = build_plan_a(net, pa, a0, net->big + static_cast<size_t>(a0) * l2_elems_per_pair, next_t1, plan.get())) return rc;
         it = net->plans_a.emplace(key, std::move(plan)).first;
       }
       const uint8_t* pair_ptr = reinterpret_cast<const uint8_t*>(pair_tensor) + static_cast<int64_t>(b0 + a0) * pair_bytes;
@@ -548,6 +689,7 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
     }
     Plan& planb = *itb->second;
     if (int rc = run_ops(planb, nullptr, pb)) return rc;
+    if (net->n_heads == 0) continue;   // feature extractor: the layer outputs are the result
     if (int rc = mark(3, 2.0 * 2 * pb * 2048.0 * net->k_total, true)) return rc;
     if (int rc = tail_launch(planb.feat, planb.hw_final, pb, net->fc_w, net->fc_b, net->k_total,
                              logits + static_cast<size_t>(b0) * 2 * net->k_total, stream))

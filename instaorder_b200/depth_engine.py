@@ -1,0 +1,183 @@
+"""InstaDepthNet^od order inference (BASELINE config 5; reference ``midas/midas_net.py:113-212`` through
+``inference.infer_order_sup_occ_depth(method="InstaDepthNet_od")``, ``inference.py:349-436, 107-137``).
+
+The order outputs depend on the ResNeXt-101 32x8d encoder's layer1..3 -- a function of the IMAGE only -- and on the two
+2-channel ResNet-50 trunks ``do_net`` / ``oo_net`` per pair direction, with the encoder features added in front of
+their layer2 / layer3 / layer4.  The reference recomputes the encoder (and the whole MiDaS decoder, which only feeds the
+disparity output) for every pair direction; here the encoder runs ONCE PER IMAGE of a batch and its three feature
+maps are broadcast into the trunks by index (``io_net_set_inject``).  Everything runs through the kernels of the
+pairwise-order path: three ``io_net_t`` handles created with ``io_net_create_arch`` -- the encoder's grouped 3x3
+convolutions as dense block-diagonal weights, the 3- / 2-channel stems embedded in the 5-channel pair-tensor stem.
+The disparity map (encoder layer4 + ``scratch.*``) is not computed: ``model(x)`` -style access to it raises."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, synth
+from .engine import OrderEngine
+
+RESNET50 = ((64, 128, 256, 512), (256, 512, 1024, 2048), (3, 4, 6, 3))
+
+
+def _i32(v):
+    return np.asarray(v, dtype=np.int32)
+
+
+class DepthOrderEngine(OrderEngine):
+    def __init__(self, input_size=384, max_pairs=64, max_images=16, device="cuda:0", **kw):
+        self.max_images = int(max_images)
+        super().__init__([2, 3], input_size, max_pairs, device, **kw)
+
+    # ---- handles -------------------------------------------------------------------------------------------------
+    def _create_arch(self, arch, n_layers, keep, ncs, pairs):
+        h = C.c_void_p()
+        w, o, b = (_i32(a) for a in arch)
+        nc = _i32(ncs) if ncs else None
+        _lib.check(self.lib.io_net_create_arch(_lib.ptr(w), _lib.ptr(o), _lib.ptr(b), n_layers, int(keep),
+                                               _lib.ptr(nc) if nc is not None else None, len(ncs) if ncs else 0,
+                                               self.d, pairs, C.byref(h)))
+        return h
+
+    def _create_nets(self):
+        self.enc = self._create_arch((synth.RESNEXT_WIDTHS, synth.RESNEXT_OUTS, synth.RESNEXT_BLOCKS), 3, True, None,
+                                     self.max_images)
+        self.do_net = self._create_arch(RESNET50, 4, False, [3], self.max_pairs)
+        self.oo_net = self._create_arch(RESNET50, 4, False, [2], self.max_pairs)
+        self.inject_idx = torch.zeros(2 * self.max_pairs, dtype=torch.int32, device=self.device)
+        feats = []
+        for li in range(3):
+            ptr, n = C.c_void_p(), C.c_int64()
+            _lib.check(self.lib.io_net_feature(self.enc, li, C.byref(ptr), C.byref(n)))
+            feats.append(ptr)
+        for net in (self.do_net, self.oo_net):
+            _lib.check(self.lib.io_net_set_inject(net, feats[0], feats[1], feats[2], self.inject_idx.data_ptr()))
+        self.enc_pair_tensor = torch.zeros(self.lib.io_pair_tensor_bytes(self.max_images, self.d), dtype=torch.uint8,
+                                           device=self.device)
+        self.logits_d = torch.empty((self.max_pairs, 2, 3), dtype=torch.float32, device=self.device)
+        self.logits_o = torch.empty((self.max_pairs, 2, 2), dtype=torch.float32, device=self.device)
+
+    def __del__(self):
+        try:
+            for name in ("enc", "do_net", "oo_net"):
+                h = getattr(self, name, None)
+                if h:
+                    self.lib.io_net_destroy(h)
+                    setattr(self, name, None)
+        except Exception:
+            pass
+
+    # ---- weights -------------------------------------------------------------------------------------------------
+    def _load_sub(self, net, sd, sub, in_ch, arch, groups, n_layers, head):
+        names, arrs = [], []
+        for key, shape in synth.bottleneck_layout(in_ch, arch[0], arch[1], arch[2], groups, n_layers):
+            v = None
+            for k in synth._sub_key(sub, key):
+                if k in sd:
+                    v = sd[k]
+                    break
+            if v is None:
+                raise KeyError("InstaDepthNet state_dict: missing '%s'" % synth._sub_key(sub, key)[0])
+            a = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            if key == "conv1.weight":
+                # 3-channel RGB conv1 -> pair-tensor channels 2..4; 2-channel mask conv1 -> channels 0..1
+                full = np.zeros((64, 5, 7, 7), np.float32)
+                if in_ch == 3:
+                    full[:, 2:5] = a
+                else:
+                    full[:, 0:2] = a
+                a = full
+            elif a.ndim == 4 and a.shape[2] == 3 and groups > 1:
+                # grouped 3x3 -> dense block-diagonal [cout, cin, 3, 3]: the implicit-GEMM kernels stay dense (the
+                # per-image encoder is a few percent of the per-pair trunk work even at 32x redundant FLOPs)
+                cout, cg = a.shape[0], a.shape[1]
+                og = cout // groups
+                full = np.zeros((cout, cg * groups, 3, 3), np.float32)
+                for g in range(groups):
+                    full[g * og:(g + 1) * og, g * cg:(g + 1) * cg] = a[g * og:(g + 1) * og]
+                a = full
+            names.append(key.encode())
+            arrs.append(a)
+        if head is not None:
+            for leaf in ("weight", "bias"):
+                names.append(("fc." + leaf).encode())
+                v = sd[head + "." + leaf]
+                arrs.append(np.ascontiguousarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32))
+        n = len(names)
+        c_names = (C.c_char_p * n)(*names)
+        c_ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        c_numel = (C.c_int64 * n)(*[a.size for a in arrs])
+        _lib.check(self.lib.io_net_load_state(net, c_names, c_ptrs, c_numel, n))
+
+    def load_state_dict(self, state_dict):
+        """Reference ``InstaDepthNet_od`` state_dict (``pretrained.*``, ``do_net.*``, ``oo_net.*``, ``depth_fc.*``,
+        ``occ_fc.*``; ``module.`` prefix optional; ``scratch.*`` / ``pretrained.layer4.*`` are ignored)."""
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        rx = (synth.RESNEXT_WIDTHS, synth.RESNEXT_OUTS, synth.RESNEXT_BLOCKS)
+        self._load_sub(self.enc, sd, "pretrained", 3, rx, synth.RESNEXT_GROUPS, 3, None)
+        self._load_sub(self.do_net, sd, "do_net", 2, RESNET50, 1, 4, "depth_fc")
+        self._load_sub(self.oo_net, sd, "oo_net", 2, RESNET50, 1, 4, "occ_fc")
+
+    # ---- per batch -----------------------------------------------------------------------------------------------
+    def stage_batch(self, items, mode="resize"):
+        s, P = super().stage_batch(items, mode)
+        jobs = self.resize_jobs
+        if len(jobs) > self.max_images:
+            raise ValueError("%d images in one batch, engine built for %d (max_images)" % (len(jobs), self.max_images))
+        if not hasattr(s, "h_idx"):       # per-slot staging of the two small tables (same life cycle as the slot's buffers)
+            s.h_idx = torch.zeros(2 * self.max_pairs, dtype=torch.int32).pin_memory()
+            s.d_idx = torch.zeros(2 * self.max_pairs, dtype=torch.int32, device=self.device)
+            s.h_enc_desc = torch.zeros(self.max_images * 48, dtype=torch.uint8).pin_memory()
+            s.d_enc_desc = torch.zeros(self.max_images * 48, dtype=torch.uint8, device=self.device)
+        # one descriptor per image for the encoder's input (its masks are ignored: zero weight columns)
+        desc = np.frombuffer(s.h_enc_desc.numpy(), dtype=_lib.PAIR_DESC_DTYPE)
+        mask_off = 0
+        k = 0
+        for (sc, pairs, crops, mat_off, _) in items:
+            d = desc[k]
+            d["image_off"] = jobs[k][0]
+            d["mask_a_off"] = d["mask_b_off"] = mask_off
+            d["h"], d["w"], d["x"], d["y"], d["s"], d["rgb_slot"] = sc.h, sc.w, 0, 0, 0, jobs[k][3]
+            mask_off += (sc.n * sc.h * sc.w + 15) // 16 * 16
+            k += 1
+        pdesc = np.frombuffer(s.h_desc.numpy(), dtype=_lib.PAIR_DESC_DTYPE)[:P]
+        idx = s.h_idx.numpy()
+        idx[0:2 * P:2] = 2 * pdesc["rgb_slot"]        # encoder image 2 * slot = its direction-0 copy
+        idx[1:2 * P:2] = 2 * pdesc["rgb_slot"]
+        compute = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            s.d_enc_desc[:k * 48].copy_(s.h_enc_desc[:k * 48], non_blocking=True)
+            s.d_idx[:2 * P].copy_(s.h_idx[:2 * P], non_blocking=True)
+            s.copied = torch.cuda.Event()
+            s.copied.record(self.copy_stream)
+        compute.wait_event(s.copied)
+        # the trunks' launch plans hold ONE index pointer: refreshed on the compute stream, behind the previous batch
+        self.inject_idx[:2 * P].copy_(s.d_idx[:2 * P], non_blocking=True)
+        self.h2d_bytes += k * 48 + 8 * P
+        return s, P
+
+    def gather(self, s, P, mode="resize"):
+        if mode != "resize":
+            raise NotImplementedError("InstaDepthNet runs in 'resize' mode (its shipped config); got %r" % (mode,))
+        super().gather(s, P, mode)
+        n_img = len(self.resize_jobs)
+        _lib.check(self.lib.io_pair_gather_resize(self._planes.data_ptr(), s.d_mask.data_ptr(),
+                                                  s.d_enc_desc.data_ptr(), n_img, self.d,
+                                                  self.enc_pair_tensor.data_ptr(), _lib.stream_ptr()))
+        self.gpu_launches += 1
+        self._n_img = n_img
+
+    def forward(self, P):
+        st = _lib.stream_ptr()
+        _lib.check(self.lib.io_net_forward_pairs(self.enc, self.enc_pair_tensor.data_ptr(), self._n_img, None, st))
+        _lib.check(self.lib.io_net_forward_pairs(self.do_net, self.pair_tensor.data_ptr(), P, self.logits_d.data_ptr(), st))
+        _lib.check(self.lib.io_net_forward_pairs(self.oo_net, self.pair_tensor.data_ptr(), P, self.logits_o.data_ptr(), st))
+        self.logits[:P, :, 0:2] = self.logits_o[:P]
+        self.logits[:P, :, 2:5] = self.logits_d[:P]
+        self.gpu_launches += sum(self.lib.io_net_last_launches(h) for h in (self.enc, self.do_net, self.oo_net)) + 2
+
+    def infer_scenes(self, scenes, algo="InstaDepthNet_od", pairs="all", patch_or_image="resize", return_details=False):
+        if algo != "InstaDepthNet_od":
+            raise ValueError("DepthOrderEngine runs InstaDepthNet_od, got %r" % (algo,))
+        return super().infer_scenes(scenes, "InstaOrderNet_od", pairs, patch_or_image, return_details)

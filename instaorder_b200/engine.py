@@ -127,10 +127,8 @@ class OrderEngine:
         self.first_batch_pairs = max(1, min(self.max_pairs, int(os.environ.get("INSTAORDER_FIRST_BATCH", "64"))))
         self.mean = np.asarray(data_mean, dtype=np.float32)
         self.std = np.asarray(data_std, dtype=np.float32)
-        ncs = np.asarray(self.ncs, dtype=np.int32)
-        h = C.c_void_p()
-        _lib.check(self.lib.io_net_create(_lib.ptr(ncs), len(self.ncs), self.d, self.max_pairs, C.byref(h)))
-        self.net = h
+        self.net = None
+        self._create_nets()
         self.pair_tensor = torch.zeros(self.lib.io_pair_tensor_bytes(self.max_pairs, self.d), dtype=torch.uint8,
                                        device=self.device)
         self.logits = torch.empty((self.max_pairs, 2, self.k_total), dtype=torch.float32, device=self.device)
@@ -142,6 +140,12 @@ class OrderEngine:
         self.gpu_launches = 0   # kernels launched by this engine since creation
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+
+    def _create_nets(self):
+        ncs = np.asarray(self.ncs, dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(self.lib.io_net_create(_lib.ptr(ncs), len(self.ncs), self.d, self.max_pairs, C.byref(h)))
+        self.net = h
 
     def __del__(self):
         try:

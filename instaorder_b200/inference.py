@@ -45,7 +45,7 @@ def infer_order_sup_depth(model, image, inmodal, bboxes, pairs, method, patch_or
 def infer_order_sup_occ_depth(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size,
                               disp_select_method):
     """reference inference.py:349-436 -> (occ_order, depth_order)."""
-    if method != "InstaOrderNet_od":
+    if method not in ("InstaOrderNet_od", "InstaDepthNet_od"):
         raise NotImplementedError("%s is outside the pairwise-order hot path (SURVEY.md section 8f)" % method)
     r = _run(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size)
     return r["occ"], r["depth"]

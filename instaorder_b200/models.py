@@ -15,7 +15,7 @@ from . import _lib
 from .engine import OrderEngine
 from .training import FlatOptim, TrainEngine
 
-__all__ = ["InstaOrderNet_o", "InstaOrderNet_d", "InstaOrderNet_od", "OrderNet"]
+__all__ = ["InstaOrderNet_o", "InstaOrderNet_d", "InstaOrderNet_od", "OrderNet", "InstaDepthNet_od"]
 
 
 class _OrderModel(object):
@@ -315,3 +315,56 @@ class OrderNet(_OrderModel):
 
     def step(self):                                                               # supervised_order.py:481-493
         return {"loss": self._step(-1, 0, int(self.num_classes), None, self.occ_order1, None)[0]}
+
+
+class InstaDepthNet_od(object):
+    """Order inference with the reference's ``models.InstaDepthNet_od`` (models/supervised_order.py:99-237 wrapping
+    midas/midas_net.py:113-212): ``load_state`` / ``load_state_dict`` / ``switch_to('eval')`` and the engine handle
+    used by ``inference.infer_order_sup_occ_depth(method="InstaDepthNet_od")``.  Inference of the two order matrices
+    only: the disparity output and training raise ``NotImplementedError``."""
+    algo = "InstaDepthNet_od"
+
+    def __init__(self, params, load_pretrain=None, dist_model=False):
+        self.params = params
+        self.world_size = 1
+        self.max_pairs = int(params.get("max_pairs", 64))
+        self.max_images = int(params.get("max_images", 16))
+        self.device = params.get("device", "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0")))
+        self._engines = {}
+        self._state = None
+        self.phase = "eval"
+        if load_pretrain is not None:
+            self.load_state(load_pretrain)
+
+    def engine_for(self, input_size):
+        from .depth_engine import DepthOrderEngine
+        e = self._engines.get(input_size)
+        if e is None:
+            if self._state is None:
+                raise RuntimeError("no weights loaded: call load_state()/load_state_dict() first")
+            e = DepthOrderEngine(input_size, self.max_pairs, self.max_images, self.device)
+            e.load_state_dict(self._state)
+            self._engines[input_size] = e
+        return e
+
+    def load_state_dict(self, sd):
+        self._state = sd
+        for e in self._engines.values():
+            e.load_state_dict(sd)
+
+    def load_state(self, path, Iter=None, resume=False):
+        if Iter is not None:
+            path = os.path.join(path, "ckpt_iter_{}.pth.tar".format(Iter))
+        if not os.path.isfile(path):
+            raise Exception("=> no checkpoint found at '{}'".format(path))
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        self.load_state_dict(ckpt["state_dict"])
+        return ckpt.get("step", 0)
+
+    def switch_to(self, phase):
+        if phase == "train":
+            raise NotImplementedError("InstaDepthNet_od: inference of the order matrices only")
+        self.phase = phase
+
+    def step(self):
+        raise NotImplementedError("InstaDepthNet_od: inference of the order matrices only")

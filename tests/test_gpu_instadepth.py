@@ -1,0 +1,85 @@
+"""InstaDepthNet^od order inference (BASELINE config 5) on the GPU against the fixture frozen from the UNMODIFIED
+reference (``infer_order_sup_occ_depth(method='InstaDepthNet_od')``, resize 384^2): logits of both heads within the
+north_star tolerance (2e-2 absolute, bf16 vs the fp32 reference), order matrices identical off ties, and against the
+ideal-bf16 CPU emulation of the same arithmetic (kernel-correctness check proper)."""
+import os
+
+import numpy as np
+import pytest
+
+from instaorder_b200 import engine, inference, models
+from instaorder_b200.depth_engine import DepthOrderEngine
+from oracle import gen_golden_instadepth as G, instadepth_oracle as IO, oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-2
+MARGIN = 5e-3      # decisions are compared where the reference's probability margin exceeds the bf16 logit noise / 4
+
+
+@pytest.fixture(scope="module")
+def setup(golden_dir):
+    z = np.load(os.path.join(golden_dir, "instadepth_order.npz"))
+    sd = IO.load_calibrated(os.path.join(golden_dir, "instadepth_calib.npz"), G.SEED)
+    eng = DepthOrderEngine(G.D, max_pairs=16, max_images=4)
+    eng.load_state_dict(sd)
+    return z, sd, eng
+
+
+def test_logits_and_matrices_match_reference(setup):
+    z, sd, eng = setup
+    image, masks, boxes = G.build_scene()
+    r = eng.infer_scenes([engine.Scene(image, masks, boxes)], "InstaDepthNet_od", "all", "resize", return_details=True)[0]
+    occ_l, depth_l = r["logits"][:, :, 0:2], r["logits"][:, :, 2:5]
+    e_o, e_d = np.abs(occ_l - z["occ_logits"]).max(), np.abs(depth_l - z["depth_logits"]).max()
+    print("InstaDepthNet_od: max |logit - reference fp32| occ %.5f depth %.5f" % (e_o, e_d))
+    assert e_o < LOGIT_TOL and e_d < LOGIT_TOL
+    n = G.N_INST
+    checked = 0
+    for p, (i, j) in enumerate(O.enumerate_pairs(n)):
+        _, m_d = O.decide_depth(z["depth_logits"][p, 0], z["depth_logits"][p, 1])
+        _, _, m_o = O.decide_occ(z["occ_logits"][p, 0], z["occ_logits"][p, 1])
+        if m_d > MARGIN:
+            assert r["depth"][i, j] == z["depth"][i, j] and r["depth"][j, i] == z["depth"][j, i]
+            checked += 1
+        if m_o > MARGIN:
+            assert r["occ"][i, j] == z["occ"][i, j] and r["occ"][j, i] == z["occ"][j, i]
+            checked += 1
+    assert checked >= 6
+
+
+def test_logits_match_ideal_bf16_emulation(setup):
+    z, sd, eng = setup
+    image, masks, boxes = G.build_scene()
+    r = eng.infer_scenes([engine.Scene(image, masks, boxes)], "InstaDepthNet_od", "all", "resize", return_details=True)[0]
+    rgb = O.resize_mode_rgb(image, G.D)[None]
+    mm = [O.resize_mode_mask(m, G.D)[None].astype(np.float32) for m in masks]
+    m1, m2 = [], []
+    for (i, j) in O.enumerate_pairs(G.N_INST):
+        m1 += [mm[i], mm[j]]
+        m2 += [mm[j], mm[i]]
+    P = len(m1) // 2
+    emu = IO.order_forward(sd, rgb, np.stack(m1), np.stack(m2), np.zeros(2 * P, np.int64), bf16=True)
+    e_d = np.abs(r["logits"][:, :, 2:5] - emu["depth"].reshape(P, 2, 3)).max()
+    e_o = np.abs(r["logits"][:, :, 0:2] - emu["occ"].reshape(P, 2, 2)).max()
+    print("InstaDepthNet_od: max |logit - ideal bf16 emulation| occ %.5f depth %.5f" % (e_o, e_d))
+    assert e_o < 1e-2 and e_d < 1e-2
+
+
+def test_batching_and_reference_api(setup, golden_dir):
+    """Two images in one batch (encoder features broadcast by index) = each image alone; the reference-shaped API."""
+    z, sd, eng = setup
+    from instaorder_b200 import synth
+    image, masks, boxes = G.build_scene()
+    rng = np.random.RandomState(9)
+    img2, masks2, boxes2 = synth.make_scene(rng, 333, 500, 3, wh_range=((50, 200), (50, 200)))
+    a = eng.infer_scenes([engine.Scene(img2, masks2, boxes2), engine.Scene(image, masks, boxes)], "InstaDepthNet_od")
+    b = eng.infer_scenes([engine.Scene(image, masks, boxes)], "InstaDepthNet_od")[0]
+    c = eng.infer_scenes([engine.Scene(img2, masks2, boxes2)], "InstaDepthNet_od")[0]
+    assert np.array_equal(a[1]["occ"], b["occ"]) and np.array_equal(a[1]["depth"], b["depth"])
+    assert np.array_equal(a[0]["occ"], c["occ"]) and np.array_equal(a[0]["depth"], c["depth"])
+    m = models.InstaDepthNet_od(dict(algo="InstaDepthNet_od", max_pairs=16, max_images=4))
+    m.load_state_dict(sd)
+    m.switch_to("eval")
+    occ, depth = inference.infer_order_sup_occ_depth(m, image, masks, boxes, "all", "InstaDepthNet_od", "resize", G.D, "")
+    assert np.array_equal(occ, b["occ"]) and np.array_equal(depth, b["depth"])
