@@ -150,6 +150,32 @@ def cpu_port_pairs_per_s(n_pairs, threads=None):
     return done / dt, done, dt, torch.get_num_threads()
 
 
+def cpu_port_instadepth(threads=None):
+    """The oracle port of InstaDepthNet^od's order branch on the host cores: one 4-instance image (6 pairs)."""
+    import torch
+    from instaorder_b200 import synth
+    from oracle import instadepth_oracle as IO, oracle as O
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = synth.instadepth_state_dict(0)
+    image, masks, _ = next(synth.coco_scene_stream(99, 1, N=4))
+    rgb = O.resize_mode_rgb(image, 384)[None]
+    mm = [O.resize_mode_mask(m, 384)[None].astype(np.float32) for m in masks]
+    m1, m2 = [], []
+    for (i, j) in O.enumerate_pairs(4):
+        m1 += [mm[i], mm[j]]
+        m2 += [mm[j], mm[i]]
+    IO.order_forward(sd, rgb, np.stack(m1[:2]), np.stack(m2[:2]), np.zeros(2, np.int64))      # warm-up
+    t0 = time.perf_counter()
+    IO.order_forward(sd, rgb, np.stack(m1), np.stack(m2), np.zeros(len(m1), np.int64))
+    dt = time.perf_counter() - t0
+    return (len(m1) // 2) / dt, len(m1) // 2, dt, torch.get_num_threads()
+
+
 def run_reference_arm(args):
     """`--impl reference`: the reference's algorithm on the host cores (the reference itself is Python and lives at
     /root/reference, which does not exist on the GPU box; oracle/oracle.py is its restatement, pinned against it by
@@ -353,7 +379,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-pairs", type=int, default=225)
-    ap.add_argument("--mode", default="patch256", choices=["patch256", "resize384"],
+    ap.add_argument("--mode", default="patch256", choices=["patch256", "resize384", "instadepth384"],
                     help="patch256 = the BASELINE.json metric (default); resize384 = the shipped InstaOrderNet^od "
                          "config (whole image -> 384^2), reported as a second row in DESIGN.md")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
@@ -369,10 +395,17 @@ def main():
     import torch
     import torch.distributed as dist
     from instaorder_b200 import _lib, engine, synth
-    global D, FLOP_PER_PAIR
+    global D, FLOP_PER_PAIR, PAIRS_PER_STEP, ALGO
     gmode = "patch"
+    depth = args.mode == "instadepth384"      # BASELINE config 5: InstaDepthNet^od order inference, 384^2
     if args.mode == "resize384":
         D, FLOP_PER_PAIR, gmode = 384, 48.970e9, "resize"
+    if depth:
+        from instaorder_b200 import depth_engine
+        D, gmode, PAIRS_PER_STEP, ALGO = 384, "resize", 128, "InstaDepthNet_od"
+        # our formulation: two trunks x two directions per pair + the encoder once per image (45 pairs per image);
+        # the reference spends 2 x 254.5 GFLOP per pair (encoder + MiDaS decoder + trunks for every direction)
+        FLOP_PER_PAIR = 4 * 24.485e9 + depth_engine.encoder_flops_per_image(D) / 45.0
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -387,9 +420,14 @@ def main():
     n_batches = 8                                    # distinct resident batches, rotated so inputs never sit in L2
     n_images = (n_batches * PAIRS_PER_STEP) // 45 + 2
     scenes = make_scenes(1000 + rank, n_images)
-    eng = engine.OrderEngine(NUM_CLASSES, D, max_pairs=PAIRS_PER_STEP, device=dev)
-    eng.load_state_dict(synth.random_state_dict(0, 5, NUM_CLASSES))
-    heads = engine.heads_for(ALGO, NUM_CLASSES)
+    if depth:
+        eng = depth_engine.DepthOrderEngine(D, max_pairs=PAIRS_PER_STEP, max_images=8, device=dev)
+        eng.load_state_dict(synth.instadepth_state_dict(0))
+        heads = engine.heads_for("InstaOrderNet_od", NUM_CLASSES)
+    else:
+        eng = engine.OrderEngine(NUM_CLASSES, D, max_pairs=PAIRS_PER_STEP, device=dev)
+        eng.load_state_dict(synth.random_state_dict(0, 5, NUM_CLASSES))
+        heads = engine.heads_for(ALGO, NUM_CLASSES)
     batches, mat_elems = eng.make_batches(scenes, PAIRS_PER_STEP, gmode)
     batches = batches[:n_batches]
     resident = [eng.upload_resident(b, mat_elems, gmode) for b in batches]
@@ -425,10 +463,11 @@ def main():
     value = world * args.steps * PAIRS_PER_STEP / (ms / 1000.0)
 
     # ---- per-kernel events (separate pass, so the events do not perturb the number above) -------------------
-    _lib.check(eng.lib.io_net_profile(eng.net, 1))
     conv_ms = conv_flops = tot_ms = 0.0
     n_conv = 0
-    prof_steps = min(args.steps, 4)
+    prof_steps = 0 if depth else min(args.steps, 4)     # three handles in the InstaDepthNet engine: roofline from the step
+    if not depth:
+        _lib.check(eng.lib.io_net_profile(eng.net, 1))
     for i in range(prof_steps):
         eng.run_resident(resident[i % len(resident)], heads, gmode)
         torch.cuda.synchronize()
@@ -438,13 +477,16 @@ def main():
         sel = (kind[:n] == 0) | (kind[:n] == 2) | (kind[:n] >= 4)
         conv_ms += float(pms[:n][sel].sum()); conv_flops += float(fl[:n][sel].sum()); n_conv += int(sel.sum())
         tot_ms += float(pms[:n].sum())
-    _lib.check(eng.lib.io_net_profile(eng.net, 0))
+    if not depth:
+        _lib.check(eng.lib.io_net_profile(eng.net, 0))
     peaks = measured_peaks()
     achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+    if depth:
+        achieved = value / world * FLOP_PER_PAIR / 1e12
     # DRAM traffic of the conv kernel per launch, from the committed ncu capture of this command (profiles/)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
-    if os.path.isfile(tp):
+    if os.path.isfile(tp) and not depth:
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
 
@@ -453,8 +495,9 @@ def main():
     o = 0
     for i in range(args.warmup + args.steps):
         # the public API takes whole images: an e2e step = 17 images = 765 pairs = 3 engine batches (256+256+253)
-        per_step_scenes.append([scenes[(o + k) % len(scenes)] for k in range(17)])
-        o += 17
+        n_e2e = 6 if depth else 17
+        per_step_scenes.append([scenes[(o + k) % len(scenes)] for k in range(n_e2e)])
+        o += n_e2e
     for i in range(args.warmup):
         eng.infer_scenes(per_step_scenes[i], ALGO, "all", gmode)
     sync_all()
@@ -476,18 +519,25 @@ def main():
 
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and depth:
+            v, n, cdt, threads = cpu_port_instadepth()
+            cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
+                       sample="%d pairs of one image (%.1f s): oracle port of the order branch (fp32 torch-CPU, encoder once "
+                              "per image, no MiDaS decoder -- an upper bound on the reference, which recomputes both per "
+                              "pair direction)" % (n, cdt))
+        elif world == 1 and not args.no_cpu_baseline:
             v, n, cdt, threads = cpu_port_pairs_per_s(args.cpu_sample_pairs)
             cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
                        sample="%d pairs of C2 images (%.1f s): oracle port of inference.py patch path + fp32 "
                               "torch-CPU ResNet-50, batched 16 forwards" % (n, cdt))
         line = dict(
-            metric="instance pairs/s (InstaOrderNet^od, %s, bf16)" % ("256^2" if gmode == "patch" else "resize 384^2"),
+            metric=("instance pairs/s (InstaDepthNet^od order inference, resize 384^2, bf16)" if depth else
+                    "instance pairs/s (InstaOrderNet^od, %s, bf16)" % ("256^2" if gmode == "patch" else "resize 384^2")),
             value=value, unit="pairs/s", n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
             scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
             config=dict(workload="C2: synthetic COCO-val-shaped images, 10 instances -> 45 pairs/image, %d pairs per "
-                                 "step, %s, InstaOrderNet^od heads [2,3], random-init weights" % (PAIRS_PER_STEP, "patch 256^2" if gmode == "patch" else "resize 384^2 (shipped config)"),
+                                 "step, %s, %s, random-init weights" % (PAIRS_PER_STEP, "patch 256^2" if gmode == "patch" else "resize 384^2 (shipped config)", "InstaDepthNet^od order branch (ResNeXt-101 encoder layer1-3 once per image + do_net / oo_net trunks)" if depth else "InstaOrderNet^od heads [2,3]"),
                         pairs_per_step=PAIRS_PER_STEP, parallelism="images sharded over %d GPU(s), no collective" % world,
                         l2="inputs rotate over %d resident batches (%.0f MB) and each step streams >10 GB of "
                            "activations, i.e. >> 126 MB L2" % (len(resident), input_bytes / 1e6)),
@@ -496,8 +546,9 @@ def main():
             gpu_launches=launches,
             clocks=clocks,
             roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
-                          frac=achieved / peaks["bf16"], traffic=traffic, kernel="conv_tc_kernel (all "
-                          "53 conv layers)", launches_timed=n_conv, avg_launch_ms=conv_ms / max(n_conv, 1),
+                          frac=achieved / peaks["bf16"], traffic=traffic,
+                          kernel=("whole step: encoder (once per image) + two trunks, algorithmic FLOPs of this "
+                                  "formulation" if depth else "conv_tc_kernel (all 53 conv layers)"), launches_timed=n_conv, avg_launch_ms=conv_ms / max(n_conv, 1),
                           conv_share_of_step=conv_ms / tot_ms if tot_ms else None, peak_source=peaks["source"],
                           step_frac=value / world * FLOP_PER_PAIR / 1e12 / peaks["bf16"]),
             cpu_baseline=cpu,

@@ -155,7 +155,18 @@ class DepthOrderEngine(OrderEngine):
         # the trunks' launch plans hold ONE index pointer: refreshed on the compute stream, behind the previous batch
         self.inject_idx[:2 * P].copy_(s.d_idx[:2 * P], non_blocking=True)
         self.h2d_bytes += k * 48 + 8 * P
+        self._last_slot = s
         return s, P
+
+    def upload_resident(self, items, mat_elems, mode="resize"):
+        r = super().upload_resident(items, mat_elems, mode)
+        r.d_enc_desc = self._last_slot.d_enc_desc.clone()
+        r.d_idx = self._last_slot.d_idx.clone()
+        return r
+
+    def run_resident(self, r, heads, mode="resize"):
+        self.inject_idx[:2 * r.P].copy_(r.d_idx[:2 * r.P], non_blocking=True)
+        super().run_resident(r, heads, mode)
 
     def gather(self, s, P, mode="resize"):
         if mode != "resize":
@@ -181,3 +192,21 @@ class DepthOrderEngine(OrderEngine):
         if algo != "InstaDepthNet_od":
             raise ValueError("DepthOrderEngine runs InstaDepthNet_od, got %r" % (algo,))
         return super().infer_scenes(scenes, "InstaOrderNet_od", pairs, patch_or_image, return_details)
+
+
+def encoder_flops_per_image(d=384):
+    """Algorithmic 2*MAC of the encoder's conv1 + layer1..3 (grouped 3x3 counted with their true group size)."""
+    total = 2.0 * (d // 2) ** 2 * 64 * 3 * 49
+    inpl, side = 64, d // 4
+    for li in range(3):
+        w, o = synth.RESNEXT_WIDTHS[li], synth.RESNEXT_OUTS[li]
+        for b in range(synth.RESNEXT_BLOCKS[li]):
+            stride = 2 if (b == 0 and li > 0) else 1
+            so = side // stride
+            total += 2.0 * side * side * inpl * w                                   # conv1 (before the stride)
+            total += 2.0 * so * so * (w // synth.RESNEXT_GROUPS) * 9 * w             # grouped 3x3
+            total += 2.0 * so * so * w * o                                           # conv3
+            if b == 0:
+                total += 2.0 * so * so * inpl * o                                    # downsample
+            inpl, side = o, so
+    return total
