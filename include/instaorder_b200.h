@@ -153,7 +153,8 @@ IO_API int io_net_create(const int32_t* num_classes, int n_heads, int input_size
 IO_API int io_net_create_arch(const int32_t* widths4, const int32_t* outs4, const int32_t* blocks4, int n_layers,
                        int keep_layers, const int32_t* num_classes, int n_heads, int input_size, int max_pairs,
                        io_net_t** out);
-/* Layer `layer` (0-based) output of a keep_layers handle: bf16 [2 * pairs, D >> (2 + layer), same, outs[layer]]. */
+/* Layer `layer` (0-based) output of a keep_layers handle: bf16 [images, D >> (2 + layer), same, outs[layer]]; a head-less
+ * handle (RGB-only encoder) computes ONE direction: images = the `p` of io_net_forward_pairs, else 2 * p. */
 IO_API int io_net_feature(io_net_t* net, int layer, void** ptr, int64_t* elems_per_image);
 /* Trunks of InstaDepthNet (midas_net.py:200-210): after layers 1, 2, 3 add f_l[idx_dev[image]] (image = 2 * pair +
  * direction; idx_dev is read at run time, int32 [2 * max_pairs]).  All NULL switches the injection off. */

@@ -61,6 +61,9 @@ struct io_net {
   int n_layers = 4;
   // feature extractor (InstaDepthNet encoder): the output of every layer is kept in its own buffer
   bool keep_layers = false;
+  // RGB-only feature extractor: the stem's two directions are identical, so the second one is written behind the
+  // first ([direction][image] order) and every later launch works on the first half only
+  bool single_dir = false;
   __nv_bfloat16* keep[4] = {nullptr, nullptr, nullptr, nullptr};
   // feature injection (InstaDepthNet trunks, midas_net.py:201-203): x += enc_l[inject_idx[image]] after layer l
   const __nv_bfloat16* inject[3] = {nullptr, nullptr, nullptr};
@@ -300,7 +303,8 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
 
 // phase A: stem + max-pool + layer1 + layer2 for `pa` pairs; layer2's output goes to `dst` ([2*pa, D/8, D/8, 512])
 static int build_plan_a(io_net* net, int pa, int a0, __nv_bfloat16* dst, __nv_bfloat16* next_t1, Plan* plan) {
-  const int b = 2 * pa, d = net->d;
+  const int dirs = net->single_dir ? 1 : 2;
+  const int b = dirs * pa, d = net->d;
   plan->ops.clear();
   __nv_bfloat16 *X = net->buf[0], *Y = net->buf[1];
   Op op;
@@ -319,12 +323,12 @@ static int build_plan_a(io_net* net, int pa, int a0, __nv_bfloat16* dst, __nv_bf
   int h = d / 4, w = d / 4;
   const __nv_bfloat16* out = nullptr;
   return build_blocks(net, plan, 0, 2, b, &h, &w, Y, X, Y, net->buf[2], net->buf[3], net->buf[4], dst, &out, next_t1,
-                      false, net->keep_layers ? 2LL * a0 : -1, 2 * a0);
+                      false, net->keep_layers ? static_cast<long long>(dirs) * a0 : -1, dirs * a0);
 }
 
 // phase B: layer3 + layer4 for `pb` pairs reading the big layer2-output buffer
 static int build_plan_b(io_net* net, int pb, Plan* plan) {
-  const int b = 2 * pb, d = net->d;
+  const int b = (net->single_dir ? 1 : 2) * pb, d = net->d;
   plan->ops.clear();
   int h = d / 8, w = d / 8;
   const __nv_bfloat16* out = nullptr;
@@ -363,6 +367,7 @@ extern "C" int io_net_create_arch(const int32_t* widths, const int32_t* outs, co
   IO_REQUIRE(n_heads == 0 || outs[3] == 2048, "io_net_create_arch: the head kernel expects 2048 features");
   net->n_layers = n_layers;
   net->keep_layers = keep_layers != 0;
+  net->single_dir = net->keep_layers && n_heads == 0;
   net->n_heads = n_heads;
   for (int i = 0; i < n_heads; ++i) {
     IO_REQUIRE(num_classes[i] >= 1 && num_classes[i] <= 4, "io_net_create: num_classes[%d] = %d", i, num_classes[i]);
@@ -435,8 +440,8 @@ extern "C" int io_net_create(const int32_t* num_classes, int n_heads, int input_
   return io_net_create_arch(widths, outs, blocks, 4, 0, num_classes, n_heads, input_size, max_pairs, out);
 }
 
-// Output of layer `layer` (0-based) of a keep_layers handle: [2 * pairs, D >> (2 + layer), same, outs[layer]] bf16, image
-// 2p = direction (A,B) of pair p (the RGB-only encoder's two directions are identical).
+// Output of layer `layer` (0-based) of a keep_layers handle: [images, D >> (2 + layer), same, outs[layer]] bf16; images =
+// the pairs of the call for a head-less handle (RGB-only encoder: one direction), else 2 * pairs (image 2p + direction).
 extern "C" int io_net_feature(io_net_t* net, int layer, void** ptr, int64_t* elems_per_image) {
   IO_REQUIRE(net && ptr && elems_per_image && net->keep_layers && layer >= 0 && layer < net->n_layers,
              "io_net_feature: bad arguments");
@@ -622,7 +627,7 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
     return IO_OK;
   };
   const int64_t pair_bytes = io_pair_tensor_bytes(1, net->d);
-  const size_t l2_elems_per_pair = 2 * per_img_out(net, 1);
+  const size_t l2_elems_per_pair = (net->single_dir ? 1 : 2) * per_img_out(net, 1);
   const size_t t1b_elems_per_pair = static_cast<size_t>(2) * (net->d / 8) * (net->d / 8) * net->widths[2];
   auto run_ops = [&](Plan& plan, const uint8_t* pair_ptr, int pa) -> int {
     for (Op& op : plan.ops) {
@@ -631,6 +636,7 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
       switch (op.kind) {
         case Op::STEM:
           rc = stem_plan(&op.p, &op.bn_tile, pa, net->d, pair_ptr, net->stem_w, net->stem_bias, net->buf[0]);
+          if (!rc && net->single_dir) { op.p.img_mul = 1; op.p.split_row_off = pa * op.p.hw_out; }
           if (!rc) rc = conv_tc_launch(op.p, op.bn_tile, stream);
           break;
         case Op::POOL:
@@ -655,6 +661,7 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
         }
         case Op::STEM_TN:
           rc = stem_tn_plan(&op.tp, pa, net->d, pair_ptr, net->stem_w, net->stem_bias, net->buf[0]);
+          if (!rc && net->single_dir) { op.tp.img_mul = 1; op.tp.split_row_off = pa * op.tp.hw_out; }
           if (!rc) rc = conv_tn_launch(op.tp, stream);
           break;
         default:

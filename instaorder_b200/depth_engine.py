@@ -143,8 +143,8 @@ class DepthOrderEngine(OrderEngine):
             k += 1
         pdesc = np.frombuffer(s.h_desc.numpy(), dtype=_lib.PAIR_DESC_DTYPE)[:P]
         idx = s.h_idx.numpy()
-        idx[0:2 * P:2] = 2 * pdesc["rgb_slot"]        # encoder image 2 * slot = its direction-0 copy
-        idx[1:2 * P:2] = 2 * pdesc["rgb_slot"]
+        idx[0:2 * P:2] = pdesc["rgb_slot"]            # both directions of a pair read their image's encoder features
+        idx[1:2 * P:2] = pdesc["rgb_slot"]
         compute = torch.cuda.current_stream()
         with torch.cuda.stream(self.copy_stream):
             s.d_enc_desc[:k * 48].copy_(s.h_enc_desc[:k * 48], non_blocking=True)
