@@ -25,8 +25,10 @@ def _i32(v):
 
 
 class DepthOrderEngine(OrderEngine):
-    def __init__(self, input_size=384, max_pairs=64, max_images=16, device="cuda:0", **kw):
+    def __init__(self, input_size=384, max_pairs=64, max_images=16, device="cuda:0", with_occ=True, **kw):
+        """``with_occ=False``: InstaDepthNet^d (midas_net.py:15-110) -- no ``oo_net``, depth order only."""
         self.max_images = int(max_images)
+        self.with_occ = bool(with_occ)
         super().__init__([2, 3], input_size, max_pairs, device, **kw)
 
     # ---- handles -------------------------------------------------------------------------------------------------
@@ -43,7 +45,7 @@ class DepthOrderEngine(OrderEngine):
         self.enc = self._create_arch((synth.RESNEXT_WIDTHS, synth.RESNEXT_OUTS, synth.RESNEXT_BLOCKS), 3, True, None,
                                      self.max_images)
         self.do_net = self._create_arch(RESNET50, 4, False, [3], self.max_pairs)
-        self.oo_net = self._create_arch(RESNET50, 4, False, [2], self.max_pairs)
+        self.oo_net = self._create_arch(RESNET50, 4, False, [2], self.max_pairs) if self.with_occ else None
         self.inject_idx = torch.zeros(2 * self.max_pairs, dtype=torch.int32, device=self.device)
         feats = []
         for li in range(3):
@@ -51,6 +53,8 @@ class DepthOrderEngine(OrderEngine):
             _lib.check(self.lib.io_net_feature(self.enc, li, C.byref(ptr), C.byref(n)))
             feats.append(ptr)
         for net in (self.do_net, self.oo_net):
+            if net is None:
+                continue
             _lib.check(self.lib.io_net_set_inject(net, feats[0], feats[1], feats[2], self.inject_idx.data_ptr()))
         self.enc_pair_tensor = torch.zeros(self.lib.io_pair_tensor_bytes(self.max_images, self.d), dtype=torch.uint8,
                                            device=self.device)
@@ -117,7 +121,8 @@ class DepthOrderEngine(OrderEngine):
         rx = (synth.RESNEXT_WIDTHS, synth.RESNEXT_OUTS, synth.RESNEXT_BLOCKS)
         self._load_sub(self.enc, sd, "pretrained", 3, rx, synth.RESNEXT_GROUPS, 3, None)
         self._load_sub(self.do_net, sd, "do_net", 2, RESNET50, 1, 4, "depth_fc")
-        self._load_sub(self.oo_net, sd, "oo_net", 2, RESNET50, 1, 4, "occ_fc")
+        if self.oo_net is not None:
+            self._load_sub(self.oo_net, sd, "oo_net", 2, RESNET50, 1, 4, "occ_fc")
 
     # ---- per batch -----------------------------------------------------------------------------------------------
     def stage_batch(self, items, mode="resize"):
@@ -183,14 +188,17 @@ class DepthOrderEngine(OrderEngine):
         st = _lib.stream_ptr()
         _lib.check(self.lib.io_net_forward_pairs(self.enc, self.enc_pair_tensor.data_ptr(), self._n_img, None, st))
         _lib.check(self.lib.io_net_forward_pairs(self.do_net, self.pair_tensor.data_ptr(), P, self.logits_d.data_ptr(), st))
-        _lib.check(self.lib.io_net_forward_pairs(self.oo_net, self.pair_tensor.data_ptr(), P, self.logits_o.data_ptr(), st))
-        self.logits[:P, :, 0:2] = self.logits_o[:P]
+        if self.oo_net is not None:
+            _lib.check(self.lib.io_net_forward_pairs(self.oo_net, self.pair_tensor.data_ptr(), P, self.logits_o.data_ptr(), st))
+            self.logits[:P, :, 0:2] = self.logits_o[:P]
+        else:
+            self.logits[:P, :, 0:2] = 0      # no occlusion head: sigmoid(0) = 0.5 is never > 0.5, the matrix stays zero
         self.logits[:P, :, 2:5] = self.logits_d[:P]
-        self.gpu_launches += sum(self.lib.io_net_last_launches(h) for h in (self.enc, self.do_net, self.oo_net)) + 2
+        self.gpu_launches += sum(self.lib.io_net_last_launches(h) for h in (self.enc, self.do_net, self.oo_net) if h) + 2
 
     def infer_scenes(self, scenes, algo="InstaDepthNet_od", pairs="all", patch_or_image="resize", return_details=False):
-        if algo != "InstaDepthNet_od":
-            raise ValueError("DepthOrderEngine runs InstaDepthNet_od, got %r" % (algo,))
+        if algo not in ("InstaDepthNet_od", "InstaDepthNet_d"):
+            raise ValueError("DepthOrderEngine runs InstaDepthNet_od / _d, got %r" % (algo,))
         return super().infer_scenes(scenes, "InstaOrderNet_od", pairs, patch_or_image, return_details)
 
 

@@ -32,8 +32,13 @@ def infer_order_sup_occ(model, image, inmodal, bboxes, pairs, method, patch_or_i
 def infer_order_sup_depth(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size,
                           disp_select_method, use_rgb=True):
     """reference inference.py:515-624 -> (int [N,N] depth order matrix, disp_clipped=None)."""
+    if method in ("InstaDepthNet_d", "InstaDepthNet_od"):
+        if disp_select_method != "":     # reference :589-599: mean / median of the network's disparity inside the masks
+            raise NotImplementedError("disp_select_method=%r needs InstaDepthNet's disparity output, which is not "
+                                      "built (DESIGN.md section 4c)" % (disp_select_method,))
+        return _run(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size)["depth"], None
     if method != "InstaOrderNet_d":
-        if method in ("midas_pretrained", "InstaDepthNet_d", "InstaDepthNet_od"):
+        if method == "midas_pretrained":
             raise NotImplementedError("%s is outside the pairwise-order hot path (SURVEY.md section 8f)" % method)
         print("method name should be one of {InstaOrderNet_d or midas_pretrained}")   # reference :608-610
         return

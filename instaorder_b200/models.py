@@ -15,7 +15,7 @@ from . import _lib
 from .engine import OrderEngine
 from .training import FlatOptim, TrainEngine
 
-__all__ = ["InstaOrderNet_o", "InstaOrderNet_d", "InstaOrderNet_od", "OrderNet", "InstaDepthNet_od"]
+__all__ = ["InstaOrderNet_o", "InstaOrderNet_d", "InstaOrderNet_od", "OrderNet", "InstaDepthNet_od", "InstaDepthNet_d"]
 
 
 class _OrderModel(object):
@@ -323,6 +323,7 @@ class InstaDepthNet_od(object):
     used by ``inference.infer_order_sup_occ_depth(method="InstaDepthNet_od")``.  Inference of the two order matrices
     only: the disparity output and training raise ``NotImplementedError``."""
     algo = "InstaDepthNet_od"
+    with_occ = True
 
     def __init__(self, params, load_pretrain=None, dist_model=False):
         self.params = params
@@ -342,7 +343,7 @@ class InstaDepthNet_od(object):
         if e is None:
             if self._state is None:
                 raise RuntimeError("no weights loaded: call load_state()/load_state_dict() first")
-            e = DepthOrderEngine(input_size, self.max_pairs, self.max_images, self.device)
+            e = DepthOrderEngine(input_size, self.max_pairs, self.max_images, self.device, with_occ=self.with_occ)
             e.load_state_dict(self._state)
             self._engines[input_size] = e
         return e
@@ -368,3 +369,10 @@ class InstaDepthNet_od(object):
 
     def step(self):
         raise NotImplementedError("InstaDepthNet_od: inference of the order matrices only")
+
+
+class InstaDepthNet_d(InstaDepthNet_od):
+    """``models.InstaDepthNet_d`` (models/supervised_order.py:240-367 wrapping midas/midas_net.py:15-110): the same
+    network without ``oo_net`` -- depth order only (``inference.infer_order_sup_depth``)."""
+    algo = "InstaDepthNet_d"
+    with_occ = False

@@ -83,3 +83,19 @@ def test_batching_and_reference_api(setup, golden_dir):
     m.switch_to("eval")
     occ, depth = inference.infer_order_sup_occ_depth(m, image, masks, boxes, "all", "InstaDepthNet_od", "resize", G.D, "")
     assert np.array_equal(occ, b["occ"]) and np.array_equal(depth, b["depth"])
+
+
+def test_instadepthnet_d_depth_only(setup):
+    """InstaDepthNet^d = the same network without oo_net: ``infer_order_sup_depth`` returns the depth matrix of ^od
+    (same encoder / do_net weights) and no disparity (disp_select_method '')."""
+    z, sd, eng = setup
+    image, masks, boxes = G.build_scene()
+    ref = eng.infer_scenes([engine.Scene(image, masks, boxes)], "InstaDepthNet_od")[0]
+    sd_d = {k: v for k, v in sd.items() if not (k.startswith("module.oo_net") or k.startswith("module.occ_fc"))}
+    m = models.InstaDepthNet_d(dict(algo="InstaDepthNet_d", max_pairs=16, max_images=4))
+    m.load_state_dict(sd_d)
+    m.switch_to("eval")
+    depth, disp = inference.infer_order_sup_depth(m, image, masks, boxes, "all", "InstaDepthNet_d", "resize", G.D, "")
+    assert disp is None and np.array_equal(depth, ref["depth"])
+    with pytest.raises(NotImplementedError):
+        inference.infer_order_sup_depth(m, image, masks, boxes, "all", "InstaDepthNet_d", "resize", G.D, "median")
