@@ -91,6 +91,7 @@ struct TnParams {
   int ch;               // 128 or 64 output channels (MMA M)
   int mode, k_iters, kpt, taps_w, pad, cin;
   int tiles, tpi, bh, w_out, hw_out;
+  int px;               // pixels per tile = MMA N: 256, or 192 (two 96-wide / four 48-wide rows at 384^2)
   int ldc, n_split, split_row_off, relu;
   int img_mul;          // CONV_STEM: output image of pair n, direction 0 (2 = interleaved 2n + dir, 1 = [dir][pair])
 };

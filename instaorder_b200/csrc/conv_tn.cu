@@ -17,7 +17,7 @@ namespace io {
 
 namespace {
 constexpr int BK = 64;
-constexpr int PX = 256;                       // pixels per tile (MMA N)
+constexpr int PX = 256;                       // pixels per tile (MMA N) at most; 192 for the 96- / 48-wide rows of 384^2 inputs
 constexpr int X_STAGE_BYTES = PX * BK * 2;    // 32 KB
 constexpr int STAGES = 3;
 constexpr int REGION_BYTES = 32 * 128;        // 32 pixels x 64 channels bf16, 128B-swizzled
@@ -41,7 +41,7 @@ struct TileTn {
 __device__ __forceinline__ TileTn tile_tn(const TnParams& p, int t) {
   TileTn r;
   if (p.mode == CONV_GEMM) {
-    r.n_img = 0; r.h0 = 0; r.base_row = t * PX;
+    r.n_img = 0; r.h0 = 0; r.base_row = t * p.px;
   } else {
     r.n_img = t / p.tpi;
     r.h0 = (t - r.n_img * p.tpi) * p.bh;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(320, 1) conv_tn_kernel(const __grid_constant__
         int tap = 0, kb = 0;
         for (int ki = 0; ki < p.k_iters; ++ki) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], W_STAGE_BYTES + X_STAGE_BYTES);
+          mbar_expect_tx(&full[stage], W_STAGE_BYTES + p.px * BK * 2);
           uint8_t* dX = sX + stage * X_STAGE_BYTES;
           tma_load_2d(sW + stage * W_STAGE_BYTES, &p.map_w, &full[stage], ki * BK, 0);
           if (p.mode == CONV_GEMM) {
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(320, 1) conv_tn_kernel(const __grid_constant__
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(CH, PX);
+      const uint32_t idesc = umma_idesc_bf16(CH, p.px);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -179,6 +179,8 @@ __global__ void __launch_bounds__(320, 1) conv_tn_kernel(const __grid_constant__
     const float my_bias = sBias[(CH == 128) ? q * 32 + lane : q * 16 + (lane & 15)];
     uint8_t* my_slots = sEpi + pair * 4 * REGION_BYTES;
     const int chunk_off = ((cl >> 3) << 4), sub_off = (cl & 7) * 2;
+    const int half_px = p.px >> 1;        // pixels per epilogue half: 128, or 96
+    const int chunks = p.px >> 6;         // 32-pixel chunks per half: 4, or 3
     int it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
       const TileTn t = tile_tn(p, tile);
@@ -187,17 +189,19 @@ __global__ void __launch_bounds__(320, 1) conv_tn_kernel(const __grid_constant__
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int px0 = hsel * 128 + c * 32;
+      for (int c = 0; c < chunks; ++c) {
+        const int px0 = hsel * half_px + c * 32;
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PX + px0, v);
         tmem_ld_wait();
-        if (c == 3) {  // accumulator fully read by this warp
+        if (c == chunks - 1) {  // accumulator fully read by this warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        if (leader) tma_store_wait_read<3>();       // the store that last read this slot (previous tile) is done
+        if (leader) {                               // the store that last read this slot (previous tile) is done
+          if (chunks == 4) tma_store_wait_read<3>(); else tma_store_wait_read<2>();
+        }
         named_bar_sync(1 + pair, GROUP_THREADS);
         uint8_t* region = my_slots + c * REGION_BYTES;
         if (lane_on) {
@@ -267,14 +271,19 @@ bool tn_enabled() {
   return on;
 }
 
+// pixels per tile (MMA N): whole output rows, 256 if the geometry allows it, else 192 (96- and 48-wide rows)
+static int tn_tile_pixels(const ConvDesc& d) {
+  const int h_out = d.h / d.stride, w_out = d.w / d.stride;
+  for (int px : {256, 192})
+    if (w_out <= px && px % w_out == 0 && h_out % (px / w_out) == 0) return px;
+  return 0;
+}
+
 // true when the transposed kernel can run this convolution: 3x3 (stride 1 or 2) with 128 or 64 output channels
 // whose output is tiled by whole 256-pixel tiles of full rows
 bool conv_tn_supported(const ConvDesc& d) {
   if (d.kernel != 3 || (d.cout != 128 && d.cout != 64) || d.cin % 64 != 0) return false;
-  const int h_out = d.h / d.stride, w_out = d.w / d.stride;
-  if (w_out > PX || PX % w_out != 0) return false;
-  const int bh = PX / w_out;
-  return h_out % bh == 0;
+  return tn_tile_pixels(d) != 0;
 }
 
 int conv_tn_plan(TnParams* p, const ConvDesc& d, const void* x, const void* wgt, const float* bias, void* y, int relu) {
@@ -289,7 +298,8 @@ int conv_tn_plan(TnParams* p, const ConvDesc& d, const void* x, const void* wgt,
   p->taps_w = 3;
   p->pad = 1;
   p->cin = d.cin;
-  p->bh = PX / w_out;
+  p->px = tn_tile_pixels(d);
+  p->bh = p->px / w_out;
   p->tpi = h_out / p->bh;
   p->tiles = d.b * p->tpi;
   p->w_out = w_out;
@@ -344,6 +354,7 @@ int stem_tn_plan(TnParams* p, int pairs, int d, const void* x, const void* wgt, 
   p->taps_w = 7;
   p->pad = 3;
   p->cin = 8;
+  p->px = PX;
   p->bh = 2;
   p->tpi = h_out / 2;
   p->tiles = pairs * p->tpi;

@@ -30,6 +30,9 @@ CASES = [
     (2, 24, 24, 256, 256, 3, 1, False, True),    # 384^2 layer3: 5 rows x 24 per tile, partial last tile
     (2, 12, 12, 512, 512, 3, 1, False, True),    # 384^2 layer4: 10 rows x 12
     (2, 48, 48, 128, 128, 3, 2, False, True),    # 384^2 s2: 24 x 24 out
+    (3, 48, 48, 128, 128, 3, 1, False, True),    # 384^2 layer2 conv2: transposed kernel, 192-pixel tiles (4 rows x 48)
+    (3, 96, 96, 128, 128, 3, 2, False, True),    # 384^2 layer2.0 conv2: stride 2, 48-wide output rows, 192-pixel tiles
+    (1, 96, 96, 64, 64, 3, 1, False, False),     # 384^2 layer1 conv2: M = 64, 192-pixel tiles (2 rows x 96), no ReLU
 ]
 
 
