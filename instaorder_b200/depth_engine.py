@@ -42,6 +42,7 @@ class DepthOrderEngine(OrderEngine):
         return h
 
     def _create_nets(self):
+        self.max_items_per_batch = self.max_images      # the encoder handle is sized for this many images per batch
         self.enc = self._create_arch((synth.RESNEXT_WIDTHS, synth.RESNEXT_OUTS, synth.RESNEXT_BLOCKS), 3, True, None,
                                      self.max_images)
         self.do_net = self._create_arch(RESNET50, 4, False, [3], self.max_pairs)

@@ -128,6 +128,7 @@ class OrderEngine:
         self.mean = np.asarray(data_mean, dtype=np.float32)
         self.std = np.asarray(data_std, dtype=np.float32)
         self.net = None
+        self.max_items_per_batch = 1 << 30    # images (or image parts) per batch; the InstaDepthNet engine caps it
         self._create_nets()
         self.pair_tensor = torch.zeros(self.lib.io_pair_tensor_bytes(self.max_pairs, self.d), dtype=torch.uint8,
                                        device=self.device)
@@ -354,7 +355,7 @@ class OrderEngine:
             o = 0
             while o < pr.shape[0]:
                 take = min(pr.shape[0] - o, cap - count)
-                if take == 0:
+                if take == 0 or len(batch) >= self.max_items_per_batch:
                     flush()
                     cap = self.max_pairs
                     continue

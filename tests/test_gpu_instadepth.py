@@ -83,6 +83,16 @@ def test_batching_and_reference_api(setup, golden_dir):
     m.switch_to("eval")
     occ, depth = inference.infer_order_sup_occ_depth(m, image, masks, boxes, "all", "InstaDepthNet_od", "resize", G.D, "")
     assert np.array_equal(occ, b["occ"]) and np.array_equal(depth, b["depth"])
+    # more images than the encoder handle holds (max_images = 4): batches are cut by image count, results unchanged;
+    # images without pairs (one instance) give 1 x 1 zero matrices
+    small = [engine.Scene(img2, masks2[k:k + 2], boxes2[k:k + 2]) for k in (0, 1)] * 3 + \
+            [engine.Scene(img2, masks2[:1], boxes2[:1])]
+    many = eng.infer_scenes(small, "InstaDepthNet_od")
+    for k in (0, 1):
+        alone = eng.infer_scenes([small[k]], "InstaDepthNet_od")[0]
+        for rep in (k, k + 2, k + 4):
+            assert np.array_equal(many[rep]["occ"], alone["occ"]) and np.array_equal(many[rep]["depth"], alone["depth"])
+    assert many[6]["occ"].shape == (1, 1) and many[6]["occ"][0, 0] == 0
 
 
 def test_instadepthnet_d_depth_only(setup):
