@@ -207,10 +207,12 @@ def bottleneck_layout(in_channels, widths, outs, blocks, groups, n_layers=4):
     return out
 
 
-def instadepth_state_dict(seed, prefix="module."):
+def instadepth_state_dict(seed, prefix="module.", with_decoder=False):
     """Random weights for the order branch of InstaDepthNet^od, keyed like the reference model's ``state_dict``
     (numpy fp32).  Same recipe as ``random_state_dict`` (kaiming fan_out convolutions, BN drawn to keep an O(1)
-    scale); the parity tests calibrate BN statistics and heads on top (oracle/instadepth_oracle.py)."""
+    scale); the parity tests calibrate BN statistics and heads on top (oracle/instadepth_oracle.py).
+    ``with_decoder``: also the tensors of the disparity branch (encoder layer4, ``scratch.*``), drawn AFTER the
+    order-branch tensors so that those do not depend on the flag."""
     rng = np.random.RandomState(seed)
     sd = {}
     subs = (("pretrained", 3, RESNEXT_WIDTHS, RESNEXT_OUTS, RESNEXT_BLOCKS, RESNEXT_GROUPS, 3),
@@ -236,4 +238,34 @@ def instadepth_state_dict(seed, prefix="module."):
     for head, k in (("depth_fc", 3), ("occ_fc", 2)):
         sd[prefix + head + ".weight"] = (rng.standard_normal((k, 2048)) * 0.05).astype(np.float32)
         sd[prefix + head + ".bias"] = (rng.standard_normal(k) * 0.1).astype(np.float32)
+    if with_decoder:
+        def draw(key, shape, groups=1):
+            leaf = key.rsplit(".", 1)[1]
+            if len(shape) == 4:
+                fan_out = shape[0] * shape[2] * shape[3] // groups
+                return rng.standard_normal(shape).astype(np.float32) * np.float32(np.sqrt(2.0 / fan_out))
+            if leaf == "running_mean":
+                return (rng.standard_normal(shape) * 0.1).astype(np.float32)
+            if leaf == "running_var":
+                return rng.uniform(0.8, 1.2, size=shape).astype(np.float32)
+            if leaf == "weight":
+                return rng.uniform(0.2, 0.4, size=shape).astype(np.float32) if ".bn3." in key \
+                    else rng.uniform(0.8, 1.2, size=shape).astype(np.float32)
+            return (rng.standard_normal(shape) * 0.05).astype(np.float32)
+        full = bottleneck_layout(3, RESNEXT_WIDTHS, RESNEXT_OUTS, RESNEXT_BLOCKS, RESNEXT_GROUPS, 4)
+        for key, shape in full:
+            if key.startswith("layer4."):
+                g = RESNEXT_GROUPS if (len(shape) == 4 and shape[2] == 3) else 1
+                sd[prefix + "pretrained." + key] = draw(key, shape, g)
+        for k, c in enumerate(RESNEXT_OUTS, start=1):
+            sd[prefix + "scratch.layer%d_rn.weight" % k] = draw("w.weight", (256, c, 3, 3)) * np.float32(0.5)
+        for k in (4, 3, 2, 1):
+            for u in (1, 2):
+                for c in (1, 2):
+                    p = "scratch.refinenet%d.resConfUnit%d.conv%d" % (k, u, c)
+                    sd[prefix + p + ".weight"] = draw("w.weight", (256, 256, 3, 3)) * np.float32(0.5)
+                    sd[prefix + p + ".bias"] = (rng.standard_normal(256) * 0.05).astype(np.float32)
+        for name, shape in (("0", (128, 256, 3, 3)), ("2", (32, 128, 3, 3)), ("4", (1, 32, 1, 1))):
+            sd[prefix + "scratch.output_conv.%s.weight" % name] = draw("w.weight", shape)
+            sd[prefix + "scratch.output_conv.%s.bias" % name] = (np.abs(rng.standard_normal(shape[0])) * 0.1).astype(np.float32)
     return sd

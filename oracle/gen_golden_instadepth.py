@@ -83,5 +83,40 @@ def main():
                                                         np.abs(out["occ"].reshape(P, 2, 2) - ol).max()))
 
 
+def disp_digest(disp):
+    """Small fingerprint of a [384, 384] disparity map: 4x4 block means + three full rows."""
+    d = np.asarray(disp, dtype=np.float64).reshape(D // 4, 4, D // 4, 4).mean(axis=(1, 3)).astype(np.float32)
+    return d, np.asarray(disp, dtype=np.float32)[[0, D // 2 - 1, D - 1]]
+
+
+def main_disp():
+    """tests/golden/instadepth_disp.npz: the reference's disparity output on the fixture image, with the decoder /
+    encoder-layer4 tensors of ``synth.instadepth_state_dict(with_decoder=True)`` loaded as well."""
+    import torch
+    import torchvision
+    torch.hub.load = lambda *a, **k: torchvision.models.resnext101_32x8d(weights=None)
+    ref_shim.load()
+    midas_net = sys.modules["_instaorder_ref.midas.midas_net"]
+    sd = IO.load_calibrated(os.path.join(GOLDEN, "instadepth_calib.npz"), SEED, with_decoder=True)
+    net = midas_net.InstaDepthNet_od(path=None)
+    missing, unexpected = net.load_state_dict({k[7:]: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
+    assert not unexpected and all(("fc." in k) or ("num_batches_tracked" in k) for k in missing), missing[:5]
+    net.eval()
+    from oracle import oracle as O
+    image, _, _ = build_scene()
+    rgb = O.resize_mode_rgb(image, D)[None]
+    zero = torch.zeros(1, 1, D, D)
+    with torch.no_grad():
+        disp = net(torch.from_numpy(rgb), zero, zero)[0][0].numpy()
+    pooled, rows = disp_digest(disp)
+    np.savez_compressed(os.path.join(GOLDEN, "instadepth_disp.npz"), pooled=pooled, rows=rows,
+                        stats=np.asarray([disp.min(), disp.max(), disp.mean(), disp.std()], np.float64))
+    mine = IO.disparity_forward(sd, rgb)[0]
+    print("disparity: range [%.3f, %.3f], oracle vs reference %.2e" % (disp.min(), disp.max(), np.abs(mine - disp).max()))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "disp":
+        main_disp()
+    else:
+        main()

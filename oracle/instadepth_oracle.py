@@ -2,9 +2,10 @@
 (``midas/midas_net.py:113-212``; BASELINE config 5): the ResNeXt-101 32x8d encoder's
 layer1..3 (``pretrained.layer1-3``, :186-188), the two 2-channel ResNet-50 trunks ``do_net`` / ``oo_net`` with the
 encoder features added in front of their layer2 / layer3 / layer4 (:200-210) and the heads ``depth_fc`` / ``occ_fc``.
-The disparity output (encoder layer4, ``scratch.*`` = the MiDaS decoder, :189-198) is not restated: the order
-matrices of ``infer_order_sup_occ_depth(method="InstaDepthNet_od")`` (``inference.py:349-436, 107-137``) do not
-depend on it.
+The order matrices of ``infer_order_sup_occ_depth(method="InstaDepthNet_od")`` (``inference.py:349-436, 107-137``)
+do not depend on the disparity output; ``disparity_forward`` restates that branch too (encoder layer4, ``scratch.*`` =
+the MiDaS decoder, :189-198, ``midas/blocks.py:124-195``) -- groundwork for the CUDA path of the disparity map, which
+is not built yet.
 
 Pinned against the unmodified reference: ``oracle/gen_golden_instadepth.py`` builds the reference module (torch.hub
 patched to torchvision's architecture-identical ``resnext101_32x8d``, SURVEY.md 8c shim 6), loads the synthetic
@@ -99,6 +100,45 @@ def order_forward(sd, rgb, m1, m2, img_index=None, prefix="module.", bn_override
         return out
 
 
+def disparity_forward(sd, rgb, prefix="module."):
+    """``InstaDepthNet_od.forward(...)[0]`` (midas_net.py:186-198): rgb [I,3,H,W] -> disparity [I,H,W] fp32.
+    Notes on the reference's arithmetic: ``ResidualConvUnit`` uses an in-place ReLU on its input, so its skip adds
+    ``relu(x)``, not ``x`` (blocks.py:146-161); the fusion blocks up-sample with ``align_corners=True`` (:191-193) but
+    ``output_conv``'s ``Interpolate`` with ``align_corners=False`` (:117-119)."""
+    import torch
+    import torch.nn.functional as F
+    t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a, dtype=np.float32))
+    g = lambda k: t(sd[prefix + k])
+    with torch.no_grad():
+        enc = _trunk(sd, prefix, "pretrained", t(rgb), synth.RESNEXT_BLOCKS, synth.RESNEXT_GROUPS, 4, None, None,
+                     lambda a: a, False)
+        rn = [F.conv2d(e, g("scratch.layer%d_rn.weight" % (k + 1)), padding=1) for k, e in enumerate(enc)]
+
+        def rcu(x, p):
+            x = F.relu(x)
+            o = F.conv2d(x, g(p + ".conv1.weight"), g(p + ".conv1.bias"), padding=1)
+            o = F.conv2d(F.relu(o), g(p + ".conv2.weight"), g(p + ".conv2.bias"), padding=1)
+            return o + x
+
+        def fuse(k, *xs):
+            p = "scratch.refinenet%d" % k
+            out = xs[0]
+            if len(xs) == 2:
+                out = out + rcu(xs[1], p + ".resConfUnit1")
+            out = rcu(out, p + ".resConfUnit2")
+            return F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
+
+        path = fuse(4, rn[3])
+        path = fuse(3, path, rn[2])
+        path = fuse(2, path, rn[1])
+        path = fuse(1, path, rn[0])
+        o = F.conv2d(path, g("scratch.output_conv.0.weight"), g("scratch.output_conv.0.bias"), padding=1)
+        o = F.interpolate(o, scale_factor=2, mode="bilinear", align_corners=False)
+        o = F.relu(F.conv2d(o, g("scratch.output_conv.2.weight"), g("scratch.output_conv.2.bias"), padding=1))
+        o = F.relu(F.conv2d(o, g("scratch.output_conv.4.weight"), g("scratch.output_conv.4.bias")))
+        return torch.squeeze(o, dim=1).numpy()
+
+
 # ---- calibrated synthetic checkpoint (same idea as oracle/calib.py) -----------------------------------------------
 def calib_inputs(seed=321, n_scenes=4, D=384):
     from oracle import oracle as O
@@ -154,8 +194,8 @@ def calibrate(sd, prefix="module.", logit_std=0.5, seed=321, D=384):
     return changed
 
 
-def load_calibrated(npz_path, seed, prefix="module."):
-    sd = synth.instadepth_state_dict(seed, prefix)
+def load_calibrated(npz_path, seed, prefix="module.", with_decoder=False):
+    sd = synth.instadepth_state_dict(seed, prefix, with_decoder)
     with np.load(npz_path) as z:
         for k in z.files:
             assert k in sd and sd[k].shape == z[k].shape, k

@@ -43,3 +43,17 @@ def test_oracle_matches_reference_fixture(golden_dir):
     occ, depth = matrices_from_logits(dl, ol, G.N_INST)
     assert np.array_equal(occ, z["occ"]) and np.array_equal(depth, z["depth"])
     assert z["depth_logits"].std() > 0.05 and z["occ_logits"].std() > 0.05      # not the all-tie random init
+
+
+def test_disparity_oracle_matches_reference_fixture(golden_dir):
+    """The disparity branch (encoder layer4 + MiDaS decoder) of the restatement against the reference's output frozen
+    in instadepth_disp.npz -- groundwork: the CUDA path does not compute the disparity yet."""
+    z = np.load(os.path.join(golden_dir, "instadepth_disp.npz"))
+    sd = IO.load_calibrated(os.path.join(golden_dir, "instadepth_calib.npz"), G.SEED, with_decoder=True)
+    image, _, _ = G.build_scene()
+    disp = IO.disparity_forward(sd, O.resize_mode_rgb(image, G.D)[None])[0]
+    pooled, rows = G.disp_digest(disp)
+    scale = float(z["stats"][1] - z["stats"][0])
+    assert np.abs(pooled - z["pooled"]).max() < 1e-4 * scale
+    assert np.abs(rows - z["rows"]).max() < 1e-4 * scale
+    assert disp.min() >= 0.0 and z["stats"][3] > 0.1        # non_negative=True output with real structure
