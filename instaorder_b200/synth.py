@@ -266,6 +266,9 @@ def instadepth_state_dict(seed, prefix="module.", with_decoder=False):
                     sd[prefix + p + ".weight"] = draw("w.weight", (256, 256, 3, 3)) * np.float32(0.5)
                     sd[prefix + p + ".bias"] = (rng.standard_normal(256) * 0.05).astype(np.float32)
         for name, shape in (("0", (128, 256, 3, 3)), ("2", (32, 128, 3, 3)), ("4", (1, 32, 1, 1))):
-            sd[prefix + "scratch.output_conv.%s.weight" % name] = draw("w.weight", shape)
+            w = draw("w.weight", shape)
+            # the last 1x1 convolution reads post-ReLU features: positive weights keep the (non-negative) disparity
+            # away from an all-zero map
+            sd[prefix + "scratch.output_conv.%s.weight" % name] = np.abs(w) if name == "4" else w
             sd[prefix + "scratch.output_conv.%s.bias" % name] = (np.abs(rng.standard_normal(shape[0])) * 0.1).astype(np.float32)
     return sd
