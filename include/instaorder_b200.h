@@ -208,9 +208,18 @@ IO_API int io_rle_from_polygon(const double* xy, int k, int h, int w, uint32_t* 
 IO_API int io_masks_from_rle(const uint32_t* cum_dev, const int32_t* comp_off_dev, const int32_t* inst_off_dev, int n_inst,
                       int h, int w, uint8_t* out_dev, void* stream);
 
+/* ---- element-wise pieces of InstaDepthNet's MiDaS decoder (reference midas/blocks.py:124-195, midas_net.py:126-140;
+ * its 3x3 convolutions go through io_conv_bn_act) ------------------------------------------------------------------
+ * out = a + b (ReLU'd if relu != 0) over n bf16 elements, n % 8 == 0 (ResidualConvUnit's in-place ReLU makes every
+ * consumer of a sum read relu(sum)). */
+IO_API int io_add_relu(const void* a_dev, const void* b_dev, void* out_dev, int64_t n, int relu, void* stream);
+/* nn.functional.interpolate(scale_factor=2, mode="bilinear", align_corners=...) on NHWC bf16 [b,h,w,c] -> [b,2h,2w,c]. */
+IO_API int io_upsample2x_bilinear(const void* x_dev, int b, int h, int w, int c, int align_corners, void* y_dev, void* stream);
+
 /* Single convolution + folded BN (+ residual) (+ ReLU) on NHWC bf16, the building block of io_net_forward_pairs,
  * exported for the per-layer parity tests.  w_dev: [Cout][kh*kw*Cin] bf16 (tap-major, channel-minor);
- * kernel 1 or 3, stride 1 or 2, padding = kernel / 2; Cin, Cout multiples of 64. */
+ * kernel 1 or 3, stride 1 or 2, padding = kernel / 2; Cin, Cout multiples of 64; output rows wider than 128 pixels
+ * (MiDaS decoder: 192, 384) are supported for 3x3 stride 1. */
 IO_API int io_conv_bn_act(const void* x_dev, int b, int h, int w, int cin, const void* w_dev, const float* bias_dev,
                    const void* residual_dev, int cout, int kernel, int stride, int relu, void* y_dev, void* stream);
 

@@ -61,6 +61,8 @@ _SIGS = {
     "io_rle_from_string": (_i, [C.c_char_p, _i64, _vp, _i, _vp]),
     "io_rle_from_polygon": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "io_masks_from_rle": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "io_add_relu": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "io_upsample2x_bilinear": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "io_conv_bn_act": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "io_conv_dual": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "io_conv_fused_dual": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),

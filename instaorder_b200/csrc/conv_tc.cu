@@ -61,6 +61,10 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int m_tile)
       t.h0 = l / p.tpr;
       t.w0 = (l - t.h0 * p.tpr) * BM;
       t.limit = min(p.rows_per_tile, p.w_out - t.w0);
+    } else if (p.tpr > 1) {   // 3x3 stride 1 on rows wider than one tile: `tpr` tiles of rows_per_tile pixels per row
+      t.h0 = l / p.tpr;
+      t.w0 = (l - t.h0 * p.tpr) * p.rows_per_tile;
+      t.limit = min(p.rows_per_tile, p.w_out - t.w0);
     } else {
       t.h0 = l * p.bh;
       t.w0 = 0;
@@ -151,8 +155,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
               for (int b = 0; b < p.kpt; ++b) tma_prefetch_2d(&p.map_a, b * BK, nx.base_row);
             } else if (p.mode == CONV_S1) {
               for (int b = 0; b < p.kpt; ++b) {
-                tma_prefetch_4d(&p.map_a, b * BK, 0, nx.h0 - 1, nx.n_img);   // taps r = 0 and r = 2 cover every
-                tma_prefetch_4d(&p.map_a, b * BK, 0, nx.h0 + 1, nx.n_img);   // input row the tile needs
+                tma_prefetch_4d(&p.map_a, b * BK, nx.w0, nx.h0 - 1, nx.n_img);   // taps r = 0 and r = 2 cover every
+                tma_prefetch_4d(&p.map_a, b * BK, nx.w0, nx.h0 + 1, nx.n_img);   // input row the tile needs
               }
             } else if (p.mode == CONV_STEM) {
               for (int r = 0; r < 7; ++r) tma_prefetch_4d(&p.map_a, 0, nx.w0, 2 * nx.h0 + r, nx.n_img);
@@ -171,8 +175,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
             tma_load_2d(dA, &p.map_a, &full[stage], kb * BK, t.base_row);
           } else if (p.mode == CONV_S1) {
             const int r = tap / 3, s = tap - r * 3;
-            if (p.flip) tma_load_4d(dA, &p.map_a, &full[stage], kb * BK, 1 - s, t.h0 + 1 - r, t.n_img);
-            else tma_load_4d(dA, &p.map_a, &full[stage], kb * BK, s - 1, t.h0 + r - 1, t.n_img);
+            if (p.flip) tma_load_4d(dA, &p.map_a, &full[stage], kb * BK, t.w0 + 1 - s, t.h0 + 1 - r, t.n_img);
+            else tma_load_4d(dA, &p.map_a, &full[stage], kb * BK, t.w0 + s - 1, t.h0 + r - 1, t.n_img);
           } else if (p.mode == CONV_S2) {
             const int r = tap / p.taps_w, s = tap - r * p.taps_w;
             const int dr = r - p.pad, ds = s - p.pad;
@@ -534,8 +538,17 @@ int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, con
     const uint32_t box[2] = {64, BM};
     rc = make_tmap_bf16(&p->map_a, x, 2, dims, str, box, true);
   } else {
-    IO_REQUIRE(w_out <= BM, "conv: output width %d > %d not supported by the spatial tiler", w_out, BM);
-    if (p->hw_out <= BM) {
+    IO_REQUIRE(w_out <= BM || (d.stride == 1 && d.kernel == 3), "conv: output width %d > %d needs a 3x3 stride-1 convolution",
+               w_out, BM);
+    if (w_out > BM) {
+      // wide rows (MiDaS decoder, 192 / 384 pixels): tpr equal tiles per row, one image row at a time
+      p->tpr = (w_out + BM - 1) / BM;
+      while (w_out % p->tpr != 0) ++p->tpr;
+      p->bh = 1;
+      p->bi = 1;
+      p->tpg = h_out * p->tpr;
+      p->m_tiles = d.b * p->tpg;
+    } else if (p->hw_out <= BM) {
       p->bh = h_out;
       p->bi = BM / p->hw_out;
       p->tpg = 1;
@@ -546,14 +559,14 @@ int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, con
       p->tpg = (h_out + p->bh - 1) / p->bh;
       p->m_tiles = d.b * p->tpg;
     }
-    p->rows_per_tile = p->bi * p->bh * w_out;
+    p->rows_per_tile = p->tpr > 1 ? w_out / p->tpr : p->bi * p->bh * w_out;
     const uint64_t C = d.cin, W = d.w, H = d.h, B = d.b;
     if (d.stride == 1) {
       p->mode = CONV_S1;
       const uint64_t dims[4] = {C, W, H, B};
       const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
-      const uint32_t box[4] = {64, static_cast<uint32_t>(w_out), static_cast<uint32_t>(p->bh),
-                               static_cast<uint32_t>(p->bi)};
+      const uint32_t box[4] = {64, static_cast<uint32_t>(p->tpr > 1 ? p->rows_per_tile : w_out),
+                               static_cast<uint32_t>(p->bh), static_cast<uint32_t>(p->bi)};
       rc = make_tmap_bf16(&p->map_a, x, 4, dims, str, box, true);
     } else {
       p->mode = CONV_S2;

@@ -335,7 +335,7 @@ static int build_plan_b(io_net* net, int pb, Plan* plan) {
   // the first block reads `big` (kept intact) and writes bufb[0]; afterwards bufb[0] / bufb[1] ping-pong
   int rc = build_blocks(net, plan, 2, net->n_layers, b, &h, &w, net->big, net->bufb[0], net->bufb[1], net->bufb[2],
                         net->bufb[3], net->bufb[4], net->keep_layers ? net->keep[net->n_layers - 1] : nullptr, &out,
-                        nullptr, net->cross_fuse, -1, 0);
+                        nullptr, net->cross_fuse, net->keep_layers ? 0 : -1, 0);
   plan->feat = out;
   plan->hw_final = h * w;
   return rc;

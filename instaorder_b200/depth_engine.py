@@ -25,10 +25,14 @@ def _i32(v):
 
 
 class DepthOrderEngine(OrderEngine):
-    def __init__(self, input_size=384, max_pairs=64, max_images=16, device="cuda:0", with_occ=True, **kw):
-        """``with_occ=False``: InstaDepthNet^d (midas_net.py:15-110) -- no ``oo_net``, depth order only."""
+    def __init__(self, input_size=384, max_pairs=64, max_images=16, device="cuda:0", with_occ=True,
+                 with_disparity=False, **kw):
+        """``with_occ=False``: InstaDepthNet^d (midas_net.py:15-110) -- no ``oo_net``, depth order only.
+        ``with_disparity=True``: the encoder also runs layer4 and ``disparity()`` evaluates the MiDaS decoder."""
         self.max_images = int(max_images)
         self.with_occ = bool(with_occ)
+        self.with_disparity = bool(with_disparity)
+        self._dec = None
         super().__init__([2, 3], input_size, max_pairs, device, **kw)
 
     # ---- handles -------------------------------------------------------------------------------------------------
@@ -43,16 +47,18 @@ class DepthOrderEngine(OrderEngine):
 
     def _create_nets(self):
         self.max_items_per_batch = self.max_images      # the encoder handle is sized for this many images per batch
-        self.enc = self._create_arch((synth.RESNEXT_WIDTHS, synth.RESNEXT_OUTS, synth.RESNEXT_BLOCKS), 3, True, None,
-                                     self.max_images)
+        self.enc_layers = 4 if self.with_disparity else 3
+        self.enc = self._create_arch((synth.RESNEXT_WIDTHS, synth.RESNEXT_OUTS, synth.RESNEXT_BLOCKS), self.enc_layers,
+                                     True, None, self.max_images)
         self.do_net = self._create_arch(RESNET50, 4, False, [3], self.max_pairs)
         self.oo_net = self._create_arch(RESNET50, 4, False, [2], self.max_pairs) if self.with_occ else None
         self.inject_idx = torch.zeros(2 * self.max_pairs, dtype=torch.int32, device=self.device)
         feats = []
-        for li in range(3):
+        for li in range(self.enc_layers):
             ptr, n = C.c_void_p(), C.c_int64()
             _lib.check(self.lib.io_net_feature(self.enc, li, C.byref(ptr), C.byref(n)))
             feats.append(ptr)
+        self._enc_feats = feats
         for net in (self.do_net, self.oo_net):
             if net is None:
                 continue
@@ -120,7 +126,9 @@ class DepthOrderEngine(OrderEngine):
         ``occ_fc.*``; ``module.`` prefix optional; ``scratch.*`` / ``pretrained.layer4.*`` are ignored)."""
         sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
         rx = (synth.RESNEXT_WIDTHS, synth.RESNEXT_OUTS, synth.RESNEXT_BLOCKS)
-        self._load_sub(self.enc, sd, "pretrained", 3, rx, synth.RESNEXT_GROUPS, 3, None)
+        self._load_sub(self.enc, sd, "pretrained", 3, rx, synth.RESNEXT_GROUPS, self.enc_layers, None)
+        if self.with_disparity:
+            self._load_decoder(sd)
         self._load_sub(self.do_net, sd, "do_net", 2, RESNET50, 1, 4, "depth_fc")
         if self.oo_net is not None:
             self._load_sub(self.oo_net, sd, "oo_net", 2, RESNET50, 1, 4, "occ_fc")
@@ -219,3 +227,103 @@ def encoder_flops_per_image(d=384):
                 total += 2.0 * so * so * inpl * o                                    # downsample
             inpl, side = o, so
     return total
+
+
+# ---- disparity branch (reference midas_net.py:189-198, midas/blocks.py:124-195) --------------------------------
+def _pack_conv(w, cin_pad=None, cout_pad=None):
+    """[cout, cin, k, k] fp32 -> bf16 [cout'][k*k*cin'] (tap-major, channel-minor), zero-padded channels."""
+    w = np.asarray(w, dtype=np.float32)
+    co, ci, k, _ = w.shape
+    cip, cop = cin_pad or ci, cout_pad or co
+    full = np.zeros((cop, k, k, cip), np.float32)
+    full[:co, :, :, :ci] = w.transpose(0, 2, 3, 1)
+    return torch.from_numpy(full.reshape(cop, k * k * cip)).to(torch.bfloat16)
+
+
+def _load_decoder(self, sd):
+    dev = self.device
+    g = lambda k: (sd[k].detach().cpu().numpy() if hasattr(sd[k], "detach") else np.asarray(sd[k]))
+    dec = {}
+
+    def put(name, wkey, bkey=None, cin_pad=None, cout_pad=None):
+        w = _pack_conv(g(wkey), cin_pad, cout_pad).to(dev).contiguous()
+        b = np.zeros(w.shape[0], np.float32)
+        if bkey is not None:
+            bb = g(bkey)
+            b[:bb.size] = bb
+        dec[name] = (w, torch.from_numpy(b).to(dev))
+
+    for k in range(1, 5):
+        put("rn%d" % k, "scratch.layer%d_rn.weight" % k)
+        for u in (1, 2):
+            for c in (1, 2):
+                p = "scratch.refinenet%d.resConfUnit%d.conv%d" % (k, u, c)
+                put("r%du%dc%d" % (k, u, c), p + ".weight", p + ".bias")
+    put("oc0", "scratch.output_conv.0.weight", "scratch.output_conv.0.bias")
+    put("oc2", "scratch.output_conv.2.weight", "scratch.output_conv.2.bias", cout_pad=64)      # 32 -> 64 output channels
+    put("oc4", "scratch.output_conv.4.weight", "scratch.output_conv.4.bias", cin_pad=64, cout_pad=64)
+    self._dec = dec
+
+
+def _disparity_current(self):
+    """Disparity maps [n_img, D, D] fp32 (CUDA) of the images of the batch the encoder has just processed."""
+    if self._dec is None:
+        raise RuntimeError("create the engine with with_disparity=True and load a state_dict with scratch.* tensors")
+    n, d, dev, st = self._n_img, self.d, self.device, _lib.stream_ptr()
+    bf = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)
+
+    def conv(x_ptr, h, cin, name, cout, k=3, relu=0, res=None):
+        w, b = self._dec[name]
+        y = bf(n, h, h, cout)
+        _lib.check(self.lib.io_conv_bn_act(x_ptr, n, h, h, cin, w.data_ptr(), b.data_ptr(),
+                                           res.data_ptr() if res is not None else None, cout, k, 1, relu, y.data_ptr(), st))
+        self.gpu_launches += 1
+        return y
+
+    def rcu(xp, h, pfx):            # xp = relu(x): blocks.py:146-161 with its in-place ReLU
+        t = conv(xp.data_ptr(), h, 256, pfx + "c1", 256, relu=1)
+        return conv(t.data_ptr(), h, 256, pfx + "c2", 256, relu=0, res=xp)
+
+    def up(x, h, c, align):
+        y = bf(n, 2 * h, 2 * h, c)
+        _lib.check(self.lib.io_upsample2x_bilinear(x.data_ptr(), n, h, h, c, align, y.data_ptr(), st))
+        self.gpu_launches += 1
+        return y
+
+    sizes = [d // 4, d // 8, d // 16, d // 32]
+    chans = synth.RESNEXT_OUTS
+    rn = [conv(self._enc_feats[k], sizes[k], chans[k], "rn%d" % (k + 1), 256, relu=1) for k in range(4)]   # relu(layer_k_rn)
+    path = up(rcu(rn[3], sizes[3], "r4u2"), sizes[3], 256, 1)                                             # refinenet4
+    for k in (3, 2, 1):
+        h = sizes[k - 1]
+        r1 = rcu(rn[k - 1], h, "r%du1" % k)
+        o = bf(n, h, h, 256)
+        _lib.check(self.lib.io_add_relu(path.data_ptr(), r1.data_ptr(), o.data_ptr(), o.numel(), 1, st))
+        self.gpu_launches += 1
+        path = up(rcu(o, h, "r%du2" % k), h, 256, 1)
+    o = conv(path.data_ptr(), d // 2, 256, "oc0", 128)                     # output_conv.0 (192^2 at D = 384)
+    o = up(o, d // 2, 128, 0)                                              # Interpolate(align_corners=False)
+    o = conv(o.data_ptr(), d, 128, "oc2", 64, relu=1)                      # output_conv.2 + ReLU (32 real channels)
+    o = conv(o.data_ptr(), d, 64, "oc4", 64, k=1, relu=1)                  # output_conv.4 + ReLU (1 real channel)
+    return o[..., 0].float()
+
+
+def _disparity(self, scenes):
+    """``InstaDepthNet_od.forward(image, ...)[0]`` for a list of scenes / images -> numpy [len, D, D] fp32."""
+    out = []
+    for i in range(0, len(scenes), self.max_images):
+        chunk = scenes[i:i + self.max_images]
+        items = [(sc, np.zeros((0, 2), np.int32), None, 0, k) for k, sc in enumerate(chunk)]
+        s, P = self.stage_batch(items, "resize")
+        self.gather(s, 0, "resize")
+        _lib.check(self.lib.io_net_forward_pairs(self.enc, self.enc_pair_tensor.data_ptr(), self._n_img, None,
+                                                 _lib.stream_ptr()))
+        self.gpu_launches += self.lib.io_net_last_launches(self.enc)
+        out.append(self._disparity_current().cpu().numpy())
+        self.finish(s)
+    return np.concatenate(out) if out else np.zeros((0, self.d, self.d), np.float32)
+
+
+DepthOrderEngine._load_decoder = _load_decoder
+DepthOrderEngine._disparity_current = _disparity_current
+DepthOrderEngine.disparity = _disparity

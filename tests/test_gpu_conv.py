@@ -170,3 +170,49 @@ def test_conv_fused_dual(case):
         err = (got - want).abs()
         tol = 1.5e-2 + 1e-2 * want.abs()
         assert not (err > tol).any(), "%s: max err %.4g, %d bad" % (name, float(err.max()), int((err > tol).sum()))
+
+
+@pytest.mark.parametrize("case", [(1, 192, 192, 256, 128, True), (2, 384, 384, 128, 64, True), (1, 384, 384, 64, 64, False),
+                                  (2, 192, 192, 64, 256, True)],
+                         ids=lambda c: "B%d_%dx%d_%d-%d_%s" % (c[0], c[1], c[2], c[3], c[4], "res" if c[5] else "nores"))
+def test_conv_wide_rows(case):
+    """3x3 stride-1 convolutions on rows wider than one 128-pixel tile (MiDaS decoder: 192 and 384 pixels): several
+    tiles per row, halo columns from the neighbouring tile, zero padding only at the image border."""
+    B, H, W, Cin, Cout, use_res = case
+    g = torch.Generator(device="cuda").manual_seed(H + Cin + Cout)
+    dev = "cuda"
+    x = torch.randn((B, H, W, Cin), generator=g, device=dev).to(torch.bfloat16).contiguous()
+    w = (torch.randn((Cout, Cin, 3, 3), generator=g, device=dev) / (Cin * 9) ** 0.5).to(torch.bfloat16).float()
+    bias = torch.randn((Cout,), generator=g, device=dev)
+    res = torch.randn((B, H, W, Cout), generator=g, device=dev).to(torch.bfloat16).contiguous() if use_res else None
+    y = torch.full((B, H, W, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().io_conv_bn_act(x.data_ptr(), B, H, W, Cin, U.pack_weight(w).data_ptr(), bias.data_ptr(),
+                                         res.data_ptr() if use_res else None, Cout, 3, 1, 1, y.data_ptr(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = U.conv_reference(x, w, None, bias, res, 1, True)
+    got = y.float()
+    assert torch.isfinite(got).all(), "unwritten outputs: %d" % int((~torch.isfinite(got)).sum())
+    err = (got - ref).abs()
+    assert not (err > 1e-2 + 1e-2 * ref.abs()).any(), "max err %.4g" % float(err.max())
+
+
+def test_decoder_elementwise_kernels():
+    """io_add_relu and io_upsample2x_bilinear (both align_corners modes) against torch."""
+    import torch.nn.functional as F
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn((2, 24, 24, 64), generator=g, device="cuda").to(torch.bfloat16)
+    b = torch.randn((2, 24, 24, 64), generator=g, device="cuda").to(torch.bfloat16)
+    out = torch.empty_like(a)
+    for relu in (0, 1):
+        _lib.check(_lib.lib().io_add_relu(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), relu, _lib.stream_ptr()))
+        want = a.float() + b.float()
+        want = torch.relu(want) if relu else want
+        assert torch.equal(out, want.to(torch.bfloat16))
+    for (h, w, c) in ((12, 12, 256), (24, 17, 64)):
+        x = torch.randn((2, h, w, c), generator=g, device="cuda").to(torch.bfloat16).contiguous()
+        for align in (0, 1):
+            y = torch.empty((2, 2 * h, 2 * w, c), dtype=torch.bfloat16, device="cuda")
+            _lib.check(_lib.lib().io_upsample2x_bilinear(x.data_ptr(), 2, h, w, c, align, y.data_ptr(), _lib.stream_ptr()))
+            want = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear",
+                                 align_corners=bool(align)).permute(0, 2, 3, 1)
+            assert (y.float() - want).abs().max() < 2e-2      # bf16 output rounding of O(1) values
