@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib, synth
-from .engine import OrderEngine
+from .engine import OrderEngine, enumerate_pairs
 
 RESNET50 = ((64, 128, 256, 512), (256, 512, 1024, 2048), (3, 4, 6, 3))
 
@@ -324,6 +324,52 @@ def _disparity(self, scenes):
     return np.concatenate(out) if out else np.zeros((0, self.d, self.d), np.float32)
 
 
+def _disparity_order(self, sc, pairs="all", disp_select_method="median"):
+    """``infer_order_sup_depth(..., method='InstaDepthNet_d'|'InstaDepthNet_od', disp_select_method='median'|'mean')``
+    (reference inference.py:589-599 with ``net_forward_midas_pretrained`` :79-104): pixel depth 1 / (disp + 1e-6), per
+    instance clipped to its own 5 % / 95 % quantiles inside the (nearest-resized) modal mask, median or mean; the
+    closer instance wins.  The statistic belongs to the INSTANCE, so it is computed N times, not once per pair
+    direction.  Returns (int64 [N, N] depth order, disparity clipped to its 5 % / 95 % quantiles as a CPU tensor)."""
+    if disp_select_method not in ("median", "mean"):
+        raise ValueError("disp_select_method must be 'median' or 'mean'")
+    items = [(sc, np.zeros((0, 2), np.int32), None, 0, 0)]
+    s, _ = self.stage_batch(items, "resize")
+    self.gather(s, 0, "resize")
+    _lib.check(self.lib.io_net_forward_pairs(self.enc, self.enc_pair_tensor.data_ptr(), self._n_img, None, _lib.stream_ptr()))
+    self.gpu_launches += self.lib.io_net_last_launches(self.enc)
+    disp = self._disparity_current()[0]
+    d = self.d
+    # modal masks at network resolution: cv2.INTER_NEAREST, src = min(floor(dst * (1 / (D / S))), S - 1) (inference.py:398-399)
+    mask_bytes = sc.n * sc.h * sc.w
+    m = s.d_mask[:mask_bytes].view(sc.n, sc.h, sc.w)
+    iy = (torch.arange(d, dtype=torch.float64) * (1.0 / (d / sc.h))).floor().long().clamp(max=sc.h - 1).to(self.device)
+    ix = (torch.arange(d, dtype=torch.float64) * (1.0 / (d / sc.w))).floor().long().clamp(max=sc.w - 1).to(self.device)
+    mr = m[:, iy][:, :, ix].bool()
+    depth = 1.0 / (disp + 1e-6)
+    stat = []
+    for k in range(sc.n):
+        v = depth[mr[k]]
+        c = torch.clip(v, torch.quantile(v, 0.05), torch.quantile(v, 0.95))
+        stat.append(torch.median(c) if disp_select_method == "median" else torch.mean(c))
+    stat = torch.stack(stat).cpu().numpy() if stat else np.zeros(0, np.float32)
+    self.finish(s)
+    pr = enumerate_pairs(sc.n)
+    if pairs == "nbor" and pr.shape[0]:
+        pr = pr[self.bordering(sc, pr)]
+    order = np.zeros((sc.n, sc.n), np.int64)
+    for (i, j) in pr:
+        if stat[i] < stat[j]:
+            order[i, j], order[j, i] = 1, 0
+        elif stat[i] > stat[j]:
+            order[i, j], order[j, i] = 0, 1
+        else:
+            order[i, j] = order[j, i] = 2
+    clipped = torch.clip(disp, torch.quantile(disp, 0.05), torch.quantile(disp, 0.95)).cpu()
+    self.d2h_bytes += clipped.numel() * 4 + stat.size * 4
+    return order, clipped, stat
+
+
+DepthOrderEngine.disparity_order = _disparity_order
 DepthOrderEngine._load_decoder = _load_decoder
 DepthOrderEngine._disparity_current = _disparity_current
 DepthOrderEngine.disparity = _disparity

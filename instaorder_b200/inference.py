@@ -34,8 +34,11 @@ def infer_order_sup_depth(model, image, inmodal, bboxes, pairs, method, patch_or
     """reference inference.py:515-624 -> (int [N,N] depth order matrix, disp_clipped=None)."""
     if method in ("InstaDepthNet_d", "InstaDepthNet_od"):
         if disp_select_method != "":     # reference :589-599: mean / median of the network's disparity inside the masks
-            raise NotImplementedError("disp_select_method=%r needs InstaDepthNet's disparity output, which is not "
-                                      "built (DESIGN.md section 4c)" % (disp_select_method,))
+            if patch_or_image != "resize":
+                raise NotImplementedError("InstaDepthNet runs in 'resize' mode (its shipped config)")
+            eng = model.engine_for(input_size, disparity=True)
+            order, clipped, _ = eng.disparity_order(_engine.Scene(image, inmodal, bboxes), pairs, disp_select_method)
+            return order, clipped
         return _run(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size)["depth"], None
     if method != "InstaOrderNet_d":
         if method == "midas_pretrained":

@@ -337,15 +337,18 @@ class InstaDepthNet_od(object):
         if load_pretrain is not None:
             self.load_state(load_pretrain)
 
-    def engine_for(self, input_size):
+    def engine_for(self, input_size, disparity=False):
+        """``disparity=True``: an engine whose encoder also runs layer4 and that can evaluate the MiDaS decoder."""
         from .depth_engine import DepthOrderEngine
-        e = self._engines.get(input_size)
+        key = (input_size, bool(disparity))
+        e = self._engines.get(key)
         if e is None:
             if self._state is None:
                 raise RuntimeError("no weights loaded: call load_state()/load_state_dict() first")
-            e = DepthOrderEngine(input_size, self.max_pairs, self.max_images, self.device, with_occ=self.with_occ)
+            e = DepthOrderEngine(input_size, self.max_pairs, self.max_images, self.device, with_occ=self.with_occ,
+                                 with_disparity=bool(disparity))
             e.load_state_dict(self._state)
-            self._engines[input_size] = e
+            self._engines[key] = e
         return e
 
     def load_state_dict(self, sd):

@@ -113,6 +113,29 @@ def main_disp():
                         stats=np.asarray([disp.min(), disp.max(), disp.mean(), disp.std()], np.float64))
     mine = IO.disparity_forward(sd, rgb)[0]
     print("disparity: range [%.3f, %.3f], oracle vs reference %.2e" % (disp.min(), disp.max(), np.abs(mine - disp).max()))
+    # depth order from the disparity map (inference.py:589-599 with :79-104), both selection methods, through the
+    # reference's own driver; plus the per-instance statistics the decisions rest on (for the tie margin of the test)
+    import types
+    ns = ref_shim.load()
+    image, masks, boxes = build_scene()
+    model = types.SimpleNamespace(model=net)
+    extra = {}
+    for sel in ("median", "mean"):
+        order, clipped = ns.inference.infer_order_sup_depth(model, image, masks, boxes, "all", "InstaDepthNet_od", "resize",
+                                                            D, sel)
+        extra["order_" + sel] = order.astype(np.int64)
+        extra["clipped_" + sel] = disp_digest(clipped.numpy())[0]
+        pd = 1.0 / (torch.from_numpy(disp) + 1e-6)
+        st = []
+        for m in masks:
+            mm = torch.from_numpy(O.resize_mode_mask(m, D).astype(bool))
+            v = pd[mm]
+            c = torch.clip(v, torch.quantile(v, 0.05), torch.quantile(v, 0.95))
+            st.append(float(torch.median(c) if sel == "median" else torch.mean(c)))
+        extra["stat_" + sel] = np.asarray(st, np.float64)
+        print(sel, order.tolist(), st)
+    np.savez_compressed(os.path.join(GOLDEN, "instadepth_disp.npz"), pooled=pooled, rows=rows,
+                        stats=np.asarray([disp.min(), disp.max(), disp.mean(), disp.std()], np.float64), **extra)
 
 
 if __name__ == "__main__":
