@@ -8,7 +8,9 @@ disparity output) for every pair direction; here the encoder runs ONCE PER IMAGE
 maps are broadcast into the trunks by index (``io_net_set_inject``).  Everything runs through the kernels of the
 pairwise-order path: three ``io_net_t`` handles created with ``io_net_create_arch`` -- the encoder's grouped 3x3
 convolutions as dense block-diagonal weights, the 3- / 2-channel stems embedded in the 5-channel pair-tensor stem.
-The disparity map (encoder layer4 + ``scratch.*``) is not computed: ``model(x)`` -style access to it raises."""
+The disparity branch (encoder layer4 + ``scratch.*`` = the MiDaS decoder, ``midas_net.py:189-198``) is evaluated on
+request (``with_disparity=True``: ``disparity()``, ``disparity_order()``), per image, through ``io_conv_bn_act`` +
+``io_add_relu`` + ``io_upsample2x_bilinear``."""
 import ctypes as C
 
 import numpy as np

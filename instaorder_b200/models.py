@@ -320,8 +320,8 @@ class OrderNet(_OrderModel):
 class InstaDepthNet_od(object):
     """Order inference with the reference's ``models.InstaDepthNet_od`` (models/supervised_order.py:99-237 wrapping
     midas/midas_net.py:113-212): ``load_state`` / ``load_state_dict`` / ``switch_to('eval')`` and the engine handle
-    used by ``inference.infer_order_sup_occ_depth(method="InstaDepthNet_od")``.  Inference of the two order matrices
-    only: the disparity output and training raise ``NotImplementedError``."""
+    used by ``inference.infer_order_sup_occ_depth`` / ``infer_order_sup_depth`` (``method="InstaDepthNet_od"``).
+    Inference only (order heads, disparity map, disparity-based depth order): training raises ``NotImplementedError``."""
     algo = "InstaDepthNet_od"
     with_occ = True
 
@@ -367,11 +367,11 @@ class InstaDepthNet_od(object):
 
     def switch_to(self, phase):
         if phase == "train":
-            raise NotImplementedError("InstaDepthNet_od: inference of the order matrices only")
+            raise NotImplementedError("InstaDepthNet: inference only")
         self.phase = phase
 
     def step(self):
-        raise NotImplementedError("InstaDepthNet_od: inference of the order matrices only")
+        raise NotImplementedError("InstaDepthNet: inference only")
 
 
 class InstaDepthNet_d(InstaDepthNet_od):
