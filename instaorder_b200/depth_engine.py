@@ -212,6 +212,141 @@ class DepthOrderEngine(OrderEngine):
             raise ValueError("DepthOrderEngine runs InstaDepthNet_od / _d, got %r" % (algo,))
         return super().infer_scenes(scenes, "InstaOrderNet_od", pairs, patch_or_image, return_details)
 
+    # ---- disparity branch (reference midas_net.py:189-198, midas/blocks.py:124-195) ------------------------------
+    def _load_decoder(self, sd):
+        dev = self.device
+        g = lambda k: (sd[k].detach().cpu().numpy() if hasattr(sd[k], "detach") else np.asarray(sd[k]))
+        dec = {}
+
+        def put(name, wkey, bkey=None, cin_pad=None, cout_pad=None):
+            w = _pack_conv(g(wkey), cin_pad, cout_pad).to(dev).contiguous()
+            b = np.zeros(w.shape[0], np.float32)
+            if bkey is not None:
+                bb = g(bkey)
+                b[:bb.size] = bb
+            dec[name] = (w, torch.from_numpy(b).to(dev))
+
+        for k in range(1, 5):
+            put("rn%d" % k, "scratch.layer%d_rn.weight" % k)
+            for u in (1, 2):
+                for c in (1, 2):
+                    p = "scratch.refinenet%d.resConfUnit%d.conv%d" % (k, u, c)
+                    put("r%du%dc%d" % (k, u, c), p + ".weight", p + ".bias")
+        put("oc0", "scratch.output_conv.0.weight", "scratch.output_conv.0.bias")
+        put("oc2", "scratch.output_conv.2.weight", "scratch.output_conv.2.bias", cout_pad=64)      # 32 -> 64 output channels
+        put("oc4", "scratch.output_conv.4.weight", "scratch.output_conv.4.bias", cin_pad=64, cout_pad=64)
+        self._dec = dec
+
+    def _disparity_current(self):
+        """Disparity maps [n_img, D, D] fp32 (CUDA) of the images of the batch the encoder has just processed."""
+        if self._dec is None:
+            raise RuntimeError("create the engine with with_disparity=True and load a state_dict with scratch.* tensors")
+        n, d, dev, st = self._n_img, self.d, self.device, _lib.stream_ptr()
+        bf = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)
+
+        def conv(x_ptr, h, cin, name, cout, k=3, relu=0, res=None):
+            w, b = self._dec[name]
+            y = bf(n, h, h, cout)
+            _lib.check(self.lib.io_conv_bn_act(x_ptr, n, h, h, cin, w.data_ptr(), b.data_ptr(),
+                                               res.data_ptr() if res is not None else None, cout, k, 1, relu, y.data_ptr(), st))
+            self.gpu_launches += 1
+            return y
+
+        def rcu(xp, h, pfx):            # xp = relu(x): blocks.py:146-161 with its in-place ReLU
+            t = conv(xp.data_ptr(), h, 256, pfx + "c1", 256, relu=1)
+            return conv(t.data_ptr(), h, 256, pfx + "c2", 256, relu=0, res=xp)
+
+        def up(x, h, c, align):
+            y = bf(n, 2 * h, 2 * h, c)
+            _lib.check(self.lib.io_upsample2x_bilinear(x.data_ptr(), n, h, h, c, align, y.data_ptr(), st))
+            self.gpu_launches += 1
+            return y
+
+        sizes = [d // 4, d // 8, d // 16, d // 32]
+        chans = synth.RESNEXT_OUTS
+        rn = [conv(self._enc_feats[k], sizes[k], chans[k], "rn%d" % (k + 1), 256, relu=1) for k in range(4)]   # relu(layer_k_rn)
+        path = up(rcu(rn[3], sizes[3], "r4u2"), sizes[3], 256, 1)                                             # refinenet4
+        for k in (3, 2, 1):
+            h = sizes[k - 1]
+            r1 = rcu(rn[k - 1], h, "r%du1" % k)
+            o = bf(n, h, h, 256)
+            _lib.check(self.lib.io_add_relu(path.data_ptr(), r1.data_ptr(), o.data_ptr(), o.numel(), 1, st))
+            self.gpu_launches += 1
+            path = up(rcu(o, h, "r%du2" % k), h, 256, 1)
+        o = conv(path.data_ptr(), d // 2, 256, "oc0", 128)                     # output_conv.0 (192^2 at D = 384)
+        o = up(o, d // 2, 128, 0)                                              # Interpolate(align_corners=False)
+        o = conv(o.data_ptr(), d, 128, "oc2", 64, relu=1)                      # output_conv.2 + ReLU (32 real channels)
+        o = conv(o.data_ptr(), d, 64, "oc4", 64, k=1, relu=1)                  # output_conv.4 + ReLU (1 real channel)
+        return o[..., 0].float()
+
+    def disparity(self, scenes):
+        """``InstaDepthNet_od.forward(image, ...)[0]`` for a list of scenes / images -> numpy [len, D, D] fp32."""
+        out = []
+        for i in range(0, len(scenes), self.max_images):
+            chunk = scenes[i:i + self.max_images]
+            items = [(sc, np.zeros((0, 2), np.int32), None, 0, k) for k, sc in enumerate(chunk)]
+            s, P = self.stage_batch(items, "resize")
+            self.gather(s, 0, "resize")
+            _lib.check(self.lib.io_net_forward_pairs(self.enc, self.enc_pair_tensor.data_ptr(), self._n_img, None,
+                                                     _lib.stream_ptr()))
+            self.gpu_launches += self.lib.io_net_last_launches(self.enc)
+            out.append(self._disparity_current().cpu().numpy())
+            self.finish(s)
+        return np.concatenate(out) if out else np.zeros((0, self.d, self.d), np.float32)
+
+    def disparity_order(self, sc, pairs="all", disp_select_method="median"):
+        """``infer_order_sup_depth(..., method='InstaDepthNet_d'|'InstaDepthNet_od', disp_select_method='median'|'mean')``
+        (reference inference.py:589-599 with ``net_forward_midas_pretrained`` :79-104): pixel depth 1 / (disp + 1e-6), per
+        instance clipped to its own 5 % / 95 % quantiles inside the (nearest-resized) modal mask, median or mean; the
+        closer instance wins.  The statistic belongs to the INSTANCE, so it is computed N times, not once per pair
+        direction.  Returns (int64 [N, N] depth order, disparity clipped to its 5 % / 95 % quantiles as a CPU tensor)."""
+        if disp_select_method not in ("median", "mean"):
+            raise ValueError("disp_select_method must be 'median' or 'mean'")
+        items = [(sc, np.zeros((0, 2), np.int32), None, 0, 0)]
+        s, _ = self.stage_batch(items, "resize")
+        self.gather(s, 0, "resize")
+        _lib.check(self.lib.io_net_forward_pairs(self.enc, self.enc_pair_tensor.data_ptr(), self._n_img, None, _lib.stream_ptr()))
+        self.gpu_launches += self.lib.io_net_last_launches(self.enc)
+        disp = self._disparity_current()[0]
+        d = self.d
+        # modal masks at network resolution: cv2.INTER_NEAREST, src = min(floor(dst * (1 / (D / S))), S - 1) (inference.py:398-399)
+        mask_bytes = sc.n * sc.h * sc.w
+        m = s.d_mask[:mask_bytes].view(sc.n, sc.h, sc.w)
+        iy = (torch.arange(d, dtype=torch.float64) * (1.0 / (d / sc.h))).floor().long().clamp(max=sc.h - 1).to(self.device)
+        ix = (torch.arange(d, dtype=torch.float64) * (1.0 / (d / sc.w))).floor().long().clamp(max=sc.w - 1).to(self.device)
+        mr = m[:, iy][:, :, ix].bool()
+        depth = 1.0 / (disp + 1e-6)
+        stat = []
+        for k in range(sc.n):
+            v = depth[mr[k]]
+            c = torch.clip(v, torch.quantile(v, 0.05), torch.quantile(v, 0.95))
+            stat.append(torch.median(c) if disp_select_method == "median" else torch.mean(c))
+        stat = torch.stack(stat).cpu().numpy() if stat else np.zeros(0, np.float32)
+        self.finish(s)
+        pr = enumerate_pairs(sc.n)
+        if pairs == "nbor" and pr.shape[0]:
+            pr = pr[self.bordering(sc, pr)]
+        order = np.zeros((sc.n, sc.n), np.int64)
+        for (i, j) in pr:
+            if stat[i] < stat[j]:
+                order[i, j], order[j, i] = 1, 0
+            elif stat[i] > stat[j]:
+                order[i, j], order[j, i] = 0, 1
+            else:
+                order[i, j] = order[j, i] = 2
+        clipped = torch.clip(disp, torch.quantile(disp, 0.05), torch.quantile(disp, 0.95)).cpu()
+        self.d2h_bytes += clipped.numel() * 4 + stat.size * 4
+        return order, clipped, stat
+
+
+def _pack_conv(w, cin_pad=None, cout_pad=None):
+    """[cout, cin, k, k] fp32 -> bf16 [cout'][k*k*cin'] (tap-major, channel-minor), zero-padded channels."""
+    w = np.asarray(w, dtype=np.float32)
+    co, ci, k, _ = w.shape
+    cip, cop = cin_pad or ci, cout_pad or co
+    full = np.zeros((cop, k, k, cip), np.float32)
+    full[:co, :, :, :ci] = w.transpose(0, 2, 3, 1)
+    return torch.from_numpy(full.reshape(cop, k * k * cip)).to(torch.bfloat16)
 
 def encoder_flops_per_image(d=384):
     """Algorithmic 2*MAC of the encoder's conv1 + layer1..3 (grouped 3x3 counted with their true group size)."""
@@ -229,149 +364,3 @@ def encoder_flops_per_image(d=384):
                 total += 2.0 * so * so * inpl * o                                    # downsample
             inpl, side = o, so
     return total
-
-
-# ---- disparity branch (reference midas_net.py:189-198, midas/blocks.py:124-195) --------------------------------
-def _pack_conv(w, cin_pad=None, cout_pad=None):
-    """[cout, cin, k, k] fp32 -> bf16 [cout'][k*k*cin'] (tap-major, channel-minor), zero-padded channels."""
-    w = np.asarray(w, dtype=np.float32)
-    co, ci, k, _ = w.shape
-    cip, cop = cin_pad or ci, cout_pad or co
-    full = np.zeros((cop, k, k, cip), np.float32)
-    full[:co, :, :, :ci] = w.transpose(0, 2, 3, 1)
-    return torch.from_numpy(full.reshape(cop, k * k * cip)).to(torch.bfloat16)
-
-
-def _load_decoder(self, sd):
-    dev = self.device
-    g = lambda k: (sd[k].detach().cpu().numpy() if hasattr(sd[k], "detach") else np.asarray(sd[k]))
-    dec = {}
-
-    def put(name, wkey, bkey=None, cin_pad=None, cout_pad=None):
-        w = _pack_conv(g(wkey), cin_pad, cout_pad).to(dev).contiguous()
-        b = np.zeros(w.shape[0], np.float32)
-        if bkey is not None:
-            bb = g(bkey)
-            b[:bb.size] = bb
-        dec[name] = (w, torch.from_numpy(b).to(dev))
-
-    for k in range(1, 5):
-        put("rn%d" % k, "scratch.layer%d_rn.weight" % k)
-        for u in (1, 2):
-            for c in (1, 2):
-                p = "scratch.refinenet%d.resConfUnit%d.conv%d" % (k, u, c)
-                put("r%du%dc%d" % (k, u, c), p + ".weight", p + ".bias")
-    put("oc0", "scratch.output_conv.0.weight", "scratch.output_conv.0.bias")
-    put("oc2", "scratch.output_conv.2.weight", "scratch.output_conv.2.bias", cout_pad=64)      # 32 -> 64 output channels
-    put("oc4", "scratch.output_conv.4.weight", "scratch.output_conv.4.bias", cin_pad=64, cout_pad=64)
-    self._dec = dec
-
-
-def _disparity_current(self):
-    """Disparity maps [n_img, D, D] fp32 (CUDA) of the images of the batch the encoder has just processed."""
-    if self._dec is None:
-        raise RuntimeError("create the engine with with_disparity=True and load a state_dict with scratch.* tensors")
-    n, d, dev, st = self._n_img, self.d, self.device, _lib.stream_ptr()
-    bf = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)
-
-    def conv(x_ptr, h, cin, name, cout, k=3, relu=0, res=None):
-        w, b = self._dec[name]
-        y = bf(n, h, h, cout)
-        _lib.check(self.lib.io_conv_bn_act(x_ptr, n, h, h, cin, w.data_ptr(), b.data_ptr(),
-                                           res.data_ptr() if res is not None else None, cout, k, 1, relu, y.data_ptr(), st))
-        self.gpu_launches += 1
-        return y
-
-    def rcu(xp, h, pfx):            # xp = relu(x): blocks.py:146-161 with its in-place ReLU
-        t = conv(xp.data_ptr(), h, 256, pfx + "c1", 256, relu=1)
-        return conv(t.data_ptr(), h, 256, pfx + "c2", 256, relu=0, res=xp)
-
-    def up(x, h, c, align):
-        y = bf(n, 2 * h, 2 * h, c)
-        _lib.check(self.lib.io_upsample2x_bilinear(x.data_ptr(), n, h, h, c, align, y.data_ptr(), st))
-        self.gpu_launches += 1
-        return y
-
-    sizes = [d // 4, d // 8, d // 16, d // 32]
-    chans = synth.RESNEXT_OUTS
-    rn = [conv(self._enc_feats[k], sizes[k], chans[k], "rn%d" % (k + 1), 256, relu=1) for k in range(4)]   # relu(layer_k_rn)
-    path = up(rcu(rn[3], sizes[3], "r4u2"), sizes[3], 256, 1)                                             # refinenet4
-    for k in (3, 2, 1):
-        h = sizes[k - 1]
-        r1 = rcu(rn[k - 1], h, "r%du1" % k)
-        o = bf(n, h, h, 256)
-        _lib.check(self.lib.io_add_relu(path.data_ptr(), r1.data_ptr(), o.data_ptr(), o.numel(), 1, st))
-        self.gpu_launches += 1
-        path = up(rcu(o, h, "r%du2" % k), h, 256, 1)
-    o = conv(path.data_ptr(), d // 2, 256, "oc0", 128)                     # output_conv.0 (192^2 at D = 384)
-    o = up(o, d // 2, 128, 0)                                              # Interpolate(align_corners=False)
-    o = conv(o.data_ptr(), d, 128, "oc2", 64, relu=1)                      # output_conv.2 + ReLU (32 real channels)
-    o = conv(o.data_ptr(), d, 64, "oc4", 64, k=1, relu=1)                  # output_conv.4 + ReLU (1 real channel)
-    return o[..., 0].float()
-
-
-def _disparity(self, scenes):
-    """``InstaDepthNet_od.forward(image, ...)[0]`` for a list of scenes / images -> numpy [len, D, D] fp32."""
-    out = []
-    for i in range(0, len(scenes), self.max_images):
-        chunk = scenes[i:i + self.max_images]
-        items = [(sc, np.zeros((0, 2), np.int32), None, 0, k) for k, sc in enumerate(chunk)]
-        s, P = self.stage_batch(items, "resize")
-        self.gather(s, 0, "resize")
-        _lib.check(self.lib.io_net_forward_pairs(self.enc, self.enc_pair_tensor.data_ptr(), self._n_img, None,
-                                                 _lib.stream_ptr()))
-        self.gpu_launches += self.lib.io_net_last_launches(self.enc)
-        out.append(self._disparity_current().cpu().numpy())
-        self.finish(s)
-    return np.concatenate(out) if out else np.zeros((0, self.d, self.d), np.float32)
-
-
-def _disparity_order(self, sc, pairs="all", disp_select_method="median"):
-    """``infer_order_sup_depth(..., method='InstaDepthNet_d'|'InstaDepthNet_od', disp_select_method='median'|'mean')``
-    (reference inference.py:589-599 with ``net_forward_midas_pretrained`` :79-104): pixel depth 1 / (disp + 1e-6), per
-    instance clipped to its own 5 % / 95 % quantiles inside the (nearest-resized) modal mask, median or mean; the
-    closer instance wins.  The statistic belongs to the INSTANCE, so it is computed N times, not once per pair
-    direction.  Returns (int64 [N, N] depth order, disparity clipped to its 5 % / 95 % quantiles as a CPU tensor)."""
-    if disp_select_method not in ("median", "mean"):
-        raise ValueError("disp_select_method must be 'median' or 'mean'")
-    items = [(sc, np.zeros((0, 2), np.int32), None, 0, 0)]
-    s, _ = self.stage_batch(items, "resize")
-    self.gather(s, 0, "resize")
-    _lib.check(self.lib.io_net_forward_pairs(self.enc, self.enc_pair_tensor.data_ptr(), self._n_img, None, _lib.stream_ptr()))
-    self.gpu_launches += self.lib.io_net_last_launches(self.enc)
-    disp = self._disparity_current()[0]
-    d = self.d
-    # modal masks at network resolution: cv2.INTER_NEAREST, src = min(floor(dst * (1 / (D / S))), S - 1) (inference.py:398-399)
-    mask_bytes = sc.n * sc.h * sc.w
-    m = s.d_mask[:mask_bytes].view(sc.n, sc.h, sc.w)
-    iy = (torch.arange(d, dtype=torch.float64) * (1.0 / (d / sc.h))).floor().long().clamp(max=sc.h - 1).to(self.device)
-    ix = (torch.arange(d, dtype=torch.float64) * (1.0 / (d / sc.w))).floor().long().clamp(max=sc.w - 1).to(self.device)
-    mr = m[:, iy][:, :, ix].bool()
-    depth = 1.0 / (disp + 1e-6)
-    stat = []
-    for k in range(sc.n):
-        v = depth[mr[k]]
-        c = torch.clip(v, torch.quantile(v, 0.05), torch.quantile(v, 0.95))
-        stat.append(torch.median(c) if disp_select_method == "median" else torch.mean(c))
-    stat = torch.stack(stat).cpu().numpy() if stat else np.zeros(0, np.float32)
-    self.finish(s)
-    pr = enumerate_pairs(sc.n)
-    if pairs == "nbor" and pr.shape[0]:
-        pr = pr[self.bordering(sc, pr)]
-    order = np.zeros((sc.n, sc.n), np.int64)
-    for (i, j) in pr:
-        if stat[i] < stat[j]:
-            order[i, j], order[j, i] = 1, 0
-        elif stat[i] > stat[j]:
-            order[i, j], order[j, i] = 0, 1
-        else:
-            order[i, j] = order[j, i] = 2
-    clipped = torch.clip(disp, torch.quantile(disp, 0.05), torch.quantile(disp, 0.95)).cpu()
-    self.d2h_bytes += clipped.numel() * 4 + stat.size * 4
-    return order, clipped, stat
-
-
-DepthOrderEngine.disparity_order = _disparity_order
-DepthOrderEngine._load_decoder = _load_decoder
-DepthOrderEngine._disparity_current = _disparity_current
-DepthOrderEngine.disparity = _disparity
