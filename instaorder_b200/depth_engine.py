@@ -28,12 +28,13 @@ def _i32(v):
 
 class DepthOrderEngine(OrderEngine):
     def __init__(self, input_size=384, max_pairs=64, max_images=16, device="cuda:0", with_occ=True,
-                 with_disparity=False, **kw):
+                 with_disparity=False, with_trunks=True, **kw):
         """``with_occ=False``: InstaDepthNet^d (midas_net.py:15-110) -- no ``oo_net``, depth order only.
         ``with_disparity=True``: the encoder also runs layer4 and ``disparity()`` evaluates the MiDaS decoder."""
         self.max_images = int(max_images)
         self.with_occ = bool(with_occ)
         self.with_disparity = bool(with_disparity)
+        self.with_trunks = bool(with_trunks)     # False: a plain MiDaS network (encoder + decoder), disparity only
         self._dec = None
         super().__init__([2, 3], input_size, max_pairs, device, **kw)
 
@@ -52,8 +53,9 @@ class DepthOrderEngine(OrderEngine):
         self.enc_layers = 4 if self.with_disparity else 3
         self.enc = self._create_arch((synth.RESNEXT_WIDTHS, synth.RESNEXT_OUTS, synth.RESNEXT_BLOCKS), self.enc_layers,
                                      True, None, self.max_images)
-        self.do_net = self._create_arch(RESNET50, 4, False, [3], self.max_pairs)
-        self.oo_net = self._create_arch(RESNET50, 4, False, [2], self.max_pairs) if self.with_occ else None
+        self.do_net = self._create_arch(RESNET50, 4, False, [3], self.max_pairs) if self.with_trunks else None
+        self.oo_net = self._create_arch(RESNET50, 4, False, [2], self.max_pairs) \
+            if (self.with_occ and self.with_trunks) else None
         self.inject_idx = torch.zeros(2 * self.max_pairs, dtype=torch.int32, device=self.device)
         feats = []
         for li in range(self.enc_layers):
@@ -131,7 +133,8 @@ class DepthOrderEngine(OrderEngine):
         self._load_sub(self.enc, sd, "pretrained", 3, rx, synth.RESNEXT_GROUPS, self.enc_layers, None)
         if self.with_disparity:
             self._load_decoder(sd)
-        self._load_sub(self.do_net, sd, "do_net", 2, RESNET50, 1, 4, "depth_fc")
+        if self.do_net is not None:
+            self._load_sub(self.do_net, sd, "do_net", 2, RESNET50, 1, 4, "depth_fc")
         if self.oo_net is not None:
             self._load_sub(self.oo_net, sd, "oo_net", 2, RESNET50, 1, 4, "occ_fc")
 
@@ -196,6 +199,8 @@ class DepthOrderEngine(OrderEngine):
         self._n_img = n_img
 
     def forward(self, P):
+        if self.do_net is None:
+            raise RuntimeError("this engine has no order trunks (plain MiDaS): use disparity() / disparity_order()")
         st = _lib.stream_ptr()
         _lib.check(self.lib.io_net_forward_pairs(self.enc, self.enc_pair_tensor.data_ptr(), self._n_img, None, st))
         _lib.check(self.lib.io_net_forward_pairs(self.do_net, self.pair_tensor.data_ptr(), P, self.logits_d.data_ptr(), st))

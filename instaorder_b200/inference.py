@@ -32,6 +32,12 @@ def infer_order_sup_occ(model, image, inmodal, bboxes, pairs, method, patch_or_i
 def infer_order_sup_depth(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size,
                           disp_select_method, use_rgb=True):
     """reference inference.py:515-624 -> (int [N,N] depth order matrix, disp_clipped=None)."""
+    if method == "midas_pretrained":       # reference :576-583: always from the disparity map
+        if patch_or_image != "resize":
+            raise NotImplementedError("midas_pretrained runs in 'resize' mode")
+        eng = model.engine_for(input_size, disparity=True)
+        order, clipped, _ = eng.disparity_order(_engine.Scene(image, inmodal, bboxes), pairs, disp_select_method)
+        return order, clipped
     if method in ("InstaDepthNet_d", "InstaDepthNet_od"):
         if disp_select_method != "":     # reference :589-599: mean / median of the network's disparity inside the masks
             if patch_or_image != "resize":
@@ -41,8 +47,6 @@ def infer_order_sup_depth(model, image, inmodal, bboxes, pairs, method, patch_or
             return order, clipped
         return _run(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size)["depth"], None
     if method != "InstaOrderNet_d":
-        if method == "midas_pretrained":
-            raise NotImplementedError("%s is outside the pairwise-order hot path (SURVEY.md section 8f)" % method)
         print("method name should be one of {InstaOrderNet_d or midas_pretrained}")   # reference :608-610
         return
     if not use_rgb:

@@ -15,7 +15,7 @@ from . import _lib
 from .engine import OrderEngine
 from .training import FlatOptim, TrainEngine
 
-__all__ = ["InstaOrderNet_o", "InstaOrderNet_d", "InstaOrderNet_od", "OrderNet", "InstaDepthNet_od", "InstaDepthNet_d"]
+__all__ = ["InstaOrderNet_o", "InstaOrderNet_d", "InstaOrderNet_od", "OrderNet", "InstaDepthNet_od", "InstaDepthNet_d", "MidasNet"]
 
 
 class _OrderModel(object):
@@ -324,6 +324,7 @@ class InstaDepthNet_od(object):
     Inference only (order heads, disparity map, disparity-based depth order): training raises ``NotImplementedError``."""
     algo = "InstaDepthNet_od"
     with_occ = True
+    with_trunks = True
 
     def __init__(self, params, load_pretrain=None, dist_model=False):
         self.params = params
@@ -346,7 +347,7 @@ class InstaDepthNet_od(object):
             if self._state is None:
                 raise RuntimeError("no weights loaded: call load_state()/load_state_dict() first")
             e = DepthOrderEngine(input_size, self.max_pairs, self.max_images, self.device, with_occ=self.with_occ,
-                                 with_disparity=bool(disparity))
+                                 with_disparity=bool(disparity), with_trunks=self.with_trunks)
             e.load_state_dict(self._state)
             self._engines[key] = e
         return e
@@ -379,3 +380,12 @@ class InstaDepthNet_d(InstaDepthNet_od):
     network without ``oo_net`` -- depth order only (``inference.infer_order_sup_depth``)."""
     algo = "InstaDepthNet_d"
     with_occ = False
+
+
+class MidasNet(InstaDepthNet_od):
+    """The plain MiDaS v2.1 network (reference midas/midas_net.py ``MidasNet``: ResNeXt-101 encoder + decoder, state_dict
+    keys ``pretrained.*`` / ``scratch.*``) as used by ``infer_order_sup_depth(method="midas_pretrained")``
+    (inference.py:576-583): disparity map and the median / mean depth order derived from it; no order heads."""
+    algo = "midas_pretrained"
+    with_occ = False
+    with_trunks = False

@@ -170,3 +170,19 @@ def test_disparity_matches_reference_fixture(golden_dir):
     a = eng.infer_scenes([engine.Scene(image, masks, boxes)], "InstaDepthNet_od")[0]
     b = eng3.infer_scenes([engine.Scene(image, masks, boxes)], "InstaDepthNet_od")[0]
     assert np.array_equal(a["occ"], b["occ"]) and np.array_equal(a["depth"], b["depth"])
+
+
+def test_midas_pretrained_ordering(golden_dir):
+    """method='midas_pretrained' (reference inference.py:576-583): a plain MiDaS checkpoint (pretrained.* + scratch.*),
+    depth order from its disparity map -- with the fixture's encoder / decoder weights it must reproduce the
+    InstaDepthNet engine's disparity-based order and the reference's statistics."""
+    z = np.load(os.path.join(golden_dir, "instadepth_disp.npz"))
+    sd = IO.load_calibrated(os.path.join(golden_dir, "instadepth_calib.npz"), G.SEED, with_decoder=True)
+    sd_midas = {k: v for k, v in sd.items() if k.startswith(("module.pretrained.", "module.scratch."))}
+    m = models.MidasNet(dict(algo="midas_pretrained", max_pairs=16, max_images=2))
+    m.load_state_dict(sd_midas)
+    image, masks, boxes = G.build_scene()
+    order, clipped = inference.infer_order_sup_depth(m, image, masks, boxes, "all", "midas_pretrained", "resize", G.D, "median")
+    assert np.array_equal(order, z["order_median"])
+    with pytest.raises(RuntimeError):
+        m.engine_for(G.D, disparity=True).infer_scenes([engine.Scene(image, masks, boxes)], "InstaDepthNet_od")
