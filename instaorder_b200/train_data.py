@@ -146,7 +146,7 @@ class TrainBatchBuilder(object):
             for k, (sc, sp, (img, msk, _)) in enumerate(zip(scenes, specs, res)):
                 if sp.s <= 0:
                     raise _lib.IoError(_lib.IO_ERR_DEGENERATE, "degenerate training pair (crop side %d)" % sp.s)
-                n, h, w = sc.n, sc.h, sc.w
+                n, h, w = (sc.n, sc.h, sc.w) if hasattr(sc, "n") else sc.masks.shape
                 a, b = (sp.idx2, sp.idx1) if sp.swapped else (sp.idx1, sp.idx2)
                 desc[k] = (img.data_ptr() - img_base, msk.data_ptr() - msk_base + a * h * w,
                            msk.data_ptr() - msk_base + b * h * w, h, w, sp.x, sp.y, sp.s, 1 if sp.flip else 0)
@@ -156,7 +156,7 @@ class TrainBatchBuilder(object):
                                                      self.pair_tensor.data_ptr(), _lib.stream_ptr()))
         else:
             for k, (sc, sp, (img, msk, slot)) in enumerate(zip(scenes, specs, res)):
-                n, h, w = sc.n, sc.h, sc.w
+                n, h, w = (sc.n, sc.h, sc.w) if hasattr(sc, "n") else sc.masks.shape
                 a, b = (sp.idx2, sp.idx1) if sp.swapped else (sp.idx1, sp.idx2)
                 sq = max(h, w) if self.mode == "image" else 0
                 desc[k] = (0, msk.data_ptr() - msk_base + a * h * w, msk.data_ptr() - msk_base + b * h * w, h, w,
