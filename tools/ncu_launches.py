@@ -32,10 +32,14 @@ def main():
             L = launches[k]
             f.write('%d,%s,"%s","%s",%.2f,%.2f,%.2f\n' % (i, L["kernel"], L["grid"], L["block"],
                     L.get("gpu__time_duration.sum", 0), L.get("dram__bytes_read.sum", 0), L.get("dram__bytes_write.sum", 0)))
-    # last step = everything after the last gather launch
+    # a step = the launches from one gather launch up to the next; the capture (-c N) may cut the last one short, so take
+    # the last step that is as long as the longest one
     names = [launches[k]["kernel"] for k in order]
-    last = max(i for i, n in enumerate(names) if n.startswith("gather_patch"))
-    step = [launches[k] for k in order[last:]]
+    starts = [i for i, n in enumerate(names) if n.startswith("gather_patch")] + [len(order)]
+    segs = [(starts[i], starts[i + 1]) for i in range(len(starts) - 1)]
+    full = max(b - a for a, b in segs)
+    a, b = [sg for sg in segs if sg[1] - sg[0] == full][-1]
+    step = [launches[k] for k in order[a:b]]
     conv = [L for L in step if L["kernel"].startswith("conv_")]
     tot = sum(L.get("gpu__time_duration.sum", 0) for L in step)
     ct = sum(L.get("gpu__time_duration.sum", 0) for L in conv)
