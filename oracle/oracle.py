@@ -196,15 +196,23 @@ def cubic_taps_f64(src_len, dst_len):
     return sx, np.stack([c0, c1, c2, c3], axis=1).astype(f32)
 
 
-def resize_mode_rgb(image, input_size):
+def get_closest_int_multiple_of(orig_num, multiplier):
+    """utils/data_utils.py:13-17 (``orig`` mode: ties go up)."""
+    r = orig_num % multiplier
+    return orig_num + multiplier - r if r >= multiplier // 2 else orig_num - r
+
+
+def resize_mode_rgb(image, input_size, out_h=None):
     """``resize`` mode rgb: inference.py:395-397 + utils/data_utils.py:37-53 + midas/transforms.py:48-235 --
     image/255. (float64) -> cv2 INTER_CUBIC on CV_64F to input_size^2 (input_size must be a multiple of 32, which
-    makes ``Resize(..., ensure_multiple_of=32)`` a plain resize) -> (x-mean)/std in float64 -> CHW fp32."""
-    assert input_size % 32 == 0
+    makes ``Resize(..., ensure_multiple_of=32)`` a plain resize) -> (x-mean)/std in float64 -> CHW fp32.
+    ``out_h``: ``orig`` mode (inference.py:401-406), width = input_size, height = out_h, both multiples of 32."""
+    out_w, out_h = input_size, (input_size if out_h is None else out_h)
+    assert out_w % 32 == 0 and out_h % 32 == 0
     src = image.astype(np.float64) / 255.
     Hs, Ws = src.shape[:2]
-    tx, ca = cubic_taps_f64(Ws, input_size)
-    ty, cb = cubic_taps_f64(Hs, input_size)
+    tx, ca = cubic_taps_f64(Ws, out_w)
+    ty, cb = cubic_taps_f64(Hs, out_h)
     ix = np.clip(tx[:, None] + np.arange(4)[None, :], 0, Ws - 1)
     iy = np.clip(ty[:, None] + np.arange(4)[None, :], 0, Hs - 1)
     h = (src[:, ix, :] * ca.astype(np.float64)[None, :, :, None]).sum(axis=2)
@@ -466,6 +474,14 @@ def infer_order(sd, image, inmodal, bboxes, pairs="all", method="InstaOrderNet_o
             elif patch_or_image == "image":
                 mi = image_mode_mask(inmodal[i], input_size).astype(np.float32)
                 mj = image_mode_mask(inmodal[j], input_size).astype(np.float32)
+                x = np.concatenate([mi[None], mj[None], rgb_whole], axis=0)
+            elif patch_or_image == "orig":       # inference.py:401-408: H, W rounded to multiples of 32, non-square network input
+                hh = get_closest_int_multiple_of(inmodal.shape[1], 32)
+                ww = get_closest_int_multiple_of(inmodal.shape[2], 32)
+                if rgb_whole is None:
+                    rgb_whole = resize_mode_rgb(image, ww, hh)
+                mi = resize_nearest(inmodal[i], ww, hh).astype(np.float32)
+                mj = resize_nearest(inmodal[j], ww, hh).astype(np.float32)
                 x = np.concatenate([mi[None], mj[None], rgb_whole], axis=0)
             else:
                 raise NotImplementedError(patch_or_image)

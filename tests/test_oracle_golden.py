@@ -104,3 +104,26 @@ def test_gt_order_golden(golden_dir):
         modal, amodal = gen_golden.kins_scene(int(z["seed%d" % t]))
         assert np.array_equal(O.infer_gt_order(modal, amodal), z["gt%d" % t])
         assert z["gt%d" % t].sum() > 0
+
+
+def test_orig_mode_oracle_matches_reference(golden_dir):
+    """``patch_or_image='orig'`` (reference inference.py:401-408): H, W rounded to multiples of 32, a
+    non-square network input.  Oracle restatement vs the unmodified reference's logits / matrices (fixture from
+    oracle/gen_golden_orig.py).  The CUDA path does not run this mode yet -- groundwork."""
+    from oracle import gen_golden_orig
+    z = np.load(os.path.join(golden_dir, "order_c2_od_orig.npz"))
+    c = gen_golden.CASES[gen_golden_orig.CASE]
+    image, masks, boxes = gen_golden.build_scene(gen_golden_orig.CASE)
+    assert tuple(z["net_input_shape"]) == (1, 5, O.get_closest_int_multiple_of(image.shape[0], 32),
+                                           O.get_closest_int_multiple_of(image.shape[1], 32))
+    assert O.get_closest_int_multiple_of(48, 32) == 64 and O.get_closest_int_multiple_of(47, 32) == 32
+    sd = calib.load_calibrated(gen_golden.calib_path(gen_golden_orig.CASE), c["wseed"], 5, c["num_classes"])
+    r = O.infer_order(sd, image, masks, boxes, "all", "InstaOrderNet_od", "orig", c["input_size"])
+    plist = r["pairs"]
+    for h, head in enumerate(("fc_occ", "fc_depth")):
+        got = np.stack([np.stack(r["logits"][p][head]) for p in plist])
+        assert np.abs(got - z["logits%d" % h]).max() < 2e-4
+    ok = r["margin_occ"] > 1e-3
+    assert np.array_equal(r["occ"][ok], z["occ"][ok])
+    ok = r["margin_depth"] > 1e-3
+    assert np.array_equal(r["depth"][ok], z["depth"][ok])
