@@ -194,11 +194,15 @@ def run_reference_arm(args):
     pairs = sum(n for n, _ in vals)
     secs = sum(dt for _, dt in vals)
     value = pairs / secs
-    line = dict(impl="reference", metric="instance pairs/s (InstaOrderNet^od, 256^2)", value=value, unit="pairs/s",
+    # same metric / config.workload strings as the b200 arm (the driver pairs the two lines); the reference arm computes in
+    # fp32 (dtype) and its step is a bounded sample of the workload (config.sample)
+    line = dict(impl="reference", metric="instance pairs/s (InstaOrderNet^od, 256^2, bf16)", value=value, unit="pairs/s",
                 n_gpus=args.gpus, steps=steps, warmup=warmup, ms_per_step=1000.0 * secs / max(len(vals), 1),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="C2: COCO-shaped 10-instance images, patch 256^2, InstaOrderNet^od; "
-                                     "bounded sample of %d pairs per step on host cores" % sample_pairs),
+                config=dict(workload="C2: synthetic COCO-val-shaped images, 10 instances -> 45 pairs/image, %d pairs per "
+                                     "step, patch 256^2, InstaOrderNet^od heads [2,3], random-init weights" % PAIRS_PER_STEP,
+                            sample="bounded sample of %d pairs per step on the host cores (fp32 torch-CPU oracle port of "
+                                   "the reference's inference.py patch path)" % sample_pairs),
                 cpu_baseline=dict(value=value, unit="pairs/s", cores=threads, kind="port",
                                   sample="%d pairs/step x %d steps, batched fp32 torch-CPU forward" % (sample_pairs, steps)),
                 e2e=dict(value=value, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
