@@ -255,7 +255,7 @@ def run_train(args):
         return
     import torch
     import torch.distributed as dist
-    from instaorder_b200 import _lib, models, synth, training
+    from instaorder_b200 import _lib, models, synth
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:

@@ -4,7 +4,6 @@ Usage: python tools/train_report.py [batch_pairs] [input_size] [steps] > report.
 import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
