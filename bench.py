@@ -243,7 +243,7 @@ def run_train(args):
         vals = [cpu_train_pairs_per_s(2, D) for _ in range(args.warmup + args.steps)][args.warmup:]
         pairs, secs = sum(v[1] for v in vals), sum(v[2] for v in vals)
         value = pairs / secs
-        emit((dict(impl="reference", metric="training pairs/s (InstaOrderNet^od step, 256^2)", value=value,
+        emit((dict(impl="reference", metric="training pairs/s (InstaOrderNet^od step: fwd + bwd + all-reduce + SGD, 256^2, bf16)", value=value,
                               unit="pairs/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                               ms_per_step=1000.0 * secs / len(vals), higher_is_better=True, scaling="weak",
                               vs_baseline=None, dtype="f32", data="synthetic",
