@@ -54,8 +54,13 @@ class Tester(object):
             scenes, gts_occ, gts_depth, names = [], [], [], []
             for i in chunk:
                 modal, category, bboxes, _, image_fn = self.reader.get_image_instances(i, with_gt=True)[:5]
-                if a.data.get("use_category", False):
-                    modal = modal * np.asarray(category)[:, None, None]          # tools/test.py:302-303
+                if a.data.get("use_category", False):                             # tools/test.py:302-303
+                    if hasattr(modal, "is_cuda"):      # masks left in HBM by the reader (device_masks=True)
+                        import torch
+                        modal = modal * torch.as_tensor(np.asarray(category), dtype=modal.dtype,
+                                                        device=modal.device)[:, None, None]
+                    else:
+                        modal = modal * np.asarray(category)[:, None, None]
                 scenes.append(_engine.Scene(self.load_image(image_fn), modal, self.expand_bbox(bboxes)))
                 names.append(image_fn)
                 if want_depth:
