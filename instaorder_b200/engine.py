@@ -174,6 +174,23 @@ class OrderEngine:
         _lib.check(self.lib.io_net_load_state(self.net, c_names, c_ptrs, c_numel, n))
 
     # ---- low-level steps (also used by the tests) ------------------------------------------------------------
+    def _ensure_capacity(self, img_bytes, mask_bytes):
+        """Grows the pinned / device staging slots when ONE scene alone does not fit them (a very large image, or
+        many instances at high resolution).  Slots in flight are drained first; happens at most a few times per
+        engine, never in the steady state."""
+        cur_i, cur_m = self._slot_args[0], self._slot_args[1]
+        if img_bytes <= cur_i and mask_bytes <= cur_m:
+            return
+        torch.cuda.synchronize(self.device)
+        grow = lambda cur, need: cur if need <= cur else max(need, 2 * cur)
+        self._slot_args = (grow(cur_i, img_bytes), grow(cur_m, mask_bytes)) + tuple(self._slot_args[2:])
+        self._slots = [None] * len(self._slots)
+        self._slot_i = 0
+
+    @staticmethod
+    def _scene_bytes(sc):
+        return (sc.h * sc.w * 3 + 15) // 16 * 16, (sc.n * sc.h * sc.w + 15) // 16 * 16
+
     def _slot(self):
         i = self._slot_i
         self._slot_i = (i + 1) % len(self._slots)
@@ -202,7 +219,10 @@ class OrderEngine:
             p = pairs.shape[0]
             ib, mb = sc.h * sc.w * 3, sc.n * sc.h * sc.w
             if img_off + ib > himg.size or mask_off + mb > hmask.size:
-                raise ValueError("staging buffers too small for this batch (image %d B, masks %d B)" % (ib, mb))
+                raise ValueError("staging buffers too small for this batch: it needs more than %d B of images / %d B "
+                                 "of masks (this scene: %d / %d B).  infer_scenes() cuts batches to fit; callers of "
+                                 "stage_batch() / make_batches() must pass fewer scenes per batch or create the "
+                                 "engine with larger img_bytes= / mask_bytes=" % (himg.size, hmask.size, ib, mb))
             himg[img_off:img_off + ib] = sc.image.reshape(-1)
             if sc.masks_dev is None:
                 hmask[mask_off:mask_off + mb] = sc.masks.reshape(-1)
@@ -321,11 +341,13 @@ class OrderEngine:
         # batches of <= max_pairs pairs; pairs + crop windows (host, float64 -- bit-exact with the reference's
         # geometry) are computed scene by scene while earlier batches already run on the GPU
         batch, count = [], 0
+        used = [0, 0]          # image / mask bytes the current batch needs in its staging slot
 
         def flush():
             nonlocal batch, count
             if not batch:
                 return
+            used[0] = used[1] = 0
             s, P = self.stage_batch(batch, mode)
             self.gather(s, P, mode)
             self.forward(P)
@@ -355,11 +377,17 @@ class OrderEngine:
             o = 0
             while o < pr.shape[0]:
                 take = min(pr.shape[0] - o, cap - count)
-                if take == 0 or len(batch) >= self.max_items_per_batch:
-                    flush()
+                ib, mb = self._scene_bytes(sc)
+                fits = used[0] + ib <= self._slot_args[0] and used[1] + mb <= self._slot_args[1]
+                if take == 0 or len(batch) >= self.max_items_per_batch or (batch and not fits):
+                    flush()                      # pair budget, item budget or staging bytes exhausted: start a new batch
                     cap = self.max_pairs
                     continue
+                if not fits:                     # a single scene larger than a slot: grow the slots once
+                    self._ensure_capacity(ib, mb)
                 batch.append((sc, pr[o:o + take], None if crops is None else crops[o:o + take], mat_offs[si], si))
+                used[0] += ib
+                used[1] += mb
                 count += take
                 o += take
                 if count == cap:
@@ -454,23 +482,35 @@ def _pack_mats(mats, device):
     return torch.from_numpy(flat).to(device), torch.from_numpy(offs).to(device), torch.from_numpy(ns).to(device)
 
 
-def metrics_prf(orders, gts, zd, device="cuda:0"):
+def _metric_device(device):
+    """The GPU the metric kernels run on: the caller's, else the process's current device (``cuda:LOCAL_RANK`` once
+    an engine exists) -- never a fixed ``cuda:0`` that another rank's stream would be launched against."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("instaorder_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def metrics_prf(orders, gts, zd, device=None):
     """Batched ``eval_order_recall_precision_f1`` (reference inference.py:794-802) -> float64 [B, 3]."""
-    o, off, ns = _pack_mats(orders, device)
-    g, _, _ = _pack_mats(gts, device)
-    out = torch.empty((len(orders), 3), dtype=torch.float64, device=device)
-    _lib.check(_lib.lib().io_metrics_prf(o.data_ptr(), g.data_ptr(), off.data_ptr(), ns.data_ptr(), len(orders),
-                                         int(zd), out.data_ptr(), _lib.stream_ptr()))
-    return out.cpu().numpy()
+    device = _metric_device(device)
+    with torch.cuda.device(device):          # stream and pointers of the same GPU
+        o, off, ns = _pack_mats(orders, device)
+        g, _, _ = _pack_mats(gts, device)
+        out = torch.empty((len(orders), 3), dtype=torch.float64, device=device)
+        _lib.check(_lib.lib().io_metrics_prf(o.data_ptr(), g.data_ptr(), off.data_ptr(), ns.data_ptr(), len(orders),
+                                             int(zd), out.data_ptr(), _lib.stream_ptr()))
+        return out.cpu().numpy()
 
 
-def metrics_whdr(orders, gt_orders, gt_overlaps, gt_counts, device="cuda:0"):
+def metrics_whdr(orders, gt_orders, gt_overlaps, gt_counts, device=None):
     """Batched ``eval_depth_order_whdr`` (reference inference.py:764-791) -> float64 [B, 9]."""
-    o, off, ns = _pack_mats(orders, device)
-    g, _, _ = _pack_mats(gt_orders, device)
-    v, _, _ = _pack_mats(gt_overlaps, device)
-    c, _, _ = _pack_mats(gt_counts, device)
-    out = torch.empty((len(orders), 9), dtype=torch.float64, device=device)
-    _lib.check(_lib.lib().io_metrics_whdr(o.data_ptr(), g.data_ptr(), v.data_ptr(), c.data_ptr(), off.data_ptr(),
-                                          ns.data_ptr(), len(orders), out.data_ptr(), _lib.stream_ptr()))
-    return out.cpu().numpy()
+    device = _metric_device(device)
+    with torch.cuda.device(device):
+        o, off, ns = _pack_mats(orders, device)
+        g, _, _ = _pack_mats(gt_orders, device)
+        v, _, _ = _pack_mats(gt_overlaps, device)
+        c, _, _ = _pack_mats(gt_counts, device)
+        out = torch.empty((len(orders), 9), dtype=torch.float64, device=device)
+        _lib.check(_lib.lib().io_metrics_whdr(o.data_ptr(), g.data_ptr(), v.data_ptr(), c.data_ptr(), off.data_ptr(),
+                                              ns.data_ptr(), len(orders), out.data_ptr(), _lib.stream_ptr()))
+        return out.cpu().numpy()

@@ -52,7 +52,7 @@ def segm_components(segm, h, w):
     return [_string_counts(counts, h, w)]
 
 
-def rasterize(segms, h, w, device="cuda:0", stream=None):
+def rasterize(segms, h, w, device=None, stream=None):
     """``np.array([decode(merge(frPyObjects(s, h, w))) for s in segms])`` as a CUDA uint8 tensor [N, h, w]."""
     parts, comp_off, inst_off = [], [0], [0]
     for s in segms:
@@ -64,6 +64,8 @@ def rasterize(segms, h, w, device="cuda:0", stream=None):
             comp_off.append(comp_off[-1] + c.size)
         inst_off.append(len(comp_off) - 1)
     n = len(segms)
+    if device is None:       # the process's current GPU (cuda:LOCAL_RANK once an engine exists), never a fixed cuda:0
+        device = torch.device("cuda", torch.cuda.current_device())
     out = torch.empty((n, h, w), dtype=torch.uint8, device=device)
     if n == 0:
         return out
@@ -77,7 +79,7 @@ def rasterize(segms, h, w, device="cuda:0", stream=None):
     return out
 
 
-def decode(segm, h=None, w=None, device="cuda:0"):
+def decode(segm, h=None, w=None, device=None):
     """``maskUtils.decode`` of one segmentation (RLE dicts carry their own ``size``) -> numpy [h, w] uint8."""
     if isinstance(segm, dict) and "size" in segm:
         h, w = int(segm["size"][0]), int(segm["size"][1])
@@ -85,14 +87,14 @@ def decode(segm, h=None, w=None, device="cuda:0"):
 
 
 # ---- the reader's per-annotation functions (same names, arguments and return values) ---------------------------
-def read_KINS(ann, device="cuda:0"):
+def read_KINS(ann, device=None):
     """reference datasets/reader.py:20-28"""
     modal = decode(ann["inmodal_seg"], device=device)
     score = ann["score"] if "score" in ann.keys() else 1.
     return modal, ann["inmodal_bbox"], ann["category_id"], score
 
 
-def read_LVIS(ann, h, w, device="cuda:0"):
+def read_LVIS(ann, h, w, device=None):
     """reference datasets/reader.py:31-46"""
     return decode(ann["segmentation"], h, w, device), ann["bbox"], ann["category_id"]
 
@@ -105,7 +107,7 @@ def mask_to_bbox(mask):
     return [int(xs.min()), int(ys.min()), int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1)]
 
 
-def read_COCOA(ann, h, w, device="cuda:0"):
+def read_COCOA(ann, h, w, device=None):
     """reference datasets/reader.py:49-66"""
     if "visible_mask" in ann.keys():
         modal = decode(ann["visible_mask"], h, w, device)
@@ -118,7 +120,7 @@ def read_COCOA(ann, h, w, device="cuda:0"):
     return modal, bbox, 1
 
 
-def image_instances(anns, h, w, device="cuda:0"):
+def image_instances(anns, h, w, device=None):
     """The mask / box / category triple of ``InstaOrderDataset.get_image_instances`` (reference
     datasets/reader.py:421-457) for the annotations of one image, masks left on the GPU: (uint8 CUDA [N, h, w],
     float64 [N, 4], int64 [N])."""

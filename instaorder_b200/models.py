@@ -13,6 +13,7 @@ import torch
 
 from . import _lib
 from .engine import OrderEngine
+from .init import reference_init_state_dict
 from .training import FlatOptim, TrainEngine
 
 __all__ = ["InstaOrderNet_o", "InstaOrderNet_d", "InstaOrderNet_od", "OrderNet", "InstaDepthNet_od", "InstaDepthNet_d", "MidasNet"]
@@ -47,7 +48,10 @@ class _OrderModel(object):
         self.max_pairs = int(params.get("max_pairs", 256))
         self.device = params.get("device", "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0")))
         self._engines = {}
-        self._state = None
+        # single_stage_model.py:24-25: the constructor always draws the reference's random initialisation from
+        # torch's global CPU generator (kaiming, then init_weights 'xavier' gain 0.02) -- bit-identical state_dict
+        # after the same torch.manual_seed, so Trainer(args).run() starts from scratch as every train.sh does
+        self._state = reference_init_state_dict(self.num_classes, bp.get("in_channels", 5))
         self.phase = "eval"
         if load_pretrain is not None:
             self.load_pretrain(load_pretrain)
@@ -56,9 +60,6 @@ class _OrderModel(object):
     def engine_for(self, input_size):
         e = self._engines.get(input_size)
         if e is None:
-            if self._state is None:
-                raise RuntimeError("no weights loaded: call load_state()/load_state_dict() first "
-                                   "(the reference's random init gives all-tie logits)")
             e = OrderEngine(self.num_classes, input_size, self.max_pairs, self.device)
             e.load_state_dict(self._state)
             self._engines[input_size] = e
@@ -122,8 +123,6 @@ class _OrderModel(object):
                                "(the reference's DistributedGivenIterationSampler only yields full batches)" %
                                (t.batch_pairs, t.input_size, batch, input_size))
         if t is None:
-            if self._state is None:
-                raise RuntimeError("no weights loaded: call load_state()/load_state_dict() first")
             t = TrainEngine(self.num_classes, input_size, batch, self.device)
             t.load_state_dict(self._state)
             if self.dist_model:
@@ -229,6 +228,16 @@ class _ModelCallable(object):
         return self.owner._state
 
 
+def _check_labels(t, k, name):
+    """Class targets must lie in [0, k): the reference's ``nn.CrossEntropyLoss`` raises on anything else (e.g. the -1
+    the dataset classes emit for an unannotated depth pair); the loss kernels index with the target unchecked."""
+    if t.numel():
+        lo, hi = int(t.min()), int(t.max())
+        if lo < 0 or hi >= k:
+            raise IndexError("%s: target %d is out of bounds for %d classes" % (name, lo if lo < 0 else hi, k))
+    return t
+
+
 def _swap01(t):
     """order2 of set_input: 0 -> 1, 1 -> 0, everything else unchanged."""
     o = t.clone()
@@ -260,7 +269,7 @@ class InstaOrderNet_d(_OrderModel):
 
     def set_input(self, rgb=None, modal1=None, modal2=None, depth_order=None, count=None, is_overlap=None):  # :383-395
         self._set_common(rgb, modal1, modal2)
-        self.depth_order1 = depth_order.to(self.rgb.device, torch.int64).contiguous()
+        self.depth_order1 = _check_labels(depth_order, 3, "depth_order").to(self.rgb.device, torch.int64).contiguous()
         self.depth_order2 = _swap01(self.depth_order1)
         self.count = count.to(self.rgb.device)
         self.is_overlap = is_overlap.to(self.rgb.device, torch.int64).contiguous()
@@ -281,7 +290,7 @@ class InstaOrderNet_od(_OrderModel):
     def set_input(self, rgb=None, modal1=None, modal2=None, depth_order=None, count=None, is_overlap=None,
                   occ_order=None):                                                # supervised_order.py:32-48
         self._set_common(rgb, modal1, modal2)
-        self.depth_order1 = depth_order.to(self.rgb.device, torch.int64).contiguous()
+        self.depth_order1 = _check_labels(depth_order, 3, "depth_order").to(self.rgb.device, torch.int64).contiguous()
         self.depth_order2 = _swap01(self.depth_order1)
         self.count = count.to(self.rgb.device)
         self.is_overlap = is_overlap.to(self.rgb.device, torch.int64).contiguous()
@@ -303,7 +312,8 @@ class OrderNet(_OrderModel):
 
     def set_input(self, rgb=None, modal1=None, modal2=None, occ_order=None):      # supervised_order.py:451-463
         self._set_common(rgb, modal1, modal2)
-        self.occ_order1 = occ_order.to(self.rgb.device, torch.int64).contiguous()
+        self.occ_order1 = _check_labels(occ_order, int(self.num_classes), "occ_order").to(
+            self.rgb.device, torch.int64).contiguous()
         self.occ_order2 = _swap01(self.occ_order1)
 
     def forward_only(self, ret_loss=True):                                        # supervised_order.py:465-479

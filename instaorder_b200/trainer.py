@@ -131,8 +131,10 @@ class Trainer(object):
     def __init__(self, args, train_dataset=None, val_dataset=None):
         import torch.distributed as dist
         seed = getattr(args, "seed", 0)
-        torch.manual_seed(seed)
-        np.random.seed(seed)
+        torch.manual_seed(seed)            # reference trainer.py:26-31 (the model constructor below draws its
+        np.random.seed(seed)               # initial weights from torch's generator right after this seeding)
+        import random
+        random.seed(seed)
         self.distributed = dist.is_available() and dist.is_initialized()
         self.world_size = dist.get_world_size() if self.distributed else 1
         self.rank = dist.get_rank() if self.distributed else 0
@@ -230,6 +232,9 @@ class Trainer(object):
     def validate(self, phase):
         args = self.args
         recorder = {rec: AverageMeter(10) for rec in args.trainer["loss_record"]}
+        if self.val_loader is None:
+            raise ValueError("validation requested (args.validate / initial_val / val_freq) but no val_dataset was "
+                             "passed to Trainer(args, train_dataset, val_dataset)")
         self.model.switch_to("eval")
         for i, inputs in enumerate(self.val_loader):
             if args.trainer.get("val_iter", -1) != -1 and i == args.trainer["val_iter"]:
