@@ -44,13 +44,18 @@ D = 256
 
 
 def measured_peaks():
+    """Roofline denominators.  ``bf16`` is the BURST cuBLAS figure: every fraction this file reports is against it
+    (kernels are event-timed, the timed region lasts well under a second -- the sustained figure, taken at a 1.3 GHz
+    median clock over a seconds-long loop, is reported beside it as ``*_sustained`` for context only)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         with open(p) as f:
             j = json.load(f)
-        return dict(bf16=j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1590.0)), hbm=j.get("hbm_gbs", 6650.0),
-                    source="measured (MEASURED_PEAKS.json, sustained bf16)")
-    return dict(bf16=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+        burst = j.get("bf16_tflops", 1590.0)
+        return dict(bf16=burst, bf16_sustained=j.get("bf16_tflops_sustained", burst), hbm=j.get("hbm_gbs", 6650.0),
+                    source="measured (MEASURED_PEAKS.json: burst bf16 %.1f TFLOP/s, HBM copy %.0f GB/s)" %
+                           (burst, j.get("hbm_gbs", 6650.0)))
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -105,25 +110,172 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def make_scenes(seed, n_images):
+WORKLOADS = {
+    # mode -> (label, scene generator args): SURVEY.md section 8d
+    "c2": ("C2: synthetic COCO-val-shaped images, 10 instances -> 45 pairs/image", None),
+    "c1": ("C1: synthetic 640x480 images, 8 instances -> 28 pairs/image", dict(H=480, W=640, N=8, float_boxes=False)),
+    "c3": ("C3: synthetic KINS-shaped 1242x375 images, 15 instances -> 105 pairs/image",
+           dict(H=375, W=1242, N=15, wh_range=((20, 200), (20, 150)), float_boxes=False)),
+}
+
+
+def make_scenes(seed, n_images, workload="c2"):
     from instaorder_b200 import engine, synth
     out = []
-    for image, masks, boxes in synth.coco_scene_stream(seed, n_images, N=10):
+    kw = WORKLOADS[workload][1]
+    if kw is None:
+        stream = synth.coco_scene_stream(seed, n_images, N=10)
+    else:
+        rng = np.random.RandomState(seed)
+        stream = (synth.make_scene(rng, **kw) for _ in range(n_images))
+    for image, masks, boxes in stream:
         out.append(engine.Scene(image, masks, engine.expand_bbox(boxes, 3.0)))
     return out
 
 
-def cpu_port_pairs_per_s(n_pairs, threads=None):
+def crop_read_bytes(batch):
+    """Algorithmic source bytes one gather launch reads: 5 B (rgb + two masks) per source pixel
+    in crop \u2229 image, summed over the pairs of the batch."""
+    tot = 0
+    for (sc, pairs, crops, _, _) in batch:
+        x0 = np.maximum(crops[:, 0], 0)
+        y0 = np.maximum(crops[:, 1], 0)
+        x1 = np.minimum(crops[:, 0] + crops[:, 2], sc.w)
+        y1 = np.minimum(crops[:, 1] + crops[:, 2], sc.h)
+        tot += int((np.maximum(x1 - x0, 0).astype(np.int64) * np.maximum(y1 - y0, 0)).sum()) * 5
+    return tot
+
+
+def time_gather(eng, resident, batches, gmode, peaks, reps=3):
+    """CUDA-event time of the fused gather kernel alone (G5-G9: crop + cubic / nearest resize + normalise + bf16
+    pair tensor) over the resident batches, against the measured HBM copy bandwidth."""
+    import torch
+    if gmode != "patch":
+        return None
+    for r in resident[:2]:
+        eng.gather(r, r.P, gmode)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for r in resident:
+            eng.gather(r, r.P, gmode)
+    e1.record()
+    torch.cuda.synchronize()
+    n = reps * len(resident)
+    ms = e0.elapsed_time(e1) / n
+    P = resident[0].P
+    read = float(np.mean([crop_read_bytes(b) for b in batches]))
+    algo = P * D * D * 5 * 2 + read                          # one 5-channel bf16 tensor per pair + the unique source bytes
+    written = int(eng.lib.io_pair_tensor_bytes(P, D))      # what the kernel actually stores (8-channel pixels + border)
+    gbs = algo / (ms / 1000.0) / 1e9
+    return dict(bound="hbm", kernel="gather_patch_kernel", achieved=gbs, peak=peaks["hbm"], unit="GB/s",
+                frac=gbs / peaks["hbm"], avg_launch_ms=ms, launches_timed=n, algorithmic_bytes_per_launch=int(algo),
+                stored_bytes_per_launch=written, stored_GBps=(written + read) / (ms / 1000.0) / 1e9)
+
+
+def time_metrics(dev, peaks, images=65536, n=16, reps=5):
+    """the metric kernels batched over 65,536 synthetic images with N = 16 instances each
+    (int64 matrices, the reference's ``np.int``): algorithmic bytes = the matrices each kernel must read once."""
+    import torch
+    from instaorder_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device=dev).manual_seed(5)
+    nn_ = n * n
+    order = torch.randint(0, 2, (images * nn_,), generator=g, device=dev, dtype=torch.int64)
+    gt = torch.randint(-1, 2, (images * nn_,), generator=g, device=dev, dtype=torch.int64)
+    dpred = torch.randint(0, 3, (images * nn_,), generator=g, device=dev, dtype=torch.int64)
+    dgt = torch.randint(0, 3, (images * nn_,), generator=g, device=dev, dtype=torch.int64)
+    ovl = torch.randint(0, 2, (images * nn_,), generator=g, device=dev, dtype=torch.int64)
+    cnt = torch.randint(1, 4, (images * nn_,), generator=g, device=dev, dtype=torch.int64)
+    off = torch.arange(images, device=dev, dtype=torch.int64) * nn_
+    ns = torch.full((images,), n, device=dev, dtype=torch.int32)
+    out3 = torch.empty((images, 3), dtype=torch.float64, device=dev)
+    out9 = torch.empty((images, 9), dtype=torch.float64, device=dev)
+    st = _lib.stream_ptr()
+    res = {}
+
+    def run(name, fn, algo_bytes):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = algo_bytes / (ms / 1000.0) / 1e9
+        res[name] = dict(bound="hbm", kernel=name + "_kernel", achieved=gbs, peak=peaks["hbm"], unit="GB/s",
+                         frac=gbs / peaks["hbm"], avg_launch_ms=ms, us_per_image=1000.0 * ms / images,
+                         algorithmic_bytes_per_launch=int(algo_bytes), images=images, n=n)
+
+    run("prf", lambda: _lib.check(L.io_metrics_prf(order.data_ptr(), gt.data_ptr(), off.data_ptr(), ns.data_ptr(), images,
+                                                   1, out3.data_ptr(), st)), images * (2 * nn_ * 8 + 24))
+    tri = n * (n - 1) // 2
+    run("whdr", lambda: _lib.check(L.io_metrics_whdr(dpred.data_ptr(), dgt.data_ptr(), ovl.data_ptr(), cnt.data_ptr(),
+                                                     off.data_ptr(), ns.data_ptr(), images, out9.data_ptr(), st)),
+        images * (4 * tri * 8 + 72))
+    return res
+
+
+def host_threads():
+    """Every host core this process may use (torchrun pins OMP_NUM_THREADS=1 by default)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+_REF_MODEL = {}
+
+
+def cpu_reference_pairs_per_s(n_pairs, threads=None):
+    """The UNMODIFIED reference (``inference.infer_order_sup_occ_depth``: per-pair cv2 crops, two batch-1 fp32
+    forwards, five host syncs per pair -- reference inference.py:349-436) on the host cores, imported from
+    ``/root/reference`` or, on the GPU box, from the archive oracle/build_ref.py packed into ``oracle/_ref/``.
+    Returns None when neither exists (the caller falls back to the oracle port run the same batch-1 way)."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        return None
+    import torch
+    from instaorder_b200 import synth
+    from oracle import gen_golden, oracle as O
+    threads = threads or host_threads()
+    torch.set_num_threads(threads)
+    ns = ref_shim.load()
+    if "m" not in _REF_MODEL:
+        _REF_MODEL["m"] = gen_golden.make_reference_model(ns, ALGO, NUM_CLASSES, synth.random_state_dict(0, 5, NUM_CLASSES))
+    model = _REF_MODEL["m"]
+    n_img = max(1, (n_pairs + 44) // 45)
+    scenes = list(synth.coco_scene_stream(99, n_img, N=10))
+    image, masks, boxes = scenes[0]
+    bexp = O.expand_bbox(boxes, 3.0)
+    ns.inference.infer_order_sup_occ_depth(model, image, masks[:2], bexp[:2], "all", ALGO, "patch", D, "")   # warm-up
+    done, dt = 0, 0.0
+    for (image, masks, boxes) in scenes:
+        left = n_pairs - done
+        if left <= 0:
+            break
+        k = 2
+        while k * (k - 1) // 2 < left and k < 10:
+            k += 1
+        bexp = O.expand_bbox(boxes, 3.0)
+        t0 = time.perf_counter()
+        ns.inference.infer_order_sup_occ_depth(model, image, masks[:k], bexp[:k], "all", ALGO, "patch", D, "")
+        dt += time.perf_counter() - t0
+        done += k * (k - 1) // 2
+    return done / dt, done, dt, torch.get_num_threads()
+
+
+def cpu_port_pairs_per_s(n_pairs, threads=None, batch1=False):
     """The oracle port (= the reference algorithm: per-pair cv2-equivalent crops, fp32 torch-CPU ResNet-50 on both
-    directions, decisions) timed on the host cores for a bounded sample of the same workload."""
+    directions, decisions) timed on the host cores for a bounded sample of the same workload.  ``batch1``: one forward
+    per network input as the reference does; otherwise 16 forwards per batch (the best case for a CPU)."""
     import torch
     from instaorder_b200 import synth
     from oracle import oracle as O
-    if threads is None:      # every host core this process may use (torchrun pins OMP_NUM_THREADS=1 by default)
-        try:
-            threads = len(os.sched_getaffinity(0))
-        except AttributeError:
-            threads = os.cpu_count() or 1
+    threads = threads or host_threads()
     torch.set_num_threads(threads)
     rng = np.random.RandomState(1234)
     sd = synth.random_state_dict(0, 5, NUM_CLASSES)
@@ -144,7 +296,8 @@ def cpu_port_pairs_per_s(n_pairs, threads=None):
             k += 1
         bexp = O.expand_bbox(boxes, 3.0)
         t0 = time.perf_counter()
-        r = O.infer_order(sd, image, masks[:k], bexp[:k], "all", ALGO, "patch", D, chunk=8)
+        r = O.infer_order(sd, image, masks[:k], bexp[:k], "all", ALGO, "patch", D, chunk=1 if batch1 else 8,
+                          batch1=batch1)
         dt += time.perf_counter() - t0
         done += len(r["pairs"])
     return done / dt, done, dt, torch.get_num_threads()
@@ -183,17 +336,24 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
     steps, warmup = args.steps, args.warmup
     sample_pairs = 10                                           # 5 instances -> 10 pairs per step
     vals = []
+    kind = "reference"
     for s in range(warmup + steps):
-        v, n, dt, threads = cpu_port_pairs_per_s(sample_pairs)
+        r = cpu_reference_pairs_per_s(sample_pairs)
+        if r is None:                                           # no reference tree / archive: the port, run batch-1
+            kind = "port"
+            r = cpu_port_pairs_per_s(sample_pairs, batch1=True)
+        v, n, dt, threads = r
         if s >= warmup:
             vals.append((n, dt))
     pairs = sum(n for n, _ in vals)
     secs = sum(dt for _, dt in vals)
     value = pairs / secs
+    how = ("the UNMODIFIED reference's inference.infer_order_sup_occ_depth (per-pair cv2 crops + two batch-1 fp32 "
+           "torch-CPU forwards, oracle/_ref archive)" if kind == "reference" else
+           "fp32 torch-CPU oracle port of the reference's inference.py patch path, two batch-1 forwards per pair")
     # same metric / config.workload strings as the b200 arm (the driver pairs the two lines); the reference arm computes in
     # fp32 (dtype) and its step is a bounded sample of the workload (config.sample)
     line = dict(impl="reference", metric="instance pairs/s (InstaOrderNet^od, 256^2, bf16)", value=value, unit="pairs/s",
@@ -201,10 +361,9 @@ def run_reference_arm(args):
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload="C2: synthetic COCO-val-shaped images, 10 instances -> 45 pairs/image, %d pairs per "
                                      "step, patch 256^2, InstaOrderNet^od heads [2,3], random-init weights" % PAIRS_PER_STEP,
-                            sample="bounded sample of %d pairs per step on the host cores (fp32 torch-CPU oracle port of "
-                                   "the reference's inference.py patch path)" % sample_pairs),
-                cpu_baseline=dict(value=value, unit="pairs/s", cores=threads, kind="port",
-                                  sample="%d pairs/step x %d steps, batched fp32 torch-CPU forward" % (sample_pairs, steps)),
+                            sample="bounded sample of %d pairs per step on the host cores: %s" % (sample_pairs, how)),
+                cpu_baseline=dict(value=value, unit="pairs/s", cores=threads, kind=kind,
+                                  sample="%d pairs/step x %d steps: %s" % (sample_pairs, steps, how)),
                 e2e=dict(value=value, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
 
@@ -235,8 +394,6 @@ def run_train(args):
     flat gradient buffer for N > 1.  Not the headline metric: run explicitly with --workload train."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    B = args.train_batch
     if args.impl == "reference":
         if rank != 0:
             return
@@ -253,14 +410,35 @@ def run_train(args):
                                                 sample="2 pairs/step x %d steps, fp32 torch-CPU autograd" % len(vals)),
                               e2e=dict(value=value, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return
+    line = measure_train(args, args.steps, args.warmup)
+    if rank == 0:
+        emit(line)
+    import torch.distributed as dist
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def init_dist():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    return world, rank, local, dev
+
+
+def measure_train(args, steps, warmup, with_e2e=True, with_cpu=True):
+    """One training measurement (all ranks call it; the returned line is complete on rank 0)."""
     import torch
     import torch.distributed as dist
     from instaorder_b200 import _lib, models, synth
-    torch.cuda.set_device(local)
-    dev = "cuda:%d" % local
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+    world, rank, local, dev = init_dist()
+    B = args.train_batch
     params = dict(algo=ALGO, backbone_arch="resnet50_cls", backbone_param=dict(in_channels=5, num_classes=NUM_CLASSES),
                   optim="SGD", lr=1e-4, weight_decay=1e-4, use_rgb=True, overlap_weight=0.1, distinct_weight=0.9,
                   device=dev)
@@ -271,9 +449,9 @@ def run_train(args):
     n_batches = 4
     host = []
     for _ in range(n_batches):     # pinned host batches in the DataLoader's collated types
-        host.append(dict(rgb=torch.randn((B, 3, D, D), generator=g).pin_memory(),
-                         modal1=(torch.rand((B, 1, D, D), generator=g) > 0.7).float().pin_memory(),
-                         modal2=(torch.rand((B, 1, D, D), generator=g) > 0.7).float().pin_memory(),
+        host.append(dict(rgb=torch.randn((B, 3, 256, 256), generator=g).pin_memory(),
+                         modal1=(torch.rand((B, 1, 256, 256), generator=g) > 0.7).float().pin_memory(),
+                         modal2=(torch.rand((B, 1, 256, 256), generator=g) > 0.7).float().pin_memory(),
                          depth_order=torch.randint(0, 3, (B,), generator=g).pin_memory(),
                          count=torch.randint(2, 4, (B,), generator=g).pin_memory(),
                          is_overlap=(torch.rand((B,), generator=g) < 0.3).long().pin_memory(),
@@ -290,7 +468,7 @@ def run_train(args):
         model.set_input(**batch)
         return model.step()
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(resident[i % n_batches])
     sync_all()
     eng = model._trainer
@@ -300,7 +478,7 @@ def run_train(args):
     l0 = eng.gpu_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(resident[i % n_batches])
     e1.record()
     sync_all()
@@ -311,22 +489,24 @@ def run_train(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * args.steps * B / (ms / 1000.0)
-    # end to end: pinned host batch -> H2D -> step -> loss read back, every step
-    for i in range(2):
-        float(step(host[i % n_batches])[1]["loss"])
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        float(step(host[i % n_batches])[1]["loss"])
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e_value = world * args.steps * B / dt
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    value = world * steps * B / (ms / 1000.0)
+    e2e = None
+    if with_e2e:
+        # end to end: pinned host batch -> H2D -> step -> loss read back, every step
+        for i in range(2):
+            float(step(host[i % n_batches])[1]["loss"])
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            float(step(host[i % n_batches])[1]["loss"])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+        e2e = dict(value=world * steps * B / dt, unit="pairs/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4)
     # per-kernel events of one step
     _lib.check(eng.lib.io_train_profile(eng.handle, 1))
     step(resident[0])
@@ -342,37 +522,34 @@ def run_train(args):
     ew = kind[:n] == 3
     tc_ms, tc_fl = float(pms[:n][tc].sum()), float(fl[:n][tc].sum())
     ew_ms, ew_by = float(pms[:n][ew].sum()), float(by[:n][ew].sum())
-    if rank == 0:
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            v, npairs, cdt, threads = cpu_train_pairs_per_s(2, D)
-            cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
-                       sample="one step() on 2 pairs (%.1f s): training oracle, fp32 torch-CPU autograd" % cdt)
-        achieved = tc_fl / (tc_ms / 1000.0) / 1e12 if tc_ms > 0 else 0.0
-        emit((dict(
-            metric="training pairs/s (InstaOrderNet^od step: fwd + bwd + all-reduce + SGD, 256^2, bf16)",
-            value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-            data="synthetic",
-            config=dict(workload="C4: InstaOrderNet^od training step, %d synthetic pairs per GPU per step at %d^2, SGD "
-                                 "lr 1e-4 momentum 0.9 wd 1e-4, random-init weights" % (B, D),
-                        pairs_per_step=B * world, parallelism="data parallel over %d GPU(s), one NCCL all-reduce of the "
-                        "flat fp32 gradient buffer (94 MB) per step" % world,
-                        l2="each step streams > 10 GB of saved activations and gradients, i.e. >> 126 MB L2"),
-            e2e=dict(value=e2e_value, unit="pairs/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4),
-            gpu_launches=launches, clocks=clocks,
-            roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
-                          frac=achieved / peaks["bf16"], traffic=None,
-                          kernel="conv_tc / conv_tn (forward + data gradient) + wgrad_kernel",
-                          tensor_share_of_step=tc_ms / float(pms[:n].sum()), peak_source=peaks["source"],
-                          elementwise=dict(bound="hbm", achieved=ew_by / (ew_ms / 1000.0) / 1e9 if ew_ms else 0.0,
-                                           peak=peaks["hbm"], unit="GB/s",
-                                           frac=ew_by / (ew_ms / 1000.0) / 1e9 / peaks["hbm"] if ew_ms else 0.0,
-                                           share_of_step=ew_ms / float(pms[:n].sum())),
-                          step_frac=value / world * 3 * FLOP_PER_PAIR / 1e12 / peaks["bf16"]),
-            cpu_baseline=cpu)))
-    if world > 1:
-        dist.destroy_process_group()
+    cpu = None
+    if rank == 0 and world == 1 and with_cpu and not args.no_cpu_baseline:
+        v, npairs, cdt, threads = cpu_train_pairs_per_s(2, 256)
+        cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
+                   sample="one step() on 2 pairs (%.1f s): training oracle, fp32 torch-CPU autograd" % cdt)
+    achieved = tc_fl / (tc_ms / 1000.0) / 1e12 if tc_ms > 0 else 0.0
+    step_tf = value / world * 3 * 21.764e9 / 1e12
+    return dict(
+        metric="training pairs/s (InstaOrderNet^od step: fwd + bwd + all-reduce + SGD, 256^2, bf16)",
+        value=value, unit="pairs/s", n_gpus=world, steps=steps, warmup=warmup,
+        ms_per_step=ms / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+        data="synthetic",
+        config=dict(workload="C4: InstaOrderNet^od training step, %d synthetic pairs per GPU per step at 256^2, SGD "
+                             "lr 1e-4 momentum 0.9 wd 1e-4, random-init weights" % B,
+                    pairs_per_step=B * world, parallelism="data parallel over %d GPU(s): the flat fp32 gradient buffer "
+                    "(94 MB) is all-reduced over NCCL every step" % world,
+                    l2="each step streams > 10 GB of saved activations and gradients, i.e. >> 126 MB L2"),
+        e2e=e2e, gpu_launches=launches, clocks=clocks,
+        roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
+                      frac=achieved / peaks["bf16"], frac_sustained=achieved / peaks["bf16_sustained"], traffic=None,
+                      kernel="conv_tc / conv_tn (forward + data gradient) + wgrad_kernel",
+                      tensor_share_of_step=tc_ms / float(pms[:n].sum()), peak_source=peaks["source"],
+                      elementwise=dict(bound="hbm", achieved=ew_by / (ew_ms / 1000.0) / 1e9 if ew_ms else 0.0,
+                                       peak=peaks["hbm"], unit="GB/s",
+                                       frac=ew_by / (ew_ms / 1000.0) / 1e9 / peaks["hbm"] if ew_ms else 0.0,
+                                       share_of_step=ew_ms / float(pms[:n].sum())),
+                      step_frac=step_tf / peaks["bf16"], step_frac_sustained=step_tf / peaks["bf16_sustained"]),
+        cpu_baseline=cpu)
 
 
 def main():
@@ -383,9 +560,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-pairs", type=int, default=225)
-    ap.add_argument("--mode", default="patch256", choices=["patch256", "resize384", "instadepth384"],
+    ap.add_argument("--mode", default="patch256", choices=["patch256", "resize384", "instadepth384", "c1_o256",
+                                                           "c3_ordernet256"],
                     help="patch256 = the BASELINE.json metric (default); resize384 = the shipped InstaOrderNet^od "
-                         "config (whole image -> 384^2), reported as a second row in DESIGN.md")
+                         "config (whole image -> 384^2); c1_o256 / c3_ordernet256 = BASELINE configs 1 and 3 "
+                         "(InstaOrderNet^o on 640x480 / 8 instances; OrderNet on KINS-shaped 1242x375 / 15 instances)")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
                     help="infer = the BASELINE.json headline (default); train = BASELINE config C4, one "
                          "InstaOrderNet^od training step (fwd + bwd + all-reduce + SGD) per step")
@@ -411,27 +590,26 @@ def main():
         # the reference spends 2 x 254.5 GFLOP per pair (encoder + MiDaS decoder + trunks for every direction)
         FLOP_PER_PAIR = 4 * 24.485e9 + depth_engine.encoder_flops_per_image(D) / 45.0
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = "cuda:%d" % local
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+    wl, ncs = "c2", NUM_CLASSES
+    if args.mode == "c1_o256":
+        wl, ALGO, ncs = "c1", "InstaOrderNet_o", 2
+    if args.mode == "c3_ordernet256":
+        wl, ALGO, ncs = "c3", "OrderNet", 3
+    world, rank, local, dev = init_dist()
 
     # ---- workload: every rank owns its own images (weak scaling: images are sharded, no data-path collective)
     n_batches = 8                                    # distinct resident batches, rotated so inputs never sit in L2
-    n_images = (n_batches * PAIRS_PER_STEP) // 45 + 2
-    scenes = make_scenes(1000 + rank, n_images)
+    ppi = {"c2": 45, "c1": 28, "c3": 105}[wl]
+    n_images = (n_batches * PAIRS_PER_STEP) // ppi + 2
+    scenes = make_scenes(1000 + rank, n_images, wl)
     if depth:
         eng = depth_engine.DepthOrderEngine(D, max_pairs=PAIRS_PER_STEP, max_images=8, device=dev)
         eng.load_state_dict(synth.instadepth_state_dict(0))
         heads = engine.heads_for("InstaOrderNet_od", NUM_CLASSES)
     else:
-        eng = engine.OrderEngine(NUM_CLASSES, D, max_pairs=PAIRS_PER_STEP, device=dev)
-        eng.load_state_dict(synth.random_state_dict(0, 5, NUM_CLASSES))
-        heads = engine.heads_for(ALGO, NUM_CLASSES)
+        eng = engine.OrderEngine(ncs, D, max_pairs=PAIRS_PER_STEP, device=dev)
+        eng.load_state_dict(synth.random_state_dict(0, 5, ncs))
+        heads = engine.heads_for(ALGO, ncs)
     batches, mat_elems = eng.make_batches(scenes, PAIRS_PER_STEP, gmode)
     batches = batches[:n_batches]
     resident = [eng.upload_resident(b, mat_elems, gmode) for b in batches]
@@ -487,6 +665,9 @@ def main():
     achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
     if depth:
         achieved = value / world * FLOP_PER_PAIR / 1e12
+    # ---- the HBM-bound kernels on their own: fused gather, batched metrics -------------
+    gather_roof = time_gather(eng, resident, batches, gmode, peaks) if not depth else None
+    metrics_roof = time_metrics(dev, peaks) if (rank == 0 and args.mode == "patch256") else None
     # DRAM traffic of the conv kernel per launch, from the committed ncu capture of this command (profiles/)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
@@ -499,7 +680,7 @@ def main():
     o = 0
     for i in range(args.warmup + args.steps):
         # the public API takes whole images: an e2e step = 17 images = 765 pairs = 3 engine batches (256+256+253)
-        n_e2e = 6 if depth else 17
+        n_e2e = 6 if depth else {"c2": 17, "c1": 27, "c3": 7}[wl]
         per_step_scenes.append([scenes[(o + k) % len(scenes)] for k in range(n_e2e)])
         o += n_e2e
     for i in range(args.warmup):
@@ -529,19 +710,35 @@ def main():
                        sample="%d pairs of one image (%.1f s): oracle port of the order branch (fp32 torch-CPU, encoder once "
                               "per image, no MiDaS decoder -- an upper bound on the reference, which recomputes both per "
                               "pair direction)" % (n, cdt))
-        elif world == 1 and not args.no_cpu_baseline:
-            v, n, cdt, threads = cpu_port_pairs_per_s(args.cpu_sample_pairs)
-            cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
-                       sample="%d pairs of C2 images (%.1f s): oracle port of inference.py patch path + fp32 "
-                              "torch-CPU ResNet-50, batched 16 forwards" % (n, cdt))
+        elif world == 1 and not args.no_cpu_baseline and args.mode == "patch256":
+            # (i) the faithful baseline: the reference as written (two batch-1 forwards per pair); (ii) beside it the
+            # best case for a CPU: the same algorithm with 16 forwards per batch (the oracle port)
+            r = cpu_reference_pairs_per_s(args.cpu_sample_pairs // 3)
+            kind = "reference"
+            if r is None:
+                kind, r = "port", cpu_port_pairs_per_s(args.cpu_sample_pairs // 3, batch1=True)
+            v, n, cdt, threads = r
+            vb, nb, cdtb, _ = cpu_port_pairs_per_s(args.cpu_sample_pairs // 2)
+            cpu = dict(value=v, unit="pairs/s", cores=threads, kind=kind,
+                       sample="%d pairs of C2 images (%.1f s): %s, two batch-1 fp32 torch-CPU forwards per pair as in "
+                              "inference.py:140-169" % (n, cdt, "the UNMODIFIED reference (oracle/_ref archive)"
+                                                        if kind == "reference" else "oracle port of the reference"),
+                       batched_port=dict(value=vb, unit="pairs/s", kind="port",
+                                         sample="%d pairs (%.1f s): oracle port, 16 forwards per batch (best case for "
+                                                "the host cores)" % (nb, cdtb)))
         line = dict(
             metric=("instance pairs/s (InstaDepthNet^od order inference, resize 384^2, bf16)" if depth else
-                    "instance pairs/s (InstaOrderNet^od, %s, bf16)" % ("256^2" if gmode == "patch" else "resize 384^2")),
+                    "instance pairs/s (%s, %s, bf16)" % ({"InstaOrderNet_od": "InstaOrderNet^od", "InstaOrderNet_o":
+                                                          "InstaOrderNet^o", "OrderNet": "OrderNet"}[ALGO],
+                                                         "256^2" if gmode == "patch" else "resize 384^2")),
             value=value, unit="pairs/s", n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
             scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-            config=dict(workload="C2: synthetic COCO-val-shaped images, 10 instances -> 45 pairs/image, %d pairs per "
-                                 "step, %s, %s, random-init weights" % (PAIRS_PER_STEP, "patch 256^2" if gmode == "patch" else "resize 384^2 (shipped config)", "InstaDepthNet^od order branch (ResNeXt-101 encoder layer1-3 once per image + do_net / oo_net trunks)" if depth else "InstaOrderNet^od heads [2,3]"),
+            config=dict(workload="%s, %d pairs per step, %s, %s, random-init weights" % (
+                WORKLOADS[wl][0], PAIRS_PER_STEP, "patch 256^2" if gmode == "patch" else "resize 384^2 (shipped config)",
+                "InstaDepthNet^od order branch (ResNeXt-101 encoder layer1-3 once per image + do_net / oo_net trunks)"
+                if depth else {"InstaOrderNet_od": "InstaOrderNet^od heads [2,3]", "InstaOrderNet_o": "InstaOrderNet^o head [2]",
+                               "OrderNet": "OrderNet head [3]"}[ALGO]),
                         pairs_per_step=PAIRS_PER_STEP, parallelism="images sharded over %d GPU(s), no collective" % world,
                         l2="inputs rotate over %d resident batches (%.0f MB) and each step streams >10 GB of "
                            "activations, i.e. >> 126 MB L2" % (len(resident), input_bytes / 1e6)),
@@ -549,14 +746,35 @@ def main():
                      pairs_per_step=pairs_e2e // args.steps),
             gpu_launches=launches,
             clocks=clocks,
+            # frac: the dominant kernel family (all convolution launches, CUDA events inside the library) against the
+            # BURST measured bf16 peak; step_frac: the whole step, pairs/s x 21.764 GFLOP / burst peak (BASELINE.md
+            # section 2) -- the headline fraction; *_sustained: the same against the seconds-long cuBLAS figure
             roofline=dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s",
-                          frac=achieved / peaks["bf16"], traffic=traffic,
+                          frac=achieved / peaks["bf16"], frac_sustained=achieved / peaks["bf16_sustained"],
+                          traffic=traffic,
                           kernel=("whole step: encoder (once per image) + two trunks, algorithmic FLOPs of this "
-                                  "formulation" if depth else "conv_tc_kernel (all 53 conv layers)"), launches_timed=n_conv, avg_launch_ms=conv_ms / max(n_conv, 1),
+                                  "formulation" if depth else
+                                  "conv_tc / conv_tn / conv_fused / stem kernels (all 53 conv layers)"),
+                          launches_timed=n_conv, avg_launch_ms=conv_ms / max(n_conv, 1),
                           conv_share_of_step=conv_ms / tot_ms if tot_ms else None, peak_source=peaks["source"],
-                          step_frac=value / world * FLOP_PER_PAIR / 1e12 / peaks["bf16"]),
+                          step_tflops=value / world * FLOP_PER_PAIR / 1e12,
+                          step_frac=value / world * FLOP_PER_PAIR / 1e12 / peaks["bf16"],
+                          step_frac_sustained=value / world * FLOP_PER_PAIR / 1e12 / peaks["bf16_sustained"],
+                          gather=gather_roof, metrics=metrics_roof),
             cpu_baseline=cpu,
         )
+    # ---- BASELINE config C4 beside the headline: the training step (the path with a real collective), so that the
+    # driver's 1 -> 8 GPU runs of this file also carry a training scaling curve.  INSTAORDER_BENCH_TRAIN=0 skips it.
+    if args.mode == "patch256" and os.environ.get("INSTAORDER_BENCH_TRAIN", "1") != "0":
+        del resident
+        eng = None
+        torch.cuda.empty_cache()
+        tr = measure_train(args, steps=min(args.steps, 20), warmup=max(3, min(args.warmup, 5)), with_e2e=False,
+                           with_cpu=False)
+        if rank == 0:
+            line["training"] = {k: tr[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                                                   "scaling", "gpu_launches", "clocks", "roofline", "config")}
+    if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()

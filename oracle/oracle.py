@@ -447,8 +447,10 @@ def write_occ(mat, i, j, i_over_j, j_over_i):
 
 
 def infer_order(sd, image, inmodal, bboxes, pairs="all", method="InstaOrderNet_od", patch_or_image="patch",
-                input_size=256, forward=None, chunk=8):
-    """The public drivers inference.py:349-436 / 439-512 / 515-624 (H6) restated with a batched fp32 forward.
+                input_size=256, forward=None, chunk=8, batch1=False):
+    """The public drivers inference.py:349-436 / 439-512 / 515-624 (H6) restated with a batched fp32 forward
+    (``batch1=True``: one forward per network input, i.e. two batch-1 forwards per pair exactly as the reference's
+    ``net_forward_*`` do -- the faithful CPU baseline of bench.py when the reference archive is absent).
 
     Returns dict(occ=int64[N,N] | None, depth=int64[N,N] | None, margin_occ, margin_depth, logits=...)."""
     forward = forward or resnet50_forward
@@ -487,7 +489,11 @@ def infer_order(sd, image, inmodal, bboxes, pairs="all", method="InstaOrderNet_o
                 raise NotImplementedError(patch_or_image)
             xs.append(x)
             xs.append(x[[1, 0, 2, 3, 4]])
-        out = forward(sd, np.stack(xs).astype(np.float32))
+        if batch1:
+            outs = [forward(sd, x[None].astype(np.float32)) for x in xs]
+            out = {h: np.concatenate([o[h] for o in outs]) for h in outs[0]}
+        else:
+            out = forward(sd, np.stack(xs).astype(np.float32))
         for k, (i, j) in enumerate(plist[c0:c0 + chunk]):
             lg = {h: (v[2 * k], v[2 * k + 1]) for h, v in out.items()}
             logits[(i, j)] = lg

@@ -12,11 +12,29 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("INSTAORDER_REFERENCE", "/root/reference")
+REFERENCE_ZIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "instaorder_ref.zip")
+
+
+def _root():
+    """The unmodified tree when it exists (build container), else the archive of the same modules that
+    oracle/build_ref.py packed (GPU box: ``oracle/_ref/`` travels with the snapshot, ``/root/reference`` does not)."""
+    r = os.environ.get("INSTAORDER_REFERENCE", "/root/reference")
+    if os.path.isfile(os.path.join(r, "inference.py")):
+        return r
+    if os.path.isfile(REFERENCE_ZIP):
+        return REFERENCE_ZIP
+    return r
+
+
+REFERENCE_ROOT = _root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "inference.py"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "inference.py")) or REFERENCE_ROOT == REFERENCE_ZIP
+
+
+def is_archive() -> bool:
+    return REFERENCE_ROOT == REFERENCE_ZIP
 
 
 _loaded = {}

@@ -15,19 +15,21 @@ LOGIT_TOL = 2e-2       # |logit - reference fp32 logit|, BASELINE.json north_sta
 BF16_EMU_TOL = 5e-3    # |logit - ideal-bf16 CPU emulation of the same arithmetic| (kernel correctness proper)
 
 
-def make_model(case, golden_dir):
+def make_model(case, golden_dir, max_pairs=32):
     c = gen_golden.CASES[case]
     params = dict(algo=c["algo"], backbone_arch="resnet50_cls",
                   backbone_param=dict(in_channels=5, num_classes=c["num_classes"]), optim="SGD", lr=1e-4,
-                  weight_decay=1e-4, use_rgb=True, max_pairs=32)
+                  weight_decay=1e-4, use_rgb=True, max_pairs=max_pairs)
     m = models.__dict__[c["algo"]](params, dist_model=False)
-    m.load_state_dict(calib.load_calibrated(gen_golden.calib_path(case), c["wseed"], 5, c["num_classes"]))
+    m.load_state_dict(gen_golden.state_dict_for(case))
     m.switch_to("eval")
     return m
 
 
+# c2_od_full / c3_ordernet_full: BASELINE.json's own sizes (10 instances -> 45 pairs; 15 instances at 1242 x 375 ->
+# 105 pairs), fixtures from the live reference like all the others
 @pytest.mark.parametrize("case", ["c1_o", "c2_od", "c3_ordernet", "c2_d", "c3_ordernet_ext", "c2_od_resize",
-                                  "c1_o_image"])
+                                  "c1_o_image", "c2_od_full", "c3_ordernet_full"])
 def test_order_matrices_match_reference(golden_dir, case):
     c = gen_golden.CASES[case]
     z = np.load(os.path.join(golden_dir, "order_%s.npz" % case))
@@ -45,7 +47,8 @@ def test_order_matrices_match_reference(golden_dir, case):
         ref = z["logits%d" % h]
         got = r["logits"][:, :, off:off + k]
         err = np.abs(got - ref).max()
-        print("%s head %d: max |logit - reference fp32| = %.5f (logit std %.3f)" % (case, h, err, ref.std()))
+        print("%s head %d: max |logit - reference fp32| = %.5f (logit std %.3f, err / std = %.3f)" %
+              (case, h, err, ref.std(), err / ref.std()))
         assert err < LOGIT_TOL, "%s head %d: max |logit - reference| = %.4f" % (case, h, err)
         off += k
     N = masks.shape[0]
@@ -71,6 +74,95 @@ def test_order_matrices_match_reference(golden_dir, case):
         assert np.array_equal(occ, r["occ"])
 
 
+def test_realistic_logit_scale(golden_dir):
+    """The same network with heads 5 x larger (logit std 1.3 - 1.8, the O(1) scale of a trained head) against the
+    live reference's fixture.  The bf16-vs-fp32 distance is a RELATIVE quantity -- it scales with the head -- so the
+    absolute 2e-2 of north_star (stated at the calibrated scale) becomes 2e-2 x 5 here; what is asserted on top is
+    what matters for the product: the order matrices equal the reference's on every pair off ties, and the fraction
+    of decisions that differ at all (ties included) is reported and bounded."""
+    case = "c2_od_big"
+    c = gen_golden.CASES[case]
+    z = np.load(os.path.join(golden_dir, "order_%s.npz" % case))
+    image, masks, boxes = gen_golden.build_scene(case)
+    bexp = engine.expand_bbox(boxes, 3.0)
+    model = make_model(case, golden_dir, max_pairs=64)
+    r = model.engine_for(256).infer_scenes([engine.Scene(image, masks, bexp)], c["algo"], "all", "patch",
+                                           return_details=True)[0]
+    off = 0
+    for h, (_, k, what) in enumerate(engine.heads_for(c["algo"], c["num_classes"])):
+        ref = z["logits%d" % h]
+        err = float(np.abs(r["logits"][:, :, off:off + k] - ref).max())
+        print("%s head %d (%s): logit std %.3f, max |logit| %.3f, max |logit - reference fp32| = %.4f, err / std = "
+              "%.4f" % (case, h, what, ref.std(), np.abs(ref).max(), err, err / ref.std()))
+        assert ref.std() > 1.0, "the case is meant to have O(1) logits"
+        assert err < LOGIT_TOL * c["head_scale"], err
+        assert err / ref.std() < 0.05
+        off += k
+    N = masks.shape[0]
+    for what in ("occ", "depth"):
+        mg = np.full((N, N), np.inf)
+        for (i, j), m in zip(r["pairs"], r["margin_" + what]):
+            mg[i, j] = mg[j, i] = m
+        ok = mg > 1e-3
+        offdiag = ~np.eye(N, dtype=bool)
+        flips = int((r[what] != z[what])[offdiag].sum())
+        print("%s %s: %d of %d entries are non-tie; %d entries differ from the reference (ties included)" %
+              (case, what, int(ok[offdiag].sum()), N * (N - 1), flips))
+        assert ok[offdiag].sum() >= 0.9 * N * (N - 1)
+        assert np.array_equal(r[what][ok], z[what][ok]), (case, what)
+        assert flips <= 0.05 * N * (N - 1)
+
+
+def test_benchmarked_batch_matches_oracle(golden_dir):
+    """The configuration bench.py measures -- OrderEngine(max_pairs=256), default fused schedule, ONE full 256-pair
+    batch (256-pair chunks, >= 1000-tile persistent launches, full phase-B chunk) of C2-shaped scenes -- compared pair
+    by pair with the CPU oracle: fp32 restatement of the reference (<= 2e-2) and the ideal-bf16 emulation of the
+    kernels' own arithmetic contract (<= 5e-3); order matrices equal on every pair off ties."""
+    from instaorder_b200 import synth
+    from oracle import oracle as O
+    case = "c2_od"
+    c = gen_golden.CASES[case]
+    sd = gen_golden.state_dict_for(case)
+    eng = engine.OrderEngine([2, 3], 256, max_pairs=256)
+    eng.load_state_dict(sd)
+    scenes, raw = [], []
+    for k, (img, masks, boxes) in enumerate(synth.coco_scene_stream(41, 5, N=10)):       # 5 x 45 pairs
+        raw.append((img, masks, boxes))
+    rng = np.random.RandomState(43)
+    raw.append(synth.make_scene(rng, 375, 500, 7, float_boxes=True))                      # + 21
+    raw.append(synth.make_scene(rng, 333, 500, 5, float_boxes=True))                      # + 10 = 256
+    for (img, masks, boxes) in raw:
+        scenes.append(engine.Scene(img, masks, engine.expand_bbox(boxes, 3.0)))
+    assert sum(s.n * (s.n - 1) // 2 for s in scenes) == 256
+    launches0 = eng.gpu_launches
+    res = eng.infer_scenes(scenes, c["algo"], "all", "patch", return_details=True)
+    per_batch = eng.gpu_launches - launches0
+    assert per_batch < 64, "expected ONE 256-pair batch, got %d launches" % per_batch
+    worst32 = worst16 = 0.0
+    nontie = total = 0
+    for sc, r in zip(scenes, res):
+        for fwd, tol in ((None, LOGIT_TOL), (O.resnet50_forward_bf16, BF16_EMU_TOL)):
+            kw = {} if fwd is None else dict(forward=fwd)
+            want = O.infer_order(sd, sc.image, sc.masks, sc.boxes.astype(np.int64), "all", c["algo"], "patch", 256, **kw)
+            ref = np.stack([np.concatenate([np.stack(want["logits"][p]["fc_occ"]), np.stack(want["logits"][p]["fc_depth"])],
+                                           axis=1) for p in want["pairs"]])
+            assert [tuple(p) for p in want["pairs"]] == [tuple(p) for p in r["pairs"]]
+            err = float(np.abs(r["logits"] - ref).max())
+            assert err < tol, "max |logit - %s oracle| = %.4f" % ("fp32" if fwd is None else "ideal-bf16", err)
+            if fwd is None:
+                worst32 = max(worst32, err)
+                for what in ("occ", "depth"):
+                    ok = want["margin_" + what] > 1e-3
+                    assert np.array_equal(r[what][ok], want[what][ok]), what
+                    nontie += int(ok.sum()) - sc.n
+                    total += sc.n * (sc.n - 1)
+            else:
+                worst16 = max(worst16, err)
+    print("256-pair batch: max |logit - fp32 oracle| = %.5f, max |logit - ideal bf16| = %.5f, %d of %d matrix entries "
+          "graded (non-tie), %d launches" % (worst32, worst16, nontie, total, per_batch))
+    assert nontie >= 0.8 * total
+
+
 @pytest.mark.parametrize("case", ["c2_od", "c3_ordernet"])
 def test_logits_match_ideal_bf16_arithmetic(golden_dir, case):
     """The CUDA path against a CPU emulation of its own arithmetic contract (bf16 weights with BN folded, bf16
@@ -83,7 +175,7 @@ def test_logits_match_ideal_bf16_arithmetic(golden_dir, case):
     model = make_model(case, golden_dir)
     r = model.engine_for(256).infer_scenes([engine.Scene(image, masks, bexp)], c["algo"], "all", "patch",
                                            return_details=True)[0]
-    sd = calib.load_calibrated(gen_golden.calib_path(case), c["wseed"], 5, c["num_classes"])
+    sd = gen_golden.state_dict_for(case)
     want = O.infer_order(sd, image, masks, bexp, "all", c["algo"], "patch", 256, forward=O.resnet50_forward_bf16)
     names = ["fc_occ", "fc_depth"] if c["algo"] == "InstaOrderNet_od" else ["fc"]
     ref = np.stack([np.concatenate([np.stack(want["logits"][p][h]) for h in names], axis=1) for p in want["pairs"]])

@@ -34,7 +34,7 @@ def test_metrics_golden(golden_dir):
 
 
 @pytest.mark.parametrize("case", ["c1_o", "c2_od", "c3_ordernet", "c2_d", "c3_ordernet_ext", "c2_od_resize",
-                                  "c1_o_image"])
+                                  "c1_o_image", "c2_od_full", "c3_ordernet_full", "c2_od_big"])
 def test_order_golden(golden_dir, case):
     c = gen_golden.CASES[case]
     z = np.load(os.path.join(golden_dir, "order_%s.npz" % case))
@@ -69,12 +69,13 @@ def test_order_golden(golden_dir, case):
             else:
                 assert np.abs(x - ref).max() < 2e-5
     # network + decisions
-    sd = calib.load_calibrated(gen_golden.calib_path(case), c["wseed"], 5, c["num_classes"])
+    sd = gen_golden.state_dict_for(case)
     r = O.infer_order(sd, image, masks, bexp, "all", c["algo"], mode, D)
     heads = ["fc_occ", "fc_depth"] if c["algo"] == "InstaOrderNet_od" else ["fc"]
     for h, head in enumerate(heads):
         got = np.stack([np.stack(r["logits"][p][head]) for p in plist])
-        assert np.abs(got - z["logits%d" % h]).max() < 2e-4, (case, head)   # batched vs batch-1 fp32 conv
+        # batched vs batch-1 fp32 conv; the tolerance follows the head scale of the case
+        assert np.abs(got - z["logits%d" % h]).max() < 2e-4 * c.get("head_scale", 1.0), (case, head)
     if c["algo"] != "InstaOrderNet_d":
         ok = r["margin_occ"] > 1e-3
         assert np.array_equal(r["occ"][ok], z["occ"][ok])
