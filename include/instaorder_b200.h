@@ -216,6 +216,13 @@ IO_API int io_add_relu(const void* a_dev, const void* b_dev, void* out_dev, int6
 /* nn.functional.interpolate(scale_factor=2, mode="bilinear", align_corners=...) on NHWC bf16 [b,h,w,c] -> [b,2h,2w,c]. */
 IO_API int io_upsample2x_bilinear(const void* x_dev, int b, int h, int w, int c, int align_corners, void* y_dev, void* stream);
 
+/* conv1 + bn1 + ReLU + MaxPool2d(3, 2, 1) (reference models/backbone/resnet_cls.py:140-146, 205-208) of both
+ * directions of every pair as ONE kernel, for 256 x 256 inputs -- the first launch of io_net_forward_pairs, exposed for
+ * the layer-level parity test.  w_host: conv1 weights [64][5][7][7] fp32 with the BN scale folded in, bias_host: [64]
+ * (host pointers); out_dev: [2 * pairs][64][64][64] bf16 NHWC, image 2 * pair + direction.  Synchronises the stream. */
+IO_API int io_stem_pool(const void* pair_tensor_dev, int pairs, int d, const float* w_host, const float* bias_host,
+                        void* out_dev, void* stream);
+
 /* Single convolution + folded BN (+ residual) (+ ReLU) on NHWC bf16, the building block of io_net_forward_pairs,
  * exported for the per-layer parity tests.  w_dev: [Cout][kh*kw*Cin] bf16 (tap-major, channel-minor);
  * kernel 1 or 3, stride 1 or 2, padding = kernel / 2; Cin, Cout multiples of 64; output rows wider than 128 pixels

@@ -64,6 +64,7 @@ _SIGS = {
     "io_add_relu": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "io_upsample2x_bilinear": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "io_conv_bn_act": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "io_stem_pool": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "io_conv_dual": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "io_conv_fused_dual": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "io_conv_fused_pair": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),

@@ -102,6 +102,21 @@ int stem_tn_plan(TnParams* p, int pairs, int d, const void* x, const void* wgt, 
 int conv_tn_launch(const TnParams& p, cudaStream_t stream);
 bool tn_enabled();
 
+// conv1 + BN + ReLU + MaxPool2d(3, 2, 1) in one kernel for 256 x 256 inputs (stem_pool.cu)
+struct StemPoolParams {
+  CUtensorMap map_w;    // weights [128][448] bf16 in stem_pool_pack_k order, box 64 x 128, 128B swizzle
+  CUtensorMap map_x;    // parity view {8, 2, pitch / 2, d + 6, pairs} of the pair tensor, box = one parity array of a row
+  CUtensorMap map_out;  // pooled output [2 * pairs * (d/4)^2][64] bf16, box 64 x 32, 128B swizzle
+  const float* bias;    // [128]
+  int items, strips, strip_len;
+  int img_mul;          // output image of pair n, direction 0 (2 = interleaved 2n + dir, 1 = [dir][pair])
+  int split_row_off;    // output rows added for direction 1
+};
+bool stem_pool_supported(int d);
+int stem_pool_plan(StemPoolParams* p, int pairs, int d, const void* x, const void* wgt, const float* bias, void* y);
+int stem_pool_pack_k(int r, int s, int c);
+int stem_pool_launch(const StemPoolParams& p, cudaStream_t stream);
+
 // Launches the persistent kernel for one convolution. bn_tile in {64, 128, 256}.
 int conv_tc_launch(const ConvParams& p, int bn_tile, cudaStream_t stream);
 

@@ -29,10 +29,11 @@ struct ConvW {
 };
 
 struct Op {
-  enum Kind { STEM, POOL, CONV, TAIL, FUSED, CONV_TN, STEM_TN, ADD } kind;
+  enum Kind { STEM, POOL, CONV, TAIL, FUSED, CONV_TN, STEM_TN, ADD, STEM_POOL } kind;
   ConvParams p;
   FusedParams fp;
   TnParams tp;
+  StemPoolParams sp;
   int bn_tile = 0;
   double flops = 0.0;  // algorithmic 2*MAC of this launch
   double bytes = 0.0;  // algorithmic HBM bytes of this launch (activations in + out + residual + weights)
@@ -77,6 +78,7 @@ struct io_net {
   int last_launches = 0;
   std::vector<io::ConvW> convs;  // [0] = stem, then the 52 bottleneck convs in execution order
   __nv_bfloat16* stem_w = nullptr;
+  __nv_bfloat16* stem_w2 = nullptr;     // the same filter in the fused stem + pool kernel's K order (stem_pool.cu)
   float* stem_bias = nullptr;
   float* fc_w = nullptr;
   float* fc_b = nullptr;
@@ -308,6 +310,19 @@ static int build_plan_a(io_net* net, int pa, int a0, __nv_bfloat16* dst, __nv_bf
   plan->ops.clear();
   __nv_bfloat16 *X = net->buf[0], *Y = net->buf[1];
   Op op;
+  if (stem_pool_supported(d)) {
+    // conv1 + BN + ReLU + max-pool in one launch: only the pooled tensor is written (maps are rebuilt per call: the
+    // pair tensor belongs to the caller)
+    op.kind = Op::STEM_POOL;
+    op.flops = 2.0 * b * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
+    op.bytes = static_cast<double>(io_pair_tensor_bytes(pa, d)) + 2.0 * b * (d / 4) * (d / 4) * 64;
+    op.tag = 3;
+    plan->ops.push_back(op);
+    int h = d / 4, w = d / 4;
+    const __nv_bfloat16* out = nullptr;
+    return build_blocks(net, plan, 0, 2, b, &h, &w, Y, X, Y, net->buf[2], net->buf[3], net->buf[4], dst, &out, next_t1,
+                        false, net->keep_layers ? static_cast<long long>(dirs) * a0 : -1, dirs * a0);
+  }
   op.kind = (tn_enabled() && stem_tn_supported(d)) ? Op::STEM_TN : Op::STEM;   // maps are rebuilt per call (the
                                                                                // pair tensor belongs to the caller)
   op.flops = 2.0 * b * (d / 2) * (d / 2) * 49.0 * 5.0 * 64.0;
@@ -399,6 +414,7 @@ extern "C" int io_net_create_arch(const int32_t* widths, const int32_t* outs, co
     }
   }
   IO_CUDA(cudaMalloc(&net->stem_w, 128 * 448 * 2));
+  IO_CUDA(cudaMalloc(&net->stem_w2, 128 * 448 * 2));
   IO_CUDA(cudaMalloc(&net->stem_bias, 128 * 4));
   if (n_heads > 0) {
     IO_CUDA(cudaMalloc(&net->fc_w, static_cast<size_t>(net->k_total) * 2048 * 4));
@@ -475,6 +491,7 @@ extern "C" int io_net_destroy(io_net_t* net) {
     cudaFree(c.bias_cat);
   }
   cudaFree(net->stem_w);
+  cudaFree(net->stem_w2);
   cudaFree(net->stem_bias);
   cudaFree(net->fc_w);
   cudaFree(net->fc_b);
@@ -527,7 +544,7 @@ extern "C" int io_net_load_state(io_net_t* net, const char* const* names, const 
     if (ci == 0) {
       // stem: rows [0,64) = direction (A,B); rows [64,128) = direction (B,A) (input channels 0 and 1 exchanged).
       // K index = r * 64 + s * 8 + c with s < 7 real taps (+1 zero tap) and c < 5 real channels (+3 zero).
-      std::vector<uint16_t> pk(128 * 448, 0);
+      std::vector<uint16_t> pk(128 * 448, 0), pk2(128 * 448, 0);
       std::vector<float> b2(128);
       for (int dir = 0; dir < 2; ++dir)
         for (int co = 0; co < 64; ++co) {
@@ -538,10 +555,12 @@ extern "C" int io_net_load_state(io_net_t* net, const char* const* names, const 
               for (int s = 0; s < 7; ++s) {
                 const float v = w[((static_cast<size_t>(co) * 5 + src_c) * 7 + r) * 7 + s] * scale[co];
                 pk[static_cast<size_t>(dir * 64 + co) * 448 + r * 64 + s * 8 + cc] = bf16_bits(v);
+                pk2[static_cast<size_t>(dir * 64 + co) * 448 + stem_pool_pack_k(r, s, cc)] = bf16_bits(v);
               }
           }
         }
       IO_CUDA(cudaMemcpy(net->stem_w, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+      IO_CUDA(cudaMemcpy(net->stem_w2, pk2.data(), pk2.size() * 2, cudaMemcpyHostToDevice));
       IO_CUDA(cudaMemcpy(net->stem_bias, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice));
     } else {
       const int kk = c.k * c.k;
@@ -659,6 +678,11 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
           rc = cudaGetLastError() == cudaSuccess ? IO_OK : IO_ERR_CUDA;
           break;
         }
+        case Op::STEM_POOL:
+          rc = stem_pool_plan(&op.sp, pa, net->d, pair_ptr, net->stem_w2, net->stem_bias, net->buf[1]);
+          if (!rc && net->single_dir) { op.sp.img_mul = 1; op.sp.split_row_off = pa * (net->d / 4) * (net->d / 4); }
+          if (!rc) rc = stem_pool_launch(op.sp, stream);
+          break;
         case Op::STEM_TN:
           rc = stem_tn_plan(&op.tp, pa, net->d, pair_ptr, net->stem_w, net->stem_bias, net->buf[0]);
           if (!rc && net->single_dir) { op.tp.img_mul = 1; op.tp.split_row_off = pa * op.tp.hw_out; }
@@ -705,6 +729,42 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
     ++net->last_launches;
   }
   return IO_OK;
+}
+
+// Building block of io_net_forward_pairs for 256 x 256 inputs, exposed for the layer-level parity test: conv1 (7x7
+// stride 2, weights with the BN scale already folded in) + bias + ReLU + MaxPool2d(3, 2, 1) of BOTH directions of every
+// pair, from the pair tensor.  w_host: [64][5][7][7] fp32, bias_host: [64] fp32 (host pointers; packed and uploaded
+// here), out_dev: [2 * pairs][d/4][d/4][64] bf16, image 2 * pair + direction.
+extern "C" int io_stem_pool(const void* pair_tensor_dev, int pairs, int d, const float* w_host, const float* bias_host,
+                            void* out_dev, void* stream_) {
+  IO_REQUIRE(pair_tensor_dev && w_host && bias_host && out_dev && pairs >= 1, "io_stem_pool: bad arguments");
+  IO_REQUIRE(d == 256, "io_stem_pool: input size %d (the fused kernel is built for 256)", d);
+  std::vector<uint16_t> pk(128 * 448, 0);
+  std::vector<float> b2(128);
+  for (int dir = 0; dir < 2; ++dir)
+    for (int co = 0; co < 64; ++co) {
+      b2[dir * 64 + co] = bias_host[co];
+      for (int cc = 0; cc < 5; ++cc) {
+        const int src_c = (dir == 1 && cc < 2) ? 1 - cc : cc;
+        for (int r = 0; r < 7; ++r)
+          for (int s = 0; s < 7; ++s)
+            pk[static_cast<size_t>(dir * 64 + co) * 448 + stem_pool_pack_k(r, s, cc)] =
+                bf16_bits(w_host[((static_cast<size_t>(co) * 5 + src_c) * 7 + r) * 7 + s]);
+      }
+    }
+  __nv_bfloat16* w_dev = nullptr;
+  float* b_dev = nullptr;
+  IO_CUDA(cudaMalloc(&w_dev, pk.size() * 2));
+  IO_CUDA(cudaMalloc(&b_dev, b2.size() * 4));
+  IO_CUDA(cudaMemcpy(w_dev, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+  IO_CUDA(cudaMemcpy(b_dev, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice));
+  StemPoolParams sp;
+  int rc = stem_pool_plan(&sp, pairs, d, pair_tensor_dev, w_dev, b_dev, out_dev);
+  if (!rc) rc = stem_pool_launch(sp, as_stream(stream_));
+  cudaStreamSynchronize(as_stream(stream_));
+  cudaFree(w_dev);
+  cudaFree(b_dev);
+  return rc;
 }
 
 extern "C" int io_net_profile(io_net_t* net, int enable) {
