@@ -693,6 +693,11 @@ extern "C" int io_conv_bn_act(const void* x_dev, int b, int h, int w, int cin, c
   io::ConvParams p;
   int bn = 0;
   io::ConvDesc d{b, h, w, cin, cout, kernel, stride};
+  if (residual_dev == nullptr && io::conv_halo_supported(d)) {
+    io::HaloParams hp;
+    if (int rc = io::conv_halo_plan(&hp, d, x_dev, w_dev, bias_dev, y_dev, relu)) return rc;
+    return io::conv_halo_launch(hp, io::as_stream(stream));
+  }
   if (residual_dev == nullptr && io::tn_enabled() && io::conv_tn_supported(d)) {
     io::TnParams tp;
     if (int rc = io::conv_tn_plan(&tp, d, x_dev, w_dev, bias_dev, y_dev, relu)) return rc;

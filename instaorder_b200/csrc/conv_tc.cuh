@@ -102,6 +102,18 @@ int stem_tn_plan(TnParams* p, int pairs, int d, const void* x, const void* wgt, 
 int conv_tn_launch(const TnParams& p, cudaStream_t stream);
 bool tn_enabled();
 
+// 3x3 stride-1 64 -> 64 convolution on 64 x 64 maps with the input rows resident in shared memory (conv_halo.cu)
+struct HaloParams {
+  CUtensorMap map_w;    // weights [64][9 * 64] bf16, box 64 x 64 (one filter tap), 128B swizzle
+  CUtensorMap map_x;    // {C, W, H, N} view of the NHWC input, box 64 x 72 x 1 x 1 (x = -1 .. 70), 128B swizzle
+  CUtensorMap map_out;  // [rows][64] bf16, box 64 x 32
+  const float* bias;
+  int items, strips, strip_len, relu;
+};
+bool conv_halo_supported(const ConvDesc& d);
+int conv_halo_plan(HaloParams* p, const ConvDesc& d, const void* x, const void* wgt, const float* bias, void* y, int relu);
+int conv_halo_launch(const HaloParams& p, cudaStream_t stream);
+
 // conv1 + BN + ReLU + MaxPool2d(3, 2, 1) in one kernel for 256 x 256 inputs (stem_pool.cu)
 struct StemPoolParams {
   CUtensorMap map_w;    // weights [128][448] bf16 in stem_pool_pack_k order, box 64 x 128, 128B swizzle

@@ -29,11 +29,12 @@ struct ConvW {
 };
 
 struct Op {
-  enum Kind { STEM, POOL, CONV, TAIL, FUSED, CONV_TN, STEM_TN, ADD, STEM_POOL } kind;
+  enum Kind { STEM, POOL, CONV, TAIL, FUSED, CONV_TN, STEM_TN, ADD, STEM_POOL, CONV_HALO } kind;
   ConvParams p;
   FusedParams fp;
   TnParams tp;
   StemPoolParams sp;
+  HaloParams hp;
   int bn_tile = 0;
   double flops = 0.0;  // algorithmic 2*MAC of this launch
   double bytes = 0.0;  // algorithmic HBM bytes of this launch (activations in + out + residual + weights)
@@ -217,7 +218,10 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       t1_ready = false;
       Op o2; o2.kind = Op::CONV;
       const ConvDesc d2{b, h, w, c2.cin, c2.cout, 3, c2.stride};
-      if (tn_enabled() && conv_tn_supported(d2)) {
+      if (conv_halo_supported(d2)) {
+        o2.kind = Op::CONV_HALO;
+        if (int rc = conv_halo_plan(&o2.hp, d2, T1, c2.w, c2.bias, T2, 1)) return rc;
+      } else if (tn_enabled() && conv_tn_supported(d2)) {
         o2.kind = Op::CONV_TN;
         if (int rc = conv_tn_plan(&o2.tp, d2, T1, c2.w, c2.bias, T2, 1)) return rc;
       } else if (int rc = conv_plan(&o2.p, &o2.bn_tile, d2, T1, c2.w, c2.bias, nullptr, T2, 1)) {
@@ -670,6 +674,9 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
         case Op::CONV_TN:
           rc = conv_tn_launch(op.tp, stream);
           break;
+        case Op::CONV_HALO:
+          rc = conv_halo_launch(op.hp, stream);
+          break;
         case Op::ADD: {
           const int per8 = op.h * op.w * op.c / 8;
           dim3 grid(std::min((per8 + 255) / 256, 64), op.b);
@@ -759,6 +766,7 @@ extern "C" int io_stem_pool(const void* pair_tensor_dev, int pairs, int d, const
   IO_CUDA(cudaMemcpy(w_dev, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
   IO_CUDA(cudaMemcpy(b_dev, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice));
   StemPoolParams sp;
+  HaloParams hp;
   int rc = stem_pool_plan(&sp, pairs, d, pair_tensor_dev, w_dev, b_dev, out_dev);
   if (!rc) rc = stem_pool_launch(sp, as_stream(stream_));
   cudaStreamSynchronize(as_stream(stream_));

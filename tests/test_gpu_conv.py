@@ -33,6 +33,8 @@ CASES = [
     (3, 48, 48, 128, 128, 3, 1, False, True),    # 384^2 layer2 conv2: transposed kernel, 192-pixel tiles (4 rows x 48)
     (3, 96, 96, 128, 128, 3, 2, False, True),    # 384^2 layer2.0 conv2: stride 2, 48-wide output rows, 192-pixel tiles
     (1, 96, 96, 64, 64, 3, 1, False, False),     # 384^2 layer1 conv2: M = 64, 192-pixel tiles (2 rows x 96), no ReLU
+    (1, 64, 64, 64, 64, 3, 1, False, False),     # conv_halo (rows resident in shared memory): one image, no ReLU
+    (75, 64, 64, 64, 64, 3, 1, False, True),     # conv_halo: 300 strips > 148 CTAs -> several work items per CTA (ring phases)
 ]
 
 
