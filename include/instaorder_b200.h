@@ -176,6 +176,19 @@ IO_API int io_net_forward_pairs(io_net_t* net, const void* pair_tensor_dev, int 
 /* number of kernel launches the last io_net_forward_pairs issued (bench.py's gpu_launches) */
 IO_API int io_net_last_launches(const io_net_t* net);
 
+/* `orig` mode (reference inference.py:401-408, utils/data_utils.py:13-17): the network input is the image at its own
+ * size rounded to the nearest multiples of 32 -- dh x dw, not square.  io_image_resize_rgb_hw / io_pair_gather_resize_hw /
+ * io_pair_tensor_bytes_hw are the `resize`-mode entry points with separate height and width (plane [dh][dw][3], pair
+ * tensor [p][dh + 6][pitch(dw)][8]); io_net_forward_pairs_hw runs the pairs of one such image through a handle created
+ * with input_size >= max(dh, dw) (general tilers, one launch per convolution; plans are rebuilt when the geometry changes). */
+IO_API int64_t io_pair_tensor_bytes_hw(int p, int dh, int dw);
+IO_API int io_image_resize_rgb_hw(const uint8_t* image_dev, int h, int w, int dh, int dw, const float* mean_host,
+                                  const float* std_host, float* rgb_plane_dev, void* stream);
+IO_API int io_pair_gather_resize_hw(const float* rgb_planes_dev, const uint8_t* masks_dev, const io_pair_desc* descs_dev,
+                                    int p, int dh, int dw, void* out_dev, void* stream);
+IO_API int io_net_forward_pairs_hw(io_net_t* net, const void* pair_tensor_dev, int p, int h, int w, float* logits_dev,
+                                   void* stream);
+
 /* Optional per-kernel timing for bench.py's roofline: when enabled, io_net_forward_pairs brackets every launch
  * with CUDA events on the launching stream.  io_net_profile_read (after the caller synchronised the stream)
  * returns the number of launches of the last forward and fills ms_host[i] (duration), kind_host[i]
@@ -304,6 +317,15 @@ IO_API int io_train_forward_backward(io_train_t* t, const void* pair_tensor_dev,
                                      const float* occ_target_dev, const int64_t* class_target_dev,
                                      const int64_t* is_overlap_dev, float overlap_w, float distinct_w, int world_size,
                                      float* out_losses_dev, int run_backward, void* stream);
+/* Gradient buckets for the data-parallel all-reduce (reference utils/distributed_utils.py:27-31: one blocking
+ * all_reduce per parameter AFTER backward).  The flat gradient buffer becomes final in io_train_num_buckets() contiguous
+ * ranges [begin, end) (elements), in this order: (layer4 + heads), layer3, layer2, (stem + layer1).
+ * io_train_wait_bucket makes `stream` wait (device side) for bucket k of the last io_train_forward_backward, so the
+ * caller can all-reduce that range on a communication stream while the rest of the backward pass still runs. */
+IO_API int io_train_num_buckets(const io_train_t* t);
+IO_API int io_train_bucket(const io_train_t* t, int k, int64_t* begin, int64_t* end);
+IO_API int io_train_wait_bucket(io_train_t* t, int k, void* stream);
+
 /* torch.optim.SGD(lr, momentum, weight_decay) / torch.optim.Adam(lr, betas, eps) over the bound flat buffers
  * (models/single_stage_model.py:34-42), fused with the refresh of the bf16 GEMM weights. */
 IO_API int io_train_sgd_step(io_train_t* t, float* momentum_buf_dev, float lr, float momentum, float weight_decay,

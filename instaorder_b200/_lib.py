@@ -55,6 +55,10 @@ _SIGS = {
     "io_net_load_state": (_i, [_vp, _vp, _vp, _i]),
     "io_net_forward_pairs": (_i, [_vp, _vp, _i, _vp, _vp]),
     "io_net_last_launches": (_i, [_vp]),
+    "io_pair_tensor_bytes_hw": (_i64, [_i, _i, _i]),
+    "io_image_resize_rgb_hw": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "io_pair_gather_resize_hw": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "io_net_forward_pairs_hw": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "io_net_profile": (_i, [_vp, _i]),
     "io_net_profile_read": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "io_order_decide": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -84,6 +88,9 @@ _SIGS.update({
     "io_train_bind": (_i, [_vp, _vp, _vp, _vp]),
     "io_train_sync_weights": (_i, [_vp, _vp]),
     "io_train_forward_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _i, _vp, _i, _vp]),
+    "io_train_num_buckets": (_i, [_vp]),
+    "io_train_bucket": (_i, [_vp, _i, _vp, _vp]),
+    "io_train_wait_bucket": (_i, [_vp, _i, _vp]),
     "io_train_sgd_step": (_i, [_vp, _vp, _f, _f, _f, _i, _vp]),
     "io_train_adam_step": (_i, [_vp, _vp, _vp, _f, _f, _f, _f, _i, _vp]),
     "io_train_read_logits": (_i, [_vp, _vp, _vp]),

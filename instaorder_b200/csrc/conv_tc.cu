@@ -607,11 +607,17 @@ int conv_plan_dual(ConvParams* p, int* bn_tile, const ConvDesc& ds, const void* 
 
 int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, const void* wgt, const float* bias,
               void* y) {
-  IO_REQUIRE(d % 2 == 0 && d >= 32, "stem: input size %d", d);
+  return stem_plan_hw(p, bn_tile, pairs, d, d, x, wgt, bias, y);
+}
+
+// network input h x w (`orig` mode: the image's own size rounded to multiples of 32, reference inference.py:401-408)
+int stem_plan_hw(ConvParams* p, int* bn_tile, int pairs, int h, int w, const void* x, const void* wgt,
+                 const float* bias, void* y) {
+  IO_REQUIRE(h % 2 == 0 && h >= 32 && w % 2 == 0 && w >= 32, "stem: input size %d x %d", h, w);
   *p = ConvParams{};
-  const int h_out = d / 2, w_out = d / 2;
-  const int64_t pitch = io_pair_tensor_row_pitch(d);
-  const int hp = d + 6;
+  const int h_out = h / 2, w_out = w / 2;
+  const int64_t pitch = io_pair_tensor_row_pitch(w);
+  const int hp = h + 6;
   p->bias = bias;
   p->residual = nullptr;
   p->out = reinterpret_cast<__nv_bfloat16*>(y);

@@ -143,6 +143,8 @@ int conv_plan_dual(ConvParams* p, int* bn_tile, const ConvDesc& ds, const void* 
                    const void* wcat, const float* bias, void* y, int relu);
 // Stem plan: x is the padded pair tensor [pairs, d+6, pitch, 8]; y is [2*pairs, d/2, d/2, 64] (image 2p + dir).
 int stem_plan(ConvParams* p, int* bn_tile, int pairs, int d, const void* x, const void* wgt, const float* bias, void* y);
+int stem_plan_hw(ConvParams* p, int* bn_tile, int pairs, int h, int w, const void* x, const void* wgt,
+                 const float* bias, void* y);
 // Data gradient of a stride-1 convolution (1x1 or 3x3 pad 1) as a convolution over dy [b, h, w, cout_f] with the
 // forward weights wgt_f [cout_f][k*k*cin_f] read MN-major and the taps mirrored; dx [b, h, w, cin_f] (+ residual).
 int dgrad_plan(ConvParams* p, int* bn_tile, int b, int h, int w, int cin_f, int cout_f, int kernel, const void* dy,

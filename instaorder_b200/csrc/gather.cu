@@ -93,9 +93,9 @@ __device__ __forceinline__ void store_pixel(__nv_bfloat16* dst, float ma, float 
 
 // zero the 3-pixel border (and the pitch padding) that belongs to this CTA's rows
 __device__ __forceinline__ void zero_borders(__nv_bfloat16* out_pair, int d, int pitch, int band, int n_bands,
-                                             int row0, int row1) {
+                                             int row0, int row1, int dh = 0) {
   const uint4 z = make_uint4(0, 0, 0, 0);
-  const int hp = d + 6;
+  const int hp = (dh > 0 ? dh : d) + 6;      // d = interior width; dh = interior height when it differs (`orig` mode)
   // left / right borders of the band's interior rows
   const int side = 3 + (pitch - d - 3);
   for (int i = threadIdx.x; i < (row1 - row0) * side; i += blockDim.x) {
@@ -278,10 +278,10 @@ struct MeanStd {
 };
 
 // One CTA per output row: image/255. (double) -> cubic with fp32 taps, double accumulation -> normalise -> fp32.
-__global__ void __launch_bounds__(GATHER_THREADS) resize_rgb_kernel(const uint8_t* __restrict__ img, int H, int W, int d,
-                                                                    MeanStd ms, float* __restrict__ plane) {
-  const int dy = blockIdx.x;
-  const AxisTabF ty = axis_entry_f(dy, H, d);
+__global__ void __launch_bounds__(GATHER_THREADS) resize_rgb_kernel(const uint8_t* __restrict__ img, int H, int W, int dh,
+                                                                    int d, MeanStd ms, float* __restrict__ plane) {
+  const int dy = blockIdx.x;                 // output [dh][d][3]: d = output width, dh = output height (`orig` mode: != d)
+  const AxisTabF ty = axis_entry_f(dy, H, dh);
   for (int dx = threadIdx.x; dx < d; dx += blockDim.x) {
     const AxisTabF tx = axis_entry_f(dx, W, d);
     double acc[3] = {0.0, 0.0, 0.0};
@@ -378,23 +378,24 @@ __global__ void __launch_bounds__(GATHER_THREADS) square_linear_rgb_kernel(const
 
 __global__ void __launch_bounds__(GATHER_THREADS) gather_resize_kernel(const float* __restrict__ planes,
                                                                        const uint8_t* __restrict__ masks,
-                                                                       const io_pair_desc* __restrict__ descs, int d,
-                                                                       int pitch, __nv_bfloat16* __restrict__ out) {
+                                                                       const io_pair_desc* __restrict__ descs, int dh,
+                                                                       int d, int pitch, __nv_bfloat16* __restrict__ out) {
+  // network input dh x d (height x width); dh == d except in `orig` mode
   const io_pair_desc ds = descs[blockIdx.y];
   const uint8_t* __restrict__ ma = masks + ds.mask_a_off;
   const uint8_t* __restrict__ mb = masks + ds.mask_b_off;
-  const float* __restrict__ plane = planes + static_cast<size_t>(ds.rgb_slot & 0x3FFFFFFF) * d * d * 3;
+  const float* __restrict__ plane = planes + static_cast<size_t>(ds.rgb_slot & 0x3FFFFFFF) * dh * d * 3;
   const bool flip = (ds.rgb_slot & 0x40000000) != 0;   // training augmentation: mirror the resized pair horizontally
   const int H = ds.h, W = ds.w;
-  __nv_bfloat16* out_pair = out + static_cast<size_t>(blockIdx.y) * (d + 6) * pitch * 8;
+  __nv_bfloat16* out_pair = out + static_cast<size_t>(blockIdx.y) * (dh + 6) * pitch * 8;
   const int row0 = blockIdx.x * GATHER_ROWS;
-  const int row1 = min(d, row0 + GATHER_ROWS);
-  zero_borders(out_pair, d, pitch, blockIdx.x, gridDim.x, row0, row1);
+  const int row1 = min(dh, row0 + GATHER_ROWS);
+  zero_borders(out_pair, d, pitch, blockIdx.x, gridDim.x, row0, row1, dh);
   // resize mode: nearest over the H x W image; image mode (ds.s > 0): nearest over the centred ds.s-square whose
   // image window starts at (ds.x, ds.y); pixels of the zero padding read as 0
   const int SH = ds.s > 0 ? ds.s : H, SW = ds.s > 0 ? ds.s : W;
   const int left = ds.s > 0 ? ds.x : 0, top = ds.s > 0 ? ds.y : 0;
-  const double sy = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(d), static_cast<double>(SH)));
+  const double sy = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dh), static_cast<double>(SH)));
   const double sx = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(d), static_cast<double>(SW)));
   for (int dy = row0; dy < row1; ++dy) {
     const int my = min(static_cast<int>(floor(__dmul_rn(static_cast<double>(dy), sy))), SH - 1) - top;
@@ -700,7 +701,42 @@ extern "C" int io_image_resize_rgb(const uint8_t* image, int h, int w, int d, co
     ms.mean[c] = static_cast<double>(mean[c]);
     ms.stdv[c] = static_cast<double>(stdv[c]);
   }
-  resize_rgb_kernel<<<d, GATHER_THREADS, 0, as_stream(stream)>>>(image, h, w, d, ms, plane);
+  resize_rgb_kernel<<<d, GATHER_THREADS, 0, as_stream(stream)>>>(image, h, w, d, d, ms, plane);
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
+// `orig` mode (reference inference.py:401-408): the image at its own size rounded to multiples of 32 -- a dh x dw network
+// input.  Same arithmetic as io_image_resize_rgb (transform_resize: /255, cv2.INTER_CUBIC on float64, normalise).
+extern "C" int io_image_resize_rgb_hw(const uint8_t* image, int h, int w, int dh, int dw, const float* mean,
+                                      const float* stdv, float* plane, void* stream) {
+  IO_REQUIRE(image && mean && stdv && plane && h > 0 && w > 0, "io_image_resize_rgb_hw: bad arguments");
+  IO_REQUIRE(dh >= 32 && dw >= 32 && dh <= 1024 && dw <= 1024 && dh % 32 == 0 && dw % 32 == 0,
+             "io_image_resize_rgb_hw: network input %d x %d (multiples of 32 in [32, 1024])", dh, dw);
+  MeanStd ms;
+  for (int c = 0; c < 3; ++c) {
+    ms.mean[c] = static_cast<double>(mean[c]);
+    ms.stdv[c] = static_cast<double>(stdv[c]);
+  }
+  resize_rgb_kernel<<<dh, GATHER_THREADS, 0, as_stream(stream)>>>(image, h, w, dh, dw, ms, plane);
+  IO_CUDA(cudaGetLastError());
+  return IO_OK;
+}
+
+extern "C" int64_t io_pair_tensor_bytes_hw(int p, int dh, int dw) {
+  return static_cast<int64_t>(p) * (dh + 6) * io_pair_tensor_row_pitch(dw) * 8 * 2;
+}
+
+// per pair: nearest-resized masks (cv2.INTER_NEAREST to (dw, dh)) + the image's plane -> pair tensor [p][dh + 6][pitch(dw)][8]
+extern "C" int io_pair_gather_resize_hw(const float* planes, const uint8_t* masks, const io_pair_desc* descs, int p,
+                                        int dh, int dw, void* out, void* stream) {
+  IO_REQUIRE(planes && masks && descs && out && p >= 0, "io_pair_gather_resize_hw: bad arguments");
+  IO_REQUIRE(dh >= 32 && dw >= 32 && dh <= 1024 && dw <= 1024 && dh % 32 == 0 && dw % 32 == 0,
+             "io_pair_gather_resize_hw: network input %d x %d (multiples of 32 in [32, 1024])", dh, dw);
+  if (p == 0) return IO_OK;
+  dim3 grid((dh + GATHER_ROWS - 1) / GATHER_ROWS, p);
+  gather_resize_kernel<<<grid, GATHER_THREADS, 0, as_stream(stream)>>>(
+      planes, masks, descs, dh, dw, static_cast<int>(io_pair_tensor_row_pitch(dw)), reinterpret_cast<__nv_bfloat16*>(out));
   IO_CUDA(cudaGetLastError());
   return IO_OK;
 }
@@ -740,7 +776,7 @@ extern "C" int io_pair_gather_resize(const float* planes, const uint8_t* masks, 
   if (p == 0) return IO_OK;
   dim3 grid((d + GATHER_ROWS - 1) / GATHER_ROWS, p);
   gather_resize_kernel<<<grid, GATHER_THREADS, 0, as_stream(stream)>>>(
-      planes, masks, descs, d, static_cast<int>(io_pair_tensor_row_pitch(d)), reinterpret_cast<__nv_bfloat16*>(out));
+      planes, masks, descs, d, d, static_cast<int>(io_pair_tensor_row_pitch(d)), reinterpret_cast<__nv_bfloat16*>(out));
   IO_CUDA(cudaGetLastError());
   return IO_OK;
 }

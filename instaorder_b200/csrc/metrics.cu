@@ -159,18 +159,25 @@ struct StagedGen {
   }
 };
 
-constexpr int WH_NMAX = 32;                              // images up to 32 instances go through shared memory
-constexpr int WH_TMAX = WH_NMAX * (WH_NMAX - 1) / 2;     // 496 upper-triangle entries
-constexpr int WH_WARPS = 8;
-constexpr int WH_WARP_BYTES = WH_TMAX * 16 + ((WH_TMAX * 2 + 15) / 16) * 16;
+constexpr int WH_NMAX = 24;                              // images up to 24 instances go through shared memory
+constexpr int WH_TMAX = WH_NMAX * (WH_NMAX - 1) / 2;     // 276 upper-triangle entries
+constexpr int WH_WARPS = 4;
+constexpr int WH_MASK_BYTES = (WH_TMAX * 2 + 15) / 16 * 16;
+constexpr int WH_IDX_BYTES = (9 * WH_TMAX * 2 + 15) / 16 * 16;
+constexpr int WH_WARP_BYTES = WH_TMAX * 16 + WH_MASK_BYTES + WH_IDX_BYTES + 48;
 
 // One WARP per image.  The first version ran one thread per (image, key): nine threads each walked the four int64
-// matrices of their image serially -- uncoalesced 8-byte loads, every matrix read nine times (ncu / bench: 2.7 % of
-// the HBM roofline on 65,536 images).  Now the warp reads the strict upper triangle of the four matrices ONCE,
-// coalesced (entry k of the row-major triangle -> (i, j) in closed form), and stages per entry the two summands
-// (err * score, score as float64) and a 9-bit selection mask in shared memory; the per-key counts come from ballots.
-// Lanes 0..8 then replay numpy's pairwise summation over their key's selected subsequence out of shared memory -- the
-// same operation order as before, so the results stay bit-identical to the reference (inference.py:757-791).
+// matrices of their image serially -- uncoalesced 8-byte loads, every matrix read nine times (bench: 2.7 % of the HBM
+// roofline on 65,536 images).  Now
+//   1. the warp reads the strict upper triangle of the four matrices ONCE, coalesced (entry k of the row-major triangle
+//      -> (i, j) in closed form), and stages per entry the two summands (err * score, score; float64) and a 9-bit
+//      selection mask in shared memory;
+//   2. per key the selected entries are compacted into an index list with ballots (order preserved);
+//   3. numpy's pairwise summation (n <= 128: eight interleaved accumulators, then a fixed tree, then the tail) is
+//      replayed with EIGHT LANES PER KEY -- lane j owns accumulator r[j], the tree is two shuffle steps in numpy's own
+//      association ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) -- four keys at a time.
+// Same operations in the same order as numpy, so the results stay bit-identical to the reference (inference.py:757-791).
+// Images with more than 24 instances, or a selection longer than 128 entries, take the serial replay.
 __global__ void __launch_bounds__(WH_WARPS * 32) whdr_kernel(const int64_t* __restrict__ order,
                                                              const int64_t* __restrict__ gto,
                                                              const int64_t* __restrict__ gtv,
@@ -202,48 +209,97 @@ __global__ void __launch_bounds__(WH_WARPS * 32) whdr_kernel(const int64_t* __re
   double* s_err = reinterpret_cast<double*>(wh_smem + warp * WH_WARP_BYTES);
   double* s_score = s_err + WH_TMAX;
   uint16_t* s_mask = reinterpret_cast<uint16_t*>(s_score + WH_TMAX);
+  uint16_t* s_idx = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(s_mask) + WH_MASK_BYTES);   // [9][WH_TMAX]
+  int* s_cnt = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s_idx) + WH_IDX_BYTES);               // [9]
   const int T = n * (n - 1) / 2;
-  int my_count = 0;       // lane key: number of selected entries of key `lane`
-  for (int k0 = 0; k0 < T; k0 += 32) {
-    const int k = k0 + lane;
-    const bool valid = k < T;
+  // ---- 1. stage the triangle
+  for (int k = lane; k < T; k += 32) {
+    // row i of the strict upper triangle starts at entry i * n - i * (i + 1) / 2
+    int i = static_cast<int>((static_cast<float>(2 * n - 1) -
+                              sqrtf(static_cast<float>((2 * n - 1) * (2 * n - 1) - 8 * k))) * 0.5f);
+    i = max(0, min(i, n - 2));
+    while (i > 0 && i * n - i * (i + 1) / 2 > k) --i;
+    while ((i + 1) * n - (i + 1) * (i + 2) / 2 <= k) ++i;
+    const int j = k - (i * n - i * (i + 1) / 2) + i + 1;
+    const int64_t idx = o0 + static_cast<int64_t>(i) * n + j;
+    const int64_t g = gto[idx], o = gtv[idx], c = gtc[idx], pr = order[idx];
+    const double score = 2.0 / static_cast<double>(c);
+    s_score[k] = score;
+    s_err[k] = (g != pr) ? score : 0.0;
+    const uint32_t mo = (o == 0 ? 1u : 0u) | (o == 1 ? 2u : 0u) | ((o == 0 || o == 1) ? 4u : 0u);   // ovlX, ovlO, ovlOX
+    const uint32_t me = (g == 2 ? 1u : 0u) | ((g == 0 || g == 1) ? 2u : 0u) | ((g == 0 || g == 1 || g == 2) ? 4u : 0u);
     uint32_t m = 0;
-    if (valid) {
-      // row i of the strict upper triangle starts at entry i * n - i * (i + 1) / 2
-      int i = static_cast<int>((static_cast<float>(2 * n - 1) -
-                                sqrtf(static_cast<float>((2 * n - 1) * (2 * n - 1) - 8 * k))) * 0.5f);
-      i = max(0, min(i, n - 2));
-      while (i > 0 && i * n - i * (i + 1) / 2 > k) --i;
-      while ((i + 1) * n - (i + 1) * (i + 2) / 2 <= k) ++i;
-      const int j = k - (i * n - i * (i + 1) / 2) + i + 1;
-      const int64_t idx = o0 + static_cast<int64_t>(i) * n + j;
-      const int64_t g = gto[idx], o = gtv[idx], c = gtc[idx], pr = order[idx];
-      const double score = 2.0 / static_cast<double>(c);
-      s_score[k] = score;
-      s_err[k] = (g != pr) ? score : 0.0;
-      const uint32_t mo = (o == 0 ? 1u : 0u) | (o == 1 ? 2u : 0u) | ((o == 0 || o == 1) ? 4u : 0u);   // ovlX, ovlO, ovlOX
-      const uint32_t me = (g == 2 ? 1u : 0u) | ((g == 0 || g == 1) ? 2u : 0u) | ((g == 0 || g == 1 || g == 2) ? 4u : 0u);
 #pragma unroll
-      for (int ko = 0; ko < 3; ++ko)
+    for (int ko = 0; ko < 3; ++ko)
 #pragma unroll
-        for (int ke = 0; ke < 3; ++ke)
-          if (((mo >> ko) & 1u) && ((me >> ke) & 1u)) m |= 1u << (ko * 3 + ke);
-      s_mask[k] = static_cast<uint16_t>(m);
-    }
-#pragma unroll
-    for (int key = 0; key < 9; ++key) {
-      const int c = __popc(__ballot_sync(0xffffffffu, valid && ((m >> key) & 1u)));
-      if (lane == key) my_count += c;
-    }
+      for (int ke = 0; ke < 3; ++ke)
+        if (((mo >> ko) & 1u) && ((me >> ke) & 1u)) m |= 1u << (ko * 3 + ke);
+    s_mask[k] = static_cast<uint16_t>(m);
   }
   __syncwarp();
-  if (lane < 9) {
-    if (my_count == 0) {
-      out[9 * b + lane] = -1.0;
-    } else {
-      StagedGen g{s_err, s_score, s_mask, 0, lane};
-      const double2 s = pairwise(g, my_count);
-      out[9 * b + lane] = s.x / s.y * 100.0;
+  // ---- 2. per key: ordered index list of the selected entries
+  const uint32_t lt = (1u << lane) - 1u;
+  int max_cnt = 0;
+#pragma unroll 1
+  for (int key = 0; key < 9; ++key) {
+    int base = 0;
+    for (int k0 = 0; k0 < T; k0 += 32) {
+      const int k = k0 + lane;
+      const bool bit = k < T && ((s_mask[k] >> key) & 1);
+      const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+      if (bit) s_idx[key * WH_TMAX + base + __popc(bal & lt)] = static_cast<uint16_t>(k);
+      base += __popc(bal);
+    }
+    if (lane == 0) s_cnt[key] = base;
+    max_cnt = max(max_cnt, base);
+  }
+  __syncwarp();
+  if (max_cnt > 128) {    // numpy recurses above 128 entries: serial replay out of shared memory, one lane per key
+    if (lane < 9) {
+      const int cnt = s_cnt[lane];
+      if (cnt == 0) {
+        out[9 * b + lane] = -1.0;
+      } else {
+        StagedGen g{s_err, s_score, s_mask, 0, lane};
+        const double2 s = pairwise(g, cnt);
+        out[9 * b + lane] = s.x / s.y * 100.0;
+      }
+    }
+    return;
+  }
+  // ---- 3. pairwise sums, eight lanes per key, four keys per round
+  const int j8 = lane & 7;
+#pragma unroll 1
+  for (int round = 0; round < 3; ++round) {
+    const int key = round * 4 + (lane >> 3);
+    const int cnt = key < 9 ? s_cnt[key] : 0;
+    const uint16_t* ix = s_idx + (key < 9 ? key : 0) * WH_TMAX;
+    const int body = cnt - (cnt & 7);          // entries covered by the eight accumulators
+    double rx = 0.0, ry = 0.0;
+    if (cnt >= 8) {
+      rx = s_err[ix[j8]];
+      ry = s_score[ix[j8]];
+      for (int i = 8; i < body; i += 8) {
+        rx += s_err[ix[i + j8]];
+        ry += s_score[ix[i + j8]];
+      }
+    }
+    // ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7))
+    rx += __shfl_down_sync(0xffffffffu, rx, 1, 8);
+    ry += __shfl_down_sync(0xffffffffu, ry, 1, 8);
+    rx += __shfl_down_sync(0xffffffffu, rx, 2, 8);
+    ry += __shfl_down_sync(0xffffffffu, ry, 2, 8);
+    rx += __shfl_down_sync(0xffffffffu, rx, 4, 8);
+    ry += __shfl_down_sync(0xffffffffu, ry, 4, 8);
+    if (j8 == 0 && key < 9) {
+      double sx, sy;
+      int i;
+      if (cnt >= 8) { sx = rx; sy = ry; i = body; } else { sx = 0.0; sy = 0.0; i = 0; }
+      for (; i < cnt; ++i) {
+        sx += s_err[ix[i]];
+        sy += s_score[ix[i]];
+      }
+      out[9 * b + key] = cnt == 0 ? -1.0 : sx / sy * 100.0;
     }
   }
 }

@@ -74,6 +74,10 @@ struct io_net {
   int num_classes[2] = {0, 0};
   int k_total = 0;
   int d = 0;
+  // network input of the CURRENT plans: d x d, or h x w <= d x d in `orig` mode (io_net_forward_pairs_hw; reference
+  // inference.py:401-408).  The back-to-back / dual-source fusions are planned for the default geometry only.
+  int h = 0, w = 0;
+  bool plain = false;   // plans of an io_net_forward_pairs_hw call: always the general one-launch-per-convolution schedule
   int max_pairs = 0;
   bool loaded = false;
   int last_launches = 0;
@@ -159,9 +163,9 @@ __global__ void __launch_bounds__(256) add_bcast_kernel(uint4* __restrict__ x, c
 
 // elements per image of layer li's output at the handle's input size
 static size_t per_img_out(const io_net* net, int li) {
-  const size_t side = static_cast<size_t>(net->d) >> (2 + li);
-  return side * side * net->outs[li];
+  return (static_cast<size_t>(net->h) >> (2 + li)) * (static_cast<size_t>(net->w) >> (2 + li)) * net->outs[li];
 }
+static bool default_geometry(const io_net* net) { return !net->plain && net->h == net->d && net->w == net->d; }
 
 // InstaDepthNet trunks: after the last block of layers 1..3 the encoder's feature of the pair's image is added in place
 static int maybe_inject(io_net* net, Plan* plan, int li, bool layer_end, int b, int h, int w, __nv_bfloat16* dst,
@@ -191,6 +195,7 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
   size_t ci = 1;
   for (int li = 0; li < l0; ++li) ci += 3 * blocks_[li] + 1;
   const bool injecting = net->inject_idx != nullptr;
+  const bool geom_ok = default_geometry(net);
   int h = *h_io, w = *w_io;
   // next_t1: where the conv1 output of the block FOLLOWING this plan's last one goes (phase A -> phase B fusion);
   // t1_in: this plan's first conv1 output has already been produced that way
@@ -237,8 +242,8 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       // (not across a layer boundary when encoder features are added in between)
       const bool has_next = (blk + 1 < blocks_[li]) || ((li + 1 < l1 || next_t1 != nullptr) && !injecting);
       __nv_bfloat16* t1_dst = ((blk + 1 < blocks_[li]) || (li + 1 < l1)) ? T1 : next_t1;
-      const bool want_fuse = net->fuse && ((net->fuse_layers >> li) & 1) && has_next;
-      if (ds && net->fuse_ds) {
+      const bool want_fuse = net->fuse && geom_ok && ((net->fuse_layers >> li) & 1) && has_next;
+      if (ds && net->fuse_ds && geom_ok) {
         // block output = ReLU(conv3(T2) + downsample(src)) as one GEMM, K = [T2 channels | src channels]; the
         // identity tensor is neither written nor re-read
         const ConvDesc dsd{b, h, w, ds->cin, ds->cout, 1, ds->stride};
@@ -314,6 +319,25 @@ static int build_plan_a(io_net* net, int pa, int a0, __nv_bfloat16* dst, __nv_bf
   plan->ops.clear();
   __nv_bfloat16 *X = net->buf[0], *Y = net->buf[1];
   Op op;
+  if (!default_geometry(net)) {
+    // `orig` mode: h x w network input, one launch per convolution (general tilers: partial tiles, wide rows)
+    const int H = net->h, W = net->w;
+    op.kind = Op::STEM;
+    op.flops = 2.0 * b * (H / 2) * (W / 2) * 49.0 * 5.0 * 64.0;
+    op.bytes = static_cast<double>(io_pair_tensor_bytes_hw(pa, H, W)) + 2.0 * b * (H / 2) * (W / 2) * 64;
+    op.tag = 1;
+    plan->ops.push_back(op);
+    Op pool;
+    pool.kind = Op::POOL;
+    pool.src = X; pool.dst = Y; pool.b = b; pool.h = H / 2; pool.w = W / 2; pool.c = 64;
+    pool.bytes = 2.0 * b * (H / 2) * (W / 2) * 64 * 1.25;
+    pool.tag = 2;
+    plan->ops.push_back(pool);
+    int h = H / 4, w = W / 4;
+    const __nv_bfloat16* out = nullptr;
+    return build_blocks(net, plan, 0, 2, b, &h, &w, Y, X, Y, net->buf[2], net->buf[3], net->buf[4], dst, &out, nullptr,
+                        false, -1, dirs * a0);
+  }
   if (stem_pool_supported(d)) {
     // conv1 + BN + ReLU + max-pool in one launch: only the pooled tensor is written (maps are rebuilt per call: the
     // pair tensor belongs to the caller)
@@ -347,14 +371,14 @@ static int build_plan_a(io_net* net, int pa, int a0, __nv_bfloat16* dst, __nv_bf
 
 // phase B: layer3 + layer4 for `pb` pairs reading the big layer2-output buffer
 static int build_plan_b(io_net* net, int pb, Plan* plan) {
-  const int b = (net->single_dir ? 1 : 2) * pb, d = net->d;
+  const int b = (net->single_dir ? 1 : 2) * pb;
   plan->ops.clear();
-  int h = d / 8, w = d / 8;
+  int h = net->h / 8, w = net->w / 8;
   const __nv_bfloat16* out = nullptr;
   // the first block reads `big` (kept intact) and writes bufb[0]; afterwards bufb[0] / bufb[1] ping-pong
   int rc = build_blocks(net, plan, 2, net->n_layers, b, &h, &w, net->big, net->bufb[0], net->bufb[1], net->bufb[2],
                         net->bufb[3], net->bufb[4], net->keep_layers ? net->keep[net->n_layers - 1] : nullptr, &out,
-                        nullptr, net->cross_fuse, net->keep_layers ? 0 : -1, 0);
+                        nullptr, net->cross_fuse && default_geometry(net), net->keep_layers ? 0 : -1, 0);
   plan->feat = out;
   plan->hw_final = h * w;
   return rc;
@@ -371,8 +395,8 @@ extern "C" int io_net_create_arch(const int32_t* widths, const int32_t* outs, co
   IO_REQUIRE(n_layers == 3 || n_layers == 4, "io_net_create_arch: n_layers %d (3 or 4)", n_layers);
   IO_REQUIRE(n_heads >= 0 && n_heads <= 2 && (n_heads == 0 || (num_classes && n_layers == 4)),
              "io_net_create_arch: n_heads must be 0 (feature extractor), 1 (fc) or 2 (fc_occ + fc_depth)");
-  IO_REQUIRE(input_size >= 64 && input_size <= 512 && input_size % 32 == 0,
-             "io_net_create: input_size %d (multiple of 32 in [64, 512])", input_size);
+  IO_REQUIRE(input_size >= 64 && input_size <= 1024 && input_size % 32 == 0,
+             "io_net_create: input_size %d (multiple of 32 in [64, 1024])", input_size);
   IO_REQUIRE(max_pairs >= 1, "io_net_create: max_pairs %d", max_pairs);
   int dev_count = 0;
   IO_CUDA(cudaGetDeviceCount(&dev_count));
@@ -394,6 +418,7 @@ extern "C" int io_net_create_arch(const int32_t* widths, const int32_t* outs, co
     net->k_total += num_classes[i];
   }
   net->d = input_size;
+  net->h = net->w = input_size;
   net->max_pairs = max_pairs;
   int chunk_a = 256, chunk_b = 256;
   if (const char* e = getenv("INSTAORDER_CHUNK_A")) chunk_a = atoi(e) > 0 ? atoi(e) : chunk_a;
@@ -618,7 +643,39 @@ extern "C" int io_net_load_state(io_net_t* net, const char* const* names, const 
   return IO_OK;
 }
 
+static int forward_pairs(io_net_t* net, const void* pair_tensor, int p, float* logits, void* stream_);
+
 extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int p, float* logits, void* stream_) {
+  IO_REQUIRE(net, "io_net_forward_pairs: null handle");
+  if (net->plain || net->h != net->d || net->w != net->d) {   // back from an `orig`-mode call: drop its plans
+    net->plain = false;
+    net->h = net->w = net->d;
+    net->plans_a.clear();
+    net->plans_b.clear();
+  }
+  return forward_pairs(net, pair_tensor, p, logits, stream_);
+}
+
+// `orig` mode (reference inference.py:401-408): the pairs of ONE image whose network input is h x w (its own size rounded
+// to multiples of 32), pair tensor [p][h + 6][pitch(w)][8].  h, w <= the handle's input_size; the convolutions run through
+// the general tilers, one launch each (no cross-convolution fusion).  Plans are rebuilt when the geometry changes.
+extern "C" int io_net_forward_pairs_hw(io_net_t* net, const void* pair_tensor, int p, int h, int w, float* logits,
+                                       void* stream_) {
+  IO_REQUIRE(net, "io_net_forward_pairs_hw: null handle");
+  IO_REQUIRE(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0 && h <= net->d && w <= net->d,
+             "io_net_forward_pairs_hw: network input %d x %d (multiples of 32, at most the handle's %d x %d)", h, w,
+             net->d, net->d);
+  if (!net->plain || h != net->h || w != net->w) {
+    net->plain = true;
+    net->h = h;
+    net->w = w;
+    net->plans_a.clear();
+    net->plans_b.clear();
+  }
+  return forward_pairs(net, pair_tensor, p, logits, stream_);
+}
+
+static int forward_pairs(io_net_t* net, const void* pair_tensor, int p, float* logits, void* stream_) {
   IO_REQUIRE(net && pair_tensor && (logits || net->n_heads == 0), "io_net_forward_pairs: null pointer");
   if (!net->loaded) {
     set_error("io_net_forward_pairs: no weights loaded (call io_net_load_state first)");
@@ -649,16 +706,17 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
     }
     return IO_OK;
   };
-  const int64_t pair_bytes = io_pair_tensor_bytes(1, net->d);
+  const int64_t pair_bytes = io_pair_tensor_bytes_hw(1, net->h, net->w);
   const size_t l2_elems_per_pair = (net->single_dir ? 1 : 2) * per_img_out(net, 1);
-  const size_t t1b_elems_per_pair = static_cast<size_t>(2) * (net->d / 8) * (net->d / 8) * net->widths[2];
+  const size_t t1b_elems_per_pair = static_cast<size_t>(2) * (net->h / 8) * (net->w / 8) * net->widths[2];
+  const bool cross = net->cross_fuse && default_geometry(net);
   auto run_ops = [&](Plan& plan, const uint8_t* pair_ptr, int pa) -> int {
     for (Op& op : plan.ops) {
       int rc = mark(static_cast<int>(op.kind), op.flops, true);
       if (rc) return rc;
       switch (op.kind) {
         case Op::STEM:
-          rc = stem_plan(&op.p, &op.bn_tile, pa, net->d, pair_ptr, net->stem_w, net->stem_bias, net->buf[0]);
+          rc = stem_plan_hw(&op.p, &op.bn_tile, pa, net->h, net->w, pair_ptr, net->stem_w, net->stem_bias, net->buf[0]);
           if (!rc && net->single_dir) { op.p.img_mul = 1; op.p.split_row_off = pa * op.p.hw_out; }
           if (!rc) rc = conv_tc_launch(op.p, op.bn_tile, stream);
           break;
@@ -712,7 +770,7 @@ extern "C" int io_net_forward_pairs(io_net_t* net, const void* pair_tensor, int 
       auto it = net->plans_a.find(key);
       if (it == net->plans_a.end()) {
         std::unique_ptr<Plan> plan(new Plan());
-        __nv_bfloat16* next_t1 = net->cross_fuse ? net->bufb[2] + static_cast<size_t>(a0) * t1b_elems_per_pair : nullptr;
+        __nv_bfloat16* next_t1 = cross ? net->bufb[2] + static_cast<size_t>(a0) * t1b_elems_per_pair : nullptr;
         if (int rc = build_plan_a(net, pa, a0, net->big + static_cast<size_t>(a0) * l2_elems_per_pair, next_t1, plan.get())) return rc;
         it = net->plans_a.emplace(key, std::move(plan)).first;
       }

@@ -103,6 +103,16 @@ struct io_train {
   bool use_side = true;
   std::vector<void*> allocs;
   std::vector<io::TOp> fwd, bwd;
+  // Gradient buckets for the data-parallel all-reduce (reference utils/distributed_utils.py:27-31): backward finishes the
+  // parameters back to front, so the flat gradient buffer is complete in four contiguous ranges -- (layer4 + heads),
+  // layer3, layer2, (stem + layer1) -- at known points of the launch list.  An event pair (main / weight-gradient
+  // stream) is recorded there; the caller's communication stream waits on it (io_train_wait_bucket) and all-reduces
+  // that range while the rest of the backward pass is still running.
+  static constexpr int kBuckets = 4;
+  int64_t bucket_begin[kBuckets] = {0, 0, 0, 0}, bucket_end[kBuckets] = {0, 0, 0, 0};
+  size_t bucket_after_op[kBuckets] = {0, 0, 0, 0};     // bucket k is complete after bwd op index bucket_after_op[k] - 1
+  cudaEvent_t bucket_ev[kBuckets][2] = {};
+  bool bucket_side[kBuckets] = {false, false, false, false};
   bool built = false;
   bool weights_synced = false;
   // per-step inputs referenced by the op closures
@@ -431,7 +441,23 @@ static int build_graph(io_train* t) {
     return pool_fc_bwd_launch(t->dlogits, t->pooled, t->params + t->fc_w_off, hw_final, t->imgs, t->k_total,
                               t->grads + t->fc_w_off, t->grads + t->fc_b_off, GA, s);
   });
+  {
+    // first block of layers 4, 3, 2 in `blks` (3 + 4 + 6 + 3 blocks): everything behind it in the flat buffer is final
+    // once its backward ops have run
+    const int first_blk[3] = {13, 7, 3};
+    int64_t hi = t->n_params;
+    for (int k = 0; k < 3; ++k) {
+      t->bucket_begin[k] = t->units[blks[first_blk[k]].c1].w_off;
+      t->bucket_end[k] = hi;
+      hi = t->bucket_begin[k];
+    }
+    t->bucket_begin[3] = 0;
+    t->bucket_end[3] = hi;
+  }
   for (int bi = static_cast<int>(blks.size()) - 1; bi >= 0; --bi) {
+    if (bi == 12) t->bucket_after_op[0] = t->bwd.size();
+    if (bi == 6) t->bucket_after_op[1] = t->bwd.size();
+    if (bi == 2) t->bucket_after_op[2] = t->bwd.size();
     const Blk& k = blks[bi];
     Unit &u1 = t->units[k.c1], &u2 = t->units[k.c2], &u3 = t->units[k.c3];
     // out = relu(bn3(conv3(a2)) + identity):  GA = d out  ->  GY = d y3, GG = masked gradient (identity branch)
@@ -490,13 +516,16 @@ static int build_graph(io_train* t) {
       return stem_unpack_grad_launch(t->stem_scratch, t->grads + off, s);
     });
   }
+  t->bucket_after_op[3] = t->bwd.size();
+  for (int k = 0; k < io_train::kBuckets; ++k)
+    for (int j = 0; j < 2; ++j) IO_CUDA(cudaEventCreateWithFlags(&t->bucket_ev[k][j], cudaEventDisableTiming));
   IO_CUDA(cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking));
   if (const char* e = getenv("INSTAORDER_TRAIN_SIDE_STREAM")) t->use_side = atoi(e) != 0;
   t->built = true;
   return IO_OK;
 }
 
-static int run_ops(io_train* t, std::vector<TOp>& ops, cudaStream_t stream) {
+static int run_ops(io_train* t, std::vector<TOp>& ops, cudaStream_t stream, bool is_bwd = false) {
   // weight gradients go to a side stream (they only feed the gradient buffer) so that their tensor work overlaps the
   // HBM-bound BatchNorm passes of the main chain; per-op profiling keeps everything on one stream
   const bool side_on = t->use_side && !t->profile && t->side_stream != nullptr;
@@ -512,7 +541,16 @@ static int run_ops(io_train* t, std::vector<TOp>& ops, cudaStream_t stream) {
     return IO_OK;
   };
   bool forked = false;
+  size_t op_i = 0;
   for (TOp& op : ops) {
+    if (is_bwd)
+      for (int k = 0; k < io_train::kBuckets - 1; ++k)
+        if (op_i == t->bucket_after_op[k]) {       // everything of bucket k has been launched
+          IO_CUDA(cudaEventRecord(t->bucket_ev[k][0], stream));
+          t->bucket_side[k] = forked;
+          if (forked) IO_CUDA(cudaEventRecord(t->bucket_ev[k][1], t->side_stream));
+        }
+    ++op_i;
     size_t idx = 0;
     if (t->profile) {
       idx = 2 * t->prof_kind.size();
@@ -562,6 +600,10 @@ static int run_ops(io_train* t, std::vector<TOp>& ops, cudaStream_t stream) {
     IO_CUDA(cudaEventRecord(join, t->side_stream));
     IO_CUDA(cudaStreamWaitEvent(stream, join, 0));
   }
+  if (is_bwd) {   // the last bucket (stem + layer1) is complete when the whole backward pass is
+    IO_CUDA(cudaEventRecord(t->bucket_ev[io_train::kBuckets - 1][0], stream));
+    t->bucket_side[io_train::kBuckets - 1] = false;
+  }
   return IO_OK;
 }
 
@@ -598,6 +640,9 @@ extern "C" int io_train_destroy(io_train_t* t) {
   for (void* p : t->allocs) cudaFree(p);
   for (cudaEvent_t e : t->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : t->side_ev) cudaEventDestroy(e);
+  for (int k = 0; k < io_train::kBuckets; ++k)
+    for (int j = 0; j < 2; ++j)
+      if (t->bucket_ev[k][j]) cudaEventDestroy(t->bucket_ev[k][j]);
   if (t->side_stream) cudaStreamDestroy(t->side_stream);
   delete t;
   return IO_OK;
@@ -666,8 +711,26 @@ extern "C" int io_train_forward_backward(io_train_t* t, const void* pair_tensor_
   if (int rc = run_ops(t, t->fwd, stream)) return rc;
   if (run_backward) {
     IO_CUDA(cudaMemsetAsync(t->grads, 0, sizeof(float) * t->n_params, stream));
-    if (int rc = run_ops(t, t->bwd, stream)) return rc;
+    if (int rc = run_ops(t, t->bwd, stream, true)) return rc;
   }
+  return IO_OK;
+}
+
+extern "C" int io_train_num_buckets(const io_train_t* t) { return t ? io_train::kBuckets : 0; }
+
+extern "C" int io_train_bucket(const io_train_t* t, int k, int64_t* begin, int64_t* end) {
+  IO_REQUIRE(t && begin && end && t->built && k >= 0 && k < io_train::kBuckets, "io_train_bucket: bad arguments");
+  *begin = t->bucket_begin[k];
+  *end = t->bucket_end[k];
+  return IO_OK;
+}
+
+// Makes `stream` wait until the gradients of bucket k of the LAST io_train_forward_backward call are complete (their
+// last kernels on the main and on the weight-gradient stream).  No host synchronisation.
+extern "C" int io_train_wait_bucket(io_train_t* t, int k, void* stream) {
+  IO_REQUIRE(t && t->built && k >= 0 && k < io_train::kBuckets, "io_train_wait_bucket: bad arguments");
+  IO_CUDA(cudaStreamWaitEvent(as_stream(stream), t->bucket_ev[k][0], 0));
+  if (t->bucket_side[k]) IO_CUDA(cudaStreamWaitEvent(as_stream(stream), t->bucket_ev[k][1], 0));
   return IO_OK;
 }
 

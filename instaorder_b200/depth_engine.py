@@ -187,7 +187,7 @@ class DepthOrderEngine(OrderEngine):
         self.inject_idx[:2 * r.P].copy_(r.d_idx[:2 * r.P], non_blocking=True)
         super().run_resident(r, heads, mode)
 
-    def gather(self, s, P, mode="resize"):
+    def gather(self, s, P, mode="resize", geom=None):
         if mode != "resize":
             raise NotImplementedError("InstaDepthNet runs in 'resize' mode (its shipped config); got %r" % (mode,))
         super().gather(s, P, mode)
@@ -198,7 +198,7 @@ class DepthOrderEngine(OrderEngine):
         self.gpu_launches += 1
         self._n_img = n_img
 
-    def forward(self, P):
+    def forward(self, P, geom=None):
         if self.do_net is None:
             raise RuntimeError("this engine has no order trunks (plain MiDaS): use disparity() / disparity_order()")
         st = _lib.stream_ptr()

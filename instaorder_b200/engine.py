@@ -82,6 +82,12 @@ def expand_bbox(bboxes, enlarge_box=3.0):
     return out.astype(np.int64)
 
 
+def closest_multiple_of(n, m=32):
+    """``get_closest_int_multiple_of`` (reference utils/data_utils.py:13-17): ties go up."""
+    r = n % m
+    return n + m - r if r >= m // 2 else n - r
+
+
 def pair_crop_boxes(boxes, pairs):
     b = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 4))
     pairs = np.ascontiguousarray(pairs, dtype=np.int32)
@@ -241,7 +247,7 @@ class OrderEngine:
             else:
                 d["x"] = d["y"] = d["s"] = 0
             d["rgb_slot"] = slot_idx
-            if mode in ("resize", "image"):
+            if mode in ("resize", "image", "orig"):
                 self.resize_jobs.append((img_off, sc.h, sc.w, slot_idx))
                 slot_idx += 1
             ij[P:P + p] = pairs
@@ -269,8 +275,23 @@ class OrderEngine:
         self.h2d_bytes += img_off + mask_off - sum(nb for (_, nb, _) in dev_masks) + P * 48 + s.h_meta.numel() * 8
         return s, P
 
-    def gather(self, s, P, mode="patch"):
+    def gather(self, s, P, mode="patch", geom=None):
         st = _lib.stream_ptr()
+        if mode == "orig":
+            # reference inference.py:401-408: the image at its own size rounded to multiples of 32 (geom = (hh, ww)),
+            # transform_resize for the rgb, cv2.INTER_NEAREST for both masks; ONE image per batch
+            hh, ww = geom
+            (img_off, h, w, slot), = self.resize_jobs
+            need = hh * ww * 3
+            if getattr(self, "_planes", None) is None or self._planes.numel() < need:
+                self._planes = torch.empty(need, dtype=torch.float32, device=self.device)
+                self._lut_scratch = torch.empty(768, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.io_image_resize_rgb_hw(s.d_img.data_ptr() + img_off, h, w, hh, ww, _lib.ptr(self.mean),
+                                                       _lib.ptr(self.std), self._planes.data_ptr(), st))
+            _lib.check(self.lib.io_pair_gather_resize_hw(self._planes.data_ptr(), s.d_mask.data_ptr(),
+                                                         s.d_desc.data_ptr(), P, hh, ww, self.pair_tensor.data_ptr(), st))
+            self.gpu_launches += 2
+            return
         if mode == "patch":
             _lib.check(self.lib.io_pair_gather_patch(s.d_img.data_ptr(), s.d_mask.data_ptr(), s.d_desc.data_ptr(), P,
                                                      self.d, _lib.ptr(self.mean), _lib.ptr(self.std),
@@ -298,9 +319,13 @@ class OrderEngine:
         else:
             raise NotImplementedError("patch_or_image=%r (supported: 'patch', 'resize', 'image')" % (mode,))
 
-    def forward(self, P):
-        _lib.check(self.lib.io_net_forward_pairs(self.net, self.pair_tensor.data_ptr(), P, self.logits.data_ptr(),
-                                                 _lib.stream_ptr()))
+    def forward(self, P, geom=None):
+        if geom is not None:      # `orig` mode: non-square network input of this image
+            _lib.check(self.lib.io_net_forward_pairs_hw(self.net, self.pair_tensor.data_ptr(), P, geom[0], geom[1],
+                                                        self.logits.data_ptr(), _lib.stream_ptr()))
+        else:
+            _lib.check(self.lib.io_net_forward_pairs(self.net, self.pair_tensor.data_ptr(), P, self.logits.data_ptr(),
+                                                     _lib.stream_ptr()))
         self.gpu_launches += self.lib.io_net_last_launches(self.net)
 
     def decide(self, s, P, heads, mats):
@@ -325,9 +350,8 @@ class OrderEngine:
         (+ 'pairs', 'logits', 'margin_occ', 'margin_depth' when ``return_details``)."""
         heads = heads_for(algo, self.ncs if len(self.ncs) > 1 else self.ncs[0])
         mode = patch_or_image
-        if mode not in ("patch", "resize", "image"):
-            raise NotImplementedError("patch_or_image=%r (supported: 'patch', 'resize', 'image'; 'orig' needs "
-                                      "non-square network inputs)" % (mode,))
+        if mode not in ("patch", "resize", "image", "orig"):
+            raise ValueError("patch_or_image=%r (one of 'patch', 'resize', 'image', 'orig')" % (mode,))
         if pairs not in ("all", "nbor"):
             raise ValueError("pairs must be 'all' or 'nbor'")
         mat_offs = []
@@ -348,9 +372,17 @@ class OrderEngine:
             if not batch:
                 return
             used[0] = used[1] = 0
+            geom = None
+            if mode == "orig":     # one image per batch: its own size rounded to multiples of 32 is the network input
+                sc0 = batch[0][0]
+                geom = (closest_multiple_of(sc0.h), closest_multiple_of(sc0.w))
+                if min(geom) < 32 or max(geom) > self.d:
+                    raise ValueError("'orig' mode: image %d x %d -> network input %d x %d, this engine handles 32 .. %d "
+                                     "(models.engine_for_orig sizes the engine from the image)" %
+                                     (sc0.h, sc0.w, geom[0], geom[1], self.d))
             s, P = self.stage_batch(batch, mode)
-            self.gather(s, P, mode)
-            self.forward(P)
+            self.gather(s, P, mode, geom)
+            self.forward(P, geom)
             self.decide(s, P, heads, mats)
             self.finish(s)
             if return_details:
@@ -379,7 +411,7 @@ class OrderEngine:
                 take = min(pr.shape[0] - o, cap - count)
                 ib, mb = self._scene_bytes(sc)
                 fits = used[0] + ib <= self._slot_args[0] and used[1] + mb <= self._slot_args[1]
-                if take == 0 or len(batch) >= self.max_items_per_batch or (batch and not fits):
+                if take == 0 or len(batch) >= (1 if mode == "orig" else self.max_items_per_batch) or (batch and not fits):
                     flush()                      # pair budget, item budget or staging bytes exhausted: start a new batch
                     cap = self.max_pairs
                     continue

@@ -14,7 +14,10 @@ WHDR_KEYS = ["%s_%s" % (o, e) for o in ("ovlX", "ovlO", "ovlOX") for e in ("eq",
 
 
 def _run(model, image, inmodal, bboxes, pairs, method, patch_or_image, input_size):
-    eng = model.engine_for(input_size)
+    if patch_or_image == "orig":       # reference inference.py:401-408: input_size is not used, the image's own size is
+        eng = model.engine_for_orig(np.shape(inmodal)[1], np.shape(inmodal)[2])
+    else:
+        eng = model.engine_for(input_size)
     sc = _engine.Scene(image, inmodal, bboxes)
     return eng.infer_scenes([sc], method, pairs=pairs, patch_or_image=patch_or_image)[0]
 

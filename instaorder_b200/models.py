@@ -65,6 +65,20 @@ class _OrderModel(object):
             self._engines[input_size] = e
         return e
 
+    def engine_for_orig(self, h, w):
+        """``patch_or_image='orig'`` (reference inference.py:401-408): an engine whose workspace holds network inputs up
+        to the image's own size rounded to multiples of 32 (grown in steps of 128 so that a dataset shares one engine)."""
+        from .engine import closest_multiple_of
+        need = max(closest_multiple_of(int(h)), closest_multiple_of(int(w)), 256)
+        cap = (need + 127) // 128 * 128
+        for key, e in self._engines.items():
+            if isinstance(key, tuple) and key[0] == "orig" and key[1] >= need:
+                return e
+        e = OrderEngine(self.num_classes, cap, min(self.max_pairs, 64), self.device)
+        e.load_state_dict(self._state)
+        self._engines[("orig", cap)] = e
+        return e
+
     def load_state_dict(self, sd):
         self._state = sd
         for e in self._engines.values():

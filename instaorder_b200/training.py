@@ -9,6 +9,7 @@ PyTorch provides device memory, streams and ``torch.distributed`` (NCCL) only; t
 """
 import ctypes as C
 import collections
+import os
 
 import numpy as np
 import torch
@@ -165,6 +166,9 @@ class TrainEngine(object):
         self.losses = torch.zeros(3, dtype=torch.float32, device=dev)
         self.gpu_launches = 0
         self.loaded = False
+        self._buckets = None
+        self._comm_stream = None
+        self.overlap_allreduce = os.environ.get("INSTAORDER_ALLREDUCE_OVERLAP", "1") != "0"
 
     def __del__(self):
         try:
@@ -280,10 +284,40 @@ class TrainEngine(object):
                                                      C.byref(n), _lib.stream_ptr()))
         return out
 
+    def buckets(self):
+        """[(begin, end)] element ranges of the flat gradient buffer in the order backward completes them:
+        (layer4 + heads), layer3, layer2, (stem + layer1)."""
+        if self._buckets is None:
+            out = []
+            b, e = C.c_int64(), C.c_int64()
+            for k in range(self.lib.io_train_num_buckets(self.handle)):
+                _lib.check(self.lib.io_train_bucket(self.handle, k, C.byref(b), C.byref(e)))
+                out.append((int(b.value), int(e.value)))
+            self._buckets = out
+        return self._buckets
+
     def all_reduce_grads(self):
-        """utils.average_gradients (utils/distributed_utils.py:27-31): SUM all-reduce (the loss is pre-divided by
-        world_size) -- one NCCL call on the flat buffer instead of one per parameter."""
-        all_reduce_sum_(self.grads)
+        """utils.average_gradients (utils/distributed_utils.py:27-31: 163 blocking per-parameter all-reduces after
+        backward; SUM, the loss is pre-divided by world_size).  Here: FOUR all-reduces of contiguous ranges of the flat
+        buffer, each issued on a communication stream that waits (device side) only for ITS range of the backward pass
+        -- the 60 MB of layer4 + heads travel over NVLink while layer3 .. stem are still being differentiated; the
+        optimiser (caller's stream) waits for all four.  INSTAORDER_ALLREDUCE_OVERLAP=0: one call after backward."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        if not self.overlap_allreduce or not self.grads.is_cuda:
+            all_reduce_sum_(self.grads)
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        comm = self._comm_stream
+        works = []
+        for k, (b, e) in enumerate(self.buckets()):
+            _lib.check(self.lib.io_train_wait_bucket(self.handle, k, comm.cuda_stream))
+            with torch.cuda.stream(comm):
+                works.append(dist.all_reduce(self.grads[b:e], async_op=True))
+        for w in works:
+            w.wait()          # the caller's stream waits for the NCCL stream; no host synchronisation
 
     def broadcast_params(self):
         """DistModule.broadcast_params (utils/distributed_utils.py:17-24): rank 0's parameters to everyone."""

@@ -74,6 +74,48 @@ def test_order_matrices_match_reference(golden_dir, case):
         assert np.array_equal(occ, r["occ"])
 
 
+def test_orig_mode_matches_reference(golden_dir):
+    """``patch_or_image='orig'`` (reference inference.py:401-408): the network input is the image at
+    its own size rounded to multiples of 32 -- 333 x 500 -> 320 x 512, NOT square -- through io_image_resize_rgb_hw /
+    io_pair_gather_resize_hw / io_net_forward_pairs_hw.  Fixture: the unmodified reference (oracle/gen_golden_orig.py)."""
+    from oracle import gen_golden_orig
+    case = gen_golden_orig.CASE
+    c = gen_golden.CASES[case]
+    z = np.load(os.path.join(golden_dir, "order_c2_od_orig.npz"))
+    image, masks, boxes = gen_golden.build_scene(case)
+    model = make_model(case, golden_dir)
+    eng = model.engine_for_orig(image.shape[0], image.shape[1])
+    r = eng.infer_scenes([engine.Scene(image, masks, boxes)], c["algo"], "all", "orig", return_details=True)[0]
+    assert tuple(z["net_input_shape"][2:]) == (engine.closest_multiple_of(image.shape[0]),
+                                               engine.closest_multiple_of(image.shape[1])) == (320, 512)
+    off = 0
+    for h, k in enumerate((2, 3)):
+        ref = z["logits%d" % h]
+        err = float(np.abs(r["logits"][:, :, off:off + k] - ref).max())
+        print("orig head %d: max |logit - reference fp32| = %.5f (logit std %.3f)" % (h, err, ref.std()))
+        assert err < LOGIT_TOL, err
+        off += k
+    N = masks.shape[0]
+    for what in ("occ", "depth"):
+        mg = np.full((N, N), np.inf)
+        for (i, j), m in zip(r["pairs"], r["margin_" + what]):
+            mg[i, j] = mg[j, i] = m
+        ok = mg > 1e-3
+        assert np.array_equal(r[what][ok], z[what][ok]), what
+    occ, depth = inference.infer_order_sup_occ_depth(model, image, masks, boxes, "all", c["algo"], "orig", 384, "")
+    assert np.array_equal(occ, r["occ"]) and np.array_equal(depth, r["depth"])
+    # a second image of another size through the same engine (plans are rebuilt), then the first one again
+    from instaorder_b200 import synth
+    img2, m2, b2 = synth.make_scene(np.random.RandomState(3), 427, 640, 3)
+    r2 = model.engine_for_orig(427, 640).infer_scenes([engine.Scene(img2, m2, b2)], c["algo"], "all", "orig")[0]
+    assert r2["occ"].shape == (3, 3)
+    again = eng.infer_scenes([engine.Scene(image, masks, boxes)], c["algo"], "all", "orig", return_details=True)[0]
+    assert np.array_equal(again["logits"], r["logits"])
+    # and the square modes still work on an engine that has served `orig` calls
+    sq = eng.infer_scenes([engine.Scene(img2, m2, engine.expand_bbox(b2, 3.0))], c["algo"], "all", "resize")[0]
+    assert sq["depth"].shape == (3, 3)
+
+
 def test_realistic_logit_scale(golden_dir):
     """The same network with heads 5 x larger (logit std 1.4 - 1.6, |logit| up to 7: the O(1) scale of a trained head)
     against the live reference's fixture.  The bf16-vs-fp32 distance is a RELATIVE quantity -- it scales with the head

@@ -45,8 +45,40 @@ def main():
                   "are per-rank: %s)" % (it, float(out["loss"]), same_params, same_grads,
                                          [float(c[3]) for c in all_cs]))
         ok = ok and same_params and same_grads
-    # the reduced gradient = sum of the per-rank gradients: recompute both on rank 0 with the pre-step weights
+    # bucketed / overlapped all-reduce against the plain one: the same backward pass twice (no optimiser step in
+    # between) -- (a) synchronise, then ONE all-reduce of the whole buffer; (b) the four bucket all-reduces issued while
+    # backward is still running.  The two gradients agree up to the run-to-run order of the fp32 atomics in the
+    # weight-gradient kernels; a bucket reduced before it was complete would be off by O(1).
+    eng = m._trainer
+    batch = T.make_batch(5000 + rank, B, D, algo)
+    m.set_input(**G.set_input_args(algo, batch))
+    eng.pack_inputs(m.rgb, m.modal1, m.modal2)
+    args = (0, 2, 3, m.occ_order1, m.depth_order1, m.is_overlap, 0.1, 0.9, world)
+    eng.forward_backward(*args)
+    torch.cuda.synchronize()
+    want = eng.grads.clone()
+    dist.all_reduce(want)
+    eng.forward_backward(*args)
+    eng.all_reduce_grads()
+    torch.cuda.synchronize()
+    worst = 0.0
+    for (b0, e0) in eng.buckets():
+        scale = float(want[b0:e0].abs().max()) + 1e-20
+        worst = max(worst, float((eng.grads[b0:e0] - want[b0:e0]).abs().max()) / scale)
+    t = torch.tensor([worst], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    bucket_ok = float(t) < 1e-3
+    ok = ok and bucket_ok
     if rank == 0:
+        print("bucketed all-reduce vs single all-reduce of a synchronised backward: max |diff| / bucket max = %.3g (%s); "
+              "buckets %s" % (float(t), "ok" if bucket_ok else "MISMATCH", eng.buckets()))
+    if rank == 0:
+        eng = m._trainer
+        # two runs of this script with INSTAORDER_ALLREDUCE_OVERLAP=1 / 0 must print the same line (2 ranks: the sum of
+        # two gradients does not depend on how the buffer is cut into all-reduce calls)
+        print("FINAL overlap=%s params_sum=%.17g params_abs=%.17g grads_abs=%.17g" % (
+            os.environ.get("INSTAORDER_ALLREDUCE_OVERLAP", "1"), float(eng.params.double().sum()),
+            float(eng.params.double().abs().sum()), float(eng.grads.double().abs().sum())))
         print("DDP CHECK", "PASSED" if ok else "FAILED")
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
