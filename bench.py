@@ -230,23 +230,36 @@ def host_threads():
 _REF_MODEL = {}
 
 
-def cpu_reference_pairs_per_s(n_pairs, threads=None):
+def cpu_reference_pairs_per_s(n_pairs, threads=None, on_gpu=False):
     """The UNMODIFIED reference (``inference.infer_order_sup_occ_depth``: per-pair cv2 crops, two batch-1 fp32
     forwards, five host syncs per pair -- reference inference.py:349-436) on the host cores, imported from
     ``/root/reference`` or, on the GPU box, from the archive oracle/build_ref.py packed into ``oracle/_ref/``.
-    Returns None when neither exists (the caller falls back to the oracle port run the same batch-1 way)."""
+    Returns None when neither exists (the caller falls back to the oracle port run the same batch-1 way).
+    ``on_gpu``: leave the reference's own ``.cuda()`` calls alone -- its stock PyTorch-eager GPU path (cuDNN / cuBLAS,
+    fp32, batch 1) on this same B200, reported beside the CPU number for context."""
     from oracle import ref_shim
     if not ref_shim.available():
         return None
     import torch
+    if on_gpu and not torch.cuda.is_available():
+        return None
+    if on_gpu:
+        return _reference_run(n_pairs, threads, "gpu")
+    with ref_shim.cpu_only():
+        return _reference_run(n_pairs, threads, "cpu")
+
+
+def _reference_run(n_pairs, threads, where):
+    import torch
     from instaorder_b200 import synth
-    from oracle import gen_golden, oracle as O
+    from oracle import gen_golden, oracle as O, ref_shim
     threads = threads or host_threads()
     torch.set_num_threads(threads)
     ns = ref_shim.load()
-    if "m" not in _REF_MODEL:
-        _REF_MODEL["m"] = gen_golden.make_reference_model(ns, ALGO, NUM_CLASSES, synth.random_state_dict(0, 5, NUM_CLASSES))
-    model = _REF_MODEL["m"]
+    if where not in _REF_MODEL:
+        _REF_MODEL[where] = gen_golden.make_reference_model(ns, ALGO, NUM_CLASSES,
+                                                            synth.random_state_dict(0, 5, NUM_CLASSES))
+    model = _REF_MODEL[where]
     n_img = max(1, (n_pairs + 44) // 45)
     scenes = list(synth.coco_scene_stream(99, n_img, N=10))
     image, masks, boxes = scenes[0]
@@ -261,8 +274,12 @@ def cpu_reference_pairs_per_s(n_pairs, threads=None):
         while k * (k - 1) // 2 < left and k < 10:
             k += 1
         bexp = O.expand_bbox(boxes, 3.0)
+        if where == "gpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         ns.inference.infer_order_sup_occ_depth(model, image, masks[:k], bexp[:k], "all", ALGO, "patch", D, "")
+        if where == "gpu":
+            torch.cuda.synchronize()
         dt += time.perf_counter() - t0
         done += k * (k - 1) // 2
     return done / dt, done, dt, torch.get_num_threads()
@@ -719,13 +736,20 @@ def main():
                 kind, r = "port", cpu_port_pairs_per_s(args.cpu_sample_pairs // 3, batch1=True)
             v, n, cdt, threads = r
             vb, nb, cdtb, _ = cpu_port_pairs_per_s(args.cpu_sample_pairs // 2)
+            rg = cpu_reference_pairs_per_s(90, on_gpu=True) if kind == "reference" else None
             cpu = dict(value=v, unit="pairs/s", cores=threads, kind=kind,
                        sample="%d pairs of C2 images (%.1f s): %s, two batch-1 fp32 torch-CPU forwards per pair as in "
                               "inference.py:140-169" % (n, cdt, "the UNMODIFIED reference (oracle/_ref archive)"
                                                         if kind == "reference" else "oracle port of the reference"),
                        batched_port=dict(value=vb, unit="pairs/s", kind="port",
                                          sample="%d pairs (%.1f s): oracle port, 16 forwards per batch (best case for "
-                                                "the host cores)" % (nb, cdtb)))
+                                                "the host cores)" % (nb, cdtb)),
+                       # context, not a CPU number: the unmodified reference's stock PyTorch-eager path (its own
+                       # .cuda() calls, cuDNN fp32, batch 1, five .item() syncs per pair) on this same B200
+                       reference_on_this_gpu=None if rg is None else dict(
+                           value=rg[0], unit="pairs/s", kind="reference",
+                           sample="%d pairs (%.1f s): inference.infer_order_sup_occ_depth as written, PyTorch eager on "
+                                  "cuda:0" % (rg[1], rg[2])))
         line = dict(
             metric=("instance pairs/s (InstaDepthNet^od order inference, resize 384^2, bf16)" if depth else
                     "instance pairs/s (%s, %s, bf16)" % ({"InstaOrderNet_od": "InstaOrderNet^od", "InstaOrderNet_o":

@@ -40,6 +40,29 @@ def is_archive() -> bool:
 _loaded = {}
 
 
+class cpu_only(object):
+    """Context manager: every ``.cuda()`` of the reference (it calls them unconditionally: models/single_stage_model.py:26,
+    models/supervised_order.py:34-48, utils/data_utils.py:34, inference.py:141-142, utils/common_utils.py:129-130) is a
+    no-op inside, so the UNMODIFIED reference runs on the host cores even on a box that has a GPU (bench.py's CPU arm).
+    The patches are undone on exit: this package's own ``.cuda()`` / ``.to(device)`` calls are not affected outside."""
+
+    def __enter__(self):
+        import torch
+        import torch.nn as nn
+        self._saved = (torch.Tensor.cuda, nn.Module.cuda, torch.UntypedStorage.cuda, torch.TypedStorage.cuda)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        nn.Module.cuda = lambda self, *a, **k: self
+        torch.UntypedStorage.cuda = lambda self, *a, **k: self
+        torch.TypedStorage.cuda = lambda self, *a, **k: self
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        import torch.nn as nn
+        torch.Tensor.cuda, nn.Module.cuda, torch.UntypedStorage.cuda, torch.TypedStorage.cuda = self._saved
+        return False
+
+
 class _Stub(types.ModuleType):
     """Module whose every attribute is a harmless callable (plotting / dataset-only imports)."""
 
