@@ -37,13 +37,50 @@ constexpr int BAR_BYTES = 512;
 // the other shapes read it through L1 instead -- their shared memory is needed for the rings
 __host__ __device__ constexpr int bias2_bytes(int n2) { return n2 <= 128 ? 512 : 1024; }
 __host__ __device__ constexpr int bias1_bytes(int n1, int n2) { return (n1 <= 512 && n2 <= 128) ? 2048 : 0; }
-__host__ __device__ constexpr int fixed_bytes(int n1, int n2) {
-  return NB * TILE_BYTES + bias2_bytes(n2) + bias1_bytes(n1, n2) + BAR_BYTES;
+constexpr int IDENT_BYTES = 64 * 128;        // 64 x 64 bf16 identity matrix, K-major, 128B-swizzled (res_mma)
+__host__ __device__ constexpr int fixed_bytes(int n1, int n2, int res_mma) {
+  return NB * TILE_BYTES + (res_mma ? IDENT_BYTES : 0) + bias2_bytes(n2) + bias1_bytes(n1, n2) + BAR_BYTES;
 }
 constexpr int MAX_SMEM = 232448;             // 227 KB
 constexpr int TMEM_COLS = 512;
 constexpr int THREADS = 384;
 }  // namespace
+
+// One epilogue unit of a warp: 32 rows x 64 columns; v = the accumulator values of this thread's row, rowp = its 128-byte
+// row of the 128B-swizzled staging region (holding the residual when ADD_RES); + bias (+ residual), ReLU, bf16, in place.
+template <bool ADD_RES>
+__device__ __forceinline__ void epi_unit(const uint32_t (&v)[2][32], const float* bias, uint8_t* rowp, int lane) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const float4* bias4 = reinterpret_cast<const float4*>(bias + half * 32);
+    float f[32];   // all eight bias loads first: the bias vector may live in global memory (L1), not shared memory
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 bb = bias4[k];
+      f[4 * k + 0] = __uint_as_float(v[half][4 * k + 0]) + bb.x;
+      f[4 * k + 1] = __uint_as_float(v[half][4 * k + 1]) + bb.y;
+      f[4 * k + 2] = __uint_as_float(v[half][4 * k + 2]) + bb.z;
+      f[4 * k + 3] = __uint_as_float(v[half][4 * k + 3]) + bb.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4* cp = reinterpret_cast<uint4*>(rowp + (((half * 4 + k) ^ (lane & 7)) << 4));
+      if (ADD_RES) {
+        const uint4 rr = *cp;
+        f[8 * k + 0] += bf16_lo(rr.x); f[8 * k + 1] += bf16_hi(rr.x);
+        f[8 * k + 2] += bf16_lo(rr.y); f[8 * k + 3] += bf16_hi(rr.y);
+        f[8 * k + 4] += bf16_lo(rr.z); f[8 * k + 5] += bf16_hi(rr.z);
+        f[8 * k + 6] += bf16_lo(rr.w); f[8 * k + 7] += bf16_hi(rr.w);
+      }
+      uint4 o;
+      o.x = pack_bf16_relu(f[8 * k + 0], f[8 * k + 1]);
+      o.y = pack_bf16_relu(f[8 * k + 2], f[8 * k + 3]);
+      o.z = pack_bf16_relu(f[8 * k + 4], f[8 * k + 5]);
+      o.w = pack_bf16_relu(f[8 * k + 6], f[8 * k + 7]);
+      *cp = o;   // inactive regions still get finite values: the second GEMM reads all 128 rows
+    }
+  }
+}
 
 __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_constant__ FusedParams fp) {
   const ConvParams& p = fp.c;
@@ -57,11 +94,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
   uint8_t* sS1 = smem;                                  // ring 1: st1 stages of 32 KB
   uint8_t* sS2 = sS1 + st1 * STAGE1_BYTES;              // ring 2: st2 slots of n2 * 128 B
   uint8_t* sT = sS2 + st2 * slot2_bytes;                // tile buffers: [NB][2 groups][4 quadrants][32 x 128 B]
-  float* sBias2 = reinterpret_cast<float*>(sT + NB * TILE_BYTES);
-  float* sBias1 = reinterpret_cast<float*>(sT + NB * TILE_BYTES + bias2_bytes(n2));
+  const bool res_mma = fp.res_mma != 0;
+  uint8_t* sI = sT + NB * TILE_BYTES;                   // identity matrix (res_mma)
+  uint8_t* sF = sI + (res_mma ? IDENT_BYTES : 0);
+  float* sBias2 = reinterpret_cast<float*>(sF);
+  float* sBias1 = reinterpret_cast<float*>(sF + bias2_bytes(n2));
   const bool bias1_smem = bias1_bytes(p.n_total, n2) != 0;
   const float* bias1p = bias1_smem ? sBias1 : p.bias;
-  uint64_t* full1 = reinterpret_cast<uint64_t*>(sT + NB * TILE_BYTES + bias2_bytes(n2) + bias1_bytes(p.n_total, n2));
+  uint64_t* full1 = reinterpret_cast<uint64_t*>(sF + bias2_bytes(n2) + bias1_bytes(p.n_total, n2));
   uint64_t* empty1 = full1 + MAX_ST1;
   uint64_t* full2 = empty1 + MAX_ST1;
   uint64_t* empty2 = full2 + MAX_ST2;
@@ -72,7 +112,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
   uint64_t* rbar = gfree + NB * 2;      // [8 warps][NB]: residual region landed
   uint64_t* d2full = rbar + 8 * NB;     // [2]
   uint64_t* d2empty = d2full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2empty + 2);
+  uint64_t* rbar_u = d2empty + 2;       // [NB]: residual of a whole unit landed (res_mma: 8 arrivals, one per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar_u + NB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,6 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
       mbar_init(&gfree[i], 1);
     }
     for (int i = 0; i < 8 * NB; ++i) mbar_init(&rbar[i], 1);
+    for (int i = 0; i < NB; ++i) mbar_init(&rbar_u[i], 8);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -118,6 +160,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
   if (bias1_smem)
     for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) sBias1[i] = p.bias[i];
   for (int i = threadIdx.x; i < n2; i += blockDim.x) sBias2[i] = fp.bias2[i];
+  if (res_mma) {
+    // I[n][k] = (n == k): row n = 128 bytes, its 16-byte chunk c stored at chunk c ^ (n & 7)
+    for (int i = threadIdx.x; i < IDENT_BYTES / 16; i += blockDim.x) {
+      const int n = i >> 3, c = (i & 7) ^ (n & 7);      // c = logical chunk held by physical chunk (i & 7)
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (c == (n >> 3)) {
+        const uint32_t one = (n & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in the high / low half
+        const int wsel = (n & 7) >> 1;
+        v.x = wsel == 0 ? one : 0u; v.y = wsel == 1 ? one : 0u; v.z = wsel == 2 ? one : 0u; v.w = wsel == 3 ? one : 0u;
+      }
+      reinterpret_cast<uint4*>(sI)[i] = v;
+    }
+    fence_proxy_async();
+  }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -176,6 +232,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
             umma_bf16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (ki > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty1[stage]);
           if (++stage == st1) { stage = 0; phase ^= 1; }
+        }
+        if (res_mma) {
+          // D1 += identity tile: the residual (TMA-loaded into tile buffer i % NB, the layout of a K-major A operand)
+          // times a 64 x 64 identity matrix -- exact in fp32, and off the epilogue warps' instruction budget
+          constexpr uint32_t idesc_r = umma_idesc_bf16(BM, 64);
+          const int b = i % NB;
+          mbar_wait(&rbar_u[b], static_cast<uint32_t>(i / NB) & 1);
+          tc_fence_after();
+          const uint64_t i_desc = umma_desc_sw128(smem_u32(sI));
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint64_t r_desc = umma_desc_sw128(smem_u32(sT + b * TILE_BYTES + g * GROUP_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d1 + g * 64, r_desc + 2 * k, i_desc + 2 * k, idesc_r, 1u);
+          }
         }
         umma_commit(&tfull[acc]);
       }
@@ -239,9 +310,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
     const int U = my_tiles * nu;
     auto issue_residual = [&](int t, int j, int b) {    // lane 0: residual region of unit (t, j) -> tile buffer b
       const int row0 = first_row + t * tile_stride_rows + q * 32;
+      uint64_t* bar = res_mma ? &rbar_u[b] : &my_rbar[b];
       if (row0 < p.m_total) {
-        mbar_expect_tx(&my_rbar[b], REGION_BYTES);
-        tma_load_2d(my_region0 + b * TILE_BYTES, &p.map_res, &my_rbar[b], j * UN + g * 64, row0);
+        mbar_expect_tx(bar, REGION_BYTES);
+        tma_load_2d(my_region0 + b * TILE_BYTES, &p.map_res, bar, j * UN + g * 64, row0);
+      } else if (res_mma) {
+        mbar_arrive(bar);   // the unit barrier counts all 8 warps; rows past the end only see their own garbage
       }
     };
     auto d2_epilogue = [&](int t) {       // D2 = conv1_next(block output) + bias2, ReLU -> T1 of the next block
@@ -262,18 +336,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
         for (int half = 0; half < 2; ++half) {
           const float4* bias4 = reinterpret_cast<const float4*>(sBias2 + gg * 64 + half * 32);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b0 = bias4[2 * i], b1 = bias4[2 * i + 1];
-            uint4 o;
-            o.x = pack_bf16(fmaxf(__uint_as_float(v[half][8 * i + 0]) + b0.x, 0.f),
-                            fmaxf(__uint_as_float(v[half][8 * i + 1]) + b0.y, 0.f));
-            o.y = pack_bf16(fmaxf(__uint_as_float(v[half][8 * i + 2]) + b0.z, 0.f),
-                            fmaxf(__uint_as_float(v[half][8 * i + 3]) + b0.w, 0.f));
-            o.z = pack_bf16(fmaxf(__uint_as_float(v[half][8 * i + 4]) + b1.x, 0.f),
-                            fmaxf(__uint_as_float(v[half][8 * i + 5]) + b1.y, 0.f));
-            o.w = pack_bf16(fmaxf(__uint_as_float(v[half][8 * i + 6]) + b1.z, 0.f),
-                            fmaxf(__uint_as_float(v[half][8 * i + 7]) + b1.w, 0.f));
-            if (row < p.m_total) dst[half * 4 + i] = o;
+          for (int i = 0; i < 4; i += 2) {
+            uint4 o[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float4 b0 = bias4[2 * (i + u)], b1 = bias4[2 * (i + u) + 1];
+              const uint32_t* vv = &v[half][8 * (i + u)];
+              o[u].x = pack_bf16_relu(__uint_as_float(vv[0]) + b0.x, __uint_as_float(vv[1]) + b0.y);
+              o[u].y = pack_bf16_relu(__uint_as_float(vv[2]) + b0.z, __uint_as_float(vv[3]) + b0.w);
+              o[u].z = pack_bf16_relu(__uint_as_float(vv[4]) + b1.x, __uint_as_float(vv[5]) + b1.y);
+              o[u].w = pack_bf16_relu(__uint_as_float(vv[6]) + b1.z, __uint_as_float(vv[7]) + b1.w);
+            }
+            if (row < p.m_total) {
+              if (fp.st256) {
+                st_global_256(dst + half * 4 + i, o[0], o[1]);   // one whole 32-byte sector per lane
+              } else {
+                dst[half * 4 + i] = o[0];
+                dst[half * 4 + i + 1] = o[1];
+              }
+            }
           }
         }
       }
@@ -308,44 +389,38 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);           // D1 buffer read: issuer 1 may refill it
-      const bool add_res = active && has_res;
+      const bool add_res = active && has_res && !res_mma;
       if (add_res) mbar_wait(&my_rbar[b], nuse & 1);
       uint8_t* region = my_region0 + b * TILE_BYTES;
       uint8_t* rowp = region + lane * 128;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const float4* bias4 = reinterpret_cast<const float4*>(bias1p + j * UN + g * 64 + half * 32);
-        float f[32];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 bb = bias4[k];
-          f[4 * k + 0] = __uint_as_float(v[half][4 * k + 0]) + bb.x;
-          f[4 * k + 1] = __uint_as_float(v[half][4 * k + 1]) + bb.y;
-          f[4 * k + 2] = __uint_as_float(v[half][4 * k + 2]) + bb.z;
-          f[4 * k + 3] = __uint_as_float(v[half][4 * k + 3]) + bb.w;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint4* cp = reinterpret_cast<uint4*>(rowp + (((half * 4 + k) ^ (lane & 7)) << 4));
-          if (add_res) {
-            const uint4 rr = *cp;
-            f[8 * k + 0] += bf16_lo(rr.x); f[8 * k + 1] += bf16_hi(rr.x);
-            f[8 * k + 2] += bf16_lo(rr.y); f[8 * k + 3] += bf16_hi(rr.y);
-            f[8 * k + 4] += bf16_lo(rr.z); f[8 * k + 5] += bf16_hi(rr.z);
-            f[8 * k + 6] += bf16_lo(rr.w); f[8 * k + 7] += bf16_hi(rr.w);
-          }
-          uint4 o;
-          o.x = pack_bf16(fmaxf(f[8 * k + 0], 0.f), fmaxf(f[8 * k + 1], 0.f));
-          o.y = pack_bf16(fmaxf(f[8 * k + 2], 0.f), fmaxf(f[8 * k + 3], 0.f));
-          o.z = pack_bf16(fmaxf(f[8 * k + 4], 0.f), fmaxf(f[8 * k + 5], 0.f));
-          o.w = pack_bf16(fmaxf(f[8 * k + 6], 0.f), fmaxf(f[8 * k + 7], 0.f));
-          *cp = o;   // inactive regions still get finite values: the second GEMM reads all 128 rows
-        }
+      // sub-sampled output (layer-end block whose output only feeds the next layer's stride-2 1x1 downsample and, on
+      // chip, its conv1): only pixels on even rows / columns are written, compactly as [img][h/2][w/2][n1]
+      // (the 32 pixels of this warp's slab lie in one image row: sub_w is a multiple of 32)
+      __nv_bfloat16* sub_dst = nullptr;
+      if (fp.sub_w > 0 && active) {
+        const int img = row0 / fp.sub_hw, rem = row0 - img * fp.sub_hw;
+        const int y = rem / fp.sub_w, x0 = rem - y * fp.sub_w;
+        if ((y & 1) == 0)
+          sub_dst = p.out + (static_cast<size_t>(img) * (fp.sub_hw >> 2) + (y >> 1) * (fp.sub_w >> 1) + (x0 >> 1)) * p.n_total +
+                    j * UN + g * 64;
       }
+      // two code paths (a uniform branch, not predication: the residual arithmetic is a third of the instructions)
+      if (add_res) epi_unit<true>(v, bias1p + j * UN + g * 64, rowp, lane);
+      else epi_unit<false>(v, bias1p + j * UN + g * 64, rowp, lane);
       fence_proxy_async();
       __syncwarp();
+      if (sub_dst != nullptr) {
+        // the 16 even pixels of the slab, 128 bytes each: 8 lanes per pixel, whole lines per store instruction
+        const int c = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int xl = 2 * (it * 4 + (lane >> 3));
+          const uint4 v4 = *reinterpret_cast<const uint4*>(region + xl * 128 + ((c ^ (xl & 7)) << 4));
+          *reinterpret_cast<uint4*>(sub_dst + static_cast<size_t>(xl >> 1) * p.n_total + c * 8) = v4;
+        }
+      }
       if (lane == 0) {
-        if (active) tma_store_2d(&p.map_out, region, j * UN + g * 64, row0);
+        if (active && fp.sub_w == 0) tma_store_2d(&p.map_out, region, j * UN + g * 64, row0);
         tma_store_commit();
         mbar_arrive(&gready[b * 2 + g]);
         if (i + 2 < U) {
@@ -401,23 +476,28 @@ int conv_fused_launch(const FusedParams& fp, cudaStream_t stream) {
 }
 
 // Ring depths: prefer 3 stages for the (x + w3) ring, then as many next-conv1 weight slots as fit (2..4).
-static bool fused_smem_plan(int n1, int n2, int* st1, int* st2, int* bytes) {
-  const int budget = MAX_SMEM - fixed_bytes(n1, n2);
+static bool fused_smem_plan(int n1, int n2, int res_mma, int* st1, int* st2, int* bytes) {
+  const int budget = MAX_SMEM - fixed_bytes(n1, n2, res_mma);
   const int slot2 = n2 * 128;
   int s1 = (3 * STAGE1_BYTES + 2 * slot2 <= budget) ? 3 : 2;
   int s2 = (budget - s1 * STAGE1_BYTES) / slot2;
   if (s2 > MAX_ST2) s2 = MAX_ST2;
   if (s2 < 2) return false;
   *st1 = s1; *st2 = s2;
-  *bytes = s1 * STAGE1_BYTES + s2 * slot2 + fixed_bytes(n1, n2);
+  *bytes = s1 * STAGE1_BYTES + s2 * slot2 + fixed_bytes(n1, n2, res_mma);
   return true;
+}
+
+void conv_fused_set_subsampled(FusedParams* fp, int h, int w) {
+  fp->sub_w = w;
+  fp->sub_hw = h * w;
 }
 
 bool conv_fused_supported(int cmid, int n1, int n2, const ConvDesc* ds) {
   if (cmid % 64 != 0 || cmid < 64 || n1 % UN != 0 || n1 < 2 * UN || n1 > 1024) return false;
   if (n2 != 64 && n2 != 128 && n2 != 256) return false;
   int a, b, c;
-  if (!fused_smem_plan(n1, n2, &a, &b, &c)) return false;
+  if (!fused_smem_plan(n1, n2, 0, &a, &b, &c)) return false;
   if (ds != nullptr) {
     // block 0 of a layer: K = [t2 | x].  The first GEMM runs N = 128 MMAs (half rate), which only pays while the
     // block is HBM-bound (layer1 / layer2); the strided source needs M tiles of exactly 128 output pixels
@@ -507,7 +587,21 @@ int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n1, int n2, const v
     if ((rc = make_tmap_bf16(&fp->map_b2, w1n, 2, dims, str, box, true))) return rc;
   }
   fp->out2 = reinterpret_cast<__nv_bfloat16*>(y2);
-  IO_REQUIRE(fused_smem_plan(n1, n2, &fp->st1, &fp->st2, &fp->smem_bytes), "fused conv: no shared-memory plan");
+  // residual through the tensor pipe where the kernel is bound by its epilogue warps (layer1: C = 64), when
+  // the identity matrix still leaves room for the rings (INSTAORDER_RES_MMA=0 disables)
+  static const bool res_mma_on = []() {
+    const char* e = getenv("INSTAORDER_RES_MMA");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  static const bool st256_on = []() {
+    const char* e = getenv("INSTAORDER_ST256");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  fp->st256 = st256_on ? 1 : 0;
+  fp->res_mma = (res_mma_on && residual != nullptr && cmid <= 64) ? 1 : 0;   // layer2 (C = 128): measured 6 % slower
+  if (fp->res_mma && !fused_smem_plan(n1, n2, 1, &fp->st1, &fp->st2, &fp->smem_bytes)) fp->res_mma = 0;
+  if (!fp->res_mma)
+    IO_REQUIRE(fused_smem_plan(n1, n2, 0, &fp->st1, &fp->st2, &fp->smem_bytes), "fused conv: no shared-memory plan");
   return IO_OK;
 }
 

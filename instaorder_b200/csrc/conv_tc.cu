@@ -40,6 +40,10 @@ struct Cfg {
   static constexpr int FIXED_BYTES = EPI_BYTES + BIAS_BYTES + BAR_BYTES + 1024;  // + 1024 B alignment slack
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
   static constexpr int MAX_SMEM = 232448;  // 227 KB
+  // CTA pair (cta_group::2, N = 256 only): every CTA stages its own 128 A rows and HALF of the weight rows
+  static constexpr int PAIR_B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + PAIR_B_BYTES;
+  static constexpr int PAIR_STAGES = 4;
 };
 
 struct TileCoord {
@@ -77,16 +81,27 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int m_tile)
   return t;
 }
 
-template <int BN>
+// PAIR: two CTAs of a cluster (one TPC) work on 256 output rows x 256 output channels with tcgen05.mma.cta_group::2:
+// CTA `rank` owns M tile 2 * pair + rank (its own A boxes, epilogue and TMEM lanes) and stages weight rows
+// [128 rank, 128 rank + 128) of the N tile; the leader (rank 0) issues the MMAs for both, its "full" barriers count
+// the bytes of both CTAs' TMA loads, "empty" / "accumulator full" arrive in both CTAs by multicast commits and the
+// peer's epilogue warps arrive on the leader's "accumulator drained" barriers.  Per K block a CTA takes in 32 KB
+// instead of 48 KB for the same 512 tensor cycles: the 128 x 256 single-CTA tiles were bound by the SM's operand
+// intake (96 B / cycle needed), not by the tensor pipe.
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   using C = Cfg<BN>;
+  constexpr int B_SLOT_BYTES = PAIR ? C::PAIR_B_BYTES : C::B_STAGE_BYTES;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int n_workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_stages = p.stages;
   const bool b_res = p.b_resident != 0;
   uint8_t* sA = smem;
   uint8_t* sB = smem + n_stages * A_STAGE_BYTES;   // ring slots, or the resident [k_iters][BN x 64] weights
-  uint8_t* sEpi = sB + (b_res ? p.k_iters : n_stages) * C::B_STAGE_BYTES;
+  uint8_t* sEpi = sB + (b_res ? p.k_iters : n_stages) * B_SLOT_BYTES;
   float* sBias = reinterpret_cast<float*>(sEpi + C::EPI_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES + C::BIAS_BYTES);
   uint64_t* empty = full + 8;
@@ -113,42 +128,87 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     mbar_init(bres_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], C::ACTIVE_EPI_WARPS);  // one arrival per participating epilogue warp
+      // one arrival per participating epilogue warp (of both CTAs in pair mode)
+      mbar_init(&tempty[i], PAIR ? 2 * C::ACTIVE_EPI_WARPS : C::ACTIVE_EPI_WARPS);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) sBias[i] = p.bias[i];  // weights: not produced upstream
   // Programmatic dependent launch: let the next convolution's CTAs start their prologue on SMs this grid has
   // already vacated, and do not touch activations before the previous grid has completed and flushed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers must exist before anything arrives
   tc_fence_after();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // work items: (M tile, N tile), or (pair of M tiles, N tile); this CTA's M tile of item `tile` is m_of(tile)
+  const int m_items = PAIR ? (p.m_tiles + 1) >> 1 : p.m_tiles;
+  const int total_tiles = m_items * p.n_tiles;
+  auto m_of = [&](int tile) { return PAIR ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles; };
 
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      if (b_res && blockIdx.x < total_tiles) {   // weights of the whole layer, once
+      if (!PAIR && b_res && worker < total_tiles) {   // weights of the whole layer, once
         mbar_expect_tx(bres_full, p.k_iters * C::B_STAGE_BYTES);
         for (int ki = 0; ki < p.k_iters; ++ki)
           tma_load_2d(sB + ki * C::B_STAGE_BYTES, &p.map_b, bres_full, ki * BK, 0);
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+        const int m_tile = m_of(tile), n_tile = tile % p.n_tiles;
         const TileCoord t = tile_coord(p, m_tile);
+        if (PAIR) {
+          // both CTAs signal the leader's "full" barrier; the leader arms it with the bytes of both
+          int tap = 0, kb = 0;
+          for (int ki = 0; ki < p.k_iters; ++ki) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * (p.a_bytes + C::PAIR_B_BYTES));
+            const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
+            void* dA = sA + stage * A_STAGE_BYTES;
+            uint8_t* dB = sB + stage * C::PAIR_B_BYTES;
+            if (ki < p.k1) {
+              tma2_load_2d(dA, &p.map_a2, fb, ki * BK, t.base_row);
+            } else if (p.mode == CONV_GEMM) {
+              tma2_load_2d(dA, &p.map_a, fb, kb * BK, t.base_row);
+            } else if (p.mode == CONV_S1) {
+              const int r = tap / 3, s = tap - r * 3;
+              if (p.flip) tma2_load_4d(dA, &p.map_a, fb, kb * BK, t.w0 + 1 - s, t.h0 + 1 - r, t.n_img);
+              else tma2_load_4d(dA, &p.map_a, fb, kb * BK, t.w0 + s - 1, t.h0 + r - 1, t.n_img);
+            } else {   // CONV_S2
+              const int r = tap / p.taps_w, s = tap - r * p.taps_w;
+              const int dr = r - p.pad, ds = s - p.pad;
+              const int ph = dr & 1, pw = ds & 1;
+              tma2_load_5d(dA, &p.map_a, fb, pw * p.cin + kb * BK, (ds - pw) / 2, ph, t.h0 + (dr - ph) / 2, t.n_img);
+            }
+            if (p.b_mn) {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j)
+                tma2_load_2d(dB + j * 8192, &p.map_b, fb,
+                             tap * p.b_tap_cols + n_tile * BN + (static_cast<int>(rank) * (BN / 128) + j) * 64, kb * BK);
+            } else {
+              tma2_load_2d(dB, &p.map_b, fb, ki * BK, n_tile * BN + static_cast<int>(rank) * (BN / 2));
+            }
+            if (ki >= p.k1 && ++kb == p.kpt) { kb = 0; ++tap; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         // The ring holds less than one tile of K blocks for the small-channel layers, so the first touch of a
         // tile's activations would expose a full DRAM latency per tile: pull the NEXT tile's rows into L2 now.
-        if (p.prefetch && tile + static_cast<int>(gridDim.x) < total_tiles) {
-          const int nm = (tile + static_cast<int>(gridDim.x)) / p.n_tiles;
+        if (p.prefetch && tile + n_workers < total_tiles) {
+          const int nm = (tile + n_workers) / p.n_tiles;
           if (nm != m_tile) {
             const TileCoord nx = tile_coord(p, nm);
             if (p.mode == CONV_GEMM) {
@@ -201,16 +261,16 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN) | (p.b_mn ? UMMA_B_MN : 0u);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN) | (p.b_mn ? UMMA_B_MN : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      if (b_res && blockIdx.x < total_tiles) {
+      if (!PAIR && b_res && worker < total_tiles) {
         mbar_wait(bres_full, 0);
         tc_fence_after();
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -220,22 +280,37 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + (b_res ? ki : stage) * C::B_STAGE_BYTES);
-          if (p.b_mn) {
+          const uint32_t b_addr = smem_u32(sB + (b_res ? ki : stage) * B_SLOT_BYTES);
+          if (PAIR) {
+            if (p.b_mn) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_mn_sw128(b_addr + k * 2048, p.mn_lbo, p.mn_sbo), idesc,
-                        (ki > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k)
+                umma2_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32),
+                           umma_desc_mn_sw128(b_addr + k * 2048, p.mn_lbo, p.mn_sbo), idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma2_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                           (ki > 0 || k > 0) ? 1u : 0u);
+            }
+            umma2_commit_mc(&empty[stage]);   // frees the slot in both CTAs
           } else {
+            if (p.b_mn) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                        (ki > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32),
+                          umma_desc_mn_sw128(b_addr + k * 2048, p.mn_lbo, p.mn_sbo), idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                          (ki > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);  // frees the smem slot when these MMAs have read it
           }
-          umma_commit(&empty[stage]);  // frees the smem slot when these MMAs have read it
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);  // accumulator complete
+        if (PAIR) umma2_commit_mc(&tfull[acc]); else umma_commit(&tfull[acc]);  // accumulator complete
       }
     }
   } else {
@@ -251,8 +326,11 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       uint64_t* my_rbar = &rbar[e * 2];
       uint32_t rphase[2] = {0, 0};
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      // "accumulator drained" lives in the leader CTA
+      const uint32_t tempty_leader[2] = {PAIR ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u,
+                                         PAIR ? mapa_u32(smem_u32(&tempty[1]), 0) : 0u};
+      for (int tile = worker; tile < total_tiles; tile += n_workers, ++it) {
+        const int m_tile = m_of(tile), n_tile = tile % p.n_tiles;
         const TileCoord t = tile_coord(p, m_tile);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -290,7 +368,9 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           if (i == MY_GROUPS - 1) {   // accumulator fully read by this warp: hand it back to the MMA warp early
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(tempty_leader[acc]); else mbar_arrive(&tempty[acc]);
+            }
           }
           if (col_base + c0 >= p.n_total || !(slab_full || valid)) {
             if (lane == 0) tma_store_commit();  // empty group: keeps one store-commit per group for wait_group.read
@@ -333,18 +413,26 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                   f[8 * j + 6] += bf16_lo(rr.w); f[8 * j + 7] += bf16_hi(rr.w);
                 }
               }
-              if (p.relu) {
+              if (p.relu) {   // ReLU folded into the conversion (cvt.rn.relu.bf16x2.f32)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-              }
+                for (int j = 0; j < 4; ++j) {
+                  uint4 o;
+                  o.x = pack_bf16_relu(f[8 * j + 0], f[8 * j + 1]);
+                  o.y = pack_bf16_relu(f[8 * j + 2], f[8 * j + 3]);
+                  o.z = pack_bf16_relu(f[8 * j + 4], f[8 * j + 5]);
+                  o.w = pack_bf16_relu(f[8 * j + 6], f[8 * j + 7]);
+                  *reinterpret_cast<uint4*>(rowp + (((kbase + j) ^ (lane & 7)) << 4)) = o;
+                }
+              } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
-                o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-                o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-                o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
-                *reinterpret_cast<uint4*>(rowp + (((kbase + j) ^ (lane & 7)) << 4)) = o;
+                for (int j = 0; j < 4; ++j) {
+                  uint4 o;
+                  o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+                  o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+                  o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+                  o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+                  *reinterpret_cast<uint4*>(rowp + (((kbase + j) ^ (lane & 7)) << 4)) = o;
+                }
               }
             } else {
               int row = t.base_row + r;
@@ -396,15 +484,51 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  __syncwarp();
+  if (PAIR) {
+    cluster_sync_all();   // the leader's MMAs read the peer's shared memory; remote arrivals need live barriers
+    if (warp == 1) tmem_dealloc2(tmem_base, C::TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+static int launch_pair(const ConvParams& p, cudaStream_t stream) {
+  using C = Cfg<256>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::MAX_SMEM));
+    attr_set = true;
+  }
+  IO_REQUIRE(p.stages >= 2 && p.stages <= 8 && p.smem_bytes <= C::MAX_SMEM && !p.b_resident,
+             "conv (pair): bad smem plan (%d stages, %d B)", p.stages, p.smem_bytes);
+  const int items = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = items < max_pairs ? items : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = p.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  IO_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, true>, p));
+  return IO_OK;
 }
 
 template <int BN>
 static int launch_bn(const ConvParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    IO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg<BN>::MAX_SMEM));
     attr_set = true;
   }
@@ -422,7 +546,7 @@ static int launch_bn(const ConvParams& p, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IO_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN>, p));
+  IO_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, false>, p));
   return IO_OK;
 }
 
@@ -431,7 +555,7 @@ int conv_tc_launch(const ConvParams& p, int bn_tile, cudaStream_t stream) {
   switch (bn_tile) {
     case 64: return launch_bn<64>(p, stream);
     case 128: return launch_bn<128>(p, stream);
-    case 256: return launch_bn<256>(p, stream);
+    case 256: return p.pair ? launch_pair(p, stream) : launch_bn<256>(p, stream);
   }
   set_error("conv_tc_launch: unsupported N tile %d", bn_tile);
   return IO_ERR_ARG;
@@ -466,6 +590,45 @@ static void plan_prefetch(ConvParams* p) {
   }();
   // worthwhile when a tile has few K blocks (the ring then covers less than a tile); never for stride-2 views
   p->prefetch = (allow && p->mode != CONV_S2 && p->k_iters <= 18) ? 1 : 0;
+}
+
+// CTA-pair mode for N = 256 tiles (INSTAORDER_PAIR=0 restores the single-CTA kernel everywhere)
+static bool pair_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("INSTAORDER_PAIR");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
+
+// switches a planned N = 256 convolution to the pair kernel: weight boxes of 128 rows, 4-stage ring of 32 KB
+static int plan_pair(ConvParams* p, const void* wgt, uint64_t ktot, uint64_t cout) {
+  using C = Cfg<256>;
+  p->pair = 0;
+  if (!pair_enabled() || p->mode == CONV_STEM || p->n_total % 256 != 0) return IO_OK;
+  // Measured on B200 (profiles/r02_pair_kernel.md): the pair kernel pays where the single-CTA tile was bound by operand
+  // intake -- 1x1 convolutions with long K, dual-source GEMMs, stride-2 3x3 -- and loses a little on HBM-bound short-K
+  // expansions (coupled epilogues) and on 3x3 stride-1 layers (already at the chip's sustained tensor rate); it also
+  // needs at least two waves of pair items.  INSTAORDER_PAIR=2 forces it wherever it is legal.
+  static const bool force = []() {
+    const char* e = getenv("INSTAORDER_PAIR");
+    return e != nullptr && atoi(e) == 2;
+  }();
+  const bool pays = (p->mode == CONV_GEMM && p->k_iters >= 12) || p->k1 > 0 || p->mode == CONV_S2;
+  const int items = ((p->m_tiles + 1) / 2) * p->n_tiles;
+  if (p->m_tiles < 2 || (!force && (!pays || items < num_sms()))) return IO_OK;
+  if (!p->b_mn) {
+    const uint64_t wdims[2] = {ktot, cout};
+    const uint64_t wstr[1] = {ktot * 2};
+    const uint32_t wbox[2] = {64, 128};
+    if (int rc = make_tmap_bf16(&p->map_b, wgt, 2, wdims, wstr, wbox, true)) return rc;
+  }
+  p->pair = 1;
+  p->b_resident = 0;
+  p->prefetch = 0;
+  p->stages = C::PAIR_STAGES;
+  p->smem_bytes = p->stages * C::PAIR_STAGE_BYTES + C::FIXED_BYTES;
+  return IO_OK;
 }
 
 static void plan_smem(ConvParams* p, int bn) {
@@ -580,6 +743,7 @@ int conv_plan(ConvParams* p, int* bn_tile, const ConvDesc& d, const void* x, con
   p->a_bytes = p->rows_per_tile * 128;
   if (rc) return rc;
   plan_smem(p, bn);
+  if (bn == 256 && (rc = plan_pair(p, wgt, ktot, d.cout))) return rc;
   return make_out_maps(p, p->m_total);
 }
 
@@ -602,6 +766,7 @@ int conv_plan_dual(ConvParams* p, int* bn_tile, const ConvDesc& ds, const void* 
   const uint32_t box[2] = {64, static_cast<uint32_t>(p->rows_per_tile)};
   if ((rc = make_tmap_bf16(&p->map_a2, t2, 2, dims, str, box, true))) return rc;
   plan_smem(p, bn);
+  if (bn == 256 && (rc = plan_pair(p, wcat, ktot, ds.cout))) return rc;
   return IO_OK;
 }
 
@@ -678,6 +843,7 @@ int dgrad_plan(ConvParams* p, int* bn_tile, int b, int h, int w, int cin_f, int 
   p->mn_sbo = mn_sbo();
   p->flip = kernel == 3 ? 1 : 0;
   p->b_tap_cols = cin_f;
+  if (p->pair) return IO_OK;   // pair ring: the 64 x 64 MN-major slabs above are what each CTA loads (two per stage)
   if (p->b_resident) {   // weight residency assumes the K-major layout: fall back to the streaming ring
     p->b_resident = 0;
     const int bn = *bn_tile;
@@ -699,6 +865,11 @@ extern "C" int io_conv_bn_act(const void* x_dev, int b, int h, int w, int cin, c
   io::ConvParams p;
   int bn = 0;
   io::ConvDesc d{b, h, w, cin, cout, kernel, stride};
+  if (residual_dev == nullptr && io::conv_row3_supported(d)) {
+    io::HaloParams hp;
+    if (int rc = io::conv_row3_plan(&hp, d, x_dev, w_dev, bias_dev, y_dev, relu)) return rc;
+    return io::conv_row3_launch(hp, io::as_stream(stream));
+  }
   if (residual_dev == nullptr && io::conv_halo_supported(d)) {
     io::HaloParams hp;
     if (int rc = io::conv_halo_plan(&hp, d, x_dev, w_dev, bias_dev, y_dev, relu)) return rc;

@@ -60,6 +60,9 @@ struct ConvParams {
   // matrix (map_a2, box 64 x rows_per_tile at the tile's first output row); the remaining blocks from map_a as usual
   CUtensorMap map_a2;
   int k1;
+  // CTA-pair kernel (cta_group::2, N = 256 tiles): map_b boxes are 64 x 128 (each CTA of the pair stages half the tile's
+  // weight rows), 4-stage ring of 32 KB
+  int pair;
 };
 
 // conv3 (+ residual + ReLU) of one bottleneck fused with conv1 (+ ReLU) of the next one (conv_fused.cu)
@@ -75,7 +78,15 @@ struct FusedParams {
   // the block input seen through the downsample convolution's activation view (flat, or the stride-2 parity view)
   int k1a;
   int a2_mode, a2_tpg, a2_bi, a2_bh;
+  // sub_w > 0: the block output is written sub-sampled (even rows / columns of sub_w-wide images of sub_hw pixels) as a
+  // compact [img][h/2][w/2][n1] tensor at c.out -- set by conv_fused_set_subsampled()
+  int sub_w, sub_hw;
+  // 1: the identity is added by the tensor pipe (D1 += residual tile x 64 x 64 identity matrix) instead of by the epilogue
+  // warps, which were the bottleneck of the layer1 / layer2 launches
+  int res_mma;
+  int st256;   // next-conv1 output rows written with 256-bit stores (whole 32-byte sectors per lane)
 };
+void conv_fused_set_subsampled(FusedParams* fp, int h, int w);
 bool conv_fused_supported(int cmid, int n1, int n2, const ConvDesc* ds);
 int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n1, int n2, const void* t2, const void* wb1,
                     const float* bias1, const void* residual, void* y, const void* w1n, const float* bias2, void* y2,
@@ -113,6 +124,10 @@ struct HaloParams {
 bool conv_halo_supported(const ConvDesc& d);
 int conv_halo_plan(HaloParams* p, const ConvDesc& d, const void* x, const void* wgt, const float* bias, void* y, int relu);
 int conv_halo_launch(const HaloParams& p, cudaStream_t stream);
+// same geometry at the full tensor rate: horizontal taps stacked along N (N = 192), shift in the epilogue (conv_row3.cu)
+bool conv_row3_supported(const ConvDesc& d);
+int conv_row3_plan(HaloParams* p, const ConvDesc& d, const void* x, const void* wgt, const float* bias, void* y, int relu);
+int conv_row3_launch(const HaloParams& p, cudaStream_t stream);
 
 // conv1 + BN + ReLU + MaxPool2d(3, 2, 1) in one kernel for 256 x 256 inputs (stem_pool.cu)
 struct StemPoolParams {

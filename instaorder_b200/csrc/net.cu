@@ -29,7 +29,7 @@ struct ConvW {
 };
 
 struct Op {
-  enum Kind { STEM, POOL, CONV, TAIL, FUSED, CONV_TN, STEM_TN, ADD, STEM_POOL, CONV_HALO } kind;
+  enum Kind { STEM, POOL, CONV, TAIL, FUSED, CONV_TN, STEM_TN, ADD, STEM_POOL, CONV_HALO, CONV_ROW3 } kind;
   ConvParams p;
   FusedParams fp;
   TnParams tp;
@@ -167,6 +167,24 @@ static size_t per_img_out(const io_net* net, int li) {
 }
 static bool default_geometry(const io_net* net) { return !net->plain && net->h == net->d && net->w == net->d; }
 
+// Layer li's output is consumed only by (a) the next layer's conv1 -- computed on chip by the fused kernel that produces
+// it -- and (b) the next layer's stride-2 1x1 downsample, which reads one pixel in four: the producing kernel then writes
+// just those pixels, compactly ([img][h/2][w/2][C]), and the dual-source GEMM of the next layer reads them as a flat
+// matrix.  INSTAORDER_SUBSAMPLE=0 restores the full tensor.
+static bool subsample_out(const io_net* net, int li) {
+  static const bool on = []() {
+    const char* e = getenv("INSTAORDER_SUBSAMPLE");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  if (!on || !default_geometry(net) || net->keep_layers || net->inject_idx != nullptr || !net->fuse || !net->fuse_ds) return false;
+  if (li + 1 >= net->n_layers || !((net->fuse_layers >> li) & 1)) return false;
+  if (li == 1 && !net->cross_fuse) return false;     // layer2 -> layer3 crosses the phase boundary
+  if (li > 1) return false;
+  const int h = net->h >> (2 + li), w = net->w >> (2 + li);
+  if ((h & 1) || (w % 32) != 0) return false;        // a 32-pixel epilogue slab must lie inside one image row
+  return conv_fused_supported(net->widths[li], net->outs[li], net->widths[li + 1], nullptr);
+}
+
 // InstaDepthNet trunks: after the last block of layers 1..3 the encoder's feature of the pair's image is added in place
 static int maybe_inject(io_net* net, Plan* plan, int li, bool layer_end, int b, int h, int w, __nv_bfloat16* dst,
                         int idx_off) {
@@ -190,7 +208,7 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
                         const __nv_bfloat16* src, __nv_bfloat16* P0, __nv_bfloat16* P1, __nv_bfloat16* T1,
                         __nv_bfloat16* T2, __nv_bfloat16* DS, __nv_bfloat16* final_dst,
                         const __nv_bfloat16** out_ptr, __nv_bfloat16* next_t1 = nullptr, bool t1_in = false,
-                        long long keep_off = -1, int idx_off = 0) {
+                        long long keep_off = -1, int idx_off = 0, bool src_sub = false) {
   const int* blocks_ = net->blocks;
   size_t ci = 1;
   for (int li = 0; li < l0; ++li) ci += 3 * blocks_[li] + 1;
@@ -223,7 +241,10 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       t1_ready = false;
       Op o2; o2.kind = Op::CONV;
       const ConvDesc d2{b, h, w, c2.cin, c2.cout, 3, c2.stride};
-      if (conv_halo_supported(d2)) {
+      if (conv_row3_supported(d2)) {
+        o2.kind = Op::CONV_ROW3;
+        if (int rc = conv_row3_plan(&o2.hp, d2, T1, c2.w, c2.bias, T2, 1)) return rc;
+      } else if (conv_halo_supported(d2)) {
         o2.kind = Op::CONV_HALO;
         if (int rc = conv_halo_plan(&o2.hp, d2, T1, c2.w, c2.bias, T2, 1)) return rc;
       } else if (tn_enabled() && conv_tn_supported(d2)) {
@@ -246,7 +267,10 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
       if (ds && net->fuse_ds && geom_ok) {
         // block output = ReLU(conv3(T2) + downsample(src)) as one GEMM, K = [T2 channels | src channels]; the
         // identity tensor is neither written nor re-read
-        const ConvDesc dsd{b, h, w, ds->cin, ds->cout, 1, ds->stride};
+        // src_sub: `src` already holds only the pixels the stride-2 downsample reads
+        const ConvDesc dsd = src_sub ? ConvDesc{b, ho, wo, ds->cin, ds->cout, 1, 1}
+                                     : ConvDesc{b, h, w, ds->cin, ds->cout, 1, ds->stride};
+        src_sub = false;
         if (want_fuse && conv_fused_supported(c3.cin, c3.cout, net->convs[ci].cout, &dsd)) {
           const ConvW& n1 = net->convs[ci];
           Op of; of.kind = Op::FUSED;
@@ -291,6 +315,12 @@ static int build_blocks(io_net* net, Plan* plan, int l0, int l1, int b, int* h_i
         of.flops = 2.0 * b * ho * wo * (static_cast<double>(c3.cin) * c3.cout + static_cast<double>(n1.cin) * n1.cout);
         of.bytes = 2.0 * b * ho * wo * (c3.cin + 2 * c3.cout + n1.cout) + 2.0 * c3.cin * c3.cout + 2.0 * n1.cin * n1.cout;
         of.tag = (li + 1) * 100 + blk * 10 + 5;
+        if (layer_end && subsample_out(net, li) && ((li + 1 < l1) || next_t1 != nullptr)) {
+          conv_fused_set_subsampled(&of.fp, ho, wo);
+          of.bytes -= 2.0 * b * ho * wo * c3.cout * 0.75;
+          of.tag += 3;   // LB8: conv3 + identity + next conv1, sub-sampled block output
+          src_sub = true;
+        }
         plan->ops.push_back(of);
         t1_ready = true;
       } else {
@@ -378,7 +408,8 @@ static int build_plan_b(io_net* net, int pb, Plan* plan) {
   // the first block reads `big` (kept intact) and writes bufb[0]; afterwards bufb[0] / bufb[1] ping-pong
   int rc = build_blocks(net, plan, 2, net->n_layers, b, &h, &w, net->big, net->bufb[0], net->bufb[1], net->bufb[2],
                         net->bufb[3], net->bufb[4], net->keep_layers ? net->keep[net->n_layers - 1] : nullptr, &out,
-                        nullptr, net->cross_fuse && default_geometry(net), net->keep_layers ? 0 : -1, 0);
+                        nullptr, net->cross_fuse && default_geometry(net), net->keep_layers ? 0 : -1, 0,
+                        net->cross_fuse && subsample_out(net, 1));
   plan->feat = out;
   plan->hw_final = h * w;
   return rc;
@@ -707,7 +738,7 @@ static int forward_pairs(io_net_t* net, const void* pair_tensor, int p, float* l
     return IO_OK;
   };
   const int64_t pair_bytes = io_pair_tensor_bytes_hw(1, net->h, net->w);
-  const size_t l2_elems_per_pair = (net->single_dir ? 1 : 2) * per_img_out(net, 1);
+  const size_t l2_elems_per_pair = (net->single_dir ? 1 : 2) * per_img_out(net, 1) / (subsample_out(net, 1) ? 4 : 1);
   const size_t t1b_elems_per_pair = static_cast<size_t>(2) * (net->h / 8) * (net->w / 8) * net->widths[2];
   const bool cross = net->cross_fuse && default_geometry(net);
   auto run_ops = [&](Plan& plan, const uint8_t* pair_ptr, int pa) -> int {
@@ -734,6 +765,9 @@ static int forward_pairs(io_net_t* net, const void* pair_tensor, int p, float* l
           break;
         case Op::CONV_HALO:
           rc = conv_halo_launch(op.hp, stream);
+          break;
+        case Op::CONV_ROW3:
+          rc = conv_row3_launch(op.hp, stream);
           break;
         case Op::ADD: {
           const int per8 = op.h * op.w * op.c / 8;
