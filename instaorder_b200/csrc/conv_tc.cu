@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   // already vacated, and do not touch activations before the previous grid has completed and flushed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers must exist before anything arrives
+  __syncthreads();
+  if (PAIR) cluster_sync_all();   // pair: the peer's barriers must exist before anything arrives
   tc_fence_after();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
@@ -327,8 +328,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       uint32_t rphase[2] = {0, 0};
       int it = 0;
       // "accumulator drained" lives in the leader CTA
-      const uint32_t tempty_leader[2] = {PAIR ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u,
-                                         PAIR ? mapa_u32(smem_u32(&tempty[1]), 0) : 0u};
+      const uint32_t tempty_leader0 = PAIR ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
       for (int tile = worker; tile < total_tiles; tile += n_workers, ++it) {
         const int m_tile = m_of(tile), n_tile = tile % p.n_tiles;
         const TileCoord t = tile_coord(p, m_tile);
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (PAIR) mbar_arrive_cluster(tempty_leader[acc]); else mbar_arrive(&tempty[acc]);
+              if (PAIR) mbar_arrive_cluster(tempty_leader0 + acc * 8); else mbar_arrive(&tempty[acc]);
             }
           }
           if (col_base + c0 >= p.n_total || !(slab_full || valid)) {
@@ -592,28 +592,24 @@ static void plan_prefetch(ConvParams* p) {
   p->prefetch = (allow && p->mode != CONV_S2 && p->k_iters <= 18) ? 1 : 0;
 }
 
-// CTA-pair mode for N = 256 tiles (INSTAORDER_PAIR=0 restores the single-CTA kernel everywhere)
-static bool pair_enabled() {
-  static const bool on = []() {
-    const char* e = getenv("INSTAORDER_PAIR");
-    return e == nullptr || atoi(e) != 0;
-  }();
-  return on;
+// CTA-pair mode for N = 256 tiles: INSTAORDER_PAIR=0 restores the single-CTA kernel everywhere, 2 forces the pair kernel
+// wherever it is legal (read at plan time, so that tests can switch it)
+static int pair_mode() {
+  const char* e = getenv("INSTAORDER_PAIR");
+  return e == nullptr ? 1 : atoi(e);
 }
 
 // switches a planned N = 256 convolution to the pair kernel: weight boxes of 128 rows, 4-stage ring of 32 KB
 static int plan_pair(ConvParams* p, const void* wgt, uint64_t ktot, uint64_t cout) {
   using C = Cfg<256>;
   p->pair = 0;
-  if (!pair_enabled() || p->mode == CONV_STEM || p->n_total % 256 != 0) return IO_OK;
+  const int pm = pair_mode();
+  if (pm == 0 || p->mode == CONV_STEM || p->n_total % 256 != 0) return IO_OK;
   // Measured on B200 (profiles/r02_pair_kernel.md): the pair kernel pays where the single-CTA tile was bound by operand
   // intake -- 1x1 convolutions with long K, dual-source GEMMs, stride-2 3x3 -- and loses a little on HBM-bound short-K
   // expansions (coupled epilogues) and on 3x3 stride-1 layers (already at the chip's sustained tensor rate); it also
-  // needs at least two waves of pair items.  INSTAORDER_PAIR=2 forces it wherever it is legal.
-  static const bool force = []() {
-    const char* e = getenv("INSTAORDER_PAIR");
-    return e != nullptr && atoi(e) == 2;
-  }();
+  // needs at least two waves of pair items.
+  const bool force = pm == 2;
   const bool pays = (p->mode == CONV_GEMM && p->k_iters >= 12) || p->k1 > 0 || p->mode == CONV_S2;
   const int items = ((p->m_tiles + 1) / 2) * p->n_tiles;
   if (p->m_tiles < 2 || (!force && (!pays || items < num_sms()))) return IO_OK;

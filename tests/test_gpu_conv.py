@@ -68,6 +68,26 @@ def test_conv_bn_act(case):
         int(bad.sum()))
 
 
+# the CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tiles) forced on geometries of every addressing mode: an odd
+# number of M tiles (phantom second tile), several N tiles, 3x3 stride 1 / 2, long K, residual, ragged rows
+PAIR_CASES = [
+    (6, 16, 16, 1024, 256, 1, 1, False, True),
+    (3, 16, 16, 256, 1024, 1, 1, True, True),
+    (5, 16, 16, 256, 256, 3, 1, False, True),
+    (3, 32, 32, 256, 256, 3, 2, False, True),
+    (3, 16, 16, 1024, 2048, 1, 2, False, False),
+    (37, 8, 8, 512, 2048, 1, 1, True, True),
+    (2, 24, 24, 256, 256, 3, 1, False, True),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=lambda c: "pair_B%d_%dx%d_%d-%d_k%ds%d%s%s" % (
+    c[0], c[1], c[2], c[3], c[4], c[5], c[6], "_res" if c[7] else "", "_relu" if c[8] else ""))
+def test_conv_pair_kernel(case, monkeypatch):
+    monkeypatch.setenv("INSTAORDER_PAIR", "2")
+    test_conv_bn_act(case)
+
+
 # (rows, cmid, n2): layer1 / layer2 / layer3 bottleneck pairs + a ragged row count (row guard by TMA clipping)
 FUSED_CASES = [(2 * 64 * 64, 64, 64), (3 * 32 * 32, 128, 128), (5 * 16 * 16, 128, 64), (1000, 64, 64),
                (148 * 128 * 2 + 77, 128, 128), (148 * 128 * 3 + 5, 64, 128), (148 * 128 * 4 + 300, 128, 64), (100, 64, 64),
@@ -139,6 +159,14 @@ def test_conv_dual(case):
 # (B, H, W, Cin, cmid, stride, n2): layer1.0 -> layer1.1.conv1, layer2.0 -> layer2.1.conv1 (+ ragged / multi-tile cases)
 FUSED_DUAL_CASES = [(2, 64, 64, 64, 64, 1, 64), (3, 64, 64, 256, 128, 2, 128), (37, 64, 64, 64, 64, 1, 64),
                     (150, 32, 32, 256, 128, 2, 128), (5, 16, 16, 256, 128, 2, 64)]
+
+
+@pytest.mark.parametrize("case", DUAL_CASES[:4], ids=lambda c: "pair_B%d_%dx%d_%d+%d_s%d" % c)
+def test_conv_dual_pair_kernel(case, monkeypatch):
+    """Dual-source K (conv3 + downsample as one GEMM) through the CTA-pair kernel."""
+    monkeypatch.setenv("INSTAORDER_PAIR", "2")
+    test_conv_dual(case)
+
 
 
 @pytest.mark.parametrize("case", FUSED_DUAL_CASES, ids=lambda c: "B%d_%dx%d_%d+%d_s%d_n%d" % c)
