@@ -82,17 +82,29 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&v)[2][32], const float
   }
 }
 
+// PAIR: two CTAs of a cluster share every weight tile (tcgen05.mma.cta_group::2, M = 256): CTA `rank` owns M tile
+// 2 * pair + rank -- its own activation rows, residual, tile buffers, epilogue and TMEM lanes -- and stages HALF of the
+// w3 rows of a unit and half of the next conv1's weight rows.  The leader's issuers run both GEMMs for the pair; "full"
+// barriers live in the leader and count both CTAs' bytes, slot releases / "accumulator complete" arrive in both CTAs by
+// multicast commits, and the peer's epilogue warps arrive on the leader's "drained" / "group ready" barriers.  Used
+// where the single-CTA kernel was bound by operand intake (layer3: 1.8 MB of operands per 16.5 k tensor cycles).
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_constant__ FusedParams fp) {
   const ConvParams& p = fp.c;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int n_workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  constexpr int B1_SLOT = PAIR ? B1_BYTES / 2 : B1_BYTES;
+  constexpr int STAGE1 = A_BYTES + B1_SLOT;
   // 128B-swizzled operands need 1024-byte aligned bases: the kernel has no static shared memory, so the dynamic
   // segment starts aligned (checked below; a mis-aligned base traps instead of computing garbage)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int k1 = p.k_iters;             // K blocks of the first GEMM
   const int n2 = fp.n2;
   const int st1 = fp.st1, st2 = fp.st2;
-  const int slot2_bytes = n2 * 128;
-  uint8_t* sS1 = smem;                                  // ring 1: st1 stages of 32 KB
-  uint8_t* sS2 = sS1 + st1 * STAGE1_BYTES;              // ring 2: st2 slots of n2 * 128 B
+  const int slot2_bytes = PAIR ? n2 * 64 : n2 * 128;
+  uint8_t* sS1 = smem;                                  // ring 1: st1 stages of 32 KB (pair: 24 KB)
+  uint8_t* sS2 = sS1 + st1 * STAGE1;                    // ring 2: st2 slots of n2 * 128 B (pair: half)
   uint8_t* sT = sS2 + st2 * slot2_bytes;                // tile buffers: [NB][2 groups][4 quadrants][32 x 128 B]
   const bool res_mma = fp.res_mma != 0;
   uint8_t* sI = sT + NB * TILE_BYTES;                   // identity matrix (res_mma)
@@ -118,10 +130,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nu = p.n_total / UN;        // units per M tile
-  const int my_tiles = (p.m_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                       static_cast<int>(gridDim.x);
-  const int tile_stride_rows = static_cast<int>(gridDim.x) * BM;
-  const int first_row = static_cast<int>(blockIdx.x) * BM;
+  // work items: M tiles, or pairs of M tiles; this CTA's M tile of item t is first_tile + t * tile_stride
+  const int m_items = PAIR ? (p.m_tiles + 1) >> 1 : p.m_tiles;
+  const int my_tiles = (m_items - worker + n_workers - 1) / n_workers;
+  const int first_tile = PAIR ? 2 * worker + static_cast<int>(rank) : worker;
+  const int tile_stride = PAIR ? 2 * n_workers : n_workers;
+  const int tile_stride_rows = tile_stride * BM;
+  const int first_row = first_tile * BM;
 
   if (warp == 0 && lane == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -141,12 +156,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], PAIR ? 16 : 8);
       mbar_init(&d2full[i], 1);
-      mbar_init(&d2empty[i], 8);
+      mbar_init(&d2empty[i], PAIR ? 16 : 8);
     }
     for (int i = 0; i < NB * 2; ++i) {
-      mbar_init(&gready[i], 4);
+      mbar_init(&gready[i], PAIR ? 8 : 4);
       mbar_init(&gfree[i], 1);
     }
     for (int i = 0; i < 8 * NB; ++i) mbar_init(&rbar[i], 1);
@@ -154,8 +169,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(tmem_slot, TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   if (bias1_smem)
     for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) sBias1[i] = p.bias[i];
@@ -177,10 +197,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers must exist before anything arrives on them
   tc_fence_after();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d2 = tmem_base + 2 * UN;
+  // barriers that live in the leader CTA are reached through their shared::cluster address
+  auto arrive_leader = [&](uint64_t* bar) {
+    if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0)); else mbar_arrive(bar);
+  };
+  auto commit = [&](uint64_t* bar) {
+    if (PAIR) umma2_commit_mc(bar); else umma_commit(bar);
+  };
   const bool two_d2 = n2 <= 128;        // D2 double buffered when it fits ([256, 512) holds 2 x 128 or 1 x 256 columns)
   const bool has_res = p.residual != nullptr;
 
@@ -192,19 +220,27 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
       for (int t = 0; t < my_tiles; ++t) {
         const int row0 = first_row + t * tile_stride_rows;
         // second A source (block 0 of a layer: the downsample branch reads the block input, possibly at stride 2)
-        const int m_tile = static_cast<int>(blockIdx.x) + t * static_cast<int>(gridDim.x);
+        const int m_tile = first_tile + t * tile_stride;
         const int grp = m_tile / fp.a2_tpg;
         const int a2_img = grp * fp.a2_bi, a2_h0 = (m_tile - grp * fp.a2_tpg) * fp.a2_bh;
         for (int j = 0; j < nu; ++j) {
           for (int ki = 0; ki < k1; ++ki) {
             mbar_wait(&empty1[stage], phase ^ 1);
-            mbar_expect_tx(&full1[stage], STAGE1_BYTES);
-            if (ki < fp.k1a) tma_load_2d(sS1 + stage * STAGE1_BYTES, &p.map_a, &full1[stage], ki * BK, row0);
-            else if (fp.a2_mode == CONV_GEMM)
-              tma_load_2d(sS1 + stage * STAGE1_BYTES, &p.map_a2, &full1[stage], (ki - fp.k1a) * BK, row0);
-            else
-              tma_load_5d(sS1 + stage * STAGE1_BYTES, &p.map_a2, &full1[stage], (ki - fp.k1a) * BK, 0, 0, a2_h0, a2_img);
-            tma_load_2d(sS1 + stage * STAGE1_BYTES + A_BYTES, &p.map_b, &full1[stage], ki * BK, j * UN);
+            uint8_t* dst = sS1 + stage * STAGE1;
+            if (PAIR) {
+              if (rank == 0) mbar_expect_tx(&full1[stage], 2 * STAGE1);
+              const uint32_t fb = mapa_u32(smem_u32(&full1[stage]), 0);
+              if (ki < fp.k1a) tma2_load_2d(dst, &p.map_a, fb, ki * BK, row0);
+              else if (fp.a2_mode == CONV_GEMM) tma2_load_2d(dst, &p.map_a2, fb, (ki - fp.k1a) * BK, row0);
+              else tma2_load_5d(dst, &p.map_a2, fb, (ki - fp.k1a) * BK, 0, 0, a2_h0, a2_img);
+              tma2_load_2d(dst + A_BYTES, &p.map_b, fb, ki * BK, j * UN + static_cast<int>(rank) * (UN / 2));
+            } else {
+              mbar_expect_tx(&full1[stage], STAGE1);
+              if (ki < fp.k1a) tma_load_2d(dst, &p.map_a, &full1[stage], ki * BK, row0);
+              else if (fp.a2_mode == CONV_GEMM) tma_load_2d(dst, &p.map_a2, &full1[stage], (ki - fp.k1a) * BK, row0);
+              else tma_load_5d(dst, &p.map_a2, &full1[stage], (ki - fp.k1a) * BK, 0, 0, a2_h0, a2_img);
+              tma_load_2d(dst + A_BYTES, &p.map_b, &full1[stage], ki * BK, j * UN);
+            }
             if (++stage == st1) { stage = 0; phase ^= 1; }
           }
         }
@@ -212,8 +248,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ======================= MMA issuer 1: D1[acc] = x * w3^T =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = umma_idesc_bf16(BM, UN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(PAIR ? 2 * BM : BM, UN);
       int stage = 0;
       uint32_t phase = 0;
       const int U = my_tiles * nu;
@@ -225,12 +261,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
         for (int ki = 0; ki < k1; ++ki) {
           mbar_wait(&full1[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = umma_desc_sw128(smem_u32(sS1 + stage * STAGE1_BYTES));
-          const uint64_t b_desc = umma_desc_sw128(smem_u32(sS1 + stage * STAGE1_BYTES + A_BYTES));
+          const uint64_t a_desc = umma_desc_sw128(smem_u32(sS1 + stage * STAGE1));
+          const uint64_t b_desc = umma_desc_sw128(smem_u32(sS1 + stage * STAGE1 + A_BYTES));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)   // + 32 bytes per K step = + 2 in the descriptor's address field
-            umma_bf16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (ki > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty1[stage]);
+          for (int k = 0; k < BK / 16; ++k) {  // + 32 bytes per K step = + 2 in the descriptor's address field
+            if (PAIR) umma2_bf16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (ki > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d1, a_desc + 2 * k, b_desc + 2 * k, idesc1, (ki > 0 || k > 0) ? 1u : 0u);
+          }
+          commit(&empty1[stage]);
           if (++stage == st1) { stage = 0; phase ^= 1; }
         }
         if (res_mma) {
@@ -248,7 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
             for (int k = 0; k < BK / 16; ++k) umma_bf16(d1 + g * 64, r_desc + 2 * k, i_desc + 2 * k, idesc_r, 1u);
           }
         }
-        umma_commit(&tfull[acc]);
+        commit(&tfull[acc]);
       }
     }
   } else if (warp == 2) {
@@ -260,8 +298,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
         for (int j = 0; j < nu; ++j) {
           for (int g = 0; g < 2; ++g) {
             mbar_wait(&empty2[slot], phase ^ 1);
-            mbar_expect_tx(&full2[slot], slot2_bytes);
-            tma_load_2d(sS2 + slot * slot2_bytes, &fp.map_b2, &full2[slot], j * UN + g * BK, 0);
+            if (PAIR) {
+              if (rank == 0) mbar_expect_tx(&full2[slot], 2 * slot2_bytes);
+              tma2_load_2d(sS2 + slot * slot2_bytes, &fp.map_b2, mapa_u32(smem_u32(&full2[slot]), 0), j * UN + g * BK,
+                           static_cast<int>(rank) * (n2 / 2));
+            } else {
+              mbar_expect_tx(&full2[slot], slot2_bytes);
+              tma_load_2d(sS2 + slot * slot2_bytes, &fp.map_b2, &full2[slot], j * UN + g * BK, 0);
+            }
             if (++slot == st2) { slot = 0; phase ^= 1; }
           }
         }
@@ -269,8 +313,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
     }
   } else if (warp == 3) {
     // ======================= MMA issuer 2: D2[t & 1] += tile * w1n^T =======================
-    if (lane == 0) {
-      const uint32_t idesc2 = umma_idesc_bf16(BM, n2);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc2 = umma_idesc_bf16(PAIR ? 2 * BM : BM, n2);
       int slot = 0;
       uint32_t phase = 0;
       int b = 0;            // tile buffer of the unit, u % NB
@@ -289,15 +333,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
             const uint64_t a_desc = umma_desc_sw128(smem_u32(sT + b * TILE_BYTES + g * GROUP_BYTES));
             const uint64_t b_desc = umma_desc_sw128(smem_u32(sS2 + slot * slot2_bytes));
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(d2, a_desc + 2 * k, b_desc + 2 * k, idesc2, (j > 0 || g > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&empty2[slot]);
-            umma_commit(&gfree[b * 2 + g]);
+            for (int k = 0; k < BK / 16; ++k) {
+              if (PAIR) umma2_bf16(d2, a_desc + 2 * k, b_desc + 2 * k, idesc2, (j > 0 || g > 0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d2, a_desc + 2 * k, b_desc + 2 * k, idesc2, (j > 0 || g > 0 || k > 0) ? 1u : 0u);
+            }
+            commit(&empty2[slot]);
+            commit(&gfree[b * 2 + g]);
             if (++slot == st2) { slot = 0; phase ^= 1; }
           }
           if (++b == NB) { b = 0; ++nuse; }
         }
-        umma_commit(&d2full[dbuf]);
+        commit(&d2full[dbuf]);
       }
     }
   } else {
@@ -360,7 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&d2empty[dbuf]);
+      if (lane == 0) arrive_leader(&d2empty[dbuf]);
     };
 
     // unit i = (t, j), tile buffer b = i % NB (use number nuse = i / NB); the residual prefetch runs two units ahead
@@ -388,7 +434,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);           // D1 buffer read: issuer 1 may refill it
+      if (lane == 0) arrive_leader(&tempty[acc]);         // D1 buffer read: issuer 1 may refill it
       const bool add_res = active && has_res && !res_mma;
       if (add_res) mbar_wait(&my_rbar[b], nuse & 1);
       uint8_t* region = my_region0 + b * TILE_BYTES;
@@ -422,7 +468,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
       if (lane == 0) {
         if (active && fp.sub_w == 0) tma_store_2d(&p.map_out, region, j * UN + g * 64, row0);
         tma_store_commit();
-        mbar_arrive(&gready[b * 2 + g]);
+        arrive_leader(&gready[b * 2 + g]);
         if (i + 2 < U) {
           // the residual of unit i + 2 goes into the buffer unit i - 1 used: wait until G2(i - 1) has consumed this
           // group and until this warp's own store of it has finished reading shared memory
@@ -449,42 +495,60 @@ __global__ void __launch_bounds__(THREADS, 1) conv_fused_kernel(const __grid_con
   }
 
   tc_fence_before();
+  __syncwarp();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (PAIR) {
+    cluster_sync_all();   // the leader's MMAs read the peer's shared memory; remote arrivals need live barriers
+    if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
+  } else {
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 int conv_fused_launch(const FusedParams& fp, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    IO_CUDA(cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    IO_CUDA(cudaFuncSetAttribute(conv_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    IO_CUDA(cudaFuncSetAttribute(conv_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     attr_set = true;
   }
   if (fp.c.m_tiles <= 0) return IO_OK;
-  const int grid = fp.c.m_tiles < num_sms() ? fp.c.m_tiles : num_sms();
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = fp.smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IO_CUDA(cudaLaunchKernelEx(&cfg, conv_fused_kernel, fp));
+  if (fp.pair) {
+    const int items = (fp.c.m_tiles + 1) / 2, max_pairs = num_sms() / 2;
+    cfg.gridDim = dim3(2 * (items < max_pairs ? items : max_pairs));
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+    IO_CUDA(cudaLaunchKernelEx(&cfg, conv_fused_kernel<true>, fp));
+    return IO_OK;
+  }
+  cfg.gridDim = dim3(fp.c.m_tiles < num_sms() ? fp.c.m_tiles : num_sms());
+  IO_CUDA(cudaLaunchKernelEx(&cfg, conv_fused_kernel<false>, fp));
   return IO_OK;
 }
 
 // Ring depths: prefer 3 stages for the (x + w3) ring, then as many next-conv1 weight slots as fit (2..4).
-static bool fused_smem_plan(int n1, int n2, int res_mma, int* st1, int* st2, int* bytes) {
+static bool fused_smem_plan(int n1, int n2, int res_mma, int* st1, int* st2, int* bytes, int pair = 0) {
   const int budget = MAX_SMEM - fixed_bytes(n1, n2, res_mma);
-  const int slot2 = n2 * 128;
-  int s1 = (3 * STAGE1_BYTES + 2 * slot2 <= budget) ? 3 : 2;
-  int s2 = (budget - s1 * STAGE1_BYTES) / slot2;
+  const int slot2 = pair ? n2 * 64 : n2 * 128;
+  const int stage1 = pair ? A_BYTES + B1_BYTES / 2 : STAGE1_BYTES;
+  int s1 = (3 * stage1 + 2 * slot2 <= budget) ? 3 : 2;
+  int s2 = (budget - s1 * stage1) / slot2;
   if (s2 > MAX_ST2) s2 = MAX_ST2;
   if (s2 < 2) return false;
   *st1 = s1; *st2 = s2;
-  *bytes = s1 * STAGE1_BYTES + s2 * slot2 + fixed_bytes(n1, n2, res_mma);
+  *bytes = s1 * stage1 + s2 * slot2 + fixed_bytes(n1, n2, res_mma);
   return true;
 }
 
@@ -567,10 +631,18 @@ int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n1, int n2, const v
     const uint32_t box[2] = {64, BM};
     if ((rc = make_tmap_bf16(&p->map_a, t2, 2, dims, str, box, true))) return rc;
   }
+  // CTA-pair kernel (INSTAORDER_FUSED_PAIR=2, read at plan time): OFF by default.  Measured on B200 (256 pairs): layer3
+  // pairs 0.20 -> 0.25 ms, layer2.0 0.33 -> 0.41 ms -- halving the weight intake does not pay for coupling the two CTAs'
+  // epilogue chains through the leader's barriers; these launches are bound by the epilogue warps' latency chain, not
+  // by operand intake (profiles/r02_ncu_fused_row3.md).  Kept for the parity tests and as the base for a wider tile.
+  {
+    const char* e = getenv("INSTAORDER_FUSED_PAIR");
+    fp->pair = (e != nullptr && atoi(e) == 2 && p->m_tiles >= 2) ? 1 : 0;
+  }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(n1)};
     const uint64_t str[1] = {static_cast<uint64_t>(ktot) * 2};
-    const uint32_t box[2] = {64, UN};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(fp->pair ? UN / 2 : UN)};
     if ((rc = make_tmap_bf16(&p->map_b, wb1, 2, dims, str, box, true))) return rc;
   }
   {
@@ -583,7 +655,7 @@ int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n1, int n2, const v
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(n1), static_cast<uint64_t>(n2)};
     const uint64_t str[1] = {static_cast<uint64_t>(n1) * 2};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(n2)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(fp->pair ? n2 / 2 : n2)};
     if ((rc = make_tmap_bf16(&fp->map_b2, w1n, 2, dims, str, box, true))) return rc;
   }
   fp->out2 = reinterpret_cast<__nv_bfloat16*>(y2);
@@ -598,10 +670,10 @@ int conv_fused_plan(FusedParams* fp, int rows, int cmid, int n1, int n2, const v
     return e == nullptr || atoi(e) != 0;
   }();
   fp->st256 = st256_on ? 1 : 0;
-  fp->res_mma = (res_mma_on && residual != nullptr && cmid <= 64) ? 1 : 0;   // layer2 (C = 128): measured 6 % slower
+  fp->res_mma = (res_mma_on && residual != nullptr && cmid <= 64 && !fp->pair) ? 1 : 0;   // layer2 (C = 128): measured 6 % slower
   if (fp->res_mma && !fused_smem_plan(n1, n2, 1, &fp->st1, &fp->st2, &fp->smem_bytes)) fp->res_mma = 0;
   if (!fp->res_mma)
-    IO_REQUIRE(fused_smem_plan(n1, n2, 0, &fp->st1, &fp->st2, &fp->smem_bytes), "fused conv: no shared-memory plan");
+    IO_REQUIRE(fused_smem_plan(n1, n2, 0, &fp->st1, &fp->st2, &fp->smem_bytes, fp->pair), "fused conv: no shared-memory plan");
   return IO_OK;
 }
 

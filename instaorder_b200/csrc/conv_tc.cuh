@@ -85,6 +85,7 @@ struct FusedParams {
   // warps, which were the bottleneck of the layer1 / layer2 launches
   int res_mma;
   int st256;   // next-conv1 output rows written with 256-bit stores (whole 32-byte sectors per lane)
+  int pair;    // CTA-pair kernel (cta_group::2): map_b boxes 64 x 64, map_b2 boxes 64 x n2 / 2, halved weight slots
 };
 void conv_fused_set_subsampled(FusedParams* fp, int h, int w);
 bool conv_fused_supported(int cmid, int n1, int n2, const ConvDesc* ds);

@@ -118,6 +118,28 @@ class _Resident:
     pass
 
 
+_PACK_POOL = None
+_PACK_THREADS = int(os.environ.get("INSTAORDER_PACK_THREADS", max(1, min(4, (os.cpu_count() or 4) // 4))))
+
+
+def _copy_one(job):
+    dst, off, nbytes, src = job
+    dst[off:off + nbytes] = src.reshape(-1)
+
+
+def _pack_copies(copies):
+    """Byte copies of a batch's images / masks into the pinned staging slot, spread over a small thread pool."""
+    global _PACK_POOL
+    if _PACK_THREADS <= 1 or len(copies) < 2:
+        for job in copies:
+            _copy_one(job)
+        return
+    if _PACK_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _PACK_POOL = ThreadPoolExecutor(max_workers=_PACK_THREADS, thread_name_prefix="io-pack")
+    list(_PACK_POOL.map(_copy_one, copies))
+
+
 class OrderEngine:
     def __init__(self, num_classes, input_size=256, max_pairs=256, device="cuda:0", data_mean=DATA_MEAN,
                  data_std=DATA_STD, img_bytes=32 << 20, mask_bytes=256 << 20, slots=2):
@@ -221,6 +243,7 @@ class OrderEngine:
         slot_idx = 0
         self.resize_jobs = []
         dev_masks = []
+        copies = []
         for (sc, pairs, crops, mat_off, _) in items:
             p = pairs.shape[0]
             ib, mb = sc.h * sc.w * 3, sc.n * sc.h * sc.w
@@ -229,9 +252,11 @@ class OrderEngine:
                                  "of masks (this scene: %d / %d B).  infer_scenes() cuts batches to fit; callers of "
                                  "stage_batch() / make_batches() must pass fewer scenes per batch or create the "
                                  "engine with larger img_bytes= / mask_bytes=" % (himg.size, hmask.size, ib, mb))
-            himg[img_off:img_off + ib] = sc.image.reshape(-1)
+            # the byte copies into the pinned slot (65 MB per 765-pair call of the bench workload) run on a few threads:
+            # numpy releases the GIL inside them, and a single thread's ~10 GB/s was the un-overlapped part of a call
+            copies.append((himg, img_off, ib, sc.image))
             if sc.masks_dev is None:
-                hmask[mask_off:mask_off + mb] = sc.masks.reshape(-1)
+                copies.append((hmask, mask_off, mb, sc.masks))
             else:
                 dev_masks.append((mask_off, mb, sc.masks_dev))
             d = desc[P:P + p]
@@ -256,6 +281,7 @@ class OrderEngine:
             img_off += (ib + 15) // 16 * 16
             mask_off += (mb + 15) // 16 * 16
             P += p
+        _pack_copies(copies)
         compute = torch.cuda.current_stream()
         with torch.cuda.stream(self.copy_stream):
             if s.event is not None:

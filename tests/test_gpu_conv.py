@@ -246,3 +246,18 @@ def test_decoder_elementwise_kernels():
             want = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear",
                                  align_corners=bool(align)).permute(0, 2, 3, 1)
             assert (y.float() - want).abs().max() < 2e-2      # bf16 output rounding of O(1) values
+
+
+# the CTA-pair variant of the back-to-back GEMM kernel (conv_fused_kernel<true>, cta_group::2) forced on every shape
+# family: an odd number of M tiles (phantom second tile of the last pair), ragged rows, N2 = 64 / 128 / 256
+@pytest.mark.parametrize("case", [FUSED_CASES[i] for i in (0, 1, 3, 4, 7, 8, 9, 10)] + [(148 * 128 + 5, 256, 256)],
+                         ids=lambda c: "fpair_rows%d_c%d_n%d" % c)
+def test_conv_fused_pair_cta_pair(case, monkeypatch):
+    monkeypatch.setenv("INSTAORDER_FUSED_PAIR", "2")
+    test_conv_fused_pair(case)
+
+
+@pytest.mark.parametrize("case", FUSED_DUAL_CASES, ids=lambda c: "fpair_B%d_%dx%d_%d+%d_s%d_n%d" % c)
+def test_conv_fused_dual_cta_pair(case, monkeypatch):
+    monkeypatch.setenv("INSTAORDER_FUSED_PAIR", "2")
+    test_conv_fused_dual(case)
