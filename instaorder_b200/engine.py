@@ -113,6 +113,14 @@ class _Slot:
         self.copied = None       # H2D copies out of the pinned buffers have finished
 
 
+class _Pending:
+    """Handle of a submitted call (OrderEngine.submit_scenes): pinned result buffers + the event behind their D2H."""
+    __slots__ = ("scenes", "mat_offs", "bufs", "event")
+
+    def __init__(self, scenes, mat_offs, bufs, event):
+        self.scenes, self.mat_offs, self.bufs, self.event = scenes, mat_offs, bufs, event
+
+
 class _Resident:
     """Device-resident inputs of one batch (same attribute names as _Slot where the kernels need them)."""
     pass
@@ -371,7 +379,8 @@ class OrderEngine:
         s.event.record()
 
     # ---- the batched driver ------------------------------------------------------------------------------
-    def infer_scenes(self, scenes, algo, pairs="all", patch_or_image="patch", return_details=False):
+    def infer_scenes(self, scenes, algo, pairs="all", patch_or_image="patch", return_details=False, _pending=False,
+                     _first_cap=None):
         """Order matrices for a list of ``Scene``.  Returns a list of dicts with 'occ' / 'depth' int64 [N,N]
         (+ 'pairs', 'logits', 'margin_occ', 'margin_depth' when ``return_details``)."""
         heads = heads_for(algo, self.ncs if len(self.ncs) > 1 else self.ncs[0])
@@ -425,6 +434,8 @@ class OrderEngine:
         # the first batch of a long call is kept short: the GPU starts while the host is still packing the second one
         # (staging = a host memcpy into pinned memory, ~0.1 ms per MB, otherwise fully exposed at the start of the call)
         cap = self.first_batch_pairs if total_pairs > self.max_pairs else self.max_pairs
+        if _first_cap is not None:
+            cap = _first_cap
         for si, sc in enumerate(scenes):
             pr = enumerate_pairs(sc.n)
             if pairs == "nbor" and pr.shape[0]:
@@ -453,6 +464,15 @@ class OrderEngine:
                     cap = self.max_pairs
         flush()
         # 3. one D2H for every matrix of the call
+        if _pending:       # submit_scenes(): the copy goes to pinned memory behind the kernels; collect() waits for it
+            bufs = {}
+            for w, m in mats.items():
+                hb = self._pinned_i64(m.numel())
+                hb.copy_(m, non_blocking=True)
+                bufs[w] = hb
+            ev = torch.cuda.Event()
+            ev.record()
+            return _Pending(scenes, mat_offs, bufs, ev)
         host = {w: m.cpu().numpy() for w, m in mats.items()}
         self.d2h_bytes += sum(v.nbytes for v in host.values())
         out = []
@@ -469,6 +489,48 @@ class OrderEngine:
                     r["margin_" + w] = mg[hi]
             out.append(r)
         return out
+
+    # ---- pipelined calls: the next call's packing / H2D runs while this call's kernels execute ----------------
+    def _pinned_i64(self, n):
+        pool = self.__dict__.setdefault("_pin_pool", {})
+        free = pool.setdefault(n, [])
+        return free.pop() if free else torch.empty(n, dtype=torch.int64).pin_memory()
+
+    def submit_scenes(self, scenes, algo, pairs="all", patch_or_image="patch", first_batch_pairs=None):
+        """``infer_scenes`` without the final wait: everything is enqueued (incl. the D2H of the order matrices into
+        pinned memory) and a handle comes back; ``collect(handle)`` returns what ``infer_scenes`` would have.  Several
+        calls may be in flight (the pinned staging slots are recycled behind CUDA events)."""
+        return self.infer_scenes(scenes, algo, pairs, patch_or_image, False, _pending=True, _first_cap=first_batch_pairs)
+
+    def collect(self, pending):
+        pending.event.synchronize()
+        out = []
+        nbytes = 0
+        for si, sc in enumerate(pending.scenes):
+            r = {}
+            for w, hb in pending.bufs.items():
+                o = pending.mat_offs[si]
+                r[w] = hb[o:o + sc.n * sc.n].numpy().reshape(sc.n, sc.n).copy()
+            out.append(r)
+        for hb in pending.bufs.values():
+            nbytes += hb.numel() * 8
+            self._pin_pool[hb.numel()].append(hb)
+        self.d2h_bytes += nbytes
+        return out
+
+    def infer_stream(self, calls, algo, pairs="all", patch_or_image="patch", depth=2):
+        """Generator over an iterable of scene lists (one list = one ``infer_scenes`` call): yields each call's result in
+        order while up to ``depth`` calls are in flight, so the host-side packing and the H2D copies of call k + 1 overlap
+        the kernels of call k.  Same results as calling ``infer_scenes`` on every list."""
+        queue = []
+        for scenes in calls:
+            # with work already in flight there is no idle GPU to feed early: full-size first batch
+            queue.append(self.submit_scenes(scenes, algo, pairs, patch_or_image,
+                                            first_batch_pairs=self.max_pairs if queue else None))
+            if len(queue) >= depth:
+                yield self.collect(queue.pop(0))
+        while queue:
+            yield self.collect(queue.pop(0))
 
     # ---- device-resident batches (bench.py `value`: inputs already in HBM when the timed region starts) -------
     def make_batches(self, scenes, pairs_per_batch=None, mode="patch"):

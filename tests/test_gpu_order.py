@@ -344,3 +344,38 @@ def test_full_size_permutation_property(golden_dir):
                     assert r[what][inv[i], inv[j]] == base[what][i, j], (what, i, j)
                     checked += 1
     assert checked >= 0.8 * 2 * n * (n - 1)
+
+
+def test_infer_stream_equals_blocking_calls(golden_dir):
+    """``OrderEngine.infer_stream`` (two calls in flight, full-size first batches, results through pinned buffers) returns
+    exactly what one blocking ``infer_scenes`` per call returns -- same kernels on the same inputs, so bit-identical."""
+    case = "c2_od"
+    c = gen_golden.CASES[case]
+    from instaorder_b200 import synth
+    sd = calib.load_calibrated(gen_golden.calib_path(case), c["wseed"], 5, c["num_classes"])
+    eng = engine.OrderEngine([2, 3], 256, max_pairs=64)
+    eng.load_state_dict(sd)
+    rng = np.random.RandomState(5)
+    calls = []
+    for k in range(5):
+        scenes = []
+        for _ in range(1 + k % 3):
+            img, masks, boxes = synth.make_scene(rng, 300 + 16 * k, 400, 3 + (k * 5) % 9, wh_range=((30, 200), (30, 200)))
+            scenes.append(engine.Scene(img, masks, engine.expand_bbox(boxes, 3.0)))
+        calls.append(scenes)
+    want = [eng.infer_scenes(s, c["algo"]) for s in calls]
+    got = list(eng.infer_stream(calls, c["algo"], depth=2))
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert len(a) == len(b)
+        for ra, rb in zip(a, b):
+            for what in ("occ", "depth"):
+                assert np.array_equal(ra[what], rb[what])
+    # a handle collected late (other calls submitted in between) still holds its own result
+    h0 = eng.submit_scenes(calls[0], c["algo"])
+    h1 = eng.submit_scenes(calls[1], c["algo"])
+    r1, r0 = eng.collect(h1), eng.collect(h0)
+    for ra, rb in zip(r0, want[0]):
+        assert np.array_equal(ra["occ"], rb["occ"]) and np.array_equal(ra["depth"], rb["depth"])
+    for ra, rb in zip(r1, want[1]):
+        assert np.array_equal(ra["occ"], rb["occ"]) and np.array_equal(ra["depth"], rb["depth"])
