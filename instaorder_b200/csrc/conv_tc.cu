@@ -605,12 +605,11 @@ static int plan_pair(ConvParams* p, const void* wgt, uint64_t ktot, uint64_t cou
   p->pair = 0;
   const int pm = pair_mode();
   if (pm == 0 || p->mode == CONV_STEM || p->n_total % 256 != 0) return IO_OK;
-  // Measured on B200 (profiles/r02_pair_kernel.md): the pair kernel pays where the single-CTA tile was bound by operand
-  // intake -- 1x1 convolutions with long K, dual-source GEMMs, stride-2 3x3 -- and loses a little on HBM-bound short-K
-  // expansions (coupled epilogues) and on 3x3 stride-1 layers (already at the chip's sustained tensor rate); it also
-  // needs at least two waves of pair items.
+  // Measured on B200, same box, 256 pairs (profiles/r02_pair_kernel.md): -8 ... -24 % on every 3x3 layer, on 1x1 layers
+  // with K >= 768 and on the dual-source GEMMs; +20 % / 0 % on the short-K (256 / 512) 1x1 expansions, which are
+  // HBM-bound and only get their two CTAs' epilogues coupled.  It also needs at least two waves of pair items.
   const bool force = pm == 2;
-  const bool pays = (p->mode == CONV_GEMM && p->k_iters >= 12) || p->k1 > 0 || p->mode == CONV_S2;
+  const bool pays = p->mode != CONV_GEMM || p->k_iters >= 12 || p->k1 > 0;
   const int items = ((p->m_tiles + 1) / 2) * p->n_tiles;
   if (p->m_tiles < 2 || (!force && (!pays || items < num_sms()))) return IO_OK;
   if (!p->b_mn) {

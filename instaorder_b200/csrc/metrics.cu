@@ -145,14 +145,13 @@ __device__ double2 pairwise(Gen& g, int n) {
 
 // The selected entries of one key out of the per-warp staging arrays (filled coalesced by the whole warp)
 struct StagedGen {
-  const double* err;
   const double* score;
-  const uint16_t* mask;
+  const uint16_t* mask;      // bits 0..8: key selection, bit 9: prediction != ground truth (err = score, else 0)
   int k, bit;
   __device__ double2 next() {
     for (;; ++k)
       if ((mask[k] >> bit) & 1) {
-        const double2 r = make_double2(err[k], score[k]);
+        const double2 r = make_double2(((mask[k] >> 9) & 1) ? score[k] : 0.0, score[k]);
         ++k;
         return r;
       }
@@ -163,8 +162,10 @@ constexpr int WH_NMAX = 24;                              // images up to 24 inst
 constexpr int WH_TMAX = WH_NMAX * (WH_NMAX - 1) / 2;     // 276 upper-triangle entries
 constexpr int WH_WARPS = 4;
 constexpr int WH_MASK_BYTES = (WH_TMAX * 2 + 15) / 16 * 16;
-constexpr int WH_IDX_BYTES = (9 * WH_TMAX * 2 + 15) / 16 * 16;
-constexpr int WH_WARP_BYTES = WH_TMAX * 16 + WH_MASK_BYTES + WH_IDX_BYTES + 48;
+constexpr int WH_IDX_BYTES = (4 * WH_TMAX * 2 + 15) / 16 * 16;   // index lists of the four keys of one round
+// per warp: score (float64) + mask / error bit + 4 index lists + 9 counts = 5 KB (10 KB before: err as a second float64
+// array and all nine lists at once kept only 20 warps per SM resident; ncu: 29 % occupancy, latency-bound)
+constexpr int WH_WARP_BYTES = WH_TMAX * 8 + WH_MASK_BYTES + WH_IDX_BYTES + 48;
 
 // One WARP per image.  The first version ran one thread per (image, key): nine threads each walked the four int64
 // matrices of their image serially -- uncoalesced 8-byte loads, every matrix read nine times (bench: 2.7 % of the HBM
@@ -206,10 +207,9 @@ __global__ void __launch_bounds__(WH_WARPS * 32) whdr_kernel(const int64_t* __re
     }
     return;
   }
-  double* s_err = reinterpret_cast<double*>(wh_smem + warp * WH_WARP_BYTES);
-  double* s_score = s_err + WH_TMAX;
+  double* s_score = reinterpret_cast<double*>(wh_smem + warp * WH_WARP_BYTES);
   uint16_t* s_mask = reinterpret_cast<uint16_t*>(s_score + WH_TMAX);
-  uint16_t* s_idx = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(s_mask) + WH_MASK_BYTES);   // [9][WH_TMAX]
+  uint16_t* s_idx = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(s_mask) + WH_MASK_BYTES);   // [4][WH_TMAX]
   int* s_cnt = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s_idx) + WH_IDX_BYTES);               // [9]
   const int T = n * (n - 1) / 2;
   // ---- 1. stage the triangle
@@ -223,12 +223,10 @@ __global__ void __launch_bounds__(WH_WARPS * 32) whdr_kernel(const int64_t* __re
     const int j = k - (i * n - i * (i + 1) / 2) + i + 1;
     const int64_t idx = o0 + static_cast<int64_t>(i) * n + j;
     const int64_t g = gto[idx], o = gtv[idx], c = gtc[idx], pr = order[idx];
-    const double score = 2.0 / static_cast<double>(c);
-    s_score[k] = score;
-    s_err[k] = (g != pr) ? score : 0.0;
+    s_score[k] = 2.0 / static_cast<double>(c);
     const uint32_t mo = (o == 0 ? 1u : 0u) | (o == 1 ? 2u : 0u) | ((o == 0 || o == 1) ? 4u : 0u);   // ovlX, ovlO, ovlOX
     const uint32_t me = (g == 2 ? 1u : 0u) | ((g == 0 || g == 1) ? 2u : 0u) | ((g == 0 || g == 1 || g == 2) ? 4u : 0u);
-    uint32_t m = 0;
+    uint32_t m = (g != pr) ? (1u << 9) : 0u;
 #pragma unroll
     for (int ko = 0; ko < 3; ++ko)
 #pragma unroll
@@ -237,7 +235,7 @@ __global__ void __launch_bounds__(WH_WARPS * 32) whdr_kernel(const int64_t* __re
     s_mask[k] = static_cast<uint16_t>(m);
   }
   __syncwarp();
-  // ---- 2. per key: ordered index list of the selected entries
+  // ---- 2. how many entries every key selects (numpy recurses above 128: serial replay out of shared memory then)
   const uint32_t lt = (1u << lane) - 1u;
   int max_cnt = 0;
 #pragma unroll 1
@@ -245,42 +243,55 @@ __global__ void __launch_bounds__(WH_WARPS * 32) whdr_kernel(const int64_t* __re
     int base = 0;
     for (int k0 = 0; k0 < T; k0 += 32) {
       const int k = k0 + lane;
-      const bool bit = k < T && ((s_mask[k] >> key) & 1);
-      const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-      if (bit) s_idx[key * WH_TMAX + base + __popc(bal & lt)] = static_cast<uint16_t>(k);
-      base += __popc(bal);
+      base += __popc(__ballot_sync(0xffffffffu, k < T && ((s_mask[k] >> key) & 1)));
     }
     if (lane == 0) s_cnt[key] = base;
     max_cnt = max(max_cnt, base);
   }
   __syncwarp();
-  if (max_cnt > 128) {    // numpy recurses above 128 entries: serial replay out of shared memory, one lane per key
+  if (max_cnt > 128) {
     if (lane < 9) {
       const int cnt = s_cnt[lane];
       if (cnt == 0) {
         out[9 * b + lane] = -1.0;
       } else {
-        StagedGen g{s_err, s_score, s_mask, 0, lane};
+        StagedGen g{s_score, s_mask, 0, lane};
         const double2 s = pairwise(g, cnt);
         out[9 * b + lane] = s.x / s.y * 100.0;
       }
     }
     return;
   }
-  // ---- 3. pairwise sums, eight lanes per key, four keys per round
+  // ---- 3. four keys per round: ordered index lists by ballot compaction, then the pairwise sums with eight lanes
+  //         per key
   const int j8 = lane & 7;
 #pragma unroll 1
   for (int round = 0; round < 3; ++round) {
+#pragma unroll 1
+    for (int kk = 0; kk < 4; ++kk) {
+      const int key = round * 4 + kk;
+      if (key >= 9) break;
+      int base = 0;
+      for (int k0 = 0; k0 < T; k0 += 32) {
+        const int k = k0 + lane;
+        const bool bit = k < T && ((s_mask[k] >> key) & 1);
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        if (bit) s_idx[kk * WH_TMAX + base + __popc(bal & lt)] = static_cast<uint16_t>(k);
+        base += __popc(bal);
+      }
+    }
+    __syncwarp();
     const int key = round * 4 + (lane >> 3);
     const int cnt = key < 9 ? s_cnt[key] : 0;
-    const uint16_t* ix = s_idx + (key < 9 ? key : 0) * WH_TMAX;
+    const uint16_t* ix = s_idx + (lane >> 3) * WH_TMAX;
     const int body = cnt - (cnt & 7);          // entries covered by the eight accumulators
+    auto err_of = [&](int e) { return ((s_mask[e] >> 9) & 1) ? s_score[e] : 0.0; };
     double rx = 0.0, ry = 0.0;
     if (cnt >= 8) {
-      rx = s_err[ix[j8]];
+      rx = err_of(ix[j8]);
       ry = s_score[ix[j8]];
       for (int i = 8; i < body; i += 8) {
-        rx += s_err[ix[i + j8]];
+        rx += err_of(ix[i + j8]);
         ry += s_score[ix[i + j8]];
       }
     }
@@ -296,11 +307,12 @@ __global__ void __launch_bounds__(WH_WARPS * 32) whdr_kernel(const int64_t* __re
       int i;
       if (cnt >= 8) { sx = rx; sy = ry; i = body; } else { sx = 0.0; sy = 0.0; i = 0; }
       for (; i < cnt; ++i) {
-        sx += s_err[ix[i]];
+        sx += err_of(ix[i]);
         sy += s_score[ix[i]];
       }
       out[9 * b + key] = cnt == 0 ? -1.0 : sx / sy * 100.0;
     }
+    __syncwarp();     // the index lists are rebuilt for the next round
   }
 }
 

@@ -212,10 +212,14 @@ class DepthOrderEngine(OrderEngine):
         self.logits[:P, :, 2:5] = self.logits_d[:P]
         self.gpu_launches += sum(self.lib.io_net_last_launches(h) for h in (self.enc, self.do_net, self.oo_net) if h) + 2
 
-    def infer_scenes(self, scenes, algo="InstaDepthNet_od", pairs="all", patch_or_image="resize", return_details=False):
+    def infer_scenes(self, scenes, algo="InstaDepthNet_od", pairs="all", patch_or_image="resize", return_details=False,
+                     _pending=False, _first_cap=None):
         if algo not in ("InstaDepthNet_od", "InstaDepthNet_d"):
             raise ValueError("DepthOrderEngine runs InstaDepthNet_od / _d, got %r" % (algo,))
-        return super().infer_scenes(scenes, "InstaOrderNet_od", pairs, patch_or_image, return_details)
+        return super().infer_scenes(scenes, "InstaOrderNet_od", pairs, patch_or_image, return_details, _pending, _first_cap)
+
+    def submit_scenes(self, scenes, algo="InstaDepthNet_od", pairs="all", patch_or_image="resize", first_batch_pairs=None):
+        return self.infer_scenes(scenes, algo, pairs, patch_or_image, False, _pending=True, _first_cap=first_batch_pairs)
 
     # ---- disparity branch (reference midas_net.py:189-198, midas/blocks.py:124-195) ------------------------------
     def _load_decoder(self, sd):

@@ -84,6 +84,32 @@ class Tester(object):
         batched = method not in ("area", "yaxis") and not per_image
         eng = self.model.engine_for(a.data["input_size"]) if batched else None
         prf_rows, whdr_rows = [], []
+        inflight = []
+
+        def finalize(entry):
+            res, gts_occ, gts_depth, names = entry
+            if batched:
+                if not isinstance(res, list):
+                    res = eng.collect(res)
+                pred_occ = [r["occ"] for r in res] if want_occ else None
+                pred_depth = [r["depth"] for r in res] if want_depth else None
+            else:
+                pred_occ, pred_depth = (res if want_occ else None), (res if want_depth else None)
+            if want_occ:
+                rows = _engine.metrics_prf(pred_occ, gts_occ, a.zd)
+                prf_rows.extend(rows.tolist())
+            if want_depth:
+                rows = _engine.metrics_whdr(pred_depth, [g[0] for g in gts_depth], [g[1] for g in gts_depth],
+                                            [g[2] for g in gts_depth])
+                whdr_rows.extend(rows.tolist())
+            for k, fn in enumerate(names):
+                if want_depth:
+                    w = whdr_rows[len(whdr_rows) - len(names) + k]
+                    self._log("[%s]\t%.3f | %.3f | %.3f" % (fn, w[2], w[5], w[8]))      # ovlX_all | ovlO_all | ovlOX_all
+                if want_occ:
+                    p = prf_rows[len(prf_rows) - len(names) + k]
+                    self._log("\t\t\trecall=%.3f / precision=%.3f / f1=%.3f" % (p[0], p[1], p[2]))
+
         for c0 in range(0, len(mine), self.images_per_call):
             chunk = mine[c0:c0 + self.images_per_call]
             scenes, gts_occ, gts_depth, names, preds = [], [], [], [], []
@@ -121,26 +147,21 @@ class Tester(object):
                         use_rgb=(getattr(a, "model", None) or {}).get("use_rgb", True))[0])
                 else:
                     preds.append(self._heuristic(kind, modal))
-            if batched:
-                res = eng.infer_scenes(scenes, method, pairs=a.pairs, patch_or_image=a.data["patch_or_image"])
-                pred_occ = [r["occ"] for r in res] if want_occ else None
-                pred_depth = [r["depth"] for r in res] if want_depth else None
+            # the batched engine runs one chunk behind: while its kernels work on this chunk, the loop above loads (and
+            # rasterises) the next one; results are collected, scored and logged in image order
+            if batched and hasattr(eng, "submit_scenes"):
+                entry = (eng.submit_scenes(scenes, method, pairs=a.pairs, patch_or_image=a.data["patch_or_image"]),
+                         gts_occ, gts_depth, names)
+            elif batched:
+                entry = (eng.infer_scenes(scenes, method, pairs=a.pairs, patch_or_image=a.data["patch_or_image"]),
+                         gts_occ, gts_depth, names)
             else:
-                pred_occ, pred_depth = (preds if want_occ else None), (preds if want_depth else None)
-            if want_occ:
-                rows = _engine.metrics_prf(pred_occ, gts_occ, a.zd)
-                prf_rows.extend(rows.tolist())
-            if want_depth:
-                rows = _engine.metrics_whdr(pred_depth, [g[0] for g in gts_depth], [g[1] for g in gts_depth],
-                                            [g[2] for g in gts_depth])
-                whdr_rows.extend(rows.tolist())
-            for k, fn in enumerate(names):
-                if want_depth:
-                    w = whdr_rows[len(whdr_rows) - len(names) + k]
-                    self._log("[%s]\t%.3f | %.3f | %.3f" % (fn, w[2], w[5], w[8]))      # ovlX_all | ovlO_all | ovlOX_all
-                if want_occ:
-                    p = prf_rows[len(prf_rows) - len(names) + k]
-                    self._log("\t\t\trecall=%.3f / precision=%.3f / f1=%.3f" % (p[0], p[1], p[2]))
+                entry = (preds, gts_occ, gts_depth, names)
+            inflight.append(entry)
+            if len(inflight) > 1:
+                finalize(inflight.pop(0))
+        while inflight:
+            finalize(inflight.pop(0))
         if world > 1:
             prf = _sharding.gather_metric_rows(np.asarray(prf_rows, np.float64).reshape(-1, 3), mine, n_total) if want_occ else None
             whdr = _sharding.gather_metric_rows(np.asarray(whdr_rows, np.float64).reshape(-1, 9), mine, n_total) if want_depth else None
