@@ -411,7 +411,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     steps, warmup = args.steps, args.warmup
-    sample_pairs = 10                                           # 5 instances -> 10 pairs per step
+    sample_pairs = 45                                           # one whole C2 image per step: 10 instances -> 45 pairs (~1.6 s)
     vals = []
     kind = "reference"
     for s in range(warmup + steps):
@@ -803,7 +803,7 @@ def main():
         elif world == 1 and not args.no_cpu_baseline and args.mode == "patch256":
             # (i) the faithful baseline: the reference as written (two batch-1 forwards per pair); (ii) beside it the
             # best case for a CPU: the same algorithm with 16 forwards per batch (the oracle port)
-            r = cpu_reference_pairs_per_s(args.cpu_sample_pairs // 3)
+            r = cpu_reference_pairs_per_s(max(args.cpu_sample_pairs, 300))     # ~ 10 s on 16 host cores
             kind = "reference"
             if r is None:
                 kind, r = "port", cpu_port_pairs_per_s(args.cpu_sample_pairs // 3, batch1=True)
@@ -854,7 +854,8 @@ def main():
                           traffic=traffic,
                           kernel=("whole step: encoder (once per image) + two trunks, algorithmic FLOPs of this "
                                   "formulation" if depth else
-                                  "conv_tc / conv_tn / conv_fused / stem kernels (all 53 conv layers)"),
+                                  "conv_tc (single CTA / CTA pair) / conv_tn / conv_row3 / conv_fused / stem_pool kernels (all 53 conv "
+                                  "layers)"),
                           launches_timed=n_conv, avg_launch_ms=conv_ms / max(n_conv, 1),
                           conv_share_of_step=conv_ms / tot_ms if tot_ms else None, peak_source=peaks["source"],
                           step_tflops=value / world * FLOP_PER_PAIR / 1e12,

@@ -40,7 +40,7 @@ def main():
     full = max(b - a for a, b in segs)
     a, b = [sg for sg in segs if sg[1] - sg[0] == full][-1]
     step = [launches[k] for k in order[a:b]]
-    conv = [L for L in step if L["kernel"].startswith("conv_")]
+    conv = [L for L in step if L["kernel"].startswith(("conv_", "stem_"))]   # stem_pool_kernel is conv1 + pool
     tot = sum(L.get("gpu__time_duration.sum", 0) for L in step)
     ct = sum(L.get("gpu__time_duration.sum", 0) for L in conv)
     out = dict(dram_bytes_per_launch=sum(L.get("dram__bytes_read.sum", 0) + L.get("dram__bytes_write.sum", 0) for L in conv) * 1e6 / len(conv),
