@@ -13,7 +13,9 @@
 // epilogue: out[x] = D[x - 1, kx = 0] + D[x, kx = 1] + D[x + 1, kx = 2], neighbours fetched with warp shuffles (TMEM
 // lane = pixel), the lane 31 | lane 0 seam between the two warps of an image row through 2 KB of shared memory, zero
 // at the image border.  Input rows are resident in a shared-memory ring as in conv_halo.cu (each row loaded once per
-// 16-row strip, +2 halo rows), the 3 x 3 x 64 x 64 filter (72 KB) too.
+// 16-row strip, +2 halo rows), the 3 x 3 x 64 x 64 filter (72 KB) too.  The epilogue -- not the MMAs -- bounds the
+// kernel, so two teams of eight warps work on alternate tiles (one TMEM accumulator each): 0.207 (conv_halo) -> 0.183
+// (one team) -> 0.160 ms per launch of 512 images.
 #include "conv_tc.cuh"
 
 namespace io {
@@ -24,8 +26,8 @@ constexpr int R3_RING = 8;                        // ring rows (4 groups of 2) +
 constexpr int R3_X_BYTES = (R3_RING + 1) * R3_ROW_BYTES;
 constexpr int R3_W_BYTES = 9 * 8192;              // slab (ky, kx) = [64 cout][64 cin]; B of ky = 3 slabs = 192 rows
 constexpr int R3_REGION = 4096;                   // 32 pixels x 64 channels
-constexpr int R3_EPI_BYTES = 4 * 2 * R3_REGION;   // 4 lane quadrants x 2 slots
-constexpr int R3_XCH_BYTES = 2 * 2 * 2 * 2 * 32 * 4;   // [tile parity][row of the tile][half][direction][32 floats]
+constexpr int R3_EPI_BYTES = 2 * 4 * 2 * R3_REGION;   // 2 teams x 4 lane quadrants x 2 slots
+constexpr int R3_XCH_BYTES = 2 * 2 * 2 * 2 * 32 * 4;   // [team][row of the tile][channel half][direction][32 floats]
 constexpr int R3_N = 192;
 constexpr int R3_ACC_COLS = 256;
 constexpr int R3_SMEM = R3_W_BYTES + R3_X_BYTES + R3_EPI_BYTES + R3_XCH_BYTES + 512 + 256 + 1024;
@@ -47,7 +49,7 @@ __device__ __forceinline__ R3Item r3_item(const HaloParams& p, int w) {
 }
 }  // namespace
 
-__global__ void __launch_bounds__(320, 1) conv_row3_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(576, 1) conv_row3_kernel(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
@@ -151,85 +153,98 @@ __global__ void __launch_bounds__(320, 1) conv_row3_kernel(const __grid_constant
       }
     }
   } else {
-    // ======================= epilogue (warps 2..9) =======================
+    // ======================= epilogue: two teams of 8 warps (2..9, 10..17), alternate tiles =======================
+    // With one team the kernel was bound by the per-tile latency CHAIN of the epilogue (TMEM load -> seam exchange ->
+    // shuffles -> staging -> store; ~2700 cycles against 1152 of MMAs, unchanged by splitting a tile over more warps):
+    // team k takes the tiles with (tile count & 1) == k, i.e. accumulator k, so two chains overlap.
+    const int team = (warp - 2) >> 3;
+    const int e = (warp - 2) & 7;
     const int q = warp & 3;             // TMEM lane quadrant: pixels 32q .. 32q+31 of the tile = image row q >> 1, x = 32 (q & 1) + lane
-    const int hs = (warp - 2) >> 2;     // output channels 32 hs .. 32 hs + 31
+    const int hs = e >> 2;              // output channels 32 hs .. 32 hs + 31 (two passes of 16)
     const int rsel = q >> 1;            // image row of the tile
     const bool right_half = (q & 1) != 0;
     const bool leader = hs == 0 && lane == 0;
-    int tcount = 0;
+    const int bar_id = 1 + team * 2 + rsel;   // the four warps of (team, image row)
+    const int src_l = (lane + 31) & 31, src_r = (lane + 1) & 31;
+    int tcount = 0, mine = 0;
     for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
       const R3Item it = r3_item(p, w);
       for (int t = it.t_begin; t < it.t_end; ++t, ++tcount) {
-        const int acc = tcount & 1;
+        if ((tcount & 1) != team) continue;
+        const int acc = team;
         mbar_wait(&tfull[acc], (tcount >> 1) & 1);
         tc_fence_after();
-        uint32_t vl[32], vm[32], vr[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * R3_ACC_COLS + 32 * hs;
-        tmem_ld32(taddr, vl);            // kx = 0: contribution of this pixel to the output pixel on its right
-        tmem_ld32(taddr + 64, vm);       // kx = 1
-        tmem_ld32(taddr + 128, vr);      // kx = 2: ... to the output pixel on its left
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        // seam between the two warps of an image row: x = 31 (left warp, lane 31) | x = 32 (right warp, lane 0)
-        float* xch = sXch + (((tcount & 1) * 2 + rsel) * 2 + hs) * 64;   // [0, 32): left warp's vl, [32, 64): right warp's vr
-        if (!right_half && lane == 31) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) xch[i] = __uint_as_float(vl[i]);
-        }
-        if (right_half && lane == 0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) xch[32 + i] = __uint_as_float(vr[i]);
-        }
-        if (leader) tma_store_wait_read<1>();     // the store that last read this warp pair's staging slot
-        r3_named_bar(1 + rsel, 128);              // the four warps of the image row
-        uint8_t* region = sEpi + (q * 2 + (tcount & 1)) * R3_REGION;
+        uint8_t* region = sEpi + ((team * 4 + q) * 2 + (mine & 1)) * R3_REGION;
         uint8_t* rowp = region + lane * 128;
-        // The value a warp's edge lane would hand to a pixel outside its image row is never used (left warp: lane 31's vl
-        // went to the seam buffer; right warp: lane 31 is x = 63), so that register takes what the opposite edge lane
-        // must RECEIVE -- the other warp's seam value, or zero at the image border -- and a rotating shuffle then serves
-        // all 32 lanes without per-element selects.
-        if (lane == 31) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) vl[i] = right_half ? __float_as_uint(xch[i]) : 0u;
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) vr[i] = right_half ? 0u : __float_as_uint(xch[32 + i]);
-        }
-        __syncwarp();
-        const float4* bias4 = reinterpret_cast<const float4*>(sBias + 32 * hs);
-        const int src_l = (lane + 31) & 31, src_r = (lane + 1) & 31;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float bb[8];
-          *reinterpret_cast<float4*>(&bb[0]) = bias4[2 * k];  *reinterpret_cast<float4*>(&bb[4]) = bias4[2 * k + 1];
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int i = 8 * k + e;
-            const float fl = __uint_as_float(__shfl_sync(0xffffffffu, vl[i], src_l));
-            const float fr = __uint_as_float(__shfl_sync(0xffffffffu, vr[i], src_r));
-            o[e] = (__uint_as_float(vm[i]) + fl) + fr + bb[e];
+        float* xch = sXch + ((team * 2 + rsel) * 2 + hs) * 64;   // [0, 32): left warp's vl, [32, 64): right warp's vr
+        if (leader) tma_store_wait_read<1>();     // the store that last read this staging slot
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {          // 16 channels at a time (register budget of 18 warps)
+          uint32_t vl[16], vm[16], vr[16];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * R3_ACC_COLS + 32 * hs + 16 * c2;
+          tmem_ld16(taddr, vl);            // kx = 0: contribution of this pixel to the output pixel on its right
+          tmem_ld16(taddr + 64, vm);       // kx = 1
+          tmem_ld16(taddr + 128, vr);      // kx = 2: ... to the output pixel on its left
+          tmem_ld_wait();
+          if (c2 == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          uint4 v4;
-          if (p.relu) {
-            v4.x = pack_bf16_relu(o[0], o[1]); v4.y = pack_bf16_relu(o[2], o[3]);
-            v4.z = pack_bf16_relu(o[4], o[5]); v4.w = pack_bf16_relu(o[6], o[7]);
-          } else {
-            v4.x = pack_bf16(o[0], o[1]); v4.y = pack_bf16(o[2], o[3]);
-            v4.z = pack_bf16(o[4], o[5]); v4.w = pack_bf16(o[6], o[7]);
+          // seam between the two warps of an image row: x = 31 (left warp, lane 31) | x = 32 (right warp, lane 0)
+          if (!right_half && lane == 31) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xch[16 * c2 + i] = __uint_as_float(vl[i]);
           }
-          *reinterpret_cast<uint4*>(rowp + (((hs * 4 + k) ^ (lane & 7)) << 4)) = v4;
+          if (right_half && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xch[32 + 16 * c2 + i] = __uint_as_float(vr[i]);
+          }
+          r3_named_bar(bar_id, 128);
+          // The value a warp's edge lane would hand to a pixel outside its image row is never used (left warp: lane 31's
+          // vl went to the seam buffer; right warp: lane 31 is x = 63), so that register takes what the opposite edge
+          // lane must RECEIVE -- the other warp's seam value, or zero at the image border -- and a rotating shuffle then
+          // serves all 32 lanes without per-element selects.
+          if (lane == 31) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vl[i] = right_half ? __float_as_uint(xch[16 * c2 + i]) : 0u;
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vr[i] = right_half ? 0u : __float_as_uint(xch[32 + 16 * c2 + i]);
+          }
+          __syncwarp();
+          const float4* bias4 = reinterpret_cast<const float4*>(sBias + 32 * hs + 16 * c2);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            float bb[8];
+            *reinterpret_cast<float4*>(&bb[0]) = bias4[2 * k];  *reinterpret_cast<float4*>(&bb[4]) = bias4[2 * k + 1];
+            float o[8];
+#pragma unroll
+            for (int el = 0; el < 8; ++el) {
+              const int i = 8 * k + el;
+              const float fl = __uint_as_float(__shfl_sync(0xffffffffu, vl[i], src_l));
+              const float fr = __uint_as_float(__shfl_sync(0xffffffffu, vr[i], src_r));
+              o[el] = (__uint_as_float(vm[i]) + fl) + fr + bb[el];
+            }
+            uint4 v4;
+            if (p.relu) {
+              v4.x = pack_bf16_relu(o[0], o[1]); v4.y = pack_bf16_relu(o[2], o[3]);
+              v4.z = pack_bf16_relu(o[4], o[5]); v4.w = pack_bf16_relu(o[6], o[7]);
+            } else {
+              v4.x = pack_bf16(o[0], o[1]); v4.y = pack_bf16(o[2], o[3]);
+              v4.z = pack_bf16(o[4], o[5]); v4.w = pack_bf16(o[6], o[7]);
+            }
+            *reinterpret_cast<uint4*>(rowp + (((hs * 4 + c2 * 2 + k) ^ (lane & 7)) << 4)) = v4;
+          }
         }
         fence_proxy_async();
-        r3_named_bar(1 + rsel, 128);
+        r3_named_bar(bar_id, 128);
         if (leader) {
           tma_store_2d(&p.map_out, region, 0, it.img * 4096 + t * 128 + q * 32);
           tma_store_commit();
         }
+        ++mine;
       }
     }
     if (leader) tma_store_wait_all();
@@ -287,7 +302,7 @@ int conv_row3_launch(const HaloParams& p, cudaStream_t stream) {
   const int grid = p.items < num_sms() ? p.items : num_sms();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(320);
+  cfg.blockDim = dim3(576);
   cfg.dynamicSmemBytes = R3_SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
