@@ -63,6 +63,7 @@ struct ConvParams {
   // CTA-pair kernel (cta_group::2, N = 256 tiles): map_b boxes are 64 x 128 (each CTA of the pair stages half the tile's
   // weight rows), 4-stage ring of 32 KB
   int pair;
+  int epi_one_slot;   // pair kernel without a residual: one epilogue staging slot per warp, one more ring stage
 };
 
 // conv3 (+ residual + ReLU) of one bottleneck fused with conv1 (+ ReLU) of the next one (conv_fused.cu)
