@@ -99,6 +99,14 @@ def test_conv_dgrad(case, use_res):
     assert not (err > tol).any(), "max err %.4g, %d bad" % (float(err.max()), int((err > tol).sum()))
 
 
+# the data gradient through the CTA-pair kernel (N = Cin >= 256 tiles): MN-major weight slabs split between the two CTAs
+@pytest.mark.parametrize("case", [c for c in DGRAD_CASES if c[3] >= 256], ids=lambda c: "pair_B%d_%dx%d_%d-%d_k%d" % c)
+@pytest.mark.parametrize("use_res", [False, True], ids=["", "res"])
+def test_conv_dgrad_pair_kernel(case, use_res, monkeypatch):
+    monkeypatch.setenv("INSTAORDER_PAIR", "2")
+    test_conv_dgrad(case, use_res)
+
+
 @pytest.mark.parametrize("pairs,d", [(3, 256), (2, 64), (2, 128)])
 def test_stem_wgrad(pairs, d):
     """two-direction stem weight gradient from the pair tensor vs fp32 autograd of the 5-channel 7x7 s2 conv."""
